@@ -1,0 +1,108 @@
+// TEST INFRASTRUCTURE ONLY -- part of the CPU oracle (see oracle/README.md).
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it.
+//
+// Philox4x32-10 counter-based RNG (Salmon et al., SC'11; Random123 v1.14 published algorithm and
+// known-answer vectors, checked in tests/test_oracle_philox.py).  The reference (Merzbild.jl) draws
+// from one sequential `AbstractRNG` passed as the first argument of every operator
+// (e.g. src/collisions/collision_ntc.jl:338, src/convection/convection_1D.jl:130); a GPU cannot replay
+// one sequential stream, so both the oracle and the CUDA path key an independent stream per
+// (seed, operator, substream, timestep, entity) -- see DESIGN.md "RNG convention".
+#pragma once
+#include <cstdint>
+
+namespace mbo {
+
+struct Philox4x32 {
+    static inline void round(uint32_t c[4], const uint32_t k[2]) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+        const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+        const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+        const uint32_t n0 = hi1 ^ c[1] ^ k[0];
+        const uint32_t n2 = hi0 ^ c[3] ^ k[1];
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    }
+    static inline void block(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+        uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+        uint32_t k[2] = {key[0], key[1]};
+        for (int r = 0; r < 10; r++) {
+            round(c, k);
+            k[0] += 0x9E3779B9u;
+            k[1] += 0xBB67AE85u;
+        }
+        out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+    }
+};
+
+// operator ids (the "stream" word of the counter); must match merzbild.jl_b200/csrc/mb_philox.cuh
+enum : uint32_t {
+    OP_NTC = 1, OP_CONVECT = 2, OP_MERGE = 3, OP_SWPM = 4, OP_FP = 5, OP_SAMPLE = 6, OP_USER = 7
+};
+
+// One stream: key = 64-bit seed; counter = (block, entity, timestep, op | substream << 8).
+// Draw d (0-based) of the stream is the (d & 1)-th double of block d >> 1:
+// u = ((hi32 << 32 | lo32) >> 11) * 2^-53 in [0, 1), words (0,1) then (2,3) with word 2k+1 the high half.
+struct PhiloxStream {
+    uint32_t key[2];
+    uint32_t ctr[4];
+    uint32_t buf[4];
+    int have;  // doubles left in buf (0, 1 or 2)
+
+    PhiloxStream() : have(0) { key[0] = key[1] = 0; ctr[0] = ctr[1] = ctr[2] = ctr[3] = 0; }
+    PhiloxStream(uint64_t seed, uint32_t op, uint32_t substream, uint32_t timestep, uint32_t entity) {
+        reset(seed, op, substream, timestep, entity);
+    }
+    void reset(uint64_t seed, uint32_t op, uint32_t substream, uint32_t timestep, uint32_t entity) {
+        key[0] = (uint32_t)seed;
+        key[1] = (uint32_t)(seed >> 32);
+        ctr[0] = 0;
+        ctr[1] = entity;
+        ctr[2] = timestep;
+        ctr[3] = (op & 0xFFu) | (substream << 8);
+        have = 0;
+    }
+    static inline double to_double(uint32_t lo, uint32_t hi) {
+        const uint64_t u = ((uint64_t)hi << 32) | lo;
+        return (double)(u >> 11) * (1.0 / 9007199254740992.0);
+    }
+    inline double rand() {
+        if (have == 0) {
+            Philox4x32::block(ctr, key, buf);
+            ctr[0]++;
+            have = 2;
+            have--;
+            return to_double(buf[0], buf[1]);
+        }
+        have--;
+        return to_double(buf[2], buf[3]);
+    }
+};
+
+// xoshiro256++ seeded with splitmix64: a plain sequential generator for the "one rng object passed
+// around" mode of the reference (used by the CPU baseline driver and the statistical tests; the
+// reference's own Xoshiro/StableRNG bit streams are not reproducible here -- see DESIGN.md).
+struct Xoshiro256pp {
+    uint64_t s[4];
+    explicit Xoshiro256pp(uint64_t seed = 1234) {
+        uint64_t z = seed;
+        for (int i = 0; i < 4; i++) {
+            z += 0x9E3779B97F4A7C15ull;
+            uint64_t x = z;
+            x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+            x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+            s[i] = x ^ (x >> 31);
+        }
+    }
+    static inline uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+    inline uint64_t next() {
+        const uint64_t result = rotl(s[0] + s[3], 23) + s[0];
+        const uint64_t t = s[1] << 17;
+        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3];
+        s[2] ^= t;
+        s[3] = rotl(s[3], 45);
+        return result;
+    }
+    inline double rand() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+};
+
+}  // namespace mbo
