@@ -1,0 +1,321 @@
+// NTC / VHS collisions: ntc! (collision_ntc.jl:338-380 one species, :412-453 two species), ntc_equal_weight!
+// (:479-521, :554-595), collide_2particles_vhs! (:223-270, variable weight: the heavier particle is split),
+// collide_2particles_vhs_equal_weight! (:294-309), compute_n_coll_* (:173-197), compute_g!/compute_com!
+// (collision_utils.jl:374-391), sigma_vhs (collision_cross_sections.jl:179-181), scatter_vhs! (collision_scattering.jl:17-29).
+//
+// Parallelisation: NTC is sequential within a cell (sigma_g_w_max is raised inside the candidate loop and a particle can
+// be picked twice), and at DSMC conditions only a few % of a cell's particles are touched per step, so the kernel runs
+// ONE THREAD PER CELL: each thread replays the reference's candidate loop for its cell with its own Philox stream
+// (OP_NTC, substream, timestep, cell) -- draw for draw the same sequence the CPU oracle consumes -- and gathers only the
+// picked particles.  All cells of the range run concurrently.
+//
+// Variable-weight splits: the reference appends each split particle at logical position n_total + 1 (particles.jl:426-433);
+// processing cells sequentially this packs the new group-2 ranges at the tail in cell order.  On the device every cell gets
+// a private window at the tail, sized by its candidate count (an upper bound on its splits, known before the loop from
+// the first draw): n_coll pre-pass -> exclusive scan -> collide -> pack the windows (scan of actual split counts).  The
+// state after the call is the reference's: same logical positions, same pia.
+#include "mb_common.cuh"
+#include "mb_scan.cuh"
+
+namespace mb {
+
+struct NtcArgs {
+    SoA p1, p2;            // p2 == p1 for one species
+    Indexer* ix1;          // indexer rows of the two species
+    Indexer* ix2;
+    int64_t* n_total1;     // device n_total of the species
+    int64_t* n_total2;
+    int64_t cap1, cap2;
+    double* sgwm;
+    int64_t *n_coll, *n_perf, *n_eqw;
+    mb_interaction it;
+    int64_t cell_lo, cell_hi;   // 1-based inclusive
+    double dt, V, dw_tol;
+    uint64_t seed;
+    uint32_t timestep, substream;
+    int equal_weight;
+    int32_t* ncoll32;      // VW: candidate count per cell of the range (pre-pass)
+    int64_t* win;          // VW: exclusive scan of ncoll32 (n_range + 1)
+    int32_t* nsplit1;      // VW: number of new particles per cell (species 1 / 2)
+    int32_t* nsplit2;
+    int* flags;
+    int single_cell_tail;  // VW: one cell whose existing group 2 ends at n_total (0-D usage)
+};
+
+__device__ __forceinline__ int64_t ncoll_of(double dt, double V, double sgwm, int64_t n1, int64_t n2, bool two, double R) {
+    // compute_n_coll_single_species (:173-176) / compute_n_coll_two_species (:195-197)
+    const double f = two ? dt * (double)n1 * (double)n2 * sgwm / V + R : 0.5 * dt * (double)n1 * (double)(n1 - 1) * sgwm / V + R;
+    return (int64_t)floor(f);
+}
+
+template <bool TWO>
+__global__ void __launch_bounds__(128) k_ntc_prepass(NtcArgs a) {
+    const int64_t nr = a.cell_hi - a.cell_lo + 1;
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nr; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t cell = a.cell_lo + r;
+        const int64_t n1 = a.ix1[cell - 1].n_local, n2 = TWO ? a.ix2[cell - 1].n_local : n1;
+        PhiloxStream rng(a.seed, OP_NTC, a.substream, a.timestep, (uint32_t)cell);
+        int64_t nc = ncoll_of(a.dt, a.V, a.sgwm[cell - 1], n1, n2, TWO, rng.rand());
+        if (nc < 0) nc = 0;
+        if (nc > 0x7fffffff) nc = 0x7fffffff;
+        a.ncoll32[r] = (int32_t)nc;
+    }
+}
+
+struct PRef {  // a particle picked for a collision: physical (0-based) position in its SoA
+    int64_t pos;
+    double w, vx, vy, vz;
+};
+__device__ __forceinline__ void load_p(const SoA& s, int64_t pos, PRef& p) {
+    p.pos = pos;
+    p.w = s.a[F_W][pos]; p.vx = s.a[F_VX][pos]; p.vy = s.a[F_VY][pos]; p.vz = s.a[F_VZ][pos];
+}
+__device__ __forceinline__ int64_t map_cont(const Indexer& q, int64_t i) {  // particles.jl:364-366, returned 0-based
+    return (i < q.n_group1 ? i + q.start1 : (i - q.n_group1) + q.start2) - 1;
+}
+// split: append (dw, v, x of the parent) as a new group-2 particle (collision_ntc.jl:238-267, particles.jl:426-433)
+__device__ __forceinline__ void append_split(const SoA& s, Indexer& q, int64_t winlo, int64_t parent, double dw, double vx, double vy, double vz) {
+    const int64_t pos = q.n_group2 > 0 ? q.end2 : winlo;  // 0-based position of the new particle (end2 is 1-based -> next slot)
+    if (q.n_group2 == 0) q.start2 = winlo + 1;
+    q.n_group2 += 1;
+    q.n_local += 1;
+    q.end2 = pos + 1;
+    s.a[F_W][pos] = dw;
+    s.a[F_VX][pos] = vx; s.a[F_VY][pos] = vy; s.a[F_VZ][pos] = vz;
+    s.a[F_X][pos] = s.a[F_X][parent]; s.a[F_Y][pos] = s.a[F_Y][parent]; s.a[F_Z][pos] = s.a[F_Z][parent];
+}
+
+template <bool TWO>
+__global__ void __launch_bounds__(128) k_ntc(NtcArgs a) {
+    const int64_t nr = a.cell_hi - a.cell_lo + 1;
+    const bool vw = !a.equal_weight;
+    int64_t nt1 = 0, nt2 = 0;
+    if (vw) {
+        nt1 = *a.n_total1;
+        nt2 = TWO ? *a.n_total2 : nt1;
+        const int64_t wtot = a.win[nr];
+        if (nt1 + wtot > a.cap1 || (TWO && nt2 + wtot > a.cap2)) {  // uniform: nobody collides, the host reports MB_ERR_CAPACITY
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                atomicOr(&a.flags[0], DEVERR_CAPACITY);
+                const int64_t need = (nt1 > nt2 ? nt1 : nt2) + wtot;
+                a.flags[1] = need > 0x7fffffff ? 0x7fffffff : (int)need;
+            }
+            return;
+        }
+    }
+    const mb_interaction it = a.it;
+    const double pw = 1.0 - 2 * it.vhs_o;
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nr; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t cell = a.cell_lo + r;
+        Indexer q1 = a.ix1[cell - 1];
+        Indexer q2 = TWO ? a.ix2[cell - 1] : q1;
+        int64_t win1 = 0, win2 = 0;
+        const int64_t g2_before1 = q1.n_group2, g2_before2 = q2.n_group2;
+        if (vw) {
+            win1 = nt1 + a.win[r];
+            win2 = nt2 + a.win[r];
+            // precondition of the reference (new particles go to n_total + 1): an existing group 2 must end at n_total
+            bool ok1 = q1.n_group2 == 0 || (a.single_cell_tail && q1.end2 == nt1);
+            bool ok2 = !TWO || q2.n_group2 == 0 || (a.single_cell_tail && q2.end2 == nt2);
+            if (!(ok1 && ok2)) { atomicOr(&a.flags[0], DEVERR_PRECONDITION); a.nsplit1[r] = 0; if (TWO) a.nsplit2[r] = 0; continue; }
+        }
+        PhiloxStream rng(a.seed, OP_NTC, a.substream, a.timestep, (uint32_t)cell);
+        double sgwm = a.sgwm[cell - 1];
+        const int64_t n_coll = ncoll_of(a.dt, a.V, sgwm, q1.n_local, q2.n_local, TWO, rng.rand());
+        int64_t n_perf = 0, n_eqw = 0;
+        for (int64_t c = 0; c < n_coll; c++) {
+            int64_t i = (int64_t)floor(rng.rand() * (double)q1.n_local);
+            int64_t k = (int64_t)floor(rng.rand() * (double)(TWO ? q2.n_local : q1.n_local));
+            if (!TWO)
+                while (i == k) k = (int64_t)floor(rng.rand() * (double)q1.n_local);
+            PRef pi, pk;
+            load_p(a.p1, map_cont(q1, i), pi);
+            load_p(TWO ? a.p2 : a.p1, map_cont(TWO ? q2 : q1, k), pk);
+            const double gx = pi.vx - pk.vx, gy = pi.vy - pk.vy, gz = pi.vz - pk.vz;  // compute_g! collision_utils.jl:388-391
+            const double g = sqrt(gx * gx + gy * gy + gz * gz);
+            if (!(g > EPS)) continue;
+            const double sigma = it.vhs_factor * pow(g, pw);  // sigma_vhs
+            const double sgw = sigma * g * fmax(pi.w, pk.w);
+            sgwm = fmax(sgw, sgwm);
+            if (rng.rand() < sgw / sgwm) {
+                n_perf += 1;
+                const double cx = it.mu1 * pi.vx + it.mu2 * pk.vx, cy = it.mu1 * pi.vy + it.mu2 * pk.vy,
+                             cz = it.mu1 * pi.vz + it.mu2 * pk.vz;  // compute_com!
+                if (!vw) {
+                    n_eqw += 1;
+                } else if (fabs(pi.w - pk.w) < a.dw_tol) {
+                    n_eqw += 1;
+                } else if (pi.w > pk.w) {
+                    append_split(a.p1, q1, win1, pi.pos, pi.w - pk.w, pi.vx, pi.vy, pi.vz);
+                    a.p1.a[F_W][pi.pos] = pk.w;
+                    if (!TWO) q2 = q1;
+                } else {
+                    if (TWO) {
+                        append_split(a.p2, q2, win2, pk.pos, pk.w - pi.w, pk.vx, pk.vy, pk.vz);
+                        a.p2.a[F_W][pk.pos] = pi.w;
+                    } else {
+                        append_split(a.p1, q1, win1, pk.pos, pk.w - pi.w, pk.vx, pk.vy, pk.vz);
+                        a.p1.a[F_W][pk.pos] = pi.w;
+                        q2 = q1;
+                    }
+                }
+                // scatter_vhs! collision_scattering.jl:17-29
+                const double phi = twopi * rng.rand();
+                double sphi, cphi;
+                sincos(phi, &sphi, &cphi);
+                const double ctheta = 2.0 * rng.rand() - 1.0;
+                const double stheta = sqrt(1.0 - ctheta * ctheta);
+                const double nx = g * (stheta * cphi), ny = g * (stheta * sphi), nz = g * ctheta;
+                a.p1.a[F_VX][pi.pos] = cx + it.mu2 * nx;
+                a.p1.a[F_VY][pi.pos] = cy + it.mu2 * ny;
+                a.p1.a[F_VZ][pi.pos] = cz + it.mu2 * nz;
+                const SoA& sk = TWO ? a.p2 : a.p1;
+                sk.a[F_VX][pk.pos] = cx - it.mu1 * nx;
+                sk.a[F_VY][pk.pos] = cy - it.mu1 * ny;
+                sk.a[F_VZ][pk.pos] = cz - it.mu1 * nz;
+            }
+        }
+        a.sgwm[cell - 1] = sgwm;
+        a.n_coll[cell - 1] = n_coll;
+        a.n_perf[cell - 1] = n_perf;
+        a.n_eqw[cell - 1] = n_eqw;
+        if (vw) {
+            a.ix1[cell - 1] = q1;
+            a.nsplit1[r] = (int32_t)(q1.n_group2 - g2_before1);
+            if (TWO) { a.ix2[cell - 1] = q2; a.nsplit2[r] = (int32_t)(q2.n_group2 - g2_before2); }
+        }
+    }
+}
+
+// pack the per-cell windows to the left (cell order) so the layout equals the reference's sequential appends
+static __global__ void __launch_bounds__(256) k_ntc_pack(SoA cur, SoA alt, Indexer* __restrict__ ix, int64_t cell_lo, int64_t nr,
+                                                         const int64_t* __restrict__ win, const int64_t* __restrict__ packed,
+                                                         const int32_t* __restrict__ nsplit, const int64_t* n_total, int phase) {
+    const int64_t nt = *n_total;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < nr; r += nwarps) {
+        const int n = nsplit[r];
+        if (n <= 0 || win[r] == packed[r]) continue;
+        const int64_t olo = nt + win[r], nlo = nt + packed[r];
+        if (phase == 0) {
+            for (int j = lane; j < n; j += 32)
+#pragma unroll
+                for (int f = 0; f < 7; f++) alt.a[f][nlo + j] = cur.a[f][olo + j];
+        } else {
+            for (int j = lane; j < n; j += 32)
+#pragma unroll
+                for (int f = 0; f < 7; f++) cur.a[f][nlo + j] = alt.a[f][nlo + j];
+            if (lane == 0) {
+                Indexer q = ix[cell_lo - 1 + r];
+                q.start2 = nlo + 1;
+                q.end2 = nlo + n;
+                ix[cell_lo - 1 + r] = q;
+            }
+        }
+    }
+}
+static __global__ void k_add_total(int64_t* n_total, const int64_t* packed, int64_t nr) {
+    *n_total += packed[nr];
+}
+
+static int ntc_impl(mb_ctx* ctx, mb_cf* cf, const mb_interaction* it, mb_pv* pv1, mb_pv* pv2, mb_pia* pia, int64_t cell_lo, int64_t cell_hi,
+                    int64_t s1, int64_t s2, double dt, double V, double dw_tol, int equal_weight, uint32_t timestep, uint32_t substream,
+                    bool two) {
+    MB_ARG(ctx && cf && it && pv1 && pv2 && pia, "NULL handle");
+    MB_ARG(s1 >= 1 && s1 <= pia->n_species && s2 >= 1 && s2 <= pia->n_species, "species out of range");
+    MB_ARG(cell_lo >= 1 && cell_hi <= pia->n_cells && cell_lo <= cell_hi, "cell range");
+    MB_ARG(cf->n_cells == pia->n_cells, "cf.n_cells != pia.n_cells");
+    MB_ARG(V > 0.0, "V must be > 0");
+    MB_ARG(!two || s1 != s2, "two-species ntc needs two different species");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    const int64_t nc = pia->n_cells, nr = cell_hi - cell_lo + 1;
+    NtcArgs a;
+    a.p1 = pv1->cur; a.p2 = pv2->cur;
+    a.ix1 = pia->d_indexer + (s1 - 1) * nc;
+    a.ix2 = pia->d_indexer + (s2 - 1) * nc;
+    a.n_total1 = pia->d_n_total + (s1 - 1);
+    a.n_total2 = pia->d_n_total + (s2 - 1);
+    a.cap1 = pv1->cap; a.cap2 = pv2->cap;
+    a.sgwm = cf->sigma_g_w_max;
+    a.n_coll = cf->n_coll; a.n_perf = cf->n_coll_performed; a.n_eqw = cf->n_eq_w;
+    a.it = *it;
+    a.cell_lo = cell_lo; a.cell_hi = cell_hi;
+    a.dt = dt; a.V = V; a.dw_tol = dw_tol;
+    a.seed = ctx->seed; a.timestep = timestep; a.substream = substream;
+    a.equal_weight = equal_weight;
+    a.flags = ctx->d_flags;
+    a.single_cell_tail = (nr == 1);
+    a.ncoll32 = nullptr; a.win = nullptr; a.nsplit1 = nullptr; a.nsplit2 = nullptr;
+    cudaStream_t st = ctx->stream;
+    const int g = grid_for(nr, 128, 16);
+    ProfScope ps(ctx, PROF_NTC);
+    if (equal_weight) {
+        if (two) k_ntc<true><<<g, 128, 0, st>>>(a);
+        else k_ntc<false><<<g, 128, 0, st>>>(a);
+        MB_LAUNCH_CHECK(ctx);
+        return MB_OK;
+    }
+    // variable weight
+    int r = pv_ensure_alt(pv1);
+    if (r) return r;
+    if (two) { r = pv_ensure_alt(pv2); if (r) return r; }
+    int32_t* p32 = (int32_t*)ctx_scratch(ctx, 4, (size_t)(3 * nr) * 4);
+    int64_t* p64 = (int64_t*)ctx_scratch(ctx, 5, ((size_t)3 * (nr + 1) + gs_partial_count(nr)) * 8);
+    if (!p32 || !p64) return MB_ERR_CUDA;
+    a.ncoll32 = p32; a.nsplit1 = p32 + nr; a.nsplit2 = p32 + 2 * nr;
+    a.win = p64;
+    int64_t* packed1 = p64 + (nr + 1);
+    int64_t* packed2 = p64 + 2 * (nr + 1);
+    int64_t* partial = p64 + 3 * (nr + 1);
+    if (two) k_ntc_prepass<true><<<g, 128, 0, st>>>(a);
+    else k_ntc_prepass<false><<<g, 128, 0, st>>>(a);
+    MB_LAUNCH_CHECK(ctx);
+    r = device_exclusive_scan(ctx, a.ncoll32, nr, a.win, partial);
+    if (r) return r;
+    MB_CUDA(cudaMemsetAsync(a.nsplit1, 0, (size_t)(2 * nr) * 4, st));
+    if (two) k_ntc<true><<<g, 128, 0, st>>>(a);
+    else k_ntc<false><<<g, 128, 0, st>>>(a);
+    MB_LAUNCH_CHECK(ctx);
+    const int gw = grid_for(nr * 32, 256, 8);
+    for (int sp = 0; sp < (two ? 2 : 1); sp++) {
+        mb_pv* pv = sp == 0 ? pv1 : pv2;
+        int32_t* ns = sp == 0 ? a.nsplit1 : a.nsplit2;
+        int64_t* packed = sp == 0 ? packed1 : packed2;
+        Indexer* ix = sp == 0 ? a.ix1 : a.ix2;
+        int64_t* nt = sp == 0 ? a.n_total1 : a.n_total2;
+        r = device_exclusive_scan(ctx, ns, nr, packed, partial);
+        if (r) return r;
+        if (nr > 1) {
+            k_ntc_pack<<<gw, 256, 0, st>>>(pv->cur, pv->alt, ix, cell_lo, nr, a.win, packed, ns, nt, 0);
+            MB_LAUNCH_CHECK(ctx);
+            k_ntc_pack<<<gw, 256, 0, st>>>(pv->cur, pv->alt, ix, cell_lo, nr, a.win, packed, ns, nt, 1);
+            MB_LAUNCH_CHECK(ctx);
+        }
+        k_add_total<<<1, 1, 0, st>>>(nt, packed, nr);
+        MB_LAUNCH_CHECK(ctx);
+        const int64_t sidx = (sp == 0 ? s1 : s2) - 1;
+        pia->sorted_layout[sidx] = 0;
+        pia->n_bound[sidx] = pv->cap;
+    }
+    pia->h_valid = false;
+    return MB_OK;
+}
+
+}  // namespace mb
+
+using namespace mb;
+
+extern "C" {
+
+int mb_ntc(mb_ctx* ctx, mb_cf* cf, const mb_interaction* it, mb_pv* pv, mb_pia* pia, int64_t cell_lo, int64_t cell_hi, int64_t species, double dt,
+           double V, double dw_tol, int32_t equal_weight, uint32_t timestep, uint32_t substream) {
+    return ntc_impl(ctx, cf, it, pv, pv, pia, cell_lo, cell_hi, species, species, dt, V, dw_tol, equal_weight, timestep, substream, false);
+}
+int mb_ntc2(mb_ctx* ctx, mb_cf* cf, const mb_interaction* it, mb_pv* pv1, mb_pv* pv2, mb_pia* pia, int64_t cell_lo, int64_t cell_hi, int64_t s1,
+            int64_t s2, double dt, double V, double dw_tol, int32_t equal_weight, uint32_t timestep, uint32_t substream) {
+    return ntc_impl(ctx, cf, it, pv1, pv2, pia, cell_lo, cell_hi, s1, s2, dt, V, dw_tol, equal_weight, timestep, substream, true);
+}
+
+}  // extern "C"

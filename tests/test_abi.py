@@ -1,0 +1,60 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol include/merzbild_b200.h
+declares, the ctypes mirror binds exactly that list, and the product path fails loudly without a CUDA device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "merzbild_b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mb_[A-Za-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(mb):
+    L = C.CDLL(mb.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 50
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_ctypes_mirror_binds_the_header(mb):
+    assert sorted(mb.SIGNATURES) == _declared()
+    mb.lib()
+    assert mb.lib().mb_version() >= 100
+
+
+def test_struct_layouts(mb):
+    assert C.sizeof(mb.Grid1D) == 56 and C.sizeof(mb.Walls1D) == 80 and C.sizeof(mb.Interaction) == 64 and C.sizeof(mb.OctreeParams) == 24
+
+
+def test_host_helpers_match_oracle(mb, oracle):
+    """Grid1DUniform / Interaction / sigma_g_w_max estimate are host arithmetic: identical to the oracle restatement."""
+    g = mb.Grid1DUniform(5e-4, 50)
+    o = oracle.grid_params(5e-4, 50)
+    assert (g.dx, g.inv_dx, g.min_x, g.max_x) == (o["dx"], o["inv_dx"], o["min_x"], o["max_x"])
+    m = oracle.MASS["Ar"]
+    it = mb.make_interaction(m, m, 4.11e-10, 0.81, 273.0)
+    ot = oracle.make_interaction(m, m, 4.11e-10, 0.81, 273.0)
+    assert [it.m_r, it.mu1, it.mu2, it.vhs_d, it.vhs_o, it.vhs_Tref, it.vhs_muref, it.vhs_factor] == ot.tolist()
+    assert mb.estimate_sigma_g_w_max(it, m, m, 300.0, 300.0, 1e10) == oracle.estimate_sigma_g_w_max(ot, m, m, 300.0, 300.0, 1e10)
+    # slab partition == ChunkSplitters.chunks(1:nx; n): first nx mod n slabs one longer
+    G = mb.Grid1DUniform(1.0, 10)
+    sl = [G.slab(r, 4) for r in range(4)]
+    assert [s.n_cells for s in sl] == [3, 3, 2, 2] and [s.cell_offset for s in sl] == [0, 3, 6, 8]
+
+
+def test_no_cpu_fallback(mb):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(mb.MerzbildError) as e:
+        mb.Context(0, 1)
+    assert e.value.status == mb.MB_ERR_NO_DEVICE

@@ -1,0 +1,476 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI, against the CPU oracle
+on the same seeded inputs.  Bit-exact for sort / indexing; 1e-12 relative for floating-point moments; the sequential-per-
+cell stochastic kernels replay the oracle's Philox streams draw for draw, so counters must match exactly and velocities
+to 1e-12 relative (libm pow/sincos/log differ from glibc in the last bits)."""
+import numpy as np
+import pytest
+
+from parity_util import AR, HE, assert_rows_close, assert_same_pia, maxwellian_rows, mirror_to_device, oracle_state
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(mb):
+    c = mb.Context(0, 1234)
+    yield c
+    c.close()
+
+
+# ------------------------------------------------------------------------------------------------------------ sort
+def test_sort_reference_kat(mb, oracle, ctx):
+    """test/test_grid_sorting.jl:26-125: 8 particles in reversed order, 2 then 4 cells, uneven 3/1/0/4 split."""
+    rows = np.zeros((8, 7))
+    rows[:, 0] = 2.5e9
+    rows[:, 4] = [0.99 * 8.0 * (9.0 - i) / 8 for i in range(1, 9)]
+    opv, opia = oracle_state(oracle, rows, 2)
+    opia.indexer[0, 0] = (4, 1, 4, 4, 0, -1, 0)
+    opia.indexer[0, 1] = (4, 5, 8, 4, 0, -1, 0)
+    pv, pia = mirror_to_device(mb, ctx, opv, opia)
+    g = mb.Grid1DUniform(8.0, 2)
+    mb.sort_particles(None, g, pv, pia, 1)
+    oracle.sort_particles(opv, opia, 1, grid=(8.0, 2))
+    assert_same_pia(opia, pia)
+    np.testing.assert_array_equal(pv.logical(1, 8), opv.logical(1, 8))
+    np.testing.assert_array_equal(pv.logical(1, 8)[:, 4], rows[[4, 5, 6, 7, 0, 1, 2, 3], 4])  # index [5,6,7,8,1,2,3,4]
+    # 4 cells, everything indexed from cell 1
+    opv, opia = oracle_state(oracle, rows, 4)
+    pv, pia = mirror_to_device(mb, ctx, opv, opia)
+    g4 = mb.Grid1DUniform(8.0, 4)
+    mb.sort_particles(None, g4, pv, pia, 1)
+    np.testing.assert_array_equal(pv.logical(1, 8)[:, 4], rows[[6, 7, 4, 5, 2, 3, 0, 1], 4])  # index [7,8,5,6,3,4,1,2]
+    ix = pia.indexer
+    for cell in range(1, 5):
+        assert ix[0, cell - 1].tolist() == [2, 1 + 2 * (cell - 1), 2 + 2 * (cell - 1), 2, 0, -1, 0]
+    # uneven 3/1/0/4 incl. an empty cell (0,-1)
+    rows2 = rows.copy()
+    rows2[0:4, 4] = 6.75
+    rows2[4, 4] = 2.5
+    rows2[5:8, 4] = 0.5
+    pv.set_logical(1, rows2)
+    mb.sort_particles(None, g4, pv, pia, 1)
+    counts, starts, ends = [3, 1, 0, 4], [1, 4, 0, 5], [3, 4, -1, 8]
+    ix = pia.indexer
+    for c in range(4):
+        assert ix[0, c].tolist() == [counts[c], starts[c], ends[c], counts[c], 0, -1, 0]
+    np.testing.assert_array_equal(pv.logical(1, 8)[:, 4], rows2[[5, 6, 7, 4, 0, 1, 2, 3], 4])  # index [6,7,8,5,1,2,3,4]
+    # cells-known variant (grid_sorting.jl:128)
+    pv.set_logical(1, rows2)
+    pv.set_cell(1, [4, 4, 4, 4, 2, 1, 1, 1])
+    mb.sort_particles(None, pv, pia, 1)
+    ix = pia.indexer
+    for c in range(4):
+        assert ix[0, c].tolist() == [counts[c], starts[c], ends[c], counts[c], 0, -1, 0]
+    np.testing.assert_array_equal(pv.logical(1, 8)[:, 4], rows2[[5, 6, 7, 4, 0, 1, 2, 3], 4])
+
+
+@pytest.mark.parametrize("n,n_cells", [(0, 5), (1, 1), (33, 7), (5000, 1), (20000, 37), (100000, 1024), (30000, 3)])
+def test_sort_general_random(mb, oracle, ctx, n, n_cells):
+    """arbitrary (unsorted) input -> general path; bit-exact logical order and pia against the oracle."""
+    rng = np.random.default_rng(n + n_cells)
+    L = 2.0
+    rows = maxwellian_rows(rng, n, L, vw=True)
+    opv, opia = oracle_state(oracle, rows, n_cells, capacity=max(n, 1))
+    pv, pia = mirror_to_device(mb, ctx, opv, opia)
+    mb.sort_particles(None, mb.Grid1DUniform(L, n_cells), pv, pia, 1)
+    oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+    assert ctx.sort_last_path == 2
+    assert_same_pia(opia, pia)
+    np.testing.assert_array_equal(pv.logical(1, max(n, 1)), opv.logical(1, max(n, 1)))
+    assert pia.check(1) == (True, 0)
+    if n > 0:
+        np.testing.assert_array_equal(pv.cell(1, n), opv.cell[:n])  # pv.cell is written by the grid variant and not permuted
+
+
+@pytest.mark.parametrize("w", [1, 2, 4, 8])
+def test_sort_band_path(mb, oracle, ctx, w):
+    """the per-timestep case: sorted layout + small displacements -> band path; same bits as the oracle and as the general path."""
+    rng = np.random.default_rng(7 + w)
+    n, n_cells, L = 60000, 300, 3.0
+    dx = L / n_cells
+    rows = maxwellian_rows(rng, n, L, vw=True)
+    opv, opia = oracle_state(oracle, rows, n_cells)
+    pv, pia = mirror_to_device(mb, ctx, opv, opia)
+    g = mb.Grid1DUniform(L, n_cells)
+    ctx.set_band_halfwidth(w)
+    try:
+        mb.sort_particles(None, g, pv, pia, 1)
+        oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+        for step in range(3):
+            cur = opv.logical(1, n)
+            # displacement up to +-0.95 * w cells, clipped at the walls
+            c0 = np.floor(cur[:, 4] / dx)
+            move = rng.uniform(-0.95 * w * dx, 0.95 * w * dx, n)
+            if step == 1:  # cells 3..7 keep still except cell 5, which empties into cell 6 (an empty cell for w <= 2)
+                move[(c0 >= 3) & (c0 <= 7)] = 0.0
+            cur[:, 4] = np.clip(cur[:, 4] + move, 1e-9, L - 1e-9)
+            if step == 1:
+                m5 = c0 == 5
+                cur[m5, 4] = 6 * dx + (cur[m5, 4] - 5 * dx) * 0.5
+            opv.set_logical(1, cur)
+            pv.set_logical(1, cur)
+            mb.sort_particles(None, g, pv, pia, 1)
+            oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+            assert ctx.sort_last_path == 1, "band path expected"
+            assert_same_pia(opia, pia)
+            np.testing.assert_array_equal(pv.logical(1, n), opv.logical(1, n))
+        # a particle that leaves the band -> automatic fall back to the general path, same result
+        cur = opv.logical(1, n)
+        cur[::997, 4] = rng.uniform(0, L, len(cur[::997]))
+        opv.set_logical(1, cur)
+        pv.set_logical(1, cur)
+        mb.sort_particles(None, g, pv, pia, 1)
+        oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+        assert ctx.sort_last_path == 2
+        assert_same_pia(opia, pia)
+        np.testing.assert_array_equal(pv.logical(1, n), opv.logical(1, n))
+    finally:
+        ctx.set_band_halfwidth(2)
+
+
+def test_sort_large_cell_segments(mb, oracle, ctx):
+    """cells larger than the shared-memory segment sort (8192) use the global-memory network."""
+    rng = np.random.default_rng(5)
+    n, n_cells, L = 50000, 2, 1.0
+    rows = maxwellian_rows(rng, n, L)
+    rows[: n // 2, 4] = rng.uniform(0.5, 1.0, n // 2)  # first half of the input goes to cell 2 -> heavy reordering
+    rows[n // 2:, 4] = rng.uniform(0.0, 1.0, n - n // 2)
+    opv, opia = oracle_state(oracle, rows, n_cells)
+    pv, pia = mirror_to_device(mb, ctx, opv, opia)
+    mb.sort_particles(None, mb.Grid1DUniform(L, n_cells), pv, pia, 1)
+    oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+    assert_same_pia(opia, pia)
+    np.testing.assert_array_equal(pv.logical(1, n), opv.logical(1, n))
+
+
+# ------------------------------------------------------------------------------------------------------------ props
+def test_compute_props_reference_kat(mb, oracle, ctx):
+    """test/test_computes.jl:6-67: 2000 identical particles -> n, v exact, T ~ 0."""
+    n = 2000
+    rows = np.tile(np.array([2.0, 1.0, -2.0, 3.0, 0.5, 0.5, 0.5]), (n, 1))
+    opv, opia = oracle_state(oracle, rows, 1)
+    pv, pia = mirror_to_device(mb, ctx, opv, opia)
+    pp = mb.PhysProps(1, 1, ctx=ctx)
+    mb.compute_props([pv], pia, [AR], pp)
+    d = pp.download()
+    assert d["np"][0, 0] == n and d["lpa"][0] == n
+    assert abs(d["n"][0, 0] - 2.0 * n) < 1e-9
+    assert np.max(np.abs(d["v"][0, 0] - [1.0, -2.0, 3.0])) < 4e-15
+    assert abs(d["T"][0, 0]) < 1e-10
+
+
+@pytest.mark.parametrize("n,n_cells", [(40000, 64), (60000, 2)])
+def test_compute_props_parity(mb, oracle, ctx, n, n_cells):
+    """compute_props!, compute_props_sorted! (Np and ndens variants) and total moments vs the oracle, 1e-12 relative."""
+    rng = np.random.default_rng(11)
+    L = 1.0
+    rows = maxwellian_rows(rng, n, L, vw=True, w=1e10)
+    rows[:, 2] += 500.0  # |vbar| = 500 m/s: a one-pass variance would lose ~6 digits here
+    opv, opia = oracle_state(oracle, rows, n_cells)
+    oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+    pv, pia = mirror_to_device(mb, ctx, opv, opia)
+    powers = [4, 6, 8]
+    pp = mb.PhysProps(n_cells, 1, powers, Tref=300.0, ctx=ctx)
+    mb.compute_props_with_total_moments([pv], pia, [AR], pp)
+    d = pp.download()
+    o = oracle.compute_props([opv], opia, [AR], powers, 300.0, True)
+    np.testing.assert_array_equal(d["np"], o.np)
+    for k in ("n", "T", "moments"):
+        np.testing.assert_allclose(d[k], getattr(o, k), rtol=1e-12, atol=0)
+    np.testing.assert_allclose(d["v"], o.v, rtol=1e-12, atol=1e-12 * 500)
+    g = mb.Grid1DUniform(L, n_cells)
+    for ndens in (False, True):
+        pps = mb.PhysProps(n_cells, 1, ndens_not_Np=ndens, ctx=ctx)
+        mb.compute_props_sorted([pv], pia, [AR], pps, grid=g if ndens else None)
+        ds = pps.download()
+        os_ = oracle.compute_props_sorted([opv], opia, [AR], grid=(L, n_cells) if ndens else None)
+        np.testing.assert_array_equal(ds["np"], os_.np)
+        np.testing.assert_allclose(ds["n"], os_.n, rtol=1e-12)
+        np.testing.assert_allclose(ds["T"], os_.T, rtol=1e-12)
+        np.testing.assert_allclose(ds["v"], os_.v, rtol=1e-12, atol=1e-12 * 500)
+
+
+def test_compute_props_two_groups(mb, oracle, ctx):
+    """compute_props! walks group 1 and group 2 (physical_props.jl:118-146); the sorted variant ignores group 2."""
+    rng = np.random.default_rng(3)
+    rows = maxwellian_rows(rng, 30, 1.0, vw=True)
+    opv, opia = oracle_state(oracle, rows, 2)
+    opia.indexer[0, 0] = (12, 1, 8, 8, 21, 24, 4)
+    opia.indexer[0, 1] = (18, 9, 20, 12, 25, 30, 6)
+    pv, pia = mirror_to_device(mb, ctx, opv, opia)
+    pp = mb.PhysProps(2, 1, ctx=ctx)
+    mb.compute_props([pv], pia, [AR], pp)
+    d, o = pp.download(), oracle.compute_props([opv], opia, [AR])
+    np.testing.assert_array_equal(d["np"], o.np)
+    np.testing.assert_allclose(d["n"], o.n, rtol=1e-13)
+    np.testing.assert_allclose(d["T"], o.T, rtol=1e-12)
+    np.testing.assert_allclose(d["v"], o.v, rtol=1e-12, atol=1e-10)
+    mb.compute_props_sorted([pv], pia, [AR], pp)
+    d, o = pp.download(), oracle.compute_props_sorted([opv], opia, [AR])
+    np.testing.assert_array_equal(d["np"], o.np)
+    np.testing.assert_allclose(d["T"], o.T, rtol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------------------------ convect
+def test_convection_specular_kat(mb, oracle, ctx):
+    """test/test_convection_1D.jl:1-75: 4 particles, specular walls, L = 50, dt = 2 -> x = 20.5, 29.0, 23.0, 3.55; cells 8,42,47,59."""
+    rows = np.array([
+        [1.0, -1.25, -1.5, 4.0, 23.0, -8.0, 7.5],
+        [2.0, 11.0, -3.0, 1.0, 49.0, 6.0, -3.0],
+        [3.0, -20.0, 0.0, 2.0, 17.0, 1.0, 3.0],
+        [4.0, -49.0, -20.0, 13.0, 1.55, -1.0, 9.0],
+    ])
+    for compute_cell in (False, True):
+        opv, opia = oracle_state(oracle, rows, 100)
+        pv, pia = mirror_to_device(mb, ctx, opv, opia)
+        g = mb.Grid1DUniform(50.0, 100)
+        walls = mb.MaxwellWalls1D(1.0, 1.0, 0.0, 0.0, 0.0, 0.0)
+        mb.convect_particles(mb.PhiloxRng(1), g, walls, pv, pia, 1, AR, 2.0, compute_cell=compute_cell)
+        if compute_cell:
+            assert pv.cell(1, 4).tolist() == [42, 59, 47, 8]
+            mb.sort_particles(None, pv, pia, 1)
+        else:
+            mb.sort_particles(None, g, pv, pia, 1)
+        lg = pv.logical(1, 4)
+        assert np.max(np.abs(lg[0, 4:7] - [3.55, -1.0, 9.0])) < 3.65e-15 and lg[0, :4].tolist() == [4.0, -49.0, -20.0, 13.0]
+        assert np.max(np.abs(lg[1, 4:7] - [20.5, -8.0, 7.5])) < 5e-16 and lg[1, :4].tolist() == [1.0, -1.25, -1.5, 4.0]
+        assert np.max(np.abs(lg[2, 4:7] - [23.0, 1.0, 3.0])) < 5e-16 and lg[2, :4].tolist() == [3.0, 20.0, 0.0, 2.0]
+        assert np.max(np.abs(lg[3, 4:7] - [29.0, 6.0, -3.0])) < 5e-16 and lg[3, :4].tolist() == [2.0, -11.0, -3.0, 1.0]
+
+
+@pytest.mark.parametrize("acc", [(1.0, 1.0), (0.3, 0.8), (0.0, 1.0)])
+def test_convection_diffuse_parity(mb, oracle, ctx, acc):
+    """Maxwell walls with the shared per-particle Philox streams: positions/velocities and SurfProps vs the oracle."""
+    rng = np.random.default_rng(21)
+    n, nx, L, dt = 50000, 50, 5e-4, 2.59e-7  # large dt: ~half of the particles reach a wall, some reflect twice
+    rows = maxwellian_rows(rng, n, L, w=1e10, vw=True)
+    opv, opia = oracle_state(oracle, rows, nx)
+    pv, pia = mirror_to_device(mb, ctx, opv, opia)
+    g = mb.Grid1DUniform(L, nx)
+    walls = mb.MaxwellWalls1D(300.0, 450.0, -500.0, 500.0, acc[0], acc[1])
+    ctx.set_seed(77)
+    s = mb.convect_particles(mb.PhiloxRng(timestep=5, substream=2), g, walls, pv, pia, 1, AR, dt, surf_props=True, compute_cell=True)
+    so = oracle.convect_particles(oracle.Rng.philox(77, 5, 2), (L, nx), (300.0, 450.0, -500.0, 500.0, acc[0], acc[1]), opv, opia, 1, [AR], dt, surf=True,
+                                  compute_cell=True)
+    a, b = pv.logical(1, n), opv.logical(1, n)
+    assert np.count_nonzero(a[:, 1] != rows[:, 1]) > n // 25  # plenty of wall hits
+    assert_rows_close(a, b, 1e-12, "convect")
+    np.testing.assert_array_equal(pv.cell(1, n), opv.cell[:n])
+    assert s[0, 0] == so[0, 0] and s[1, 0] == so[1, 0]
+    np.testing.assert_allclose(s, so, rtol=1e-10, atol=1e-10 * np.abs(so).max())
+    ctx.set_seed(1234)
+
+
+def test_convection_noncontiguous(mb, oracle, ctx):
+    """test/test_convection_1D.jl:236-290: only particles the pia points to are moved."""
+    rows = np.zeros((30, 7))
+    for i in range(1, 31):
+        heavy = 11 <= i <= 25
+        rows[i - 1] = [10000.0 if heavy else 1.0, -1000.0 if heavy else 1.0, 0, 0, 0.75, 0, 0]
+    opv, opia = oracle_state(oracle, rows, 100)
+    opia.n_total[0] = 15
+    opia.indexer[0, 0] = (0, 0, -1, 0, 0, -1, 0)
+    opia.indexer[0, 1] = (15, 1, 10, 10, 26, 30, 5)
+    opia.contiguous[0] = 0
+    pv, pia = mirror_to_device(mb, ctx, opv, opia)
+    g = mb.Grid1DUniform(50.0, 100)
+    mb.convect_particles(mb.PhiloxRng(0), g, mb.MaxwellWalls1D(1.0, 1.0, 0, 0, 0, 0), pv, pia, 1, AR, 1.0)
+    oracle.convect_particles(oracle.Rng.philox(1234, 0, 0), (50.0, 100), (1.0, 1.0, 0, 0, 0, 0), opv, opia, 1, [AR], 1.0)
+    np.testing.assert_array_equal(pv.logical(1, 30), opv.logical(1, 30))
+    lg = pv.logical(1, 30)
+    assert np.all(lg[10:25, 4] == 0.75) and np.all(lg[:10, 4] == 1.75) and np.all(lg[25:, 4] == 1.75)
+
+
+# ------------------------------------------------------------------------------------------------------------ NTC
+def _couette_like(oracle, mb, ctx, n_cells, ppc, seed, vw=False, capacity_mult=1.0):
+    rng = np.random.default_rng(seed)
+    L = n_cells * 1e-5
+    n = n_cells * ppc
+    Fnum = 1e-5 * 5e22 / ppc
+    rows = maxwellian_rows(rng, n, L, w=Fnum, vw=vw)
+    cap = int(n * capacity_mult)
+    opv, opia = oracle_state(oracle, rows, n_cells, capacity=cap)
+    oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+    pv, pia = mirror_to_device(mb, ctx, opv, opia, capacity=cap)
+    return L, n, Fnum, opv, opia, pv, pia
+
+
+def test_ntc_equal_weight_parity(mb, oracle, ctx):
+    """ntc_equal_weight! over all cells, 5 steps: candidate / collision counters identical, sigma_g_w_max and velocities 1e-12."""
+    n_cells, ppc, dt = 40, 400, 2.59e-9 * 40  # enlarged dt: ~20-40 candidates per cell and step
+    L, n, Fnum, opv, opia, pv, pia = _couette_like(oracle, mb, ctx, n_cells, ppc, 101)
+    it, oit = mb.make_interaction(AR, AR, 4.11e-10, 0.81, 273.0), oracle.interaction("Ar", "Ar")
+    s0 = mb.estimate_sigma_g_w_max(it, AR, AR, 300.0, 300.0, Fnum)
+    cf, ocf = mb.CollisionFactors(n_cells, s0, ctx), oracle.CF(n_cells, s0)
+    V = L / n_cells
+    total = 0
+    for t in range(1, 6):
+        mb.ntc_equal_weight(mb.PhiloxRng(t), cf, None, it, pv, pia, (1, n_cells), 1, dt, V)
+        oracle.ntc(oracle.Rng.philox(1234, t), ocf, oit, opv, opia, 1, n_cells, 1, dt, V, equal_weight=True)
+        d = cf.download()
+        np.testing.assert_array_equal(d["n_coll"], ocf.n_coll)
+        np.testing.assert_array_equal(d["n_coll_performed"], ocf.n_coll_performed)
+        np.testing.assert_array_equal(d["n_eq_w_coll_performed"], ocf.n_eq_w_coll_performed)
+        np.testing.assert_allclose(d["sigma_g_w_max"], ocf.sigma_g_w_max, rtol=1e-13)
+        total += int(ocf.n_coll_performed.sum())
+    assert total > 1000
+    a, b = pv.logical(1, n), opv.logical(1, n)
+    assert_rows_close(a, b, 1e-12, "ntc equal weight")
+    np.testing.assert_array_equal(a[:, [0, 4, 5, 6]], b[:, [0, 4, 5, 6]])
+    # momentum and energy of the whole population conserved
+    for d in range(1, 4):
+        assert abs(a[:, d].sum() - rows_sum(opv, n, d)) <= 1e-9 * np.abs(a[:, d]).sum()
+
+
+def rows_sum(opv, n, d):
+    return opv.logical(1, n)[:, d].sum()
+
+
+def test_ntc_per_cell_call_equals_range_call(mb, oracle, ctx):
+    """the reference's per-cell call (cell_lo == cell_hi) gives the same state as one launch over the range."""
+    n_cells, ppc, dt = 12, 200, 2.59e-9 * 60
+    L, n, Fnum, opv, opia, pv, pia = _couette_like(oracle, mb, ctx, n_cells, ppc, 55)
+    pv2, pia2 = mirror_to_device(mb, ctx, opv, opia)
+    it = mb.make_interaction(AR, AR, 4.11e-10, 0.81, 273.0)
+    s0 = mb.estimate_sigma_g_w_max(it, AR, AR, 300.0, 300.0, Fnum)
+    cf, cf2 = mb.CollisionFactors(n_cells, s0, ctx), mb.CollisionFactors(n_cells, s0, ctx)
+    mb.ntc_equal_weight(mb.PhiloxRng(3), cf, None, it, pv, pia, (1, n_cells), 1, dt, L / n_cells)
+    for cell in range(1, n_cells + 1):
+        mb.ntc_equal_weight(mb.PhiloxRng(3), cf2, None, it, pv2, pia2, cell, 1, dt, L / n_cells)
+    np.testing.assert_array_equal(pv.logical(1, n), pv2.logical(1, n))
+    assert cf.download()["n_coll_performed"].tolist() == cf2.download()["n_coll_performed"].tolist()
+
+
+def test_ntc_variable_weight_parity(mb, oracle, ctx):
+    """ntc! with splitting (collision_ntc.jl:223-270): new particles, group-2 ranges, n_total and weights vs the oracle."""
+    n_cells, ppc, dt = 24, 300, 2.59e-9 * 60
+    L, n, Fnum, opv, opia, pv, pia = _couette_like(oracle, mb, ctx, n_cells, ppc, 202, vw=True, capacity_mult=1.5)
+    it, oit = mb.make_interaction(AR, AR, 4.11e-10, 0.81, 273.0), oracle.interaction("Ar", "Ar")
+    s0 = mb.estimate_sigma_g_w_max(it, AR, AR, 300.0, 300.0, 2 * Fnum)
+    cf, ocf = mb.CollisionFactors(n_cells, s0, ctx), oracle.CF(n_cells, s0)
+    V = L / n_cells
+    g = mb.Grid1DUniform(L, n_cells)
+    for t in range(1, 4):
+        mb.ntc(mb.PhiloxRng(t), cf, None, it, pv, pia, (1, n_cells), 1, dt, V)
+        oracle.ntc(oracle.Rng.philox(1234, t), ocf, oit, opv, opia, 1, n_cells, 1, dt, V)
+        d = cf.download()
+        np.testing.assert_array_equal(d["n_coll"], ocf.n_coll)
+        np.testing.assert_array_equal(d["n_coll_performed"], ocf.n_coll_performed)
+        np.testing.assert_array_equal(d["n_eq_w_coll_performed"], ocf.n_eq_w_coll_performed)
+        assert_same_pia(opia, pia)
+        nt = int(opia.n_total[0])
+        assert nt > n
+        a, b = pv.logical(1, nt), opv.logical(1, nt)
+        assert_rows_close(a, b, 1e-12, "ntc vw")
+        np.testing.assert_array_equal(a[:, 0], b[:, 0])  # weights are exact
+        assert pia.check(1) == (True, 0)
+        # the sort merges group 2 back (and must take the general path: the layout is no longer sorted)
+        mb.sort_particles(None, g, pv, pia, 1)
+        oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+        assert_same_pia(opia, pia)
+        np.testing.assert_array_equal(pv.logical(1, nt), a[np.lexsort((np.arange(nt), np.floor(a[:, 4] * g.inv_dx)))])
+        n = nt
+    # mass is conserved by splitting
+    assert abs(pv.logical(1, n)[:, 0].sum() - opv.logical(1, n)[:, 0].sum()) == 0.0
+
+
+def test_ntc_capacity_error(mb, oracle, ctx):
+    """the reference would resize!; the device reports MB_ERR_CAPACITY and leaves the state untouched."""
+    n_cells, ppc, dt = 4, 300, 2.59e-9 * 60
+    L, n, Fnum, opv, opia, pv, pia = _couette_like(oracle, mb, ctx, n_cells, ppc, 203, vw=True, capacity_mult=1.0)
+    it = mb.make_interaction(AR, AR, 4.11e-10, 0.81, 273.0)
+    cf = mb.CollisionFactors(n_cells, mb.estimate_sigma_g_w_max(it, AR, AR, 300.0, 300.0, 2 * Fnum), ctx)
+    before = pv.logical(1, n)
+    mb.ntc(mb.PhiloxRng(1), cf, None, it, pv, pia, (1, n_cells), 1, dt, L / n_cells)
+    with pytest.raises(mb.CapacityError):
+        ctx.sync()
+    np.testing.assert_array_equal(pv.logical(1, n), before)
+    pv.resize(int(1.5 * n))
+    mb.ntc(mb.PhiloxRng(1), cf, None, it, pv, pia, (1, n_cells), 1, dt, L / n_cells)
+    ctx.sync()
+    assert int(pia.n_total[0]) > n
+
+
+def test_ntc_two_species_parity(mb, oracle, ctx):
+    """README 2-species case shape (400 Ar @3000 K + 4000 He @360 K, Fnum 5e12, dt 2.5e-3, V = 1): the three ntc! calls of a
+    step in the reference's order (Ar-Ar, He-Ar via the two-ParticleVector method, He-He), equal weight, 20 steps."""
+    rng = np.random.default_rng(1)
+    nAr, nHe, Fnum, dt, V = 400, 4000, 5e12, 2.5e-3, 1.0
+    rAr = maxwellian_rows(rng, nAr, 1.0, T=3000.0, m=AR, w=Fnum)
+    rHe = maxwellian_rows(rng, nHe, 1.0, T=360.0, m=HE, w=Fnum)
+    opvA, opvH = oracle.OPV(nAr), oracle.OPV(nHe)
+    opvA.fill_identity(rAr)
+    opvH.particles[:nHe] = rHe
+    opvH.index[:nHe] = np.arange(1, nHe + 1)
+    opvH.nbuffer = 0
+    opia = oracle.OPIA(1, 2)
+    opia.indexer[0, 0] = (nAr, 1, nAr, nAr, 0, -1, 0)
+    opia.indexer[1, 0] = (nHe, 1, nHe, nHe, 0, -1, 0)
+    opia.n_total[:] = (nAr, nHe)
+    pvA, pvH = mb.ParticleVector(nAr, ctx), mb.ParticleVector(nHe, ctx)
+    pvA.set_logical(1, rAr)
+    pvH.set_logical(1, rHe)
+    pia = mb.ParticleIndexerArray(1, 2, ctx)
+    pia.upload(opia.indexer.copy(), opia.n_total.copy(), opia.contiguous.copy())
+    names = [("Ar", "Ar"), ("He", "Ar"), ("He", "He")]
+    m = {"Ar": AR, "He": HE}
+    T0 = {"Ar": 3000.0, "He": 360.0}
+    its, oits, cfs, ocfs = [], [], [], []
+    for a, b in names:
+        d, o, Tref = oracle.VHS.get((a, b)) or oracle.VHS[(b, a)]
+        its.append(mb.make_interaction(m[a], m[b], d, o, Tref))
+        oits.append(oracle.make_interaction(m[a], m[b], d, o, Tref))
+        s0 = mb.estimate_sigma_g_w_max(its[-1], m[a], m[b], T0[a], T0[b], Fnum)
+        cfs.append(mb.CollisionFactors(1, s0, ctx))
+        ocfs.append(oracle.CF(1, s0))
+    for t in range(1, 21):
+        mb.ntc(mb.PhiloxRng(t, 0), cfs[0], None, its[0], pvA, pia, 1, 1, dt, V, equal_weight=True)
+        mb.ntc2(mb.PhiloxRng(t, 1), cfs[1], None, its[1], pvH, pvA, pia, 1, 2, 1, dt, V, equal_weight=True)
+        mb.ntc(mb.PhiloxRng(t, 2), cfs[2], None, its[2], pvH, pia, 1, 2, dt, V, equal_weight=True)
+        oracle.ntc(oracle.Rng.philox(1234, t, 0), ocfs[0], oits[0], opvA, opia, 1, 1, 1, dt, V, equal_weight=True)
+        oracle.ntc2(oracle.Rng.philox(1234, t, 1), ocfs[1], oits[1], opvH, opvA, opia, 1, 1, 2, 1, dt, V, equal_weight=True)
+        oracle.ntc(oracle.Rng.philox(1234, t, 2), ocfs[2], oits[2], opvH, opia, 1, 1, 2, dt, V, equal_weight=True)
+        for cf, ocf in zip(cfs, ocfs):
+            d = cf.download()
+            assert d["n_coll"][0] == ocf.n_coll[0] and d["n_coll_performed"][0] == ocf.n_coll_performed[0]
+    assert sum(int(o.n_coll_performed[0]) for o in ocfs) > 0
+    assert_rows_close(pvA.logical(1, nAr), opvA.logical(1, nAr), 1e-11, "Ar")
+    assert_rows_close(pvH.logical(1, nHe), opvH.logical(1, nHe), 1e-11, "He")
+    pp = mb.PhysProps(1, 2, ctx=ctx)
+    mb.compute_props([pvA, pvH], pia, [AR, HE], pp)
+    d, o = pp.download(), oracle.compute_props([opvA, opvH], opia, [AR, HE])
+    np.testing.assert_allclose(d["T"], o.T, rtol=1e-11)
+
+
+# ------------------------------------------------------------------------------------------------------------ time loop
+def test_couette_loop_parity(mb, oracle, ctx):
+    """simulations/1D/couette_benchmarking.jl:58-85 order (collide all cells -> convect -> sort -> props), 25 steps on a small
+    Couette case, device vs oracle with shared Philox streams: same cell populations, same pia, profiles to 1e-10."""
+    n_cells, ppc = 50, 200
+    dt = 2.59e-9 * 4  # sigma_v * dt = 0.26 cells: the band (w = 2) holds
+    L, n, Fnum, opv, opia, pv, pia = _couette_like(oracle, mb, ctx, n_cells, ppc, 404)
+    it, oit = mb.make_interaction(AR, AR, 4.11e-10, 0.81, 273.0), oracle.interaction("Ar", "Ar")
+    s0 = mb.estimate_sigma_g_w_max(it, AR, AR, 300.0, 300.0, Fnum)
+    cf, ocf = mb.CollisionFactors(n_cells, s0, ctx), oracle.CF(n_cells, s0)
+    g = mb.Grid1DUniform(L, n_cells)
+    walls = mb.MaxwellWalls1D(300.0, 300.0, -500.0, 500.0, 1.0, 1.0)
+    owalls = (300.0, 300.0, -500.0, 500.0, 1.0, 1.0)
+    pp = mb.PhysProps(n_cells, 1, ctx=ctx)
+    V = L / n_cells
+    paths = []
+    for t in range(1, 26):
+        mb.ntc_equal_weight(mb.PhiloxRng(t), cf, None, it, pv, pia, (1, n_cells), 1, dt, V)
+        mb.convect_particles(mb.PhiloxRng(t), g, walls, pv, pia, 1, AR, dt)
+        mb.sort_particles(None, g, pv, pia, 1)
+        mb.compute_props_sorted([pv], pia, [AR], pp)
+        oracle.ntc(oracle.Rng.philox(1234, t), ocf, oit, opv, opia, 1, n_cells, 1, dt, V, equal_weight=True)
+        oracle.convect_particles(oracle.Rng.philox(1234, t), (L, n_cells), owalls, opv, opia, 1, [AR], dt)
+        oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+        paths.append(ctx.sort_last_path)
+        assert_same_pia(opia, pia)
+    assert paths.count(1) >= 20, paths  # the steady-state steps take the band path
+    assert_rows_close(pv.logical(1, n), opv.logical(1, n), 1e-10, "couette loop")
+    d, o = pp.download(), oracle.compute_props_sorted([opv], opia, [AR])
+    np.testing.assert_array_equal(d["np"], o.np)
+    np.testing.assert_allclose(d["T"], o.T, rtol=1e-10)
+    np.testing.assert_allclose(d["v"], o.v, rtol=1e-9, atol=1e-9 * 500)
