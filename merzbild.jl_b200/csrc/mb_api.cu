@@ -123,7 +123,7 @@ int mb_ctx_destroy(mb_ctx* c) {
     if (!c) return MB_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < 12; i++)
         if (c->scratch[i]) cudaFree(c->scratch[i]);
     if (c->l2_scratch) cudaFree(c->l2_scratch);
     for (int i = 0; i < 2; i++) {
@@ -151,7 +151,7 @@ int mb_sync(mb_ctx* c) {
     MB_CUDA(cudaStreamSynchronize(c->stream));
     const int f = c->h_flags[0];
     if (f) {
-        MB_CUDA(cudaMemsetAsync(c->d_flags, 0, 16 * sizeof(int), c->stream));
+        MB_CUDA(cudaMemsetAsync(c->d_flags, 0, 2 * sizeof(int), c->stream));
         char buf[256];
         snprintf(buf, sizeof buf, "device-side error flags 0x%x (1 capacity, 2 precondition, 4 band overflow, 8 bad cell, 16 octree); aux=%d", f,
                  c->h_flags[1]);
@@ -408,6 +408,7 @@ int mb_pia_create(mb_ctx* ctx, int64_t n_cells, int64_t n_species, mb_pia** out)
     p->contiguous.assign(n_species, 1);
     p->sorted_layout.assign(n_species, 0);
     p->n_bound.assign(n_species, 0);
+    p->contig_pending.assign(n_species, 0);
     k_pia_init<<<grid_for(n_cells * n_species, 256), 256, 0, ctx->stream>>>(p->d_indexer, n_cells * n_species);
     MB_LAUNCH_CHECK(ctx);
     *out = p;
@@ -438,7 +439,7 @@ int mb_pia_upload(mb_pia* p, const int64_t* indexer, const int64_t* n_total, con
         p->h_valid = true;
     }
     if (contiguous)
-        for (int64_t s = 0; s < p->n_species; s++) p->contiguous[s] = contiguous[s];
+        for (int64_t s = 0; s < p->n_species; s++) { p->contiguous[s] = contiguous[s]; p->contig_pending[s] = 0; }
     MB_CUDA(cudaStreamSynchronize(ctx->stream));
     return MB_OK;
 }
@@ -459,6 +460,21 @@ int mb_pia_download(mb_pia* p, int64_t* indexer, int64_t* n_total, uint8_t* cont
     p->h_valid = false;
     int r = pia_refresh_host(p);
     if (r) return r;
+    {   // resolve the exact contiguous flag after merges (merging_octree_N2.jl:806-808): device flag 4 + s
+        bool any = false;
+        for (int64_t s = 0; s < p->n_species; s++) any |= p->contig_pending[s] != 0;
+        if (any) {
+            int f[16];
+            MB_CUDA(cudaMemcpyAsync(f, p->ctx->d_flags, sizeof f, cudaMemcpyDeviceToHost, p->ctx->stream));
+            MB_CUDA(cudaStreamSynchronize(p->ctx->stream));
+            for (int64_t s = 0; s < p->n_species; s++)
+                if (p->contig_pending[s]) {
+                    if (f[4 + s % 8] == 0) p->contiguous[s] = 1;  // every deletion fitted into group 2 of the last cell
+                    p->contig_pending[s] = 0;
+                }
+            MB_CUDA(cudaMemsetAsync(p->ctx->d_flags + 4, 0, 8 * sizeof(int), p->ctx->stream));
+        }
+    }
     if (n_total)
         for (int64_t s = 0; s < p->n_species; s++) n_total[s] = p->h_n_total[s];
     if (contiguous)

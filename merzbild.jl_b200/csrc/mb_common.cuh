@@ -103,8 +103,8 @@ struct mb_ctx {
     void* l2_scratch;
     size_t l2_scratch_bytes;
     // generic scratch arena (grown on demand, stream-ordered reuse)
-    void* scratch[8];
-    size_t scratch_bytes[8];
+    void* scratch[12];
+    size_t scratch_bytes[12];
     int sort_last_path;
     int band_w;
     // per-section event profiling
@@ -141,6 +141,7 @@ struct mb_pia {
     std::vector<uint8_t> contiguous;   // host-side flag per species (changes are statically known per operator)
     std::vector<uint8_t> sorted_layout; // host-side: group1 ranges tile 1..n_total in cell order and group2 is empty everywhere
     std::vector<int64_t> n_bound;      // host upper bound on n_total (for launch sizing only)
+    std::vector<uint8_t> contig_pending; // a merge ran: the exact contiguous flag is !d_flags[4 + species % 8] (resolved at download)
 };
 
 struct mb_cf {

@@ -1,0 +1,138 @@
+// fp_linear! -- linear Fokker-Planck collision operator (collisions/collision_fp.jl:24-125), compute_relaxation_time
+// (:143-151), sample_normal_rands! (:164-170), scale_norm_rands! (:182-211).  Defined for sorted cells (n_group2 == 0), as
+// in the reference (its group-2 branch uses an undefined variable, collision_fp.jl:57); cells with n_local < 7 are skipped.
+//
+// One warp per cell; the cell is streamed from HBM once (w, v: 32 B/particle) and written once (v: 24 B); the intermediate
+// passes hit L1/L2.  The standard normals are counter-based: particle j of the cell uses Philox blocks 2j and 2j+1 of the
+// (OP_FP, substream, timestep, cell) stream through Box-Muller -- regenerated in each pass that needs them instead of being
+// stored -- and are standardised exactly (mean 0, variance 1 over the cell) like scale_norm_rands!.
+#include "mb_common.cuh"
+
+namespace mb {
+
+struct FpArgs {
+    SoA pv;
+    const Indexer* ix;
+    int64_t cell_lo, cell_hi;
+    mb_interaction it;
+    double mass, dt, V;
+    uint64_t seed;
+    uint32_t timestep, substream;
+};
+
+__device__ __forceinline__ void fp_normals(const FpArgs& a, uint32_t cell, int64_t j, double o[3]) {
+    const uint32_t c3 = (OP_FP & 0xFFu) | (a.substream << 8);
+    uint32_t r[4];
+    philox4x32_10((uint32_t)(2 * j), cell, a.timestep, c3, (uint32_t)a.seed, (uint32_t)(a.seed >> 32), r);
+    double u1 = u64_to_unit_double(r[0], r[1]), u2 = u64_to_unit_double(r[2], r[3]);
+    double rad = sqrt(-2.0 * log(fmax(1e-300, u1)));
+    double sn, cs;
+    sincos(twopi * u2, &sn, &cs);
+    o[0] = rad * cs;
+    o[1] = rad * sn;
+    philox4x32_10((uint32_t)(2 * j + 1), cell, a.timestep, c3, (uint32_t)a.seed, (uint32_t)(a.seed >> 32), r);
+    u1 = u64_to_unit_double(r[0], r[1]);
+    u2 = u64_to_unit_double(r[2], r[3]);
+    rad = sqrt(-2.0 * log(fmax(1e-300, u1)));
+    o[2] = rad * cos(twopi * u2);
+}
+__device__ __forceinline__ double wsum(double x) {
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+static __global__ void __launch_bounds__(256) k_fp_linear(FpArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t nr = a.cell_hi - a.cell_lo + 1;
+    double* __restrict__ VX = a.pv.a[F_VX];
+    double* __restrict__ VY = a.pv.a[F_VY];
+    double* __restrict__ VZ = a.pv.a[F_VZ];
+    const double* __restrict__ W = a.pv.a[F_W];
+    for (int64_t r = warp0; r < nr; r += nwarps) {
+        const int64_t cell = a.cell_lo + r;
+        const Indexer q = a.ix[cell - 1];
+        const int64_t n = q.n_local, lo = q.start1 - 1;
+        if (n < 7) continue;  // :35-37
+        // scale_norm_rands!: exact standardisation over the n draws of each component
+        double m[3] = {0, 0, 0}, s2[3] = {0, 0, 0};
+        for (int64_t j = lane; j < n; j += 32) {
+            double o[3];
+            fp_normals(a, (uint32_t)cell, j, o);
+            for (int d = 0; d < 3; d++) m[d] += o[d];
+        }
+        for (int d = 0; d < 3; d++) m[d] = wsum(m[d]) / (double)n;
+        for (int64_t j = lane; j < n; j += 32) {
+            double o[3];
+            fp_normals(a, (uint32_t)cell, j, o);
+            for (int d = 0; d < 3; d++) { const double x = o[d] - m[d]; s2[d] += x * x; }
+        }
+        for (int d = 0; d < 3; d++) s2[d] = sqrt((double)n / wsum(s2[d]));
+        // weighted mean velocity and thermal energy (:60-77)
+        double lw = 0, ux = 0, uy = 0, uz = 0;
+        for (int64_t j = lane; j < n; j += 32) {
+            const double w = W[lo + j];
+            lw += w;
+            ux += VX[lo + j] * w; uy += VY[lo + j] * w; uz += VZ[lo + j] * w;
+        }
+        lw = wsum(lw);
+        ux = wsum(ux) / lw; uy = wsum(uy) / lw; uz = wsum(uz) / lw;
+        double es_old = 0;
+        for (int64_t j = lane; j < n; j += 32) {
+            const double cx = VX[lo + j] - ux, cy = VY[lo + j] - uy, cz = VZ[lo + j] - uz;
+            es_old += (cx * cx + cy * cy + cz * cz) * W[lo + j];
+        }
+        es_old = 0.5 * wsum(es_old) / lw;
+        // compute_relaxation_time (:143-151)
+        const double T = es_old * a.mass / ((3.0 / 2.0) * k_B);
+        const double p = (lw / a.V) * k_B * T;
+        const double mu = a.it.vhs_muref * pow(T / a.it.vhs_Tref, a.it.vhs_o);
+        const double tau = 2.0 * mu / p;
+        const double A = exp(-a.dt / tau);
+        const double C = sqrt(((2.0 / 3.0) * es_old) * (1.0 - exp(-2.0 * a.dt / tau)));
+        // v <- (v - u) A + C xi ; energy of the new thermal velocities (:95-110)
+        double es_new = 0;
+        for (int64_t j = lane; j < n; j += 32) {
+            double o[3];
+            fp_normals(a, (uint32_t)cell, j, o);
+            const double vx = (VX[lo + j] - ux) * A + C * ((o[0] - m[0]) * s2[0]);
+            const double vy = (VY[lo + j] - uy) * A + C * ((o[1] - m[1]) * s2[1]);
+            const double vz = (VZ[lo + j] - uz) * A + C * ((o[2] - m[2]) * s2[2]);
+            VX[lo + j] = vx; VY[lo + j] = vy; VZ[lo + j] = vz;
+            es_new += (vx * vx + vy * vy + vz * vz) * W[lo + j];
+        }
+        es_new = 0.5 * wsum(es_new) / lw;
+        const double alpha = sqrt(es_old / es_new);  // exact energy conservation (:112-123)
+        __syncwarp();
+        for (int64_t j = lane; j < n; j += 32) {
+            VX[lo + j] = alpha * VX[lo + j] + ux;
+            VY[lo + j] = alpha * VY[lo + j] + uy;
+            VZ[lo + j] = alpha * VZ[lo + j] + uz;
+        }
+    }
+}
+
+}  // namespace mb
+
+using namespace mb;
+
+extern "C" int mb_fp_linear(mb_ctx* ctx, const mb_interaction* it, double mass, mb_pv* pv, mb_pia* pia, int64_t cell_lo, int64_t cell_hi,
+                            int64_t species, double dt, double V, uint32_t timestep, uint32_t substream) {
+    MB_ARG(ctx && it && pv && pia, "NULL handle");
+    MB_ARG(species >= 1 && species <= pia->n_species, "species out of range");
+    MB_ARG(cell_lo >= 1 && cell_hi <= pia->n_cells && cell_lo <= cell_hi, "cell range");
+    MB_ARG(mass > 0 && V > 0, "mass, V");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    FpArgs a;
+    a.pv = pv->cur;
+    a.ix = pia->d_indexer + (species - 1) * pia->n_cells;
+    a.cell_lo = cell_lo; a.cell_hi = cell_hi;
+    a.it = *it;
+    a.mass = mass; a.dt = dt; a.V = V;
+    a.seed = ctx->seed; a.timestep = timestep; a.substream = substream;
+    ProfScope ps(ctx, PROF_FP);
+    k_fp_linear<<<grid_for((cell_hi - cell_lo + 1) * 32, 256, 8), 256, 0, ctx->stream>>>(a);
+    MB_LAUNCH_CHECK(ctx);
+    return MB_OK;
+}

@@ -16,6 +16,7 @@
 // state after the call is the reference's: same logical positions, same pia.
 #include "mb_common.cuh"
 #include "mb_scan.cuh"
+#include "mb_append.cuh"
 
 namespace mb {
 
@@ -60,29 +61,6 @@ __global__ void __launch_bounds__(128) k_ntc_prepass(NtcArgs a) {
         if (nc > 0x7fffffff) nc = 0x7fffffff;
         a.ncoll32[r] = (int32_t)nc;
     }
-}
-
-struct PRef {  // a particle picked for a collision: physical (0-based) position in its SoA
-    int64_t pos;
-    double w, vx, vy, vz;
-};
-__device__ __forceinline__ void load_p(const SoA& s, int64_t pos, PRef& p) {
-    p.pos = pos;
-    p.w = s.a[F_W][pos]; p.vx = s.a[F_VX][pos]; p.vy = s.a[F_VY][pos]; p.vz = s.a[F_VZ][pos];
-}
-__device__ __forceinline__ int64_t map_cont(const Indexer& q, int64_t i) {  // particles.jl:364-366, returned 0-based
-    return (i < q.n_group1 ? i + q.start1 : (i - q.n_group1) + q.start2) - 1;
-}
-// split: append (dw, v, x of the parent) as a new group-2 particle (collision_ntc.jl:238-267, particles.jl:426-433)
-__device__ __forceinline__ void append_split(const SoA& s, Indexer& q, int64_t winlo, int64_t parent, double dw, double vx, double vy, double vz) {
-    const int64_t pos = q.n_group2 > 0 ? q.end2 : winlo;  // 0-based position of the new particle (end2 is 1-based -> next slot)
-    if (q.n_group2 == 0) q.start2 = winlo + 1;
-    q.n_group2 += 1;
-    q.n_local += 1;
-    q.end2 = pos + 1;
-    s.a[F_W][pos] = dw;
-    s.a[F_VX][pos] = vx; s.a[F_VY][pos] = vy; s.a[F_VZ][pos] = vz;
-    s.a[F_X][pos] = s.a[F_X][parent]; s.a[F_Y][pos] = s.a[F_Y][parent]; s.a[F_Z][pos] = s.a[F_Z][parent];
 }
 
 template <bool TWO>
@@ -187,39 +165,6 @@ __global__ void __launch_bounds__(128) k_ntc(NtcArgs a) {
     }
 }
 
-// pack the per-cell windows to the left (cell order) so the layout equals the reference's sequential appends
-static __global__ void __launch_bounds__(256) k_ntc_pack(SoA cur, SoA alt, Indexer* __restrict__ ix, int64_t cell_lo, int64_t nr,
-                                                         const int64_t* __restrict__ win, const int64_t* __restrict__ packed,
-                                                         const int32_t* __restrict__ nsplit, const int64_t* n_total, int phase) {
-    const int64_t nt = *n_total;
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = warp0; r < nr; r += nwarps) {
-        const int n = nsplit[r];
-        if (n <= 0 || win[r] == packed[r]) continue;
-        const int64_t olo = nt + win[r], nlo = nt + packed[r];
-        if (phase == 0) {
-            for (int j = lane; j < n; j += 32)
-#pragma unroll
-                for (int f = 0; f < 7; f++) alt.a[f][nlo + j] = cur.a[f][olo + j];
-        } else {
-            for (int j = lane; j < n; j += 32)
-#pragma unroll
-                for (int f = 0; f < 7; f++) cur.a[f][nlo + j] = alt.a[f][nlo + j];
-            if (lane == 0) {
-                Indexer q = ix[cell_lo - 1 + r];
-                q.start2 = nlo + 1;
-                q.end2 = nlo + n;
-                ix[cell_lo - 1 + r] = q;
-            }
-        }
-    }
-}
-static __global__ void k_add_total(int64_t* n_total, const int64_t* packed, int64_t nr) {
-    *n_total += packed[nr];
-}
-
 static int ntc_impl(mb_ctx* ctx, mb_cf* cf, const mb_interaction* it, mb_pv* pv1, mb_pv* pv2, mb_pia* pia, int64_t cell_lo, int64_t cell_hi,
                     int64_t s1, int64_t s2, double dt, double V, double dw_tol, int equal_weight, uint32_t timestep, uint32_t substream,
                     bool two) {
@@ -278,23 +223,11 @@ static int ntc_impl(mb_ctx* ctx, mb_cf* cf, const mb_interaction* it, mb_pv* pv1
     if (two) k_ntc<true><<<g, 128, 0, st>>>(a);
     else k_ntc<false><<<g, 128, 0, st>>>(a);
     MB_LAUNCH_CHECK(ctx);
-    const int gw = grid_for(nr * 32, 256, 8);
     for (int sp = 0; sp < (two ? 2 : 1); sp++) {
         mb_pv* pv = sp == 0 ? pv1 : pv2;
-        int32_t* ns = sp == 0 ? a.nsplit1 : a.nsplit2;
-        int64_t* packed = sp == 0 ? packed1 : packed2;
-        Indexer* ix = sp == 0 ? a.ix1 : a.ix2;
-        int64_t* nt = sp == 0 ? a.n_total1 : a.n_total2;
-        r = device_exclusive_scan(ctx, ns, nr, packed, partial);
+        r = pack_windows(ctx, pv, sp == 0 ? a.ix1 : a.ix2, cell_lo, nr, a.win, sp == 0 ? a.nsplit1 : a.nsplit2, sp == 0 ? packed1 : packed2, partial,
+                         sp == 0 ? a.n_total1 : a.n_total2);
         if (r) return r;
-        if (nr > 1) {
-            k_ntc_pack<<<gw, 256, 0, st>>>(pv->cur, pv->alt, ix, cell_lo, nr, a.win, packed, ns, nt, 0);
-            MB_LAUNCH_CHECK(ctx);
-            k_ntc_pack<<<gw, 256, 0, st>>>(pv->cur, pv->alt, ix, cell_lo, nr, a.win, packed, ns, nt, 1);
-            MB_LAUNCH_CHECK(ctx);
-        }
-        k_add_total<<<1, 1, 0, st>>>(nt, packed, nr);
-        MB_LAUNCH_CHECK(ctx);
         const int64_t sidx = (sp == 0 ? s1 : s2) - 1;
         pia->sorted_layout[sidx] = 0;
         pia->n_bound[sidx] = pv->cap;

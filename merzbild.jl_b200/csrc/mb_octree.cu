@@ -1,0 +1,512 @@
+// merge_octree_N2_based! (merging/merging_octree_N2.jl:1060-1094) and everything it calls: init_octree! (:947-984),
+// compute_octree! (:998-1039, greedy refinement of the heaviest refinable bin), split_bin! (:503-633, 8-way stable
+// counting sort of the bin's index slice), bin_bounds_inherit! / bin_bounds_recompute! (:341-418), compute_bin_props!
+// (:646-700, two-pass weighted mean / variance of v and x), compute_new_particles! (:736-813 0-D, :830-933 1-D with the
+// x clamp), delete_particle_end! bookkeeping (particles.jl:478-566).
+//
+// One CTA per merging cell, all merging cells of the range concurrently.  The refinement loop of a cell is inherently
+// sequential (each split depends on the previous one); inside a step the CTA works in parallel: arg-max over the bins,
+// octant classification, deterministic block reductions of the octant counts / weights, an order-exact partition of the
+// bin's index slice (warp match + shared prefix; reversed inside each octant like the reference's fill-from-the-end loop), and a warp per bin for the moments.  The octree of a cell is bit-identical to
+// the reference's for OctreeBinMidSplit (the splits only compare velocities with 0.5 * (v_min + v_max)); merged
+// particles agree to rounding (different summation order), conservation holds to ~1e-15 relative.
+//
+// Workspace: every merging cell gets a private slice of three index arrays at offset = exclusive scan of n_local over
+// the range (so the total is <= n_total <= capacity); bins live in a per-CTA global workspace of
+// min(max_Nbins, target_np) + 8 entries (a split is only made while total_post_merge_np + 14 <= target_np, and every bin
+// holds at least one post-merge particle).
+#include "mb_common.cuh"
+#include "mb_scan.cuh"
+
+namespace mb {
+
+constexpr int MT = 256;  // max threads per CTA
+
+struct MergeArgs {
+    SoA pv;
+    Indexer* ix;
+    int64_t* n_total;
+    int64_t cell_lo, cell_hi, n_cells_total;
+    int64_t threshold, target;
+    mb_octree_params oc;
+    int has_grid;
+    double min_x, max_x;
+    uint64_t seed;
+    uint32_t timestep, substream;
+    int32_t *idx, *tmp;
+    uint8_t* oct;
+    const int64_t* slice;  // [nr + 1]
+    int Bmax;
+    int32_t *b_np, *b_depth, *b_start, *b_end, *b_out;  // [nCTA][Bmax (+1 for b_out)]
+    double *b_w, *b_vmin, *b_vmax;                       // [nCTA][Bmax], [nCTA][3 * Bmax]
+    double* outbuf;                                      // [nCTA][2 * Bmax][7]
+    int* flags;
+    int* noncontig;
+};
+
+static __global__ void k_merge_counts(const Indexer* __restrict__ ix, int64_t cell_lo, int64_t nr, int64_t threshold, int32_t* __restrict__ cnt) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nr; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = ix[cell_lo - 1 + r].n_local;
+        cnt[r] = (n > 0 && (threshold < 0 || n > threshold)) ? (int32_t)n : 0;
+    }
+}
+
+__device__ __forceinline__ int64_t mpos(const Indexer& q, int64_t j) {  // map_cont_index, 0-based physical position
+    return (j < q.n_group1 ? j + q.start1 : (j - q.n_group1) + q.start2) - 1;
+}
+
+// deterministic block reductions through shared memory (all threads get the result)
+__device__ __forceinline__ double block_sum(double x, double* sh) {
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[wid] = x;
+    __syncthreads();
+    double t = 0;
+    for (int i = 0; i < nw; i++) t += sh[i];
+    return t;
+}
+__device__ __forceinline__ double block_min(double x, double* sh) {
+    for (int o = 16; o > 0; o >>= 1) x = fmin(x, __shfl_xor_sync(0xffffffffu, x, o));
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[wid] = x;
+    __syncthreads();
+    double t = sh[0];
+    for (int i = 1; i < nw; i++) t = fmin(t, sh[i]);
+    return t;
+}
+__device__ __forceinline__ double block_max(double x, double* sh) { return -block_min(-x, sh); }
+
+// bounds of the particles idx[bs..be] (bin_bounds_recompute! :382-418)
+__device__ void slice_bounds(const MergeArgs& a, const int32_t* idx, int bs, int be, double* sh, double mn[3], double mx[3]) {
+    double lmn[3] = {9299792458.0, 9299792458.0, 9299792458.0}, lmx[3] = {-9299792458.0, -9299792458.0, -9299792458.0};
+    for (int j = bs + threadIdx.x; j <= be; j += blockDim.x) {
+        const int64_t p = idx[j];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const double v = a.pv.a[F_VX + d][p];
+            if (v < lmn[d]) lmn[d] = v;
+            if (v > lmx[d]) lmx[d] = v;
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; d++) { mn[d] = block_min(lmn[d], sh); mx[d] = block_max(lmx[d], sh); }
+}
+
+__global__ void __launch_bounds__(MT) k_merge(MergeArgs a) {
+    __shared__ double sh[MT / 32];
+    __shared__ double sh_w[MT / 32][8];
+    __shared__ int sh_c[MT / 32][8];
+    __shared__ double s_best_w[MT / 32];
+    __shared__ int s_best_id[MT / 32];
+    __shared__ int s_Nbins, s_total_post, s_refine, s_stop;
+    __shared__ int s_cnt[8], s_base[8], s_run[8];
+    __shared__ double s_wsum[8];
+    __shared__ int s_scan[MT];
+    __shared__ int s_carry;
+
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const int64_t nr = a.cell_hi - a.cell_lo + 1;
+    const int B = a.Bmax;
+    int32_t* b_np = a.b_np + (int64_t)blockIdx.x * B;
+    int32_t* b_depth = a.b_depth + (int64_t)blockIdx.x * B;
+    int32_t* b_start = a.b_start + (int64_t)blockIdx.x * B;
+    int32_t* b_end = a.b_end + (int64_t)blockIdx.x * B;
+    int32_t* b_out = a.b_out + (int64_t)blockIdx.x * (B + 1);
+    double* b_w = a.b_w + (int64_t)blockIdx.x * B;
+    double* b_vmin = a.b_vmin + (int64_t)blockIdx.x * 3 * B;
+    double* b_vmax = a.b_vmax + (int64_t)blockIdx.x * 3 * B;
+    double* outbuf = a.outbuf + (int64_t)blockIdx.x * 2 * B * 7;
+    const double* __restrict__ PW = a.pv.a[F_W];
+
+    for (int64_t r = blockIdx.x; r < nr; r += gridDim.x) {
+        const int64_t cell = a.cell_lo + r;
+        const Indexer q = a.ix[cell - 1];
+        const int N = (int)q.n_local;
+        if (N <= 0 || !(a.threshold < 0 || N > a.threshold)) continue;  // block-uniform
+        int32_t* idx = a.idx + a.slice[r];
+        int32_t* tmp = a.tmp + a.slice[r];
+        uint8_t* oct = a.oct + a.slice[r];
+        __syncthreads();
+        // ---- init_octree! (:947-984)
+        for (int j = tid; j < N; j += nt) idx[j] = (int32_t)mpos(q, j);
+        __syncthreads();
+        {
+            double mn[3], mx[3];
+            if (a.oc.init_bin_bounds == 3) {
+                for (int d = 0; d < 3; d++) { mn[d] = -c_light; mx[d] = c_light; }
+            } else {
+                slice_bounds(a, idx, 0, N - 1, sh, mn, mx);
+                if (a.oc.init_bin_bounds == 2)
+                    for (int d = 0; d < 3; d++) { const double m = fmax(fabs(mn[d]), fabs(mx[d])); mn[d] = -m; mx[d] = m; }
+            }
+            if (tid == 0) {
+                b_np[0] = N; b_w[0] = 1e50; b_depth[0] = 0; b_start[0] = 0; b_end[0] = N - 1;
+                for (int d = 0; d < 3; d++) { b_vmin[d] = mn[d]; b_vmax[d] = mx[d]; }
+                s_Nbins = 1;
+                s_total_post = N >= 2 ? 2 : N;
+                s_stop = 0;
+            }
+        }
+        __syncthreads();
+        // ---- compute_octree! (:998-1039)
+        while (true) {
+            const int Nbins = s_Nbins;
+            double bw = -1.0;
+            int bid = -1;
+            for (int b = tid; b < Nbins; b += nt) {
+                const double w = b_w[b];
+                if (w > bw && b_np[b] > 2 && b_depth[b] < a.oc.max_depth) { bw = w; bid = b; }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ow = __shfl_xor_sync(0xffffffffu, bw, o);
+                const int oid = __shfl_xor_sync(0xffffffffu, bid, o);
+                if (oid >= 0 && (bid < 0 || ow > bw || (ow == bw && oid < bid))) { bw = ow; bid = oid; }
+            }
+            if (lane == 0) { s_best_w[wid] = bw; s_best_id[wid] = bid; }
+            __syncthreads();
+            if (tid == 0) {
+                double w0 = -1.0;
+                int i0 = -1;
+                for (int i = 0; i < nw; i++) {
+                    const int oid = s_best_id[i];
+                    const double ow = s_best_w[i];
+                    if (oid >= 0 && (i0 < 0 || ow > w0 || (ow == w0 && oid < i0))) { w0 = ow; i0 = oid; }
+                }
+                s_refine = i0;
+                if (i0 < 0 || s_total_post + 14 > a.target) s_stop = 1;
+            }
+            __syncthreads();
+            if (s_stop) break;
+            // ---- split_bin! (:503-633)
+            const int bin = s_refine;
+            const int bs = b_start[bin], be = b_end[bin];
+            const int depth = b_depth[bin];
+            double pmn[3], pmx[3];
+            if (a.oc.bin_bounds_compute == 2) {
+                slice_bounds(a, idx, bs, be, sh, pmn, pmx);
+            } else {
+                for (int d = 0; d < 3; d++) { pmn[d] = b_vmin[3 * bin + d]; pmx[d] = b_vmax[3 * bin + d]; }
+            }
+            double mid[3];
+            if (a.oc.split == 1) {
+                for (int d = 0; d < 3; d++) mid[d] = 0.5 * (pmn[d] + pmx[d]);
+            } else {  // OctreeBinMeanSplit: weighted mean of the bin (the evident intent of compute_v_mean! :431-439)
+                double sw = 0, sv[3] = {0, 0, 0};
+                for (int j = bs + tid; j <= be; j += nt) {
+                    const int64_t p = idx[j];
+                    const double w = PW[p];
+                    sw += w;
+                    for (int d = 0; d < 3; d++) sv[d] += w * a.pv.a[F_VX + d][p];
+                }
+                sw = block_sum(sw, sh);
+                for (int d = 0; d < 3; d++) mid[d] = block_sum(sv[d], sh) / sw;
+            }
+            // octants, per-octant counts and weights
+            int cnt[8];
+            double ws[8];
+#pragma unroll
+            for (int o = 0; o < 8; o++) { cnt[o] = 0; ws[o] = 0.0; }
+            for (int j = bs + tid; j <= be; j += nt) {
+                const int64_t p = idx[j];
+                const int o = (a.pv.a[F_VX][p] > mid[0] ? 1 : 0) + (a.pv.a[F_VY][p] > mid[1] ? 2 : 0) + (a.pv.a[F_VZ][p] > mid[2] ? 4 : 0);
+                oct[j] = (uint8_t)o;
+                const double w = PW[p];
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (o == k) { cnt[k] += 1; ws[k] += w; }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                for (int o = 16; o > 0; o >>= 1) {
+                    cnt[k] += __shfl_xor_sync(0xffffffffu, cnt[k], o);
+                    ws[k] += __shfl_xor_sync(0xffffffffu, ws[k], o);
+                }
+                if (lane == 0) { sh_c[wid][k] = cnt[k]; sh_w[wid][k] = ws[k]; }
+            }
+            __syncthreads();
+            if (tid < 8) {
+                int c = 0;
+                double w = 0;
+                for (int i = 0; i < nw; i++) { c += sh_c[i][tid]; w += sh_w[i][tid]; }
+                s_cnt[tid] = c;
+                s_wsum[tid] = w;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                // children: the first non-empty octant reuses the parent id, the others get Nbins+1.. in octant order (:487-489,:563-572)
+                int run = 0, n_ne = 0, nb = s_Nbins, tp = s_total_post - 2;
+                for (int o = 0; o < 8; o++) {
+                    s_base[o] = run;
+                    s_run[o] = 0;
+                    const int c = s_cnt[o];
+                    if (c > 0) {
+                        const int id = n_ne == 0 ? bin : nb + n_ne - 1;
+                        n_ne += 1;
+                        b_start[id] = bs + run;
+                        b_end[id] = bs + run + c - 1;
+                        b_np[id] = c;
+                        b_w[id] = s_wsum[o];
+                        b_depth[id] = depth + 1;
+                        if (a.oc.bin_bounds_compute == 1) {  // bin_bounds_inherit! (:341-367)
+                            for (int d = 0; d < 3; d++) {
+                                const bool upper = (o >> d) & 1;
+                                b_vmin[3 * id + d] = upper ? mid[d] : pmn[d];
+                                b_vmax[3 * id + d] = upper ? pmx[d] : mid[d];
+                            }
+                        } else {
+                            for (int d = 0; d < 3; d++) { b_vmin[3 * id + d] = pmn[d]; b_vmax[3 * id + d] = pmx[d]; }
+                        }
+                        tp += c >= 2 ? 2 : c;
+                    }
+                    run += c;
+                }
+                s_Nbins = nb + n_ne - 1;
+                s_total_post = tp;
+                if (s_Nbins + 7 > a.oc.max_Nbins) s_stop = 1;
+            }
+            __syncthreads();
+            // stable partition of idx[bs..be] by octant
+            const int n = be - bs + 1;
+            for (int c0 = 0; c0 < n; c0 += nt) {
+                const int j = c0 + tid;
+                const bool valid = j < n;
+                int o = -1, rank = 0;
+                const unsigned act = __ballot_sync(0xffffffffu, valid);
+                if (tid < 8 * nw) sh_c[tid >> 3][tid & 7] = 0;
+                __syncthreads();
+                if (valid) {
+                    o = oct[bs + j];
+                    const unsigned peers = __match_any_sync(act, o);
+                    rank = __popc(peers & lt);
+                    if (rank == 0) sh_c[wid][o] = __popc(peers);
+                }
+                __syncthreads();
+                if (valid) {
+                    // the reference walks the slice forwards while filling each octant's range from its END
+                    // (merging_octree_N2.jl:618-623), i.e. the order inside an octant is reversed at every split
+                    int before = s_run[o] + rank;
+                    for (int i = 0; i < wid; i++) before += sh_c[i][o];
+                    tmp[bs + s_base[o] + (s_cnt[o] - 1 - before)] = idx[bs + j];
+                }
+                __syncthreads();
+                if (tid < 8) {
+                    int t = 0;
+                    for (int i = 0; i < nw; i++) t += sh_c[i][tid];
+                    s_run[tid] += t;
+                }
+                __syncthreads();
+            }
+            for (int j = tid; j < n; j += nt) idx[bs + j] = tmp[bs + j];
+            __syncthreads();
+            if (s_stop) break;
+        }
+        __syncthreads();
+        const int Nbins = s_Nbins;
+        if (Nbins == 1) {  // :1028-1034
+            double sw = 0;
+            for (int j = tid; j < N; j += nt) sw += PW[idx[j]];
+            sw = block_sum(sw, sh);
+            if (tid == 0) b_w[0] = sw;
+            __syncthreads();
+        }
+        // ---- compute_bin_props! (:646-700) + the per-bin part of compute_new_particles! (:742-784): a warp per bin
+        for (int b = wid; b < Nbins; b += nw) {
+            int np = b_np[b];
+            const double w = b_w[b];
+            if (w == 0) np = 0;
+            const int bs = b_start[b], be = b_end[b];
+            double* o1 = outbuf + (int64_t)(2 * b) * 7;
+            double* o2 = o1 + 7;
+            if (np > 2) {
+                const double inv_w = 1.0 / w;
+                double m[6] = {0, 0, 0, 0, 0, 0};
+                for (int j = bs + lane; j <= be; j += 32) {
+                    const int64_t p = idx[j];
+                    const double pw = PW[p];
+#pragma unroll
+                    for (int d = 0; d < 6; d++) m[d] += pw * a.pv.a[F_VX + d][p];  // vx,vy,vz,x,y,z are consecutive fields
+                }
+#pragma unroll
+                for (int d = 0; d < 6; d++) {
+                    for (int o = 16; o > 0; o >>= 1) m[d] += __shfl_xor_sync(0xffffffffu, m[d], o);
+                    m[d] *= inv_w;
+                }
+                double s2[6] = {0, 0, 0, 0, 0, 0};
+                for (int j = bs + lane; j <= be; j += 32) {
+                    const int64_t p = idx[j];
+                    const double pw = PW[p];
+#pragma unroll
+                    for (int d = 0; d < 6; d++) { const double dd = a.pv.a[F_VX + d][p] - m[d]; s2[d] += pw * dd * dd; }
+                }
+#pragma unroll
+                for (int d = 0; d < 6; d++) {
+                    for (int o = 16; o > 0; o >>= 1) s2[d] += __shfl_xor_sync(0xffffffffu, s2[d], o);
+                    s2[d] = sqrt(s2[d] * inv_w);
+                }
+                if (lane == 0) {
+                    // rand(rng, direction_signs, 3) twice (:749,:753): Philox block (bin_id - 1) of the cell's merge stream
+                    uint32_t rb[4];
+                    philox4x32_10((uint32_t)b, (uint32_t)cell, a.timestep, (OP_MERGE & 0xFFu) | (a.substream << 8), (uint32_t)a.seed,
+                                  (uint32_t)(a.seed >> 32), rb);
+                    o1[0] = 0.5 * w; o2[0] = 0.5 * w;
+#pragma unroll
+                    for (int d = 0; d < 6; d++) {
+                        const double sg = ((rb[0] >> d) & 1u) ? 1.0 : -1.0;
+                        double x1 = m[d] + sg * s2[d], x2 = m[d] - sg * s2[d];
+                        if (d == 3 && a.has_grid) {  // :878-897: clamp x1 of the np > 2 outputs into [min_x, max_x]
+                            x1 = x1 < a.min_x ? a.min_x : (x1 > a.max_x ? a.max_x : x1);
+                            x2 = x2 < a.min_x ? a.min_x : (x2 > a.max_x ? a.max_x : x2);
+                        }
+                        o1[1 + d] = x1;
+                        o2[1 + d] = x2;
+                    }
+                }
+            } else if (np >= 1) {
+                if (lane < 7) {
+                    o1[lane] = a.pv.a[lane][idx[bs]];
+                    if (np == 2) o2[lane] = a.pv.a[lane][idx[bs + 1]];
+                }
+            }
+            if (lane == 0) b_out[b] = np >= 2 ? 2 : np;
+        }
+        __syncthreads();
+        // exclusive scan of the per-bin output counts (bins in id order)
+        if (tid == 0) s_carry = 0;
+        __syncthreads();
+        for (int c0 = 0; c0 < Nbins; c0 += nt) {
+            const int b = c0 + tid;
+            const int v = b < Nbins ? b_out[b] : 0;
+            s_scan[tid] = v;
+            __syncthreads();
+            for (int o = 1; o < nt; o <<= 1) {
+                const int t = tid >= o ? s_scan[tid - o] : 0;
+                __syncthreads();
+                s_scan[tid] += t;
+                __syncthreads();
+            }
+            const int incl = s_scan[tid], carry = s_carry;
+            if (b < Nbins) b_out[b] = carry + incl - v;
+            __syncthreads();
+            if (tid == nt - 1) s_carry = carry + incl;
+            __syncthreads();
+            // keep the count recoverable: stash it in the sign bit-free upper part is not needed -- recompute below from b_np / b_w
+        }
+        const int curr = s_carry;
+        // ---- write the merged particles into the first `curr` logical slots of the cell (:786-799)
+        for (int b = wid; b < Nbins; b += nw) {
+            int np = b_np[b];
+            if (b_w[b] == 0) np = 0;
+            const int no = np >= 2 ? 2 : np;
+            const int off = b_out[b];
+            for (int k = 0; k < no; k++) {
+                const int64_t p = mpos(q, off + k);
+                if (lane < 7) a.pv.a[lane][p] = outbuf[(int64_t)(2 * b + k) * 7 + lane];
+            }
+        }
+        // ---- delete_particle_end! x n_delete (:800-812): group 2 shrinks first, then group 1; deleted slots get w = 0
+        const int n_del = N - curr;
+        for (int j = curr + tid; j < N; j += nt) a.pv.a[F_W][mpos(q, j)] = 0.0;
+        if (tid == 0) {
+            Indexer u = q;
+            int64_t d = n_del;
+            const int64_t d2 = d < u.n_group2 ? d : u.n_group2;
+            u.n_group2 -= d2; u.end2 -= d2;
+            if (u.n_group2 == 0) { u.start2 = 0; u.end2 = -1; }
+            d -= d2;
+            u.n_group1 -= d; u.end1 -= d;
+            if (u.n_group1 == 0) { u.start1 = 0; u.end1 = -1; }
+            u.n_local = curr;
+            a.ix[cell - 1] = u;
+            if (n_del > 0) atomicAdd((unsigned long long*)a.n_total, (unsigned long long)(-(long long)n_del));
+            if (!(cell == a.n_cells_total) || n_del > q.n_group2) *a.noncontig = 1;  // :806-808
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace mb
+
+using namespace mb;
+
+extern "C" int mb_merge_octree_N2(mb_ctx* ctx, const mb_octree_params* oc, mb_pv* pv, mb_pia* pia, int64_t cell_lo, int64_t cell_hi,
+                                  int64_t species, int64_t threshold, int64_t target_np, const mb_grid1d* grid, uint32_t timestep,
+                                  uint32_t substream) {
+    MB_ARG(ctx && oc && pv && pia, "NULL handle");
+    MB_ARG(species >= 1 && species <= pia->n_species, "species out of range");
+    MB_ARG(cell_lo >= 1 && cell_hi <= pia->n_cells && cell_lo <= cell_hi, "cell range");
+    MB_ARG(target_np >= 1, "target_np");
+    MB_ARG(oc->max_Nbins >= 8 && oc->max_depth >= 0, "OctreeN2Merge: max_Nbins >= 8");
+    if (!(oc->split == 1 || oc->split == 2)) {
+        set_error("OctreeBinMedianSplit is not supported (documented 'probably not fully correct' in the reference, merging_octree_N2.jl:444)");
+        return MB_ERR_UNSUPPORTED;
+    }
+    MB_ARG(oc->init_bin_bounds >= 1 && oc->init_bin_bounds <= 3 && (oc->bin_bounds_compute == 1 || oc->bin_bounds_compute == 2), "octree enums");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    const int s = (int)species - 1;
+    const int64_t nc = pia->n_cells, nr = cell_hi - cell_lo + 1, cap = pv->cap;
+    ProfScope ps(ctx, PROF_MERGE);
+    cudaStream_t st = ctx->stream;
+    MergeArgs a;
+    a.pv = pv->cur;
+    a.ix = pia->d_indexer + (int64_t)s * nc;
+    a.n_total = pia->d_n_total + s;
+    a.cell_lo = cell_lo; a.cell_hi = cell_hi; a.n_cells_total = nc;
+    a.threshold = threshold; a.target = target_np;
+    a.oc = *oc;
+    a.has_grid = grid != nullptr;
+    a.min_x = grid ? grid->min_x : 0.0;
+    a.max_x = grid ? grid->max_x : 0.0;
+    a.seed = ctx->seed; a.timestep = timestep; a.substream = substream;
+    a.flags = ctx->d_flags;
+    // index slices
+    a.idx = (int32_t*)ctx_scratch(ctx, 0, (size_t)cap * 4);
+    a.tmp = (int32_t*)ctx_scratch(ctx, 3, (size_t)cap * 4);
+    a.oct = (uint8_t*)ctx_scratch(ctx, 8, (size_t)cap);
+    int32_t* cnt = (int32_t*)ctx_scratch(ctx, 4, (size_t)nr * 4);
+    int64_t* p64 = (int64_t*)ctx_scratch(ctx, 5, ((size_t)(nr + 1) + gs_partial_count(nr)) * 8);
+    if (!a.idx || !a.tmp || !a.oct || !cnt || !p64) return MB_ERR_CUDA;
+    a.slice = p64;
+    k_merge_counts<<<grid_for(nr, 256), 256, 0, st>>>(a.ix, cell_lo, nr, threshold, cnt);
+    MB_LAUNCH_CHECK(ctx);
+    int r = device_exclusive_scan(ctx, cnt, nr, p64, p64 + (nr + 1));
+    if (r) return r;
+    // per-CTA bin workspace
+    const int64_t bcap = (oc->max_Nbins < target_np ? oc->max_Nbins : target_np) + 8;
+    a.Bmax = (int)bcap;
+    const int64_t avg = (pia->n_bound[s] > 0 ? pia->n_bound[s] : cap) / nc;
+    const int threads = avg > 2048 ? 256 : 128;
+    int64_t nCTA = nr < (int64_t)N_SM * (threads == 256 ? 4 : 8) ? nr : (int64_t)N_SM * (threads == 256 ? 4 : 8);
+    const size_t per = (size_t)bcap * (5 * 4 + 8 + 24 + 24 + 2 * 7 * 8) + 64;
+    char* ws = (char*)ctx_scratch(ctx, 9, per * (size_t)nCTA + 4096);
+    if (!ws) return MB_ERR_CUDA;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* p = ws + off; off += ((bytes + 255) / 256) * 256; return p; };
+    a.b_w = (double*)take((size_t)nCTA * bcap * 8);
+    a.b_vmin = (double*)take((size_t)nCTA * bcap * 24);
+    a.b_vmax = (double*)take((size_t)nCTA * bcap * 24);
+    a.outbuf = (double*)take((size_t)nCTA * bcap * 2 * 7 * 8);
+    a.b_np = (int32_t*)take((size_t)nCTA * bcap * 4);
+    a.b_depth = (int32_t*)take((size_t)nCTA * bcap * 4);
+    a.b_start = (int32_t*)take((size_t)nCTA * bcap * 4);
+    a.b_end = (int32_t*)take((size_t)nCTA * bcap * 4);
+    a.b_out = (int32_t*)take((size_t)nCTA * (bcap + 1) * 4);
+    if (off > per * (size_t)nCTA + 4096) {
+        ws = (char*)ctx_scratch(ctx, 9, off + 4096);
+        if (!ws) return MB_ERR_CUDA;
+        set_error("internal: merge workspace sizing");
+        return MB_ERR_UNSUPPORTED;
+    }
+    a.noncontig = ctx->d_flags + 4 + s % 8;
+    if (!pia->contig_pending[s]) MB_CUDA(cudaMemsetAsync(a.noncontig, 0, sizeof(int), st));
+    k_merge<<<(int)nCTA, threads, 0, st>>>(a);
+    MB_LAUNCH_CHECK(ctx);
+    // conservative on the host (operators dispatch on it); mb_pia_download resolves the exact reference value (:806-808)
+    if (pia->contiguous[s]) pia->contig_pending[s] = 1;
+    pia->contiguous[s] = 0;
+    pia->sorted_layout[s] = 0;
+    pia->h_valid = false;
+    return MB_OK;
+}

@@ -533,6 +533,7 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
     pv->cur = pv->alt;
     pv->alt = t;
     pia->contiguous[s] = 1;      // grid_sorting.jl:112
+    pia->contig_pending[s] = 0;
     pia->sorted_layout[s] = 1;
     ctx->sort_last_path = try_band ? 1 : 2;
     return MB_OK;

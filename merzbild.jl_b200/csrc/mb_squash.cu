@@ -94,5 +94,6 @@ extern "C" int mb_squash_pia(mb_ctx* ctx, mb_pv* pv, mb_pia* pia, int64_t specie
     k_squash_fix_indexer<<<grid_for(nc, 256), 256, 0, st>>>(ix, nc, newlo);
     MB_LAUNCH_CHECK(ctx);
     pia->contiguous[s] = 1;
+    pia->contig_pending[s] = 0;
     return MB_OK;
 }

@@ -1,0 +1,226 @@
+"""GPU parity tests, part 2: octree N:2 merging, squash_pia!, SWPM, linear Fokker-Planck -- CUDA path (through the C ABI)
+against the CPU oracle.  Merging: identical bin structure (same surviving particle counts per cell, same pia), merged
+particles to 1e-12, mass / momentum / energy conserved to 1e-12 relative."""
+import numpy as np
+import pytest
+
+from parity_util import AR, assert_rows_close, assert_same_pia, maxwellian_rows, mirror_to_device, oracle_state
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(mb):
+    c = mb.Context(0, 1234)
+    yield c
+    c.close()
+
+
+def _moments(rows):
+    w = rows[:, 0]
+    return np.array([w.sum(), *(w[:, None] * rows[:, 1:4]).sum(0), (w[:, None] * rows[:, 1:4] ** 2).sum(0).sum()])
+
+
+def _octant_particles():
+    """test/test_octree_merging.jl:3-40: 24 particles, 3 per velocity octant, weight = octant id."""
+    rows = []
+    signs = [(-1, -1, -1), (1, -1, -1), (-1, 1, -1), (1, 1, -1), (-1, -1, 1), (1, -1, 1), (-1, 1, 1), (1, 1, 1)]
+    for i, s in enumerate(signs, start=1):
+        for k, dv in enumerate((-1.0, 0.0, 1.0)):
+            v = np.array(s, dtype=float) * (9.0 - i) + dv * 0.25 * np.array([1.0, -1.0, 0.5])
+            rows.append([float(i), *v, 0.1 * i + 0.01 * k, 0.5, 0.25])
+    return np.array(rows)
+
+
+def test_octree_merge_reference_kat(mb, oracle, ctx):
+    """24 particles in 8 octants -> merge to 16 (8 bins x 2) and then to 2; n, v, T conserved (test_octree_merging.jl:70-163)."""
+    rows = _octant_particles()
+    for target, expect in ((16, 16), (2, 2)):
+        opv, opia = oracle_state(oracle, rows, 1)
+        pv, pia = mirror_to_device(mb, ctx, opv, opia)
+        oc = oracle.Octree(oracle.MID_SPLIT, oracle.INIT_C, oracle.BOUNDS_INHERIT, 4096, 10)
+        oracle.merge_octree_N2(oracle.Rng.philox(1234, 7, 0), oc, opv, opia, 1, 1, 1, target)
+        moc = mb.OctreeN2Merge(mb.OctreeN2Merge.OctreeBinMidSplit, mb.OctreeN2Merge.OctreeInitBinC)
+        mb.merge_octree_N2_based(mb.PhiloxRng(7, 0), moc, pv, pia, 1, 1, target)
+        assert_same_pia(opia, pia)
+        nt = int(opia.n_total[0])
+        assert nt == expect
+        a, b = pv.logical(1, 24), opv.logical(1, 24)
+        assert_rows_close(a[:nt], b[:nt], 1e-13, "merged particles")
+        assert np.all(a[nt:, 0] == 0.0)  # deleted particles carry zero weight (particles.jl:506,547)
+        m0, m1 = _moments(rows), _moments(a[:nt])
+        np.testing.assert_allclose(m1, m0, rtol=1e-14, atol=1e-12)
+
+
+@pytest.mark.parametrize("init,bounds,split", [(1, 1, 1), (2, 1, 1), (1, 2, 1), (3, 1, 1), (1, 1, 2)])
+def test_octree_merge_single_cell_parity(mb, oracle, ctx, init, bounds, split):
+    """0-D shape of test_bkw_varweight_octree.jl (scaled down): 6000 variable-weight particles -> 800."""
+    rng = np.random.default_rng(17)
+    n, target = 6000, 800
+    rows = maxwellian_rows(rng, n, 1.0, vw=True, w=1e15)
+    rows[:, 1:4] *= rng.uniform(0.5, 1.5, (n, 1))
+    opv, opia = oracle_state(oracle, rows, 1)
+    pv, pia = mirror_to_device(mb, ctx, opv, opia)
+    oc = oracle.Octree(split, init, bounds, 6000, 10)
+    oracle.merge_octree_N2(oracle.Rng.philox(1234, 3, 1), oc, opv, opia, 1, 1, 1, target)
+    moc = mb.OctreeN2Merge(split, init, bounds, max_Nbins=6000)
+    mb.merge_octree_N2_based(mb.PhiloxRng(3, 1), moc, pv, pia, 1, 1, target)
+    nt_dev = int(pia.n_total[0])
+    a = pv.logical(1, n)
+    m0, m1 = _moments(rows), _moments(a[:nt_dev])
+    np.testing.assert_allclose(m1, m0, rtol=1e-12)  # mass, momentum, energy
+    if init != 3:  # with +-c root bounds 10 levels of halving never resolve thermal velocities: 8 bins, as in the reference
+        assert target - 14 <= nt_dev <= target
+    assert pia.check(1) == (True, 0)
+    if split == 1:  # mid split: the octree is identical, merged particles agree to rounding
+        assert_same_pia(opia, pia)
+        b = opv.logical(1, n)
+        assert_rows_close(a[:nt_dev], b[:nt_dev], 1e-12, "merged particles")
+    # squash is a no-op for a single cell whose deletions came from the tail
+    mb.squash_pia(pv, pia, 1)
+    oracle.squash_pia(opv, opia, 1)
+    if split == 1:
+        assert_same_pia(opia, pia)
+
+
+def test_octree_merge_1d_cells_and_squash(mb, oracle, ctx):
+    """Couette variable-weight shape (couette_varweight_octree.jl:86-135): ntc! -> merge cells over the threshold (1-D variant
+    with the x clamp) -> squash_pia!, then sort; state identical to the oracle's per-cell loop."""
+    n_cells, ppc = 30, 400
+    rng = np.random.default_rng(23)
+    L = n_cells * 1e-5
+    n = n_cells * ppc
+    Fnum = 1e-5 * 5e22 / ppc
+    rows = maxwellian_rows(rng, n, L, w=Fnum, vw=True)
+    rows[:, 4] = rng.beta(0.7, 0.7, n) * L  # uneven cells: some over the threshold, some under; crowd the walls
+    cap = 3 * n
+    opv, opia = oracle_state(oracle, rows, n_cells, capacity=cap)
+    oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+    pv, pia = mirror_to_device(mb, ctx, opv, opia, capacity=cap)
+    it, oit = mb.make_interaction(AR, AR, 4.11e-10, 0.81, 273.0), oracle.interaction("Ar", "Ar")
+    s0 = mb.estimate_sigma_g_w_max(it, AR, AR, 300.0, 300.0, 2 * Fnum)
+    cf, ocf = mb.CollisionFactors(n_cells, s0, ctx), oracle.CF(n_cells, s0)
+    g = mb.Grid1DUniform(L, n_cells)
+    oc = oracle.Octree(oracle.MID_SPLIT, oracle.INIT_MINMAX, oracle.BOUNDS_INHERIT, 6000, 10)
+    moc = mb.OctreeN2Merge(max_Nbins=6000)
+    threshold, target = 390, 250
+    dt, V = 2.59e-9 * 6, L / n_cells
+    for t in range(1, 4):
+        before = _moments(opv.logical(1, int(opia.n_total[0])))
+        mb.ntc(mb.PhiloxRng(t), cf, None, it, pv, pia, (1, n_cells), 1, dt, V)
+        mb.merge_octree_N2_based(mb.PhiloxRng(t), moc, pv, pia, (1, n_cells), 1, target, grid=g, threshold=threshold)
+        oracle.ntc(oracle.Rng.philox(1234, t), ocf, oit, opv, opia, 1, n_cells, 1, dt, V)
+        oracle.merge_octree_N2(oracle.Rng.philox(1234, t), oc, opv, opia, 1, n_cells, 1, target, threshold=threshold, grid=(L, n_cells))
+        assert_same_pia(opia, pia)  # incl. contiguous == 0
+        assert pia.check(1) == (True, 0)
+        mb.squash_pia(pv, pia, 1)
+        oracle.squash_pia(opv, opia, 1)
+        assert_same_pia(opia, pia)
+        nt = int(opia.n_total[0])
+        a, b = pv.logical(1, nt), opv.logical(1, nt)
+        assert_rows_close(a, b, 1e-11, "after merge + squash")
+        np.testing.assert_allclose(_moments(a), before, rtol=1e-12)
+        assert a[:, 4].min() >= g.min_x and a[:, 4].max() <= g.max_x
+        mb.sort_particles(None, g, pv, pia, 1)
+        oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+        assert_same_pia(opia, pia)
+        assert_rows_close(pv.logical(1, nt), opv.logical(1, nt), 1e-11, "after sort")
+    assert int(opia.indexer[0, :, 0].max()) <= threshold + 60
+
+
+def test_sort_squashes_noncontiguous(mb, oracle, ctx):
+    """sort_particles! calls squash_pia! first when the species is not contiguous (grid_sorting.jl:69-71)."""
+    n_cells, ppc = 8, 100
+    rng = np.random.default_rng(29)
+    L = n_cells * 1e-5
+    rows = maxwellian_rows(rng, n_cells * ppc, L, vw=True)
+    opv, opia = oracle_state(oracle, rows, n_cells)
+    oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+    pv, pia = mirror_to_device(mb, ctx, opv, opia)
+    oc = oracle.Octree(oracle.MID_SPLIT, oracle.INIT_MINMAX, oracle.BOUNDS_INHERIT, 6000, 10)
+    oracle.merge_octree_N2(oracle.Rng.philox(1234, 1), oc, opv, opia, 1, n_cells, 1, 40, threshold=-1, grid=(L, n_cells))
+    mb.merge_octree_N2_based(mb.PhiloxRng(1), mb.OctreeN2Merge(max_Nbins=6000), pv, pia, (1, n_cells), 1, 40, grid=mb.Grid1DUniform(L, n_cells))
+    assert_same_pia(opia, pia)
+    mb.sort_particles(None, mb.Grid1DUniform(L, n_cells), pv, pia, 1)
+    oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+    assert_same_pia(opia, pia)
+    nt = int(opia.n_total[0])
+    assert_rows_close(pv.logical(1, nt), opv.logical(1, nt), 1e-12, "sort after merge")
+
+
+# ------------------------------------------------------------------------------------------------------------ SWPM
+def test_swpm_parity(mb, oracle, ctx):
+    """swpm! (collision_swpm.jl:201-287): two children per accepted pair, parents lose dw; vs the oracle, 3 steps, multi-cell."""
+    n_cells, ppc = 10, 300
+    rng = np.random.default_rng(31)
+    L = n_cells * 1e-5
+    n = n_cells * ppc
+    Fnum = 1e-5 * 5e22 / ppc
+    rows = maxwellian_rows(rng, n, L, w=Fnum, vw=True)
+    cap = 6 * n
+    opv, opia = oracle_state(oracle, rows, n_cells, capacity=cap)
+    oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+    pv, pia = mirror_to_device(mb, ctx, opv, opia, capacity=cap)
+    it, oit = mb.make_interaction(AR, AR, 4.11e-10, 0.81, 273.0), oracle.interaction("Ar", "Ar")
+    s0 = mb.estimate_sigma_g_w_max(it, AR, AR, 300.0, 300.0, 1.0)  # sigma_g_max (no weight) for SWPM
+    cf, ocf = mb.CollisionFactors(n_cells, s0, ctx), oracle.CF(n_cells, s0)
+    g = mb.Grid1DUniform(L, n_cells)
+    G, dt, V = 0.5, 2.59e-9 * 4, L / n_cells
+    m0 = _moments(rows)
+    for t in range(1, 4):
+        mb.swpm(mb.PhiloxRng(t), cf, None, it, pv, pia, (1, n_cells), 1, G, dt, V)
+        oracle.swpm(oracle.Rng.philox(1234, t), ocf, oit, opv, opia, 1, n_cells, 1, G, dt, V)
+        d = cf.download()
+        np.testing.assert_array_equal(d["n_coll"], ocf.n_coll)
+        np.testing.assert_array_equal(d["n_coll_performed"], ocf.n_coll_performed)
+        assert_same_pia(opia, pia)
+        nt = int(opia.n_total[0])
+        a, b = pv.logical(1, nt), opv.logical(1, nt)
+        assert_rows_close(a, b, 1e-12, "swpm")
+        np.testing.assert_allclose(_moments(a), m0, rtol=1e-12)
+        mb.sort_particles(None, g, pv, pia, 1)
+        oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+        assert_same_pia(opia, pia)
+    assert nt > n
+
+
+# ------------------------------------------------------------------------------------------------------------ FP
+def test_fp_linear_parity(mb, oracle, ctx):
+    """fp_linear! (collision_fp.jl:24-125) over cells of 100-200 particles (test_collision_fp.jl / test_1D_couette_fp.jl shapes):
+    same Philox normals as the oracle; per-cell momentum and energy conserved exactly; cells with n < 7 untouched."""
+    n_cells = 64
+    rng = np.random.default_rng(37)
+    L = n_cells * 1e-5
+    counts = rng.integers(100, 200, n_cells)
+    counts[5] = 6
+    counts[9] = 0
+    n = int(counts.sum())
+    Fnum = 2.5e15
+    rows = maxwellian_rows(rng, n, L, w=Fnum, vw=False)  # equal weights: sum(xi) = 0 makes the momentum exactly conserved
+    cells = np.repeat(np.arange(n_cells), counts)
+    rows[:, 4] = (cells + rng.uniform(0.01, 0.99, n)) * 1e-5
+    rows[:, 1] *= 1.8  # anisotropic: T_x > T_y, relaxes towards isotropy
+    rows[:, 2] += 300.0
+    opv, opia = oracle_state(oracle, rows, n_cells)
+    oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+    pv, pia = mirror_to_device(mb, ctx, opv, opia)
+    it, oit = mb.make_interaction(AR, AR, 4.11e-10, 0.81, 273.0), oracle.interaction("Ar", "Ar")
+    dt, V = 2.59e-9 * 50, 1e-5
+    start = opv.logical(1, n)
+    for t in range(1, 4):
+        mb.fp_linear(mb.PhiloxRng(t, 4), None, it, AR, pv, pia, (1, n_cells), 1, dt, V)
+        oracle.fp_linear(oracle.Rng.philox(1234, t, 4), oit, AR, opv, opia, 1, n_cells, 1, dt, V)
+    a, b = pv.logical(1, n), opv.logical(1, n)
+    assert_rows_close(a, b, 1e-11, "fp_linear")
+    np.testing.assert_array_equal(a[:, [0, 4, 5, 6]], start[:, [0, 4, 5, 6]])
+    off = np.concatenate(([0], np.cumsum(counts)))
+    Tx0 = Tx1 = 0.0
+    for c in range(n_cells):
+        s, e = off[c], off[c + 1]
+        if counts[c] < 7:
+            np.testing.assert_array_equal(a[s:e], start[s:e])
+            continue
+        np.testing.assert_allclose(_moments(a[s:e]), _moments(start[s:e]), rtol=1e-12)
+        Tx0 += np.var(start[s:e, 1])
+        Tx1 += np.var(a[s:e, 1])
+    assert Tx1 < Tx0  # the hot component cools
