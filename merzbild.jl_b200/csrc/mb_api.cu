@@ -103,6 +103,7 @@ int mb_ctx_create(int device, uint64_t seed, mb_ctx** out) {
     c->device = device;
     c->seed = seed;
     c->band_w = 2;
+    c->state_gen = 1;
     MB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     MB_CUDA(cudaMalloc(&c->d_flags, 16 * sizeof(int)));
     MB_CUDA(cudaMemset(c->d_flags, 0, 16 * sizeof(int)));
@@ -255,6 +256,8 @@ int mb_pv_create(mb_ctx* ctx, int64_t np, mb_pv** out) {
     p->ctx = ctx;
     p->cap = np;
     p->has_alt = false;
+    p->drop_oob = false;
+    p->n_arrivals = 0;
     p->cell = nullptr;
     for (int f = 0; f < 7; f++) p->alt.a[f] = nullptr;
     int r = alloc_soa(p->cur, np);
@@ -285,6 +288,7 @@ int mb_pv_resize(mb_pv* p, int64_t np) {  // particles.jl:269-298 (new slots hol
     MB_ARG(p && np >= p->cap, "resize can only grow");
     if (np == p->cap) return MB_OK;
     mb_ctx* ctx = p->ctx;
+    ctx->state_gen++;
     MB_CUDA(cudaSetDevice(ctx->device));
     SoA ns;
     int r = alloc_soa(ns, np);
@@ -319,6 +323,7 @@ int mb_pv_upload_soa(mb_pv* p, int64_t lo, int64_t n, const double* w, const dou
     if (r) return r;
     if (n == 0) return MB_OK;
     MB_CUDA(cudaSetDevice(p->ctx->device));
+    p->ctx->state_gen++;
     const double* src[7] = {w, vx, vy, vz, x, y, z};
     for (int f = 0; f < 7; f++)
         if (src[f]) MB_CUDA(cudaMemcpyAsync(p->cur.a[f] + (lo - 1), src[f], (size_t)n * 8, cudaMemcpyHostToDevice, p->ctx->stream));
@@ -365,6 +370,7 @@ int mb_pv_upload_cell(mb_pv* p, int64_t lo, int64_t n, const int64_t* cell) {
     std::vector<int32_t> t((size_t)n);
     for (int64_t i = 0; i < n; i++) t[i] = (int32_t)cell[i];
     MB_CUDA(cudaSetDevice(p->ctx->device));
+    p->ctx->state_gen++;
     MB_CUDA(cudaMemcpyAsync(p->cell + (lo - 1), t.data(), (size_t)n * 4, cudaMemcpyHostToDevice, p->ctx->stream));
     MB_CUDA(cudaStreamSynchronize(p->ctx->stream));
     return MB_OK;
@@ -427,6 +433,7 @@ int mb_pia_destroy(mb_pia* p) {
 int mb_pia_upload(mb_pia* p, const int64_t* indexer, const int64_t* n_total, const uint8_t* contiguous) {
     MB_ARG(p != nullptr, "pia == NULL");
     mb_ctx* ctx = p->ctx;
+    ctx->state_gen++;
     MB_CUDA(cudaSetDevice(ctx->device));
     if (indexer) {
         MB_CUDA(cudaMemcpyAsync(p->d_indexer, indexer, (size_t)p->n_cells * p->n_species * sizeof(Indexer), cudaMemcpyHostToDevice, ctx->stream));

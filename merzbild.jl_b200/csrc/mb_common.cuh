@@ -107,6 +107,11 @@ struct mb_ctx {
     size_t scratch_bytes[12];
     int sort_last_path;
     int band_w;
+    // moments cached by the band sort's gather pass (valid while state_gen == pc_gen)
+    uint64_t state_gen, pc_gen;
+    void* pc_pv;
+    void* pc_pia;
+    int pc_species;
     // per-section event profiling
     int prof_on;
     std::vector<cudaEvent_t>* prof_ev;   // pairs (begin, end)
@@ -129,6 +134,8 @@ struct mb_pv {
     mb::SoA cur, alt;   // alt allocated lazily (sort ping-pong)
     bool has_alt;
     int32_t* cell;      // 1-based cell id per logical position (pv.cell); int32 on device
+    bool drop_oob;      // set by the slab exchange: the next sort drops particles whose cell is outside the slab
+    int64_t n_arrivals; // slab-exchange arrivals appended after the sorted layout (merged by the next sort)
 };
 
 struct mb_pia {

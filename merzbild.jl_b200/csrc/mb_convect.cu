@@ -136,6 +136,7 @@ extern "C" int mb_convect_particles(mb_ctx* ctx, const mb_grid1d* grid, const mb
     a.seed = ctx->seed; a.timestep = timestep; a.substream = substream;
     a.compute_cell = compute_cell;
     a.surf = nullptr;
+    ctx->state_gen++;
     if (surf22) {
         a.surf = (double*)ctx_scratch(ctx, 6, 22 * 8);
         if (!a.surf) return MB_ERR_CUDA;

@@ -1,0 +1,316 @@
+// Slab exchange over NCCL: the B200 replacement of the reference's shared-memory chunk exchange (src/parallel.jl:21-581:
+// ChunkExchanger, exchange_particles!, push_particles!, sort_particles_after_exchange!).  Every GPU owns a contiguous slab of
+// cells (mb_grid1d_slab, the ChunkSplitters rule); after convection the particles whose cell lies outside the slab are packed
+// (stable, in logical order) into a left and a right send buffer, the neighbours swap counts and payloads with
+// ncclSend/ncclRecv in one group over NVLink, and the arrivals are appended after n_total (left arrivals first).  The
+// leavers stay where they are and are dropped by the next sort_particles! (their cell is outside the slab), which also
+// places the arrivals -- they are just more keys -- so no hole filling or free-list bookkeeping is needed (the reference's
+// swap-vs-push distinction, parallel.jl:373-413, exists only because its sort moves indices, not particles).
+//
+// NCCL is loaded lazily with dlopen (libnccl.so.2, e.g. the one PyTorch bundles): a single-GPU user never needs it.
+#include <dlfcn.h>
+
+#include <cstdlib>
+#include <cstring>
+
+#include "mb_common.cuh"
+#include "mb_scan.cuh"
+
+namespace mb {
+
+// ---- minimal NCCL binding (nccl.h, 2.x ABI)
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclInt64 = 4, ncclFloat64 = 8 };
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load() {
+    if (g_nccl.h) return MB_OK;
+    const char* env = getenv("MB_NCCL_LIB");
+    const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) {
+        if (!n) continue;
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) {
+        set_error("NCCL not found: dlopen(libnccl.so.2) failed (import torch first, or set MB_NCCL_LIB / LD_LIBRARY_PATH)");
+        return MB_ERR_NCCL;
+    }
+#define MB_SYM(field, name)                                            \
+    *(void**)(&g_nccl.field) = dlsym(h, name);                         \
+    if (!g_nccl.field) { set_error(std::string("NCCL symbol missing: ") + name); return MB_ERR_NCCL; }
+    MB_SYM(GetUniqueId, "ncclGetUniqueId");
+    MB_SYM(CommInitRank, "ncclCommInitRank");
+    MB_SYM(CommDestroy, "ncclCommDestroy");
+    MB_SYM(Send, "ncclSend");
+    MB_SYM(Recv, "ncclRecv");
+    MB_SYM(GroupStart, "ncclGroupStart");
+    MB_SYM(GroupEnd, "ncclGroupEnd");
+    MB_SYM(GetErrorString, "ncclGetErrorString");
+#undef MB_SYM
+    g_nccl.h = h;
+    return MB_OK;
+}
+#define MB_NCCL(x)                                                                        \
+    do {                                                                                  \
+        int e__ = (x);                                                                    \
+        if (e__ != ncclSuccess) {                                                         \
+            set_error(std::string("NCCL error in " #x ": ") + g_nccl.GetErrorString(e__)); \
+            return MB_ERR_NCCL;                                                           \
+        }                                                                                 \
+    } while (0)
+
+constexpr int XB = 256;      // threads per block
+constexpr int XI = 8;        // particles per thread (blocked)
+constexpr int XT = XB * XI;  // particles per block
+
+// direction of a particle: 0 stays, 1 leaves to the left neighbour, 2 to the right
+__device__ __forceinline__ int xch_dir(double x, double inv_dx, int64_t cell_offset, int64_t n_cells) {
+    const int64_t c = (int64_t)floor(x * inv_dx) - cell_offset;
+    return c < 0 ? 1 : (c >= n_cells ? 2 : 0);
+}
+
+static __global__ void __launch_bounds__(XB) k_xch_count(const double* __restrict__ X, const int64_t* n_total_p, double inv_dx, int64_t cell_offset,
+                                                        int64_t n_cells, int32_t* __restrict__ cntL, int32_t* __restrict__ cntR) {
+    __shared__ int sl[XB / 32], sr[XB / 32];
+    const int64_t n = *n_total_p;
+    const int64_t base = (int64_t)blockIdx.x * XT + (int64_t)threadIdx.x * XI;
+    int l = 0, r = 0;
+    for (int k = 0; k < XI; k++) {
+        const int64_t i = base + k;
+        if (i < n) {
+            const int d = xch_dir(X[i], inv_dx, cell_offset, n_cells);
+            l += d == 1;
+            r += d == 2;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) { l += __shfl_down_sync(0xffffffffu, l, o); r += __shfl_down_sync(0xffffffffu, r, o); }
+    if ((threadIdx.x & 31) == 0) { sl[threadIdx.x >> 5] = l; sr[threadIdx.x >> 5] = r; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int a = 0, b = 0;
+        for (int i = 0; i < XB / 32; i++) { a += sl[i]; b += sr[i]; }
+        cntL[blockIdx.x] = a;
+        cntR[blockIdx.x] = b;
+    }
+}
+
+// stable pack (logical order) of the leavers into particle-major send buffers (7 doubles per particle)
+static __global__ void __launch_bounds__(XB) k_xch_pack(SoA pv, const int64_t* n_total_p, double inv_dx, int64_t cell_offset, int64_t n_cells,
+                                                       const int64_t* __restrict__ offL, const int64_t* __restrict__ offR, double* __restrict__ sendL,
+                                                       double* __restrict__ sendR, int64_t cap, int64_t nblocks, int64_t* counts, int* flags) {
+    __shared__ int sl[XB], sr[XB];
+    const int64_t n = *n_total_p;
+    const int64_t base = (int64_t)blockIdx.x * XT + (int64_t)threadIdx.x * XI;
+    int dir[XI];
+    int l = 0, r = 0;
+#pragma unroll
+    for (int k = 0; k < XI; k++) {
+        const int64_t i = base + k;
+        dir[k] = i < n ? xch_dir(pv.a[F_X][i], inv_dx, cell_offset, n_cells) : 0;
+        l += dir[k] == 1;
+        r += dir[k] == 2;
+    }
+    sl[threadIdx.x] = l;
+    sr[threadIdx.x] = r;
+    __syncthreads();
+    for (int o = 1; o < XB; o <<= 1) {  // inclusive scans over the block
+        const int a = threadIdx.x >= o ? sl[threadIdx.x - o] : 0, b = threadIdx.x >= o ? sr[threadIdx.x - o] : 0;
+        __syncthreads();
+        sl[threadIdx.x] += a;
+        sr[threadIdx.x] += b;
+        __syncthreads();
+    }
+    int64_t pl = offL[blockIdx.x] + sl[threadIdx.x] - l, pr = offR[blockIdx.x] + sr[threadIdx.x] - r;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t tl = offL[nblocks], tr = offR[nblocks];
+        counts[0] = tl;
+        counts[1] = tr;
+        if (tl > cap || tr > cap) {
+            atomicOr(&flags[0], DEVERR_CAPACITY);
+            flags[1] = (int)(tl > tr ? tl : tr);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < XI; k++) {
+        if (dir[k] == 0) continue;
+        const int64_t i = base + k;
+        double* dst;
+        if (dir[k] == 1) { if (pl >= cap) { pl++; continue; } dst = sendL + 7 * pl; pl++; }
+        else { if (pr >= cap) { pr++; continue; } dst = sendR + 7 * pr; pr++; }
+#pragma unroll
+        for (int f = 0; f < 7; f++) dst[f] = pv.a[f][i];
+    }
+}
+
+// arrivals (left neighbour's first, then the right neighbour's) are appended after n_total
+static __global__ void __launch_bounds__(256) k_xch_unpack(SoA pv, int64_t* n_total_p, int64_t cap, const double* __restrict__ recvL, int64_t nL,
+                                                          const double* __restrict__ recvR, int64_t nR, int* flags) {
+    const int64_t n0 = *n_total_p;
+    if (n0 + nL + nR > cap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            atomicOr(&flags[0], DEVERR_CAPACITY);
+            flags[1] = (int)(n0 + nL + nR);
+        }
+        return;
+    }
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nL + nR; t += (int64_t)gridDim.x * blockDim.x) {
+        const double* src = t < nL ? recvL + 7 * t : recvR + 7 * (t - nL);
+#pragma unroll
+        for (int f = 0; f < 7; f++) pv.a[f][n0 + t] = src[f];
+    }
+}
+static __global__ void k_xch_add_total(int64_t* n_total_p, int64_t cap, int64_t add) {
+    if (*n_total_p + add <= cap) *n_total_p += add;
+}
+
+}  // namespace mb
+
+using namespace mb;
+
+extern "C" {
+
+int mb_comm_unique_id(void* out128) {
+    MB_ARG(out128 != nullptr, "NULL");
+    int r = nccl_load();
+    if (r) return r;
+    ncclUniqueId id;
+    MB_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(out128, &id, 128);
+    return MB_OK;
+}
+
+int mb_comm_init(mb_ctx* ctx, const void* id128, int rank, int nranks) {
+    MB_ARG(ctx && id128 && nranks >= 1 && rank >= 0 && rank < nranks, "comm_init");
+    int r = nccl_load();
+    if (r) return r;
+    MB_CUDA(cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclComm_t comm;
+    MB_NCCL(g_nccl.CommInitRank(&comm, nranks, id, rank));
+    ctx->nccl_comm = comm;
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    return MB_OK;
+}
+
+int mb_exchange_slab(mb_ctx* ctx, const mb_grid1d* slab, mb_pv* pv, mb_pia* pia, int64_t species, int64_t* n_sent2, int64_t* n_recv2) {
+    MB_ARG(ctx && slab && pv && pia, "NULL handle");
+    MB_ARG(species >= 1 && species <= pia->n_species, "species out of range");
+    MB_ARG(pia->n_cells == slab->n_cells, "slab.n_cells != pia.n_cells");
+    if (ctx->nranks > 1 && !ctx->nccl_comm) {
+        set_error("mb_exchange_slab: call mb_comm_init first");
+        return MB_ERR_NCCL;
+    }
+    MB_CUDA(cudaSetDevice(ctx->device));
+    const int s = (int)species - 1;
+    if (!pia->contiguous[s]) {
+        set_error("mb_exchange_slab needs a contiguous species (sort or squash first)");
+        return MB_ERR_PRECONDITION;
+    }
+    ProfScope ps(ctx, PROF_EXCHANGE);
+    ctx->state_gen++;
+    cudaStream_t st = ctx->stream;
+    // staging buffers: capacity / 8 particles per direction
+    const size_t want = (size_t)pv->cap / 8 + 65536;
+    if (ctx->xch_cap < want) {
+        MB_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < 2; i++) {
+            if (ctx->xch_send[i]) cudaFree(ctx->xch_send[i]);
+            if (ctx->xch_recv[i]) cudaFree(ctx->xch_recv[i]);
+            MB_CUDA(cudaMalloc(&ctx->xch_send[i], want * 56));
+            MB_CUDA(cudaMalloc(&ctx->xch_recv[i], want * 56));
+        }
+        ctx->xch_cap = want;
+    }
+    const int64_t nb_part = pia->n_bound[s] > 0 ? pia->n_bound[s] : pv->cap;
+    const int64_t nblocks = (nb_part + XT - 1) / XT;
+    int32_t* cnt = (int32_t*)ctx_scratch(ctx, 4, (size_t)(2 * nblocks) * 4);
+    int64_t* p64 = (int64_t*)ctx_scratch(ctx, 5, ((size_t)2 * (nblocks + 1) + gs_partial_count(nblocks)) * 8);
+    if (!cnt || !p64) return MB_ERR_CUDA;
+    int64_t* offL = p64;
+    int64_t* offR = p64 + (nblocks + 1);
+    int64_t* partial = p64 + 2 * (nblocks + 1);
+    int64_t* d_nt = pia->d_n_total + s;
+    k_xch_count<<<(int)nblocks, XB, 0, st>>>(pv->cur.a[F_X], d_nt, slab->inv_dx, slab->cell_offset, slab->n_cells, cnt, cnt + nblocks);
+    MB_LAUNCH_CHECK(ctx);
+    int r = device_exclusive_scan(ctx, cnt, nblocks, offL, partial);
+    if (r) return r;
+    r = device_exclusive_scan(ctx, cnt + nblocks, nblocks, offR, partial);
+    if (r) return r;
+    k_xch_pack<<<(int)nblocks, XB, 0, st>>>(pv->cur, d_nt, slab->inv_dx, slab->cell_offset, slab->n_cells, offL, offR, (double*)ctx->xch_send[0],
+                                            (double*)ctx->xch_send[1], (int64_t)ctx->xch_cap, nblocks, ctx->d_xch_counts, ctx->d_flags);
+    MB_LAUNCH_CHECK(ctx);
+    const int left = ctx->rank - 1, right = ctx->rank + 1;
+    const bool hasL = ctx->nranks > 1 && left >= 0, hasR = ctx->nranks > 1 && right < ctx->nranks;
+    // counts: send [nL, nR] to the neighbours, receive theirs
+    MB_CUDA(cudaMemsetAsync(ctx->d_xch_counts + 2, 0, 2 * 8, st));
+    if (hasL || hasR) {
+        MB_NCCL(g_nccl.GroupStart());
+        if (hasL) {
+            MB_NCCL(g_nccl.Send(ctx->d_xch_counts + 0, 1, ncclInt64, left, (ncclComm_t)ctx->nccl_comm, st));
+            MB_NCCL(g_nccl.Recv(ctx->d_xch_counts + 2, 1, ncclInt64, left, (ncclComm_t)ctx->nccl_comm, st));
+        }
+        if (hasR) {
+            MB_NCCL(g_nccl.Send(ctx->d_xch_counts + 1, 1, ncclInt64, right, (ncclComm_t)ctx->nccl_comm, st));
+            MB_NCCL(g_nccl.Recv(ctx->d_xch_counts + 3, 1, ncclInt64, right, (ncclComm_t)ctx->nccl_comm, st));
+        }
+        MB_NCCL(g_nccl.GroupEnd());
+    }
+    MB_CUDA(cudaMemcpyAsync(ctx->h_xch_counts, ctx->d_xch_counts, 4 * 8, cudaMemcpyDeviceToHost, st));
+    r = mb_sync(ctx);  // the payload sizes must be known on the host to post the receives
+    if (r) return r;
+    const int64_t sL = ctx->h_xch_counts[0], sR = ctx->h_xch_counts[1], rL = ctx->h_xch_counts[2], rR = ctx->h_xch_counts[3];
+    if (rL > (int64_t)ctx->xch_cap || rR > (int64_t)ctx->xch_cap) {
+        set_error("mb_exchange_slab: arrivals exceed the staging capacity");
+        return MB_ERR_CAPACITY;
+    }
+    if ((!hasL && sL > 0) || (!hasR && sR > 0)) {
+        set_error("mb_exchange_slab: particles left the global domain (convect must clamp them to [min_x, max_x])");
+        return MB_ERR_PRECONDITION;
+    }
+    if (hasL || hasR) {
+        MB_NCCL(g_nccl.GroupStart());
+        if (hasL) {
+            if (sL > 0) MB_NCCL(g_nccl.Send(ctx->xch_send[0], (size_t)sL * 7, ncclFloat64, left, (ncclComm_t)ctx->nccl_comm, st));
+            if (rL > 0) MB_NCCL(g_nccl.Recv(ctx->xch_recv[0], (size_t)rL * 7, ncclFloat64, left, (ncclComm_t)ctx->nccl_comm, st));
+        }
+        if (hasR) {
+            if (sR > 0) MB_NCCL(g_nccl.Send(ctx->xch_send[1], (size_t)sR * 7, ncclFloat64, right, (ncclComm_t)ctx->nccl_comm, st));
+            if (rR > 0) MB_NCCL(g_nccl.Recv(ctx->xch_recv[1], (size_t)rR * 7, ncclFloat64, right, (ncclComm_t)ctx->nccl_comm, st));
+        }
+        MB_NCCL(g_nccl.GroupEnd());
+    }
+    if (rL + rR > 0) {
+        k_xch_unpack<<<grid_for(rL + rR, 256), 256, 0, st>>>(pv->cur, d_nt, pv->cap, (const double*)ctx->xch_recv[0], rL,
+                                                           (const double*)ctx->xch_recv[1], rR, ctx->d_flags);
+        MB_LAUNCH_CHECK(ctx);
+        k_xch_add_total<<<1, 1, 0, st>>>(d_nt, pv->cap, rL + rR);
+        MB_LAUNCH_CHECK(ctx);
+    }
+    // the layout of the own particles is untouched: the next sort drops the leavers and merges the arrivals (band path if sorted)
+    pv->drop_oob = (sL + sR) > 0 || pv->drop_oob;
+    pv->n_arrivals += rL + rR;
+    pia->h_valid = false;
+    pia->n_bound[s] = pv->cap;
+    if (n_sent2) { n_sent2[0] = sL; n_sent2[1] = sR; }
+    if (n_recv2) { n_recv2[0] = rL; n_recv2[1] = rR; }
+    return MB_OK;
+}
+
+}  // extern "C"

@@ -132,6 +132,7 @@ extern "C" int mb_fp_linear(mb_ctx* ctx, const mb_interaction* it, double mass, 
     a.mass = mass; a.dt = dt; a.V = V;
     a.seed = ctx->seed; a.timestep = timestep; a.substream = substream;
     ProfScope ps(ctx, PROF_FP);
+    ctx->state_gen++;
     k_fp_linear<<<grid_for((cell_hi - cell_lo + 1) * 32, 256, 8), 256, 0, ctx->stream>>>(a);
     MB_LAUNCH_CHECK(ctx);
     return MB_OK;

@@ -196,6 +196,7 @@ static int ntc_impl(mb_ctx* ctx, mb_cf* cf, const mb_interaction* it, mb_pv* pv1
     cudaStream_t st = ctx->stream;
     const int g = grid_for(nr, 128, 16);
     ProfScope ps(ctx, PROF_NTC);
+    ctx->state_gen++;
     if (equal_weight) {
         if (two) k_ntc<true><<<g, 128, 0, st>>>(a);
         else k_ntc<false><<<g, 128, 0, st>>>(a);

@@ -448,6 +448,7 @@ extern "C" int mb_merge_octree_N2(mb_ctx* ctx, const mb_octree_params* oc, mb_pv
     const int s = (int)species - 1;
     const int64_t nc = pia->n_cells, nr = cell_hi - cell_lo + 1, cap = pv->cap;
     ProfScope ps(ctx, PROF_MERGE);
+    ctx->state_gen++;
     cudaStream_t st = ctx->stream;
     MergeArgs a;
     a.pv = pv->cur;

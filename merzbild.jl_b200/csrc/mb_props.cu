@@ -20,6 +20,7 @@ struct PropsArgs {
     const int32_t* powers;
     double moment_factor, moment_vref;  // physical_props.jl:176-177
     double n_scale;        // 1 or inv_V (ndens variant :425)
+    const int* run_if_flag;  // nullable: run only if *run_if_flag != 0 (the sort's cached moments are not valid)
 };
 
 template <int G>
@@ -39,6 +40,7 @@ __device__ __forceinline__ double group_sum(double x, double* sh) {
 template <int G>
 __global__ void __launch_bounds__(256) k_props(PropsArgs a) {
     __shared__ double sh[8];
+    if (a.run_if_flag != nullptr && *a.run_if_flag == 0) return;
     const int tid = G == 32 ? (threadIdx.x & 31) : threadIdx.x;
     const int64_t grp0 = G == 32 ? ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5) : blockIdx.x;
     const int64_t ngrp = G == 32 ? (((int64_t)gridDim.x * blockDim.x) >> 5) : gridDim.x;
@@ -108,6 +110,26 @@ __global__ void __launch_bounds__(256) k_props(PropsArgs a) {
     }
 }
 
+// compute_props_sorted! right after a band sort: the gather pass already holds np, n, vbar and sum w |v - vbar|^2 per cell
+static __global__ void k_props_cached(PropsArgs a, const double* __restrict__ pcache, const int* flags) {
+    if (flags[2] != 0) return;  // the general sort path ran: no cache
+    const int64_t nr = a.cell_hi - a.cell_lo + 1;
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nr; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = a.cell_lo - 1 + r;
+        const double* pc = pcache + 6 * c;
+        const double n = pc[1];
+        a.np[c] = pc[0];
+        a.n[c] = n * a.n_scale;
+        a.v[3 * c + 0] = pc[2]; a.v[3 * c + 1] = pc[3]; a.v[3 * c + 2] = pc[4];
+        double T = 0.0;
+        if (n > 0.0) {
+            const double E = pc[5] * (0.5 * a.mass / (n * k_B));
+            T = (2.0 / 3.0) * E;
+        }
+        a.T[c] = T;
+    }
+}
+
 static __global__ void k_axpy(double* __restrict__ y, const double* __restrict__ x, int64_t n, double a) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] += x[i] * a;
 }
@@ -132,7 +154,14 @@ static int props_launch(mb_ctx* ctx, mb_pv* const* pvs, mb_pia* pia, const doubl
         a.moment_factor = 4 * M_PI * std::pow(masses[s] / (twopi * k_B * P->Tref), 1.5) * 0.5;  // :176
         a.moment_vref = std::pow(masses[s] / (2 * k_B * P->Tref), 0.5);                         // :177
         a.n_scale = n_scale;
+        a.run_if_flag = nullptr;
         const int64_t nr = cell_hi - cell_lo + 1;
+        if (sorted && ctx->pc_gen == ctx->state_gen && ctx->pc_pv == (void*)pvs[s] && ctx->pc_pia == (void*)pia && ctx->pc_species == (int)s + 1 &&
+            ctx->scratch[10] != nullptr) {
+            k_props_cached<<<grid_for(nr, 256), 256, 0, ctx->stream>>>(a, (const double*)ctx->scratch[10], ctx->d_flags);
+            MB_LAUNCH_CHECK(ctx);
+            a.run_if_flag = ctx->d_flags + 2;  // the regular kernel below only runs if the sort fell back to the general path
+        }
         const int64_t avg = (pia->n_bound[s] > 0 ? pia->n_bound[s] : pvs[s]->cap) / (nc > 0 ? nc : 1);
         if (avg > 4096) k_props<256><<<(int)(nr < N_SM * 8 ? nr : N_SM * 8), 256, 0, ctx->stream>>>(a);
         else k_props<32><<<grid_for(nr * 32, 256, 8), 256, 0, ctx->stream>>>(a);

@@ -45,17 +45,27 @@ __device__ __forceinline__ int cell_of(double x, double inv_dx, int64_t cell_off
 }
 
 // ------------------------------------------------------------------------------------------------ band path
+// Pass A, a warp per OLD cell c': destination counts M(c', d) (d = c - c' + w) and `lperm`, the positions of the cell's
+// particles grouped by destination (inside a group: original order).  Particles outside the slab are skipped when
+// drop != 0 (they were sent to a neighbour by mb_exchange_slab).
 template <int W>
 __global__ void __launch_bounds__(256) k_band_classify(const double* __restrict__ X, const int32_t* cell_in, int32_t* cell_out,
-                                                       int32_t* __restrict__ key, const Indexer* __restrict__ ix, int64_t n_cells, double inv_dx,
-                                                       int64_t cell_offset, int use_x, int32_t* __restrict__ M, int* flags) {
+                                                       const Indexer* __restrict__ ix, int64_t n_cells, double inv_dx, int64_t cell_offset,
+                                                       int use_x, int drop, int32_t* __restrict__ M, int64_t* __restrict__ seg_lo,
+                                                       int32_t* __restrict__ seg_n, uint16_t* __restrict__ lperm, int* flags) {
     constexpr int w = W / 2;
     const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t c = warp0; c < n_cells; c += nwarps) {
         const Indexer q = ix[c];
         const int64_t lo = q.start1 - 1, n = q.n_group1;
+        if (lane == 0) { seg_lo[c] = lo; seg_n[c] = (int32_t)n; }
+        if (n > 65535 || q.n_group2 != 0) {  // lperm is 16 bit; group 2 must be empty in a sorted layout
+            if (lane == 0) atomicOr(&flags[2], 1);
+            continue;
+        }
         int cnt[W];
 #pragma unroll
         for (int d = 0; d < W; d++) cnt[d] = 0;
@@ -65,28 +75,54 @@ __global__ void __launch_bounds__(256) k_band_classify(const double* __restrict_
             const bool valid = b + lane < n;
             int nc = 0;
             if (valid) {
-                if (use_x) {
-                    nc = cell_of(X[i], inv_dx, cell_offset);
-                    cell_out[i] = nc + 1;
-                } else {
-                    nc = cell_in[i] - 1;
-                }
-                key[i] = nc;
+                if (use_x) { nc = cell_of(X[i], inv_dx, cell_offset); cell_out[i] = nc + 1; }
+                else nc = cell_in[i] - 1;
             }
+            const bool inside = nc >= 0 && nc < n_cells;
             const int64_t dd = (int64_t)nc - c + w;
-            const bool inband = dd >= 0 && dd < W && nc >= 0 && nc < n_cells;
-            if (valid && !inband) bad = true;
+            const bool inband = inside && dd >= 0 && dd < W;
+            if (valid && !inband && !(drop && !inside)) bad = true;
 #pragma unroll
             for (int d = 0; d < W; d++) cnt[d] += __popc(__ballot_sync(0xffffffffu, valid && inband && dd == d));
         }
-        if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&flags[2], 1);
+        if (__any_sync(0xffffffffu, bad)) {
+            if (lane == 0) atomicOr(&flags[2], 1);
+            continue;
+        }
+        int off[W];
+        int run = 0;
 #pragma unroll
-        for (int d = 0; d < W; d++)
-            if (lane == d) M[c * W + d] = cnt[d];
+        for (int d = 0; d < W; d++) { off[d] = run; run += cnt[d]; if (lane == d) M[c * W + d] = cnt[d]; }
+        for (int64_t b = 0; b < n; b += 32) {
+            const int64_t i = lo + b + lane;
+            const bool valid = b + lane < n;
+            int nc = -1;
+            if (valid) nc = use_x ? cell_of(X[i], inv_dx, cell_offset) : cell_in[i] - 1;
+            const int64_t dd = (valid && nc >= 0 && nc < n_cells) ? (int64_t)nc - c + w : -1;
+#pragma unroll
+            for (int d = 0; d < W; d++) {
+                const unsigned bal = __ballot_sync(0xffffffffu, dd == d);
+                if (dd == d) lperm[lo + off[d] + __popc(bal & lt)] = (uint16_t)(b + lane);
+                off[d] += __popc(bal);
+            }
+        }
     }
 }
 
-// hist[c] = sum over sources of M(c', c)
+// arrivals of the slab exchange (appended after the old layout): key + per-cell arrival count
+static __global__ void k_band_arrivals(const double* __restrict__ X, const int64_t* n_total_p, int64_t n_arr, int64_t n_cells, double inv_dx,
+                                       int64_t cell_offset, int32_t* cell_out, int32_t* __restrict__ key_arr, int32_t* __restrict__ acnt, int* flags) {
+    const int64_t base = *n_total_p - n_arr;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_arr; t += (int64_t)gridDim.x * blockDim.x) {
+        const int nc = cell_of(X[base + t], inv_dx, cell_offset);
+        cell_out[base + t] = nc + 1;
+        if (nc < 0 || nc >= n_cells) { atomicOr(&flags[2], 1); key_arr[t] = -1; continue; }  // the general path reports it
+        key_arr[t] = nc;
+        atomicAdd(&acnt[nc], 1);
+    }
+}
+
+// hist[c] = sum over sources of M(c', c) (+ arrivals)
 template <int W>
 __device__ __forceinline__ int band_hist(const int32_t* __restrict__ M, int64_t c, int64_t n_cells) {
     constexpr int w = W / 2;
@@ -101,8 +137,9 @@ __device__ __forceinline__ int band_hist(const int32_t* __restrict__ M, int64_t 
 
 // scan step 1: per-block sums of the per-cell counts (band: derived from M and stored to hist; general: hist given)
 template <int W>
-__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_reduce(const int32_t* __restrict__ M, int32_t* __restrict__ hist, int64_t n_cells,
-                                                           int64_t* __restrict__ partial, const int* flags, int mode) {
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_reduce(const int32_t* __restrict__ M, const int32_t* __restrict__ acnt,
+                                                           int32_t* __restrict__ hist, int64_t n_cells, int64_t* __restrict__ partial,
+                                                           const int* flags, int mode) {
     // mode 0: band (runs always; cheap), mode 1: general (runs only if flags[2])
     if (mode == 1 && flags[2] == 0) return;
     __shared__ int64_t red[SCAN_BLOCK / 32];
@@ -112,7 +149,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_reduce(const int32_t* __res
         const int64_t c = base + k * SCAN_BLOCK + threadIdx.x;
         if (c < n_cells) {
             int h;
-            if (mode == 0) { h = band_hist<W>(M, c, n_cells); hist[c] = h; }
+            if (mode == 0) { h = band_hist<W>(M, c, n_cells) + (acnt ? acnt[c] : 0); hist[c] = h; }
             else h = hist[c];
             s += h;
         }
@@ -196,81 +233,123 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_apply(const int32_t* __rest
             run += np;
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) start[n_cells] = partial[gridDim.x];  // n_total is unchanged by a sort
-}
-
-// destination offsets O(c', d) = start(c) + sum_{c'' in [c-w, c'-1]} M(c'', c), c = c' + d - w
-template <int W>
-__global__ void __launch_bounds__(256) k_band_offsets(const int32_t* __restrict__ M, const int64_t* __restrict__ start, int64_t* __restrict__ O,
-                                                      int64_t n_cells) {
-    constexpr int w = W / 2;
-    const int64_t total = n_cells * W;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t cs = t / W;
-        const int d = (int)(t - cs * W);
-        const int64_t c = cs + d - w;
-        int64_t o = -1;
-        if (c >= 0 && c < n_cells) {
-            o = start[c];
-            for (int64_t c2 = (c - w > 0 ? c - w : 0); c2 < cs; c2++) o += M[c2 * W + (int)(c - c2 + w)];
-        }
-        O[t] = o;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        start[n_cells] = partial[gridDim.x];
+        if (n_total) *n_total = partial[gridDim.x];  // only after a slab exchange (leavers dropped); otherwise a sort keeps n_total
     }
 }
 
+// Pass B, a warp per DESTINATION cell c: gathers the (c' -> c) groups of the sources c' = c-w .. c+w in source order
+// (== ascending original position, i.e. the stable order of the reference's counting sort), then the slab-exchange
+// arrivals, and writes the cell's particles as one contiguous, fully coalesced run.  While the particles stream through the
+// registers the warp also accumulates the cell's moments (shifted one-pass sums; the shift K is the velocity of the first
+// particle of the old cell) -- compute_props_sorted! on the freshly sorted state then costs no HBM traffic.
 template <int W>
-__global__ void __launch_bounds__(256) k_band_scatter(SoA in, SoA out, const int32_t* __restrict__ key, const Indexer* __restrict__ ix_old_ranges_lo,
-                                                      const int64_t* __restrict__ seg_lo, const int32_t* __restrict__ seg_n, int64_t n_cells,
-                                                      const int64_t* __restrict__ O, const int* flags) {
+__global__ void __launch_bounds__(256) k_band_gather(SoA in_, SoA out_, const uint16_t* __restrict__ lperm, const int32_t* __restrict__ M,
+                                                     const int64_t* __restrict__ seg_lo, const int32_t* __restrict__ seg_n,
+                                                     const int64_t* __restrict__ start, int64_t n_cells, const int32_t* __restrict__ acnt,
+                                                     const int32_t* __restrict__ key_arr, int64_t n_arr, const int64_t* n_old_p,
+                                                     double* __restrict__ pcache, const int* flags) {
     if (flags[2] != 0) return;  // general path takes over
     constexpr int w = W / 2;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const double* __restrict__ i0 = in_.a[0]; const double* __restrict__ i1 = in_.a[1]; const double* __restrict__ i2 = in_.a[2];
+    const double* __restrict__ i3 = in_.a[3]; const double* __restrict__ i4 = in_.a[4]; const double* __restrict__ i5 = in_.a[5];
+    const double* __restrict__ i6 = in_.a[6];
+    double* __restrict__ o0 = out_.a[0]; double* __restrict__ o1 = out_.a[1]; double* __restrict__ o2 = out_.a[2];
+    double* __restrict__ o3 = out_.a[3]; double* __restrict__ o4 = out_.a[4]; double* __restrict__ o5 = out_.a[5];
+    double* __restrict__ o6 = out_.a[6];
     for (int64_t c = warp0; c < n_cells; c += nwarps) {
-        const int64_t lo = seg_lo[c];
-        const int64_t n = seg_n[c];
-        int64_t off[W];
+        int64_t dst = start[c];
+        const int64_t dst0 = dst;
+        double K1 = 0, K2 = 0, K3 = 0;
+        if (seg_n[c] > 0) { const int64_t f = seg_lo[c]; K1 = i1[f]; K2 = i2[f]; K3 = i3[f]; }
+        double an = 0, ax = 0, ay = 0, az = 0, aq = 0;
+#define MB_ACC(pw, pvx, pvy, pvz)                                  \
+    {                                                              \
+        const double cx_ = pvx - K1, cy_ = pvy - K2, cz_ = pvz - K3; \
+        an += pw; ax += pw * cx_; ay += pw * cy_; az += pw * cz_;    \
+        aq += pw * (cx_ * cx_ + cy_ * cy_ + cz_ * cz_);              \
+    }
 #pragma unroll
-        for (int d = 0; d < W; d++) off[d] = O[c * W + d];
-        for (int64_t b = 0; b < n; b += 32) {
-            const int64_t i = lo + b + lane;
-            const bool valid = b + lane < n;
-            int dd = -1;
-            double p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0, p5 = 0, p6 = 0;
-            if (valid) {
-                dd = (int)((int64_t)key[i] - c + w);
-                p0 = in.a[0][i]; p1 = in.a[1][i]; p2 = in.a[2][i]; p3 = in.a[3][i]; p4 = in.a[4][i]; p5 = in.a[5][i]; p6 = in.a[6][i];
-            }
-            int64_t dst = -1;
+        for (int k = 0; k < W; k++) {
+            const int64_t cs = c - w + k;  // sources in ascending order
+            if (cs < 0 || cs >= n_cells) continue;
+            const int d = W - 1 - k;       // d = c - cs + w
+            int lo_local = 0, cnt = 0;
 #pragma unroll
-            for (int d = 0; d < W; d++) {
-                const unsigned bal = __ballot_sync(0xffffffffu, dd == d);
-                if (dd == d) dst = off[d] + __popc(bal & lt);
-                off[d] += __popc(bal);
+            for (int d2 = 0; d2 < W; d2++) {
+                const int m = M[cs * W + d2];
+                if (d2 < d) lo_local += m;
+                if (d2 == d) cnt = m;
             }
-            if (valid) {
-                out.a[0][dst] = p0; out.a[1][dst] = p1; out.a[2][dst] = p2; out.a[3][dst] = p3; out.a[4][dst] = p4; out.a[5][dst] = p5;
-                out.a[6][dst] = p6;
+            if (cnt == 0) continue;
+            const int64_t base = seg_lo[cs];
+            const uint16_t* __restrict__ lp = lperm + base + lo_local;
+            int t = lane;
+            for (; t + 32 < cnt; t += 64) {  // two particles per lane in flight
+                const int64_t ia = base + lp[t], ib = base + lp[t + 32];
+                const double a0 = i0[ia], a1 = i1[ia], a2 = i2[ia], a3 = i3[ia], a4 = i4[ia], a5 = i5[ia], a6 = i6[ia];
+                const double b0 = i0[ib], b1 = i1[ib], b2 = i2[ib], b3 = i3[ib], b4 = i4[ib], b5 = i5[ib], b6 = i6[ib];
+                const int64_t pa = dst + t, pb = dst + t + 32;
+                o0[pa] = a0; o1[pa] = a1; o2[pa] = a2; o3[pa] = a3; o4[pa] = a4; o5[pa] = a5; o6[pa] = a6;
+                o0[pb] = b0; o1[pb] = b1; o2[pb] = b2; o3[pb] = b3; o4[pb] = b4; o5[pb] = b5; o6[pb] = b6;
+                MB_ACC(a0, a1, a2, a3);
+                MB_ACC(b0, b1, b2, b3);
+            }
+            if (t < cnt) {
+                const int64_t ia = base + lp[t];
+                const double a0 = i0[ia], a1 = i1[ia], a2 = i2[ia], a3 = i3[ia], a4 = i4[ia], a5 = i5[ia], a6 = i6[ia];
+                const int64_t pa = dst + t;
+                o0[pa] = a0; o1[pa] = a1; o2[pa] = a2; o3[pa] = a3; o4[pa] = a4; o5[pa] = a5; o6[pa] = a6;
+                MB_ACC(a0, a1, a2, a3);
+            }
+            dst += cnt;
+        }
+        if (acnt != nullptr && acnt[c] > 0) {
+            const int64_t abase = *n_old_p - n_arr;
+            for (int64_t b = 0; b < n_arr; b += 32) {
+                const bool hit = b + lane < n_arr && key_arr[b + lane] == (int32_t)c;
+                const unsigned bal = __ballot_sync(0xffffffffu, hit);
+                if (hit) {
+                    const int64_t ia = abase + b + lane, pa = dst + __popc(bal & lt);
+                    const double a0 = i0[ia], a1 = i1[ia], a2 = i2[ia], a3 = i3[ia], a4 = i4[ia], a5 = i5[ia], a6 = i6[ia];
+                    o0[pa] = a0; o1[pa] = a1; o2[pa] = a2; o3[pa] = a3; o4[pa] = a4; o5[pa] = a5; o6[pa] = a6;
+                    MB_ACC(a0, a1, a2, a3);
+                }
+                dst += __popc(bal);
             }
         }
-    }
-}
-
-// the old segment table must survive the pia rebuild: (lo, n) per old cell
-__global__ void k_save_segments(const Indexer* __restrict__ ix, int64_t n_cells, int64_t* __restrict__ seg_lo, int32_t* __restrict__ seg_n) {
-    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < n_cells; c += (int64_t)gridDim.x * blockDim.x) {
-        const Indexer q = ix[c];
-        seg_lo[c] = q.start1 - 1;
-        seg_n[c] = (int32_t)q.n_group1;
+#undef MB_ACC
+        if (pcache != nullptr) {
+            for (int o = 16; o > 0; o >>= 1) {
+                an += __shfl_xor_sync(0xffffffffu, an, o); ax += __shfl_xor_sync(0xffffffffu, ax, o);
+                ay += __shfl_xor_sync(0xffffffffu, ay, o); az += __shfl_xor_sync(0xffffffffu, az, o);
+                aq += __shfl_xor_sync(0xffffffffu, aq, o);
+            }
+            if (lane == 0) {
+                double* pc = pcache + 6 * c;
+                pc[0] = (double)(dst - dst0);
+                if (an > 0.0) {
+                    const double mx = ax / an, my = ay / an, mz = az / an;  // mean of (v - K)
+                    pc[1] = an; pc[2] = K1 + mx; pc[3] = K2 + my; pc[4] = K3 + mz;
+                    pc[5] = aq - an * (mx * mx + my * my + mz * mz);        // sum w |v - vbar|^2
+                } else {
+                    pc[1] = 0; pc[2] = 0; pc[3] = 0; pc[4] = 0; pc[5] = 0;
+                }
+            }
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------ general path
 __global__ void __launch_bounds__(256) k_gen_classify(const double* __restrict__ X, const int32_t* cell_in, int32_t* cell_out,
                                                       int32_t* __restrict__ key, const int64_t* n_total_p, int64_t n_cells, double inv_dx,
-                                                      int64_t cell_offset, int use_x, int need_key, int32_t* __restrict__ hist, int* flags) {
+                                                      int64_t cell_offset, int use_x, int drop, int32_t* __restrict__ hist, int* flags) {
+    // drop != 0 (after a slab exchange): a particle whose cell is outside [0, n_cells) left the slab and is dropped
     if (flags[2] == 0) return;
     const int64_t n_total = *n_total_p;
     const int lane = threadIdx.x & 31;
@@ -281,20 +360,20 @@ __global__ void __launch_bounds__(256) k_gen_classify(const double* __restrict__
         const int64_t i = r * stride + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
         const bool valid = i < n_total;
         int nc = -1;
+        bool counted = false;
         if (valid) {
-            if (need_key) {
-                if (use_x) { nc = cell_of(X[i], inv_dx, cell_offset); cell_out[i] = nc + 1; }
-                else nc = cell_in[i] - 1;
-                if (nc < 0 || nc >= n_cells) { atomicOr(&flags[0], DEVERR_BAD_CELL); nc = nc < 0 ? 0 : (int)(n_cells - 1); }
-                key[i] = nc;
-            } else {
-                nc = key[i];
-                if (nc < 0 || nc >= n_cells) { atomicOr(&flags[0], DEVERR_BAD_CELL); nc = nc < 0 ? 0 : (int)(n_cells - 1); key[i] = nc; }
+            if (use_x) { nc = cell_of(X[i], inv_dx, cell_offset); cell_out[i] = nc + 1; }
+            else nc = cell_in[i] - 1;
+            if (nc < 0 || nc >= n_cells) {
+                if (drop) nc = -1;
+                else { atomicOr(&flags[0], DEVERR_BAD_CELL); nc = nc < 0 ? 0 : (int)(n_cells - 1); }
             }
+            key[i] = nc;
+            counted = nc >= 0;
         }
         // run-length aggregation: keys of neighbouring lanes are mostly equal
-        const unsigned act = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
+        const unsigned act = __ballot_sync(0xffffffffu, counted);
+        if (counted) {
             const unsigned peers = __match_any_sync(act, nc);
             const int leader = __ffs(peers) - 1;
             if (lane == leader) atomicAdd(&hist[nc], __popc(peers));
@@ -312,10 +391,10 @@ __global__ void __launch_bounds__(256) k_gen_scatter_idx(const int32_t* __restri
     const int64_t nround = (n_total + stride - 1) / stride;
     for (int64_t r = 0; r < nround; r++) {
         const int64_t i = r * stride + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-        const bool valid = i < n_total;
+        const int nc = i < n_total ? key[i] : -1;
+        const bool valid = nc >= 0;
         const unsigned act = __ballot_sync(0xffffffffu, valid);
         if (valid) {
-            const int nc = key[i];
             const unsigned peers = __match_any_sync(act, nc);
             const int leader = __ffs(peers) - 1;
             int base = 0;
@@ -398,8 +477,21 @@ __global__ void __launch_bounds__(256) k_gen_gather(SoA in, SoA out, const int32
 
 __global__ void k_set_flag(int* flags, int idx, int v) { flags[idx] = v; }
 
+struct BandBufs {
+    int64_t* seg_lo;
+    int32_t* seg_n;
+    uint16_t* lperm;
+    int32_t* acnt;     // nullable (no arrivals)
+    int32_t* key_arr;
+    int64_t n_arr;
+    int64_t* n_old;    // device copy of n_total before the sort
+    double* pcache;    // nullable
+    int drop;
+    int64_t* d_nt_write;  // nullable: rewrite n_total (after a slab exchange)
+};
+
 template <int W>
-static int launch_band(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia, int64_t species, SortScratch& S, int64_t* seg_lo, int32_t* seg_n) {
+static int launch_band(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia, int64_t species, SortScratch& S, const BandBufs& B) {
     const int64_t nc = pia->n_cells;
     Indexer* ix = pia->d_indexer + (species - 1) * nc;
     cudaStream_t st = ctx->stream;
@@ -408,26 +500,29 @@ static int launch_band(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pi
     const int wgrid = grid_for(nc * 32, 256, 8);
     {
         ProfScope ps(ctx, PROF_SORT_CLASSIFY);
-        k_save_segments<<<grid_for(nc, 256), 256, 0, st>>>(ix, nc, seg_lo, seg_n);
+        k_band_classify<W><<<wgrid, 256, 0, st>>>(pv->cur.a[F_X], pv->cell, pv->cell, ix, nc, use_x ? grid->inv_dx : 0.0,
+                                                 use_x ? grid->cell_offset : 0, use_x, B.drop, S.M, B.seg_lo, B.seg_n, B.lperm, S.flags);
         MB_LAUNCH_CHECK(ctx);
-        k_band_classify<W><<<wgrid, 256, 0, st>>>(pv->cur.a[F_X], pv->cell, pv->cell, S.key, ix, nc, use_x ? grid->inv_dx : 0.0,
-                                                 use_x ? grid->cell_offset : 0, use_x, S.M, S.flags);
-        MB_LAUNCH_CHECK(ctx);
+        if (B.n_arr > 0) {
+            MB_CUDA(cudaMemsetAsync(B.acnt, 0, (size_t)nc * 4, st));
+            k_band_arrivals<<<grid_for(B.n_arr, 256), 256, 0, st>>>(pv->cur.a[F_X], B.n_old, B.n_arr, nc, grid->inv_dx, grid->cell_offset, pv->cell,
+                                                                  B.key_arr, B.acnt, S.flags);
+            MB_LAUNCH_CHECK(ctx);
+        }
     }
     {
         ProfScope ps(ctx, PROF_SORT_SCAN);
-        k_scan_reduce<W><<<nscan, SCAN_BLOCK, 0, st>>>(S.M, S.hist, nc, S.partial, S.flags, 0);
+        k_scan_reduce<W><<<nscan, SCAN_BLOCK, 0, st>>>(S.M, B.n_arr > 0 ? B.acnt : nullptr, S.hist, nc, S.partial, S.flags, 0);
         MB_LAUNCH_CHECK(ctx);
         k_scan_partials<<<1, 1024, 0, st>>>(S.partial, nscan, S.flags, 0);
         MB_LAUNCH_CHECK(ctx);
-        k_scan_apply<<<nscan, SCAN_BLOCK, 0, st>>>(S.hist, nc, S.partial, S.start, nullptr, ix, pia->d_n_total + (species - 1), S.flags, 0);
-        MB_LAUNCH_CHECK(ctx);
-        k_band_offsets<W><<<grid_for(nc * W, 256), 256, 0, st>>>(S.M, S.start, S.O, nc);
+        k_scan_apply<<<nscan, SCAN_BLOCK, 0, st>>>(S.hist, nc, S.partial, S.start, nullptr, ix, B.d_nt_write, S.flags, 0);
         MB_LAUNCH_CHECK(ctx);
     }
     {
         ProfScope ps(ctx, PROF_SORT_SCATTER);
-        k_band_scatter<W><<<wgrid, 256, 0, st>>>(pv->cur, pv->alt, S.key, ix, seg_lo, seg_n, nc, S.O, S.flags);
+        k_band_gather<W><<<wgrid, 256, 0, st>>>(pv->cur, pv->alt, B.lperm, S.M, B.seg_lo, B.seg_n, S.start, nc, B.n_arr > 0 ? B.acnt : nullptr,
+                                               B.key_arr, B.n_arr, B.n_old, B.pcache, S.flags);
         MB_LAUNCH_CHECK(ctx);
     }
     return MB_OK;
@@ -468,38 +563,55 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
     const int64_t nc = pia->n_cells, cap = pv->cap;
     const int w = ctx->band_w;
     const int W = 2 * w + 1;
-    const bool try_band = w > 0 && pia->sorted_layout[s];
+    const bool drop = pv->drop_oob;
+    const int64_t n_arr = pv->n_arrivals;
+    const bool use_x = grid != nullptr;
+    // band path: sorted layout; slab-exchange arrivals are merged in as long as they are few (each receiving cell scans the list)
+    const bool try_band = w > 0 && pia->sorted_layout[s] && n_arr <= 4096 && (n_arr == 0 || use_x);
     const int nscan = (int)((nc + SCAN_TILE - 1) / SCAN_TILE);
 
     SortScratch S;
     S.flags = ctx->d_flags;
-    S.key = (int32_t*)ctx_scratch(ctx, 0, (size_t)cap * 4);
-    // slot 1: hist | cursor | seg_n | M   (int32)
-    const size_t n32 = (size_t)nc * (3 + (size_t)W) + 64;
+    S.key = (int32_t*)ctx_scratch(ctx, 0, (size_t)cap * 4);  // general: keys; band: lperm (16 bit)
+    // slot 1: hist | cursor | seg_n | acnt | key_arr | M   (int32)
+    const size_t n32 = (size_t)nc * (4 + (size_t)W) + 4096 + 64;
     int32_t* p32 = (int32_t*)ctx_scratch(ctx, 1, n32 * 4);
-    // slot 2: start | partial | seg_lo | O   (int64)
-    const size_t n64 = (size_t)(nc + 1) + (size_t)(nscan + 2) + (size_t)nc + (size_t)nc * W + 64;
+    // slot 2: start | partial | n_old | seg_lo   (int64)
+    const size_t n64 = (size_t)(nc + 1) + (size_t)(nscan + 2) + 2 + (size_t)nc + 64;
     int64_t* p64 = (int64_t*)ctx_scratch(ctx, 2, n64 * 8);
     if (!S.key || !p32 || !p64) return MB_ERR_CUDA;
     S.hist = p32;
     S.cursor = p32 + nc;
-    int32_t* seg_n = p32 + 2 * nc;
-    S.M = p32 + 3 * nc;
+    S.M = p32 + 4 * nc + 4096;
     S.start = p64;
     S.partial = p64 + (nc + 1);
-    int64_t* seg_lo = S.partial + (nscan + 2);
-    S.O = seg_lo + nc;
+    S.O = nullptr;
+    BandBufs B;
+    B.seg_n = p32 + 2 * nc;
+    B.acnt = p32 + 3 * nc;
+    B.key_arr = p32 + 4 * nc;
+    B.n_old = S.partial + (nscan + 2);
+    B.seg_lo = B.n_old + 2;
+    B.lperm = (uint16_t*)S.key;
+    B.n_arr = n_arr;
+    B.drop = drop ? 1 : 0;
     cudaStream_t st = ctx->stream;
     Indexer* ix = pia->d_indexer + (species - 1) * nc;
     int64_t* d_nt = pia->d_n_total + (species - 1);
+    const bool rewrite_total = drop || n_arr > 0;
+    B.d_nt_write = rewrite_total ? d_nt : nullptr;
+    // moments of the sorted cells come for free in the gather pass (used by compute_props_sorted! if nothing changes in between)
+    B.pcache = (double*)ctx_scratch(ctx, 10, (size_t)nc * 6 * 8);
+    if (!B.pcache) return MB_ERR_CUDA;
 
+    MB_CUDA(cudaMemcpyAsync(B.n_old, d_nt, 8, cudaMemcpyDeviceToDevice, st));  // n_total before the sort (the scan may rewrite it)
     k_set_flag<<<1, 1, 0, st>>>(ctx->d_flags, 2, try_band ? 0 : 1);
     MB_LAUNCH_CHECK(ctx);
     if (try_band) {
-        if (w == 1) r = launch_band<3>(ctx, grid, pv, pia, species, S, seg_lo, seg_n);
-        else if (w == 2) r = launch_band<5>(ctx, grid, pv, pia, species, S, seg_lo, seg_n);
-        else if (w == 4) r = launch_band<9>(ctx, grid, pv, pia, species, S, seg_lo, seg_n);
-        else r = launch_band<17>(ctx, grid, pv, pia, species, S, seg_lo, seg_n);
+        if (w == 1) r = launch_band<3>(ctx, grid, pv, pia, species, S, B);
+        else if (w == 2) r = launch_band<5>(ctx, grid, pv, pia, species, S, B);
+        else if (w == 4) r = launch_band<9>(ctx, grid, pv, pia, species, S, B);
+        else r = launch_band<17>(ctx, grid, pv, pia, species, S, B);
         if (r) return r;
     }
     // general path (every kernel returns immediately unless flags[2] != 0)
@@ -507,31 +619,33 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
         ProfScope ps(ctx, PROF_SORT_GENERAL);
         S.perm = (int32_t*)ctx_scratch(ctx, 3, (size_t)cap * 4);
         if (!S.perm) return MB_ERR_CUDA;
-        const int use_x = grid != nullptr;
         MB_CUDA(cudaMemsetAsync(S.hist, 0, (size_t)nc * 4, st));  // harmless for the band result: hist is not read again
         const int pgrid = grid_for(pia->n_bound[s] > 0 ? pia->n_bound[s] : cap, 256, 16);
-        // after a band attempt the keys are already classified (and n_total is still the old one: the band pass
-        // re-wrote it with the same value), so reuse them
-        k_gen_classify<<<pgrid, 256, 0, st>>>(pv->cur.a[F_X], pv->cell, pv->cell, S.key, d_nt, nc, use_x ? grid->inv_dx : 0.0,
-                                             use_x ? grid->cell_offset : 0, use_x, 1, S.hist, S.flags);
+        k_gen_classify<<<pgrid, 256, 0, st>>>(pv->cur.a[F_X], pv->cell, pv->cell, S.key, B.n_old, nc, use_x ? grid->inv_dx : 0.0,
+                                             use_x ? grid->cell_offset : 0, use_x ? 1 : 0, drop ? 1 : 0, S.hist, S.flags);
         MB_LAUNCH_CHECK(ctx);
-        k_scan_reduce<3><<<nscan, SCAN_BLOCK, 0, st>>>(nullptr, S.hist, nc, S.partial, S.flags, 1);
+        k_scan_reduce<3><<<nscan, SCAN_BLOCK, 0, st>>>(nullptr, nullptr, S.hist, nc, S.partial, S.flags, 1);
         MB_LAUNCH_CHECK(ctx);
         k_scan_partials<<<1, 1024, 0, st>>>(S.partial, nscan, S.flags, 1);
         MB_LAUNCH_CHECK(ctx);
-        k_scan_apply<<<nscan, SCAN_BLOCK, 0, st>>>(S.hist, nc, S.partial, S.start, S.cursor, ix, d_nt, S.flags, 1);
+        k_scan_apply<<<nscan, SCAN_BLOCK, 0, st>>>(S.hist, nc, S.partial, S.start, S.cursor, ix, rewrite_total ? d_nt : nullptr, S.flags, 1);
         MB_LAUNCH_CHECK(ctx);
-        k_gen_scatter_idx<<<pgrid, 256, 0, st>>>(S.key, d_nt, S.start, S.cursor, S.perm, S.flags);
+        k_gen_scatter_idx<<<pgrid, 256, 0, st>>>(S.key, B.n_old, S.start, S.cursor, S.perm, S.flags);
         MB_LAUNCH_CHECK(ctx);
         k_gen_sort_segments<<<grid_for(nc * 256, 256, 8), 256, 0, st>>>(S.perm, S.start, nc, S.flags);
         MB_LAUNCH_CHECK(ctx);
-        k_gen_gather<<<pgrid, 256, 0, st>>>(pv->cur, pv->alt, S.perm, d_nt, S.flags);
+        k_gen_gather<<<pgrid, 256, 0, st>>>(pv->cur, pv->alt, S.perm, S.start + nc, S.flags);
         MB_LAUNCH_CHECK(ctx);
     }
     // ping-pong
     SoA t = pv->cur;
     pv->cur = pv->alt;
     pv->alt = t;
+    if (rewrite_total) { pv->drop_oob = false; pv->n_arrivals = 0; pia->h_valid = false; }
+    // the cached moments are valid only if the band path ran (device flag 2 == 0): the props kernel checks the flag itself
+    ctx->state_gen++;
+    ctx->pc_gen = try_band ? ctx->state_gen : 0;
+    ctx->pc_pv = pv; ctx->pc_pia = pia; ctx->pc_species = (int)species;
     pia->contiguous[s] = 1;      // grid_sorting.jl:112
     pia->contig_pending[s] = 0;
     pia->sorted_layout[s] = 1;

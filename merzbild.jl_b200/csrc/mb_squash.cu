@@ -82,6 +82,7 @@ extern "C" int mb_squash_pia(mb_ctx* ctx, mb_pv* pv, mb_pia* pia, int64_t specie
     int64_t* partial = p64 + (2 * nc + 1);
     cudaStream_t st = ctx->stream;
     ProfScope ps(ctx, PROF_SQUASH);
+    ctx->state_gen++;
     k_squash_counts<<<grid_for(nc, 256), 256, 0, st>>>(ix, nc, cnt);
     MB_LAUNCH_CHECK(ctx);
     r = device_exclusive_scan(ctx, cnt, 2 * nc, newlo, partial);

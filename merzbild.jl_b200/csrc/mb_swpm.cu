@@ -141,6 +141,7 @@ extern "C" int mb_swpm(mb_ctx* ctx, mb_cf* cf, const mb_interaction* it, mb_pv* 
     if (r) return r;
     const int64_t nc = pia->n_cells, nr = cell_hi - cell_lo + 1, s = species - 1;
     ProfScope ps(ctx, PROF_NTC);
+    ctx->state_gen++;
     SwpmArgs a;
     a.p = pv->cur;
     a.ix = pia->d_indexer + s * nc;
