@@ -58,3 +58,32 @@ def test_no_cpu_fallback(mb):
     with pytest.raises(mb.MerzbildError) as e:
         mb.Context(0, 1)
     assert e.value.status == mb.MB_ERR_NO_DEVICE
+
+
+def _julia_ccalls():
+    """(symbol, n_argument_types) for every ccall of the Julia shim."""
+    src = open(os.path.join(ROOT, "merzbild.jl_b200", "julia", "MerzbildB200.jl")).read()
+    src = re.sub(r"#[^\n]*", "", src)
+    out = {}
+    for m in re.finditer(r"ccall\(\(:(mb_[A-Za-z0-9_]+),\s*libmb\),\s*[A-Za-z0-9_{}]+,\s*\(", src):
+        i, depth = m.end(), 1
+        while depth:  # the tuple of argument types, with nested Ptr{...} / NTuple{...}
+            depth += {"(": 1, ")": -1}.get(src[i], 0)
+            i += 1
+        body = src[m.end():i - 1]
+        flat, d = "", 0
+        for ch in body:
+            d += {"{": 1, "}": -1}.get(ch, 0)
+            flat += ch if not (ch == "," and d) else ";"
+        n = len([t for t in flat.split(",") if t.strip()])
+        out.setdefault(m.group(1), set()).add(n)
+    return out
+
+
+def test_julia_shim_binds_the_header(mb):
+    """The Julia shim cannot run here (no Julia toolchain): check statically that it binds every symbol the header declares
+    and that each ccall passes as many arguments as the ctypes mirror (which the GPU tests exercise)."""
+    calls = _julia_ccalls()
+    assert sorted(calls) == _declared()
+    for name, arities in calls.items():
+        assert arities == {len(mb.SIGNATURES[name][1])}, (name, arities, len(mb.SIGNATURES[name][1]))
