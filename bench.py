@@ -104,7 +104,7 @@ def reference_arm(args, rank):
     if rank != 0:
         return
     threads = host_threads()
-    nx = 8000  # 8e6 particles: a bounded sample of the same workload (ppc, dx, dt, physics identical)
+    nx = 16000  # 1.6e7 particles: a bounded sample of the same workload (ppc, dx, dt, physics identical)
     r = run_cpu_port(nx, PPC, args.steps, args.warmup, threads)
     v = r["particle_steps_per_s"]
     line = {
@@ -304,8 +304,18 @@ def main():
     if sort_path != 1 or sc_n == 0:
         sc_ms, sc_n = sections.get("sort.general", (0.0, 0))
     achieved = BYTES_SCATTER * n_now / (sc_ms / max(sc_n, 1) * 1e-3) / 1e9 if sc_ms > 0 else None
-    roofline = {"bound": "hbm", "kernel": "k_band_scatter (sort_particles! stable scatter)" if sort_path == 1 else "general sort path",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json); only quoted for the
+    # particle count it was captured at
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_band_gather"]
+        if sort_path == 1 and abs(tr["particles"] - n_now) <= 0.01 * n_now:
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except (OSError, ValueError, KeyError):
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_band_gather (sort_particles! stable gather/scatter pass)" if sort_path == 1 else "general sort path",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "algorithmic_bytes": BYTES_SCATTER * n_now,
                 "peak_source": peak_src, "algorithmic_bytes_per_particle": BYTES_SCATTER,
                 "step_achieved_GBps": BYTES_STEP * particles_all * args.steps / (ms_max * 1e-3) / 1e9 / world,
                 "step_frac": BYTES_STEP * particles_all * args.steps / (ms_max * 1e-3) / 1e9 / world / peak,
@@ -326,10 +336,13 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
-        r = run_cpu_port(4000, PPC, 40, 5, threads)
+        nx_cpu = 8000
+        cal = run_cpu_port(nx_cpu, PPC, 5, 2, threads)  # calibration: size the sample to ~15 s of CPU work
+        k_cpu = int(min(max(15.0 * cal["particle_steps_per_s"] / (nx_cpu * PPC), 20), 2000))
+        r = run_cpu_port(nx_cpu, PPC, k_cpu, 3, threads)
         line["cpu_baseline"] = {"value": r["particle_steps_per_s"], "unit": "particle-timesteps/s", "cores": threads, "kind": "port",
-                                "sample": "C++ restatement of the reference's multithreaded Couette loop: 4000 cells x 1000 ppc (4e6 particles), 40 steps, "
-                                          "%d OpenMP threads, %.1f s" % (threads, r["seconds"])}
+                                "sample": "C++ restatement of the reference's multithreaded Couette loop (couette_multithreaded.jl:97-173): %d cells x %d ppc "
+                                          "(%.0e particles), %d steps, %d OpenMP threads, %.1f s" % (nx_cpu, PPC, nx_cpu * PPC, k_cpu, threads, r["seconds"])}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

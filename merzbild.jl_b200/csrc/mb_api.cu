@@ -389,6 +389,7 @@ int mb_pv_download_cell(mb_pv* p, int64_t lo, int64_t n, int64_t* cell) {
 int mb_pv_device_ptrs(mb_pv* p, void** out7) {
     MB_ARG(p && out7, "NULL");
     for (int f = 0; f < 7; f++) out7[f] = p->cur.a[f];
+    p->ctx->state_gen++;  // the caller may write through the pointers: cached moments / classification are void
     return MB_OK;
 }
 

@@ -112,6 +112,13 @@ struct mb_ctx {
     void* pc_pv;
     void* pc_pia;
     int pc_species;
+    // band classification cached by the fused convect kernel (valid while state_gen == cls_gen)
+    uint64_t cls_gen;
+    void* cls_pv;
+    void* cls_pia;
+    int cls_species, cls_w;
+    double cls_inv_dx;
+    int64_t cls_cell_offset, cls_cap;
     // per-section event profiling
     int prof_on;
     std::vector<cudaEvent_t>* prof_ev;   // pairs (begin, end)

@@ -224,7 +224,11 @@ int mb_exchange_slab(mb_ctx* ctx, const mb_grid1d* slab, mb_pv* pv, mb_pia* pia,
         return MB_ERR_PRECONDITION;
     }
     ProfScope ps(ctx, PROF_EXCHANGE);
-    ctx->state_gen++;
+    {   // the own particles are not touched: a classification cached by the fused convect kernel stays valid
+        const bool keep = ctx->cls_gen == ctx->state_gen;
+        ctx->state_gen++;
+        if (keep) ctx->cls_gen = ctx->state_gen;
+    }
     cudaStream_t st = ctx->stream;
     // staging buffers: capacity / 8 particles per direction
     const size_t want = (size_t)pv->cap / 8 + 65536;

@@ -18,7 +18,7 @@
 //      buckets, per-cell ascending sort of the indices (== stable order), gather of the payload.
 #include <climits>
 
-#include "mb_common.cuh"
+#include "mb_convect.cuh"
 
 namespace mb {
 
@@ -345,6 +345,114 @@ __global__ void __launch_bounds__(256) k_band_gather(SoA in_, SoA out_, const ui
     }
 }
 
+// ------------------------------------------------------------------------------------------------ fused convect + classify
+// convect_particles! on a sorted layout knows everything pass A of the band sort needs: it holds x_new of every particle of
+// old cell c' in registers.  This kernel is k_convect_contiguous and k_band_classify in one pass over HBM (x, vx read; x
+// written; lperm written; no second read of x): a warp per old cell moves its particles, stages their destination offsets
+// d = c - c' + w in shared memory (one byte each), counts them with match.any, and derives lperm from the staged bytes.
+// The following sort_particles! finds the classification cached (ctx->cls_gen == ctx->state_gen) and starts at the scan.
+// Device flags: F_OUTSIDE = a particle left the slab (legal only if a slab exchange follows), F_CLS_BAD = band overflow
+// (the sort takes the general path), F_FAR = a particle left the slab from a cell further than w from that edge.
+enum { F_OUTSIDE = 12, F_CLS_BAD = 13, F_FAR = 14 };
+constexpr int CB_STAGE = 2048;  // staged destination bytes per warp; bigger cells re-read x in pass 2
+
+template <int W>
+__global__ void __launch_bounds__(256) k_convect_band(ConvectArgs a, int32_t* __restrict__ M, int64_t* __restrict__ seg_lo,
+                                                      int32_t* __restrict__ seg_n, uint16_t* __restrict__ lperm, int* flags) {
+    constexpr int w = W / 2;
+    __shared__ uint8_t s_dd[8][CB_STAGE];
+    __shared__ int s_cnt[8][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const double* __restrict__ X = a.pv.a[F_X];
+    for (int64_t c = warp0; c < a.n_cells; c += nwarps) {
+        const Indexer q = a.ix[c];
+        const int64_t lo = q.start1 - 1, n = q.n_group1;
+        if (lane == 0) { seg_lo[c] = lo; seg_n[c] = (int32_t)n; }
+        if (n > 65535 || q.n_group2 != 0) {  // not a sorted layout after all: just move the particles
+            for (int64_t j = lo + lane; j < q.end1; j += 32) convect_one(a, j);
+            if (q.n_group2 > 0)
+                for (int64_t j = q.start2 - 1 + lane; j < q.end2; j += 32) convect_one(a, j);
+            if (lane == 0) atomicOr(&flags[F_CLS_BAD], 1);
+            continue;
+        }
+        __syncwarp();
+        s_cnt[wid][lane] = 0;
+        __syncwarp();
+        const bool staged = n <= CB_STAGE;
+        bool bad = false, outside = false, far = false;
+        for (int64_t b = 0; b < n; b += 32) {
+            int dd = 255;
+            if (b + lane < n) {
+                const double x_new = convect_one(a, lo + b + lane);
+                const int nc = cell_of(x_new, a.inv_dx, a.cell_offset);
+                const int64_t d = (int64_t)nc - c + w;
+                if (nc >= 0 && nc < a.n_cells) {
+                    if (d >= 0 && d < W) dd = (int)d;
+                    else bad = true;
+                } else {
+                    outside = true;
+                    if ((nc < 0 && c >= w) || (nc >= a.n_cells && c < a.n_cells - w)) far = true;
+                }
+                if (staged) s_dd[wid][b + lane] = (uint8_t)dd;
+            }
+            const unsigned act = __ballot_sync(0xffffffffu, dd != 255);
+            if (dd != 255) {
+                const unsigned peers = __match_any_sync(act, dd);
+                if ((peers & lt) == 0) s_cnt[wid][dd] += __popc(peers);  // one leader per destination
+            }
+            __syncwarp();
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        outside = __any_sync(0xffffffffu, outside);
+        far = __any_sync(0xffffffffu, far);
+        if (lane == 0) {
+            if (bad) atomicOr(&flags[F_CLS_BAD], 1);
+            if (outside) atomicOr(&flags[F_OUTSIDE], 1);
+            if (far) atomicOr(&flags[F_FAR], 1);
+        }
+        if (bad) continue;
+        const int cnt = lane < W ? s_cnt[wid][lane] : 0;
+        if (lane < W) M[c * W + lane] = cnt;
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        __syncwarp();
+        s_cnt[wid][lane] = incl - cnt;  // running offset of every destination group inside the old cell
+        __syncwarp();
+        for (int64_t b = 0; b < n; b += 32) {
+            int dd = 255;
+            if (b + lane < n) {
+                if (staged) dd = s_dd[wid][b + lane];
+                else {
+                    const int nc = cell_of(X[lo + b + lane], a.inv_dx, a.cell_offset);
+                    if (nc >= 0 && nc < a.n_cells) dd = (int)((int64_t)nc - c + w);
+                }
+            }
+            const unsigned act = __ballot_sync(0xffffffffu, dd != 255);
+            unsigned peers = 0;
+            int base = 0;
+            if (dd != 255) {
+                peers = __match_any_sync(act, dd);
+                base = s_cnt[wid][dd];
+                lperm[lo + base + __popc(peers & lt)] = (uint16_t)(b + lane);
+            }
+            __syncwarp();
+            if (dd != 255 && (peers & lt) == 0) s_cnt[wid][dd] = base + __popc(peers);
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void k_clear_cls_flags(int* flags) { flags[F_OUTSIDE] = 0; flags[F_CLS_BAD] = 0; flags[F_FAR] = 0; }
+// flags[2] (general path needed) from the cached classification: band overflow, or a particle outside the slab with no exchange
+__global__ void k_flag_from_cls(int* flags, int drop) { flags[2] = (flags[F_CLS_BAD] != 0 || (!drop && flags[F_OUTSIDE] != 0)) ? 1 : 0; }
+
 // ------------------------------------------------------------------------------------------------ general path
 __global__ void __launch_bounds__(256) k_gen_classify(const double* __restrict__ X, const int32_t* cell_in, int32_t* cell_out,
                                                       int32_t* __restrict__ key, const int64_t* n_total_p, int64_t n_cells, double inv_dx,
@@ -490,8 +598,73 @@ struct BandBufs {
     int64_t* d_nt_write;  // nullable: rewrite n_total (after a slab exchange)
 };
 
+
+// The scratch layout of a sort is a pure function of (capacity, n_cells, W), so the fused convect + classify kernel (which runs
+// before the sort call) and the sort itself address the same buffers.
+static int sort_scratch_layout(mb_ctx* ctx, int64_t cap, int64_t nc, int W, SortScratch& S, BandBufs& B) {
+    const int nscan = (int)((nc + SCAN_TILE - 1) / SCAN_TILE);
+    S.flags = ctx->d_flags;
+    S.key = (int32_t*)ctx_scratch(ctx, 0, (size_t)cap * 4);  // general: keys; band: lperm (16 bit)
+    // slot 1: hist | cursor | seg_n | acnt | key_arr | M   (int32); sized for the widest band so that W may change between calls
+    const size_t n32 = (size_t)nc * (4 + 17) + 4096 + 64;
+    int32_t* p32 = (int32_t*)ctx_scratch(ctx, 1, n32 * 4);
+    // slot 2: start | partial | n_old | seg_lo   (int64)
+    const size_t n64 = (size_t)(nc + 1) + (size_t)(nscan + 2) + 2 + (size_t)nc + 64;
+    int64_t* p64 = (int64_t*)ctx_scratch(ctx, 2, n64 * 8);
+    if (!S.key || !p32 || !p64) return MB_ERR_CUDA;
+    S.hist = p32;
+    S.cursor = p32 + nc;
+    S.M = p32 + 4 * nc + 4096;
+    S.start = p64;
+    S.partial = p64 + (nc + 1);
+    S.O = nullptr;
+    S.perm = nullptr;
+    B.seg_n = p32 + 2 * nc;
+    B.acnt = p32 + 3 * nc;
+    B.key_arr = p32 + 4 * nc;
+    B.n_old = S.partial + (nscan + 2);
+    B.seg_lo = B.n_old + 2;
+    B.lperm = (uint16_t*)S.key;
+    B.n_arr = 0;
+    B.drop = 0;
+    B.pcache = nullptr;
+    B.d_nt_write = nullptr;
+    (void)W;
+    return MB_OK;
+}
+
+int convect_band_launch(mb_ctx* ctx, const ConvectArgs& a, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia, int64_t species, bool* done) {
+    *done = false;
+    const int s = (int)species - 1;
+    const int w = ctx->band_w;
+    if (w <= 0 || !pia->contiguous[s] || !pia->sorted_layout[s] || pv->n_arrivals != 0 || pv->drop_oob || grid->n_cells != pia->n_cells ||
+        pia->n_cells >= (int64_t)INT_MAX || pv->cap >= (int64_t)INT_MAX)
+        return MB_OK;
+    const int W = 2 * w + 1;
+    const int64_t nc = pia->n_cells;
+    SortScratch S;
+    BandBufs B;
+    if (sort_scratch_layout(ctx, pv->cap, nc, W, S, B)) return MB_ERR_CUDA;
+    cudaStream_t st = ctx->stream;
+    k_clear_cls_flags<<<1, 1, 0, st>>>(ctx->d_flags);
+    MB_LAUNCH_CHECK(ctx);
+    const int g = grid_for(nc * 32, 256, 8);
+    if (w == 1) k_convect_band<3><<<g, 256, 0, st>>>(a, S.M, B.seg_lo, B.seg_n, B.lperm, ctx->d_flags);
+    else if (w == 2) k_convect_band<5><<<g, 256, 0, st>>>(a, S.M, B.seg_lo, B.seg_n, B.lperm, ctx->d_flags);
+    else if (w == 4) k_convect_band<9><<<g, 256, 0, st>>>(a, S.M, B.seg_lo, B.seg_n, B.lperm, ctx->d_flags);
+    else k_convect_band<17><<<g, 256, 0, st>>>(a, S.M, B.seg_lo, B.seg_n, B.lperm, ctx->d_flags);
+    MB_LAUNCH_CHECK(ctx);
+    // the classification stays valid until something other than a slab exchange touches the particles
+    ctx->cls_gen = ctx->state_gen;
+    ctx->cls_pv = pv; ctx->cls_pia = pia; ctx->cls_species = (int)species; ctx->cls_w = w;
+    ctx->cls_inv_dx = grid->inv_dx; ctx->cls_cell_offset = grid->cell_offset; ctx->cls_cap = pv->cap;
+    *done = true;
+    return MB_OK;
+}
+
 template <int W>
-static int launch_band(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia, int64_t species, SortScratch& S, const BandBufs& B) {
+static int launch_band(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia, int64_t species, SortScratch& S, const BandBufs& B,
+                       bool cls_cached) {
     const int64_t nc = pia->n_cells;
     Indexer* ix = pia->d_indexer + (species - 1) * nc;
     cudaStream_t st = ctx->stream;
@@ -500,9 +673,11 @@ static int launch_band(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pi
     const int wgrid = grid_for(nc * 32, 256, 8);
     {
         ProfScope ps(ctx, PROF_SORT_CLASSIFY);
-        k_band_classify<W><<<wgrid, 256, 0, st>>>(pv->cur.a[F_X], pv->cell, pv->cell, ix, nc, use_x ? grid->inv_dx : 0.0,
-                                                 use_x ? grid->cell_offset : 0, use_x, B.drop, S.M, B.seg_lo, B.seg_n, B.lperm, S.flags);
-        MB_LAUNCH_CHECK(ctx);
+        if (!cls_cached) {
+            k_band_classify<W><<<wgrid, 256, 0, st>>>(pv->cur.a[F_X], pv->cell, pv->cell, ix, nc, use_x ? grid->inv_dx : 0.0,
+                                                     use_x ? grid->cell_offset : 0, use_x, B.drop, S.M, B.seg_lo, B.seg_n, B.lperm, S.flags);
+            MB_LAUNCH_CHECK(ctx);
+        }
         if (B.n_arr > 0) {
             MB_CUDA(cudaMemsetAsync(B.acnt, 0, (size_t)nc * 4, st));
             k_band_arrivals<<<grid_for(B.n_arr, 256), 256, 0, st>>>(pv->cur.a[F_X], B.n_old, B.n_arr, nc, grid->inv_dx, grid->cell_offset, pv->cell,
@@ -571,28 +746,8 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
     const int nscan = (int)((nc + SCAN_TILE - 1) / SCAN_TILE);
 
     SortScratch S;
-    S.flags = ctx->d_flags;
-    S.key = (int32_t*)ctx_scratch(ctx, 0, (size_t)cap * 4);  // general: keys; band: lperm (16 bit)
-    // slot 1: hist | cursor | seg_n | acnt | key_arr | M   (int32)
-    const size_t n32 = (size_t)nc * (4 + (size_t)W) + 4096 + 64;
-    int32_t* p32 = (int32_t*)ctx_scratch(ctx, 1, n32 * 4);
-    // slot 2: start | partial | n_old | seg_lo   (int64)
-    const size_t n64 = (size_t)(nc + 1) + (size_t)(nscan + 2) + 2 + (size_t)nc + 64;
-    int64_t* p64 = (int64_t*)ctx_scratch(ctx, 2, n64 * 8);
-    if (!S.key || !p32 || !p64) return MB_ERR_CUDA;
-    S.hist = p32;
-    S.cursor = p32 + nc;
-    S.M = p32 + 4 * nc + 4096;
-    S.start = p64;
-    S.partial = p64 + (nc + 1);
-    S.O = nullptr;
     BandBufs B;
-    B.seg_n = p32 + 2 * nc;
-    B.acnt = p32 + 3 * nc;
-    B.key_arr = p32 + 4 * nc;
-    B.n_old = S.partial + (nscan + 2);
-    B.seg_lo = B.n_old + 2;
-    B.lperm = (uint16_t*)S.key;
+    if (sort_scratch_layout(ctx, cap, nc, W, S, B)) return MB_ERR_CUDA;
     B.n_arr = n_arr;
     B.drop = drop ? 1 : 0;
     cudaStream_t st = ctx->stream;
@@ -605,13 +760,18 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
     if (!B.pcache) return MB_ERR_CUDA;
 
     MB_CUDA(cudaMemcpyAsync(B.n_old, d_nt, 8, cudaMemcpyDeviceToDevice, st));  // n_total before the sort (the scan may rewrite it)
-    k_set_flag<<<1, 1, 0, st>>>(ctx->d_flags, 2, try_band ? 0 : 1);
+    // classification cached by the fused convect kernel?  (same particles, same grid, nothing but a slab exchange in between)
+    const bool cls_cached = try_band && use_x && ctx->cls_gen == ctx->state_gen && ctx->cls_pv == (void*)pv && ctx->cls_pia == (void*)pia &&
+                            ctx->cls_species == (int)species && ctx->cls_w == w && ctx->cls_inv_dx == grid->inv_dx &&
+                            ctx->cls_cell_offset == grid->cell_offset && ctx->cls_cap == cap;
+    if (cls_cached) k_flag_from_cls<<<1, 1, 0, st>>>(ctx->d_flags, drop ? 1 : 0);
+    else k_set_flag<<<1, 1, 0, st>>>(ctx->d_flags, 2, try_band ? 0 : 1);
     MB_LAUNCH_CHECK(ctx);
     if (try_band) {
-        if (w == 1) r = launch_band<3>(ctx, grid, pv, pia, species, S, B);
-        else if (w == 2) r = launch_band<5>(ctx, grid, pv, pia, species, S, B);
-        else if (w == 4) r = launch_band<9>(ctx, grid, pv, pia, species, S, B);
-        else r = launch_band<17>(ctx, grid, pv, pia, species, S, B);
+        if (w == 1) r = launch_band<3>(ctx, grid, pv, pia, species, S, B, cls_cached);
+        else if (w == 2) r = launch_band<5>(ctx, grid, pv, pia, species, S, B, cls_cached);
+        else if (w == 4) r = launch_band<9>(ctx, grid, pv, pia, species, S, B, cls_cached);
+        else r = launch_band<17>(ctx, grid, pv, pia, species, S, B, cls_cached);
         if (r) return r;
     }
     // general path (every kernel returns immediately unless flags[2] != 0)
@@ -644,6 +804,7 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
     if (rewrite_total) { pv->drop_oob = false; pv->n_arrivals = 0; pia->h_valid = false; }
     // the cached moments are valid only if the band path ran (device flag 2 == 0): the props kernel checks the flag itself
     ctx->state_gen++;
+    ctx->cls_gen = 0;
     ctx->pc_gen = try_band ? ctx->state_gen : 0;
     ctx->pc_pv = pv; ctx->pc_pia = pia; ctx->pc_species = (int)species;
     pia->contiguous[s] = 1;      // grid_sorting.jl:112

@@ -474,3 +474,57 @@ def test_couette_loop_parity(mb, oracle, ctx):
     np.testing.assert_array_equal(d["np"], o.np)
     np.testing.assert_allclose(d["T"], o.T, rtol=1e-10)
     np.testing.assert_allclose(d["v"], o.v, rtol=1e-9, atol=1e-9 * 500)
+
+
+# --------------------------------------------------------------------------------------- fused convect + band classification
+@pytest.mark.parametrize("n_cells,ppc,w,dt_mult,acc", [(40, 300, 2, 4, 1.0), (6, 3000, 1, 2, 0.5), (64, 50, 4, 12, 1.0), (3, 700, 8, 30, 0.0),
+                                                        (200, 7, 2, 4, 1.0)])
+def test_convect_then_sort_uses_cached_classification(mb, oracle, ctx, n_cells, ppc, w, dt_mult, acc):
+    """convect_particles! on a sorted layout classifies while it moves the particles and the following sort_particles! starts at the
+    scan: the result must be the bit-exact stable counting sort of the oracle (grid_sorting.jl:58-113), including cells bigger
+    than the shared-memory staging (3000 ppc), tiny cells, wide bands and walls of every accommodation."""
+    ctx.set_band_halfwidth(w)
+    try:
+        dt = 2.59e-9 * dt_mult
+        L, n, Fnum, opv, opia, pv, pia = _couette_like(oracle, mb, ctx, n_cells, ppc, 900 + n_cells)
+        g = mb.Grid1DUniform(L, n_cells)
+        walls, owalls = mb.MaxwellWalls1D(300.0, 350.0, -500.0, 500.0, acc, acc), (300.0, 350.0, -500.0, 500.0, acc, acc)
+        mb.sort_particles(None, g, pv, pia, 1)  # establishes the sorted layout on the device (general path)
+        paths = []
+        for t in range(1, 7):
+            l0 = ctx.kernel_launches
+            mb.convect_particles(mb.PhiloxRng(t), g, walls, pv, pia, 1, AR, dt)
+            mb.sort_particles(None, g, pv, pia, 1)
+            launches = ctx.kernel_launches - l0
+            oracle.convect_particles(oracle.Rng.philox(1234, t), (L, n_cells), owalls, opv, opia, 1, [AR], dt)
+            oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+            paths.append(ctx.sort_last_path)
+            assert_same_pia(opia, pia)
+            assert_rows_close(pv.logical(1, n), opv.logical(1, n), 1e-12, f"fused convect+sort step {t}")
+        if paths.count(1) == len(paths):
+            # clear + convect_band | flag, 3 scan, gather, 7 general-path stubs -- and no k_band_classify
+            assert launches == 14, launches
+    finally:
+        ctx.set_band_halfwidth(2)
+
+
+def test_cached_classification_is_invalidated(mb, oracle, ctx):
+    """Anything that touches the particles between convect and sort (here: an upload that moves particles) voids the cache."""
+    n_cells, ppc, dt = 30, 200, 2.59e-9 * 4
+    L, n, Fnum, opv, opia, pv, pia = _couette_like(oracle, mb, ctx, n_cells, ppc, 77)
+    g = mb.Grid1DUniform(L, n_cells)
+    walls, owalls = mb.MaxwellWalls1D(300.0, 300.0, 0.0, 0.0, 1.0, 1.0), (300.0, 300.0, 0.0, 0.0, 1.0, 1.0)
+    mb.sort_particles(None, g, pv, pia, 1)
+    for t in (1, 2, 3):
+        mb.convect_particles(mb.PhiloxRng(t), g, walls, pv, pia, 1, AR, dt)
+        oracle.convect_particles(oracle.Rng.philox(1234, t), (L, n_cells), owalls, opv, opia, 1, [AR], dt)
+        # teleport a few particles (same edit on both sides): the cached classification is now wrong and must not be used
+        rows = pv.logical(1, n)
+        for i in (5, 1234, n - 3):
+            rows[i - 1, 4] = (L - rows[i - 1, 4]) * 0.999 + 1e-9
+        pv.set_logical(1, rows)
+        opv.set_logical(1, rows)
+        mb.sort_particles(None, g, pv, pia, 1)
+        oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+        assert_same_pia(opia, pia)
+        assert_rows_close(pv.logical(1, n), opv.logical(1, n), 1e-12, "invalidate")
