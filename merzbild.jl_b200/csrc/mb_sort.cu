@@ -52,7 +52,9 @@ template <int W>
 __global__ void __launch_bounds__(256) k_band_classify(const double* __restrict__ X, const int32_t* cell_in, int32_t* cell_out,
                                                        const Indexer* __restrict__ ix, int64_t n_cells, double inv_dx, int64_t cell_offset,
                                                        int use_x, int drop, int32_t* __restrict__ M, int64_t* __restrict__ seg_lo,
-                                                       int32_t* __restrict__ seg_n, uint16_t* __restrict__ lperm, int* flags) {
+                                                       int32_t* __restrict__ seg_n, uint16_t* __restrict__ lperm, int* flags,
+                                                       const int* only_if) {
+    if (only_if != nullptr && *only_if == 0) return;  // the fused convect kernel already classified every cell
     constexpr int w = W / 2;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
@@ -352,59 +354,119 @@ __global__ void __launch_bounds__(256) k_band_gather(SoA in_, SoA out_, const ui
 // d = c - c' + w in shared memory (one byte each), counts them with match.any, and derives lperm from the staged bytes.
 // The following sort_particles! finds the classification cached (ctx->cls_gen == ctx->state_gen) and starts at the scan.
 // Device flags: F_OUTSIDE = a particle left the slab (legal only if a slab exchange follows), F_CLS_BAD = band overflow
-// (the sort takes the general path), F_FAR = a particle left the slab from a cell further than w from that edge.
-enum { F_OUTSIDE = 12, F_CLS_BAD = 13, F_FAR = 14 };
-constexpr int CB_STAGE = 2048;  // staged destination bytes per warp; bigger cells re-read x in pass 2
+// (the sort takes the general path), F_FAR = a particle left the slab from a cell further than w from that edge,
+// F_CLS_REDO = a cell could not be classified here (bigger than the staging area): the sort runs k_band_classify after all.
+enum { F_OUTSIDE = 12, F_CLS_BAD = 13, F_FAR = 14, F_CLS_REDO = 15 };
+#ifndef MB_CB_MINB
+#define MB_CB_MINB 2  // resident CTAs per SM the fused kernel is compiled for (register budget)
+#endif
+#ifndef MB_CB_PF
+#define MB_CB_PF 8
+#endif
+constexpr int CB_PF = MB_CB_PF;  // batches of 32 particles in flight per warp (cp.async ring)
+constexpr int CB_STAGE = 2048;
+constexpr int CB_SMEM_WARP = 2 * CB_PF * 32 * 8 + 32 * 4 + CB_STAGE * 2;
+constexpr int CB_SMEM = 8 * CB_SMEM_WARP;  // particles of a cell staged in shared memory per warp (2 bytes each); bigger cells take k_band_classify
 
+// Pass 1 moves the particles and stages (d, rank inside the destination group) per particle; the group sizes follow from the
+// running counters, pass 2 turns the staged pairs into lperm without touching HBM again (except the 2-byte lperm store).
 template <int W>
-__global__ void __launch_bounds__(256) k_convect_band(ConvectArgs a, int32_t* __restrict__ M, int64_t* __restrict__ seg_lo,
+__global__ void __launch_bounds__(256, MB_CB_MINB) k_convect_band(ConvectArgs a, int32_t* __restrict__ M, int64_t* __restrict__ seg_lo,
                                                       int32_t* __restrict__ seg_n, uint16_t* __restrict__ lperm, int* flags) {
     constexpr int w = W / 2;
-    __shared__ uint8_t s_dd[8][CB_STAGE];
-    __shared__ int s_cnt[8][32];
+    extern __shared__ __align__(16) unsigned char cb_smem[];  // CB_SMEM bytes: per warp rx | rv | cnt | st
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const double* __restrict__ X = a.pv.a[F_X];
-    for (int64_t c = warp0; c < a.n_cells; c += nwarps) {
+    unsigned char* wbase = cb_smem + (size_t)wid * CB_SMEM_WARP;
+    double* rx = (double*)wbase;
+    double* rv = rx + CB_PF * 32;
+    int* cnt_s = (int*)(rv + CB_PF * 32);
+    uint16_t* st = (uint16_t*)(cnt_s + 32);  // d << 11 | rank-in-group (rank < 2048)
+    const double dt = a.dt, L = a.L, inv_dx = a.inv_dx, min_x = a.min_x, max_x = a.max_x;
+    const int cell_offset = (int)a.cell_offset, n_cells = (int)a.n_cells;  // the launcher checks that the global cell count fits 31 bits
+    const int compute_cell = a.compute_cell;
+    for (int64_t c64 = warp0; c64 < a.n_cells; c64 += nwarps) {
+        const int c = (int)c64;
         const Indexer q = a.ix[c];
-        const int64_t lo = q.start1 - 1, n = q.n_group1;
-        if (lane == 0) { seg_lo[c] = lo; seg_n[c] = (int32_t)n; }
-        if (n > 65535 || q.n_group2 != 0) {  // not a sorted layout after all: just move the particles
+        const int64_t lo = q.start1 - 1;
+        const int n = (int)q.n_group1;
+        if (lane == 0) { seg_lo[c] = lo; seg_n[c] = n; }
+        if (q.n_group1 > CB_STAGE || q.n_group2 != 0) {  // big cell or not a sorted layout after all: just move the particles
             for (int64_t j = lo + lane; j < q.end1; j += 32) convect_one(a, j);
             if (q.n_group2 > 0)
                 for (int64_t j = q.start2 - 1 + lane; j < q.end2; j += 32) convect_one(a, j);
-            if (lane == 0) atomicOr(&flags[F_CLS_BAD], 1);
+            if (lane == 0) atomicOr(&flags[F_CLS_REDO], 1);
             continue;
         }
+        double* __restrict__ Xc = a.pv.a[F_X] + lo;
+        const double* __restrict__ VXc = a.pv.a[F_VX] + lo;
         __syncwarp();
-        s_cnt[wid][lane] = 0;
+        cnt_s[lane] = 0;
         __syncwarp();
-        const bool staged = n <= CB_STAGE;
         bool bad = false, outside = false, far = false;
-        for (int64_t b = 0; b < n; b += 32) {
-            int dd = 255;
-            if (b + lane < n) {
-                const double x_new = convect_one(a, lo + b + lane);
-                const int nc = cell_of(x_new, a.inv_dx, a.cell_offset);
-                const int64_t d = (int64_t)nc - c + w;
-                if (nc >= 0 && nc < a.n_cells) {
-                    if (d >= 0 && d < W) dd = (int)d;
-                    else bad = true;
-                } else {
-                    outside = true;
-                    if ((nc < 0 && c >= w) || (nc >= a.n_cells && c < a.n_cells - w)) far = true;
-                }
-                if (staged) s_dd[wid][b + lane] = (uint8_t)dd;
+        // one particle: returns d (255: not counted)
+        auto move = [&](int j, double x_old, double vx) -> int {
+            double x_new = fma(vx, dt, x_old);  // @muladd x[1] + v[1] * dt
+            if (x_new >= L || x_new <= 0.0) x_new = convect_wall(a, lo + j, x_old, vx, x_new);
+            if (x_new < min_x) x_new = min_x;
+            else if (x_new > max_x) x_new = max_x;
+            Xc[j] = x_new;
+            const int nc = __double2int_rd(x_new * inv_dx) - cell_offset;  // == cell_of(): 0 <= x * inv_dx < 2^31
+            if (compute_cell) a.cell[lo + j] = nc + 1;
+            const int d = nc - c + w;
+            if (nc >= 0 && nc < n_cells) {
+                if (d >= 0 && d < W) return d;
+                bad = true;
+                return 255;
             }
-            const unsigned act = __ballot_sync(0xffffffffu, dd != 255);
-            if (dd != 255) {
-                const unsigned peers = __match_any_sync(act, dd);
-                if ((peers & lt) == 0) s_cnt[wid][dd] += __popc(peers);  // one leader per destination
+            outside = true;
+            if ((nc < 0 && c >= w) || (nc >= n_cells && c < n_cells - w)) far = true;
+            return 255;
+        };
+        // count one batch and stage (d, rank); every lane of the warp calls it
+        auto stage = [&](int j, bool valid, int d) {
+            const unsigned act = __ballot_sync(0xffffffffu, d != 255);
+            unsigned peers = 0;
+            int before = 0;
+            if (d != 255) {
+                peers = __match_any_sync(act, d);
+                before = cnt_s[d];
+                st[j] = (uint16_t)((d << 11) | (before + __popc(peers & lt)));
+            } else if (valid) {
+                st[j] = 0xFFFFu;
             }
             __syncwarp();
+            if (d != 255 && (peers & lt) == 0) cnt_s[d] = before + __popc(peers);  // one leader per destination
+            __syncwarp();
+        };
+        // x and vx stream through a per-warp ring of CB_PF batches filled with cp.async (each lane copies and later reads its
+        // own 8 bytes, so no warp barrier is needed): CB_PF * 512 B per warp in flight hide the HBM latency.
+        const int nb = (n + 31) >> 5;
+        auto issue = [&](int k) {
+            const int j = (k << 5) + lane;
+            if (k < nb && j < n) {
+                const int slot = k & (CB_PF - 1);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(&rx[slot * 32 + lane])), "l"(Xc + j));
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(&rv[slot * 32 + lane])), "l"(VXc + j));
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+#pragma unroll
+        for (int k = 0; k < CB_PF; k++) issue(k);
+        for (int k = 0; k < nb; k++) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(CB_PF - 1) : "memory");
+            const int j = (k << 5) + lane;
+            const bool valid = j < n;
+            const int slot = k & (CB_PF - 1);
+            const double x0 = rx[slot * 32 + lane], v0 = rv[slot * 32 + lane];
+            issue(k + CB_PF);
+            int d = 255;
+            if (valid) d = move(j, x0, v0);
+            stage(j, valid, d);
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         bad = __any_sync(0xffffffffu, bad);
         outside = __any_sync(0xffffffffu, outside);
         far = __any_sync(0xffffffffu, far);
@@ -414,8 +476,8 @@ __global__ void __launch_bounds__(256) k_convect_band(ConvectArgs a, int32_t* __
             if (far) atomicOr(&flags[F_FAR], 1);
         }
         if (bad) continue;
-        const int cnt = lane < W ? s_cnt[wid][lane] : 0;
-        if (lane < W) M[c * W + lane] = cnt;
+        const int cnt = lane < W ? cnt_s[lane] : 0;
+        if (lane < W) M[(int64_t)c * W + lane] = cnt;
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -423,33 +485,17 @@ __global__ void __launch_bounds__(256) k_convect_band(ConvectArgs a, int32_t* __
             if (lane >= o) incl += t;
         }
         __syncwarp();
-        s_cnt[wid][lane] = incl - cnt;  // running offset of every destination group inside the old cell
+        cnt_s[lane] = incl - cnt;  // offset of every destination group inside the old cell
         __syncwarp();
-        for (int64_t b = 0; b < n; b += 32) {
-            int dd = 255;
-            if (b + lane < n) {
-                if (staged) dd = s_dd[wid][b + lane];
-                else {
-                    const int nc = cell_of(X[lo + b + lane], a.inv_dx, a.cell_offset);
-                    if (nc >= 0 && nc < a.n_cells) dd = (int)((int64_t)nc - c + w);
-                }
-            }
-            const unsigned act = __ballot_sync(0xffffffffu, dd != 255);
-            unsigned peers = 0;
-            int base = 0;
-            if (dd != 255) {
-                peers = __match_any_sync(act, dd);
-                base = s_cnt[wid][dd];
-                lperm[lo + base + __popc(peers & lt)] = (uint16_t)(b + lane);
-            }
-            __syncwarp();
-            if (dd != 255 && (peers & lt) == 0) s_cnt[wid][dd] = base + __popc(peers);
-            __syncwarp();
+        uint16_t* __restrict__ lp = lperm + lo;
+        for (int j = lane; j < n; j += 32) {
+            const unsigned v = st[j];
+            if (v != 0xFFFFu) lp[cnt_s[v >> 11] + (v & 0x7FFu)] = (uint16_t)j;
         }
     }
 }
 
-__global__ void k_clear_cls_flags(int* flags) { flags[F_OUTSIDE] = 0; flags[F_CLS_BAD] = 0; flags[F_FAR] = 0; }
+__global__ void k_clear_cls_flags(int* flags) { flags[F_OUTSIDE] = 0; flags[F_CLS_BAD] = 0; flags[F_FAR] = 0; flags[F_CLS_REDO] = 0; }
 // flags[2] (general path needed) from the cached classification: band overflow, or a particle outside the slab with no exchange
 __global__ void k_flag_from_cls(int* flags, int drop) { flags[2] = (flags[F_CLS_BAD] != 0 || (!drop && flags[F_OUTSIDE] != 0)) ? 1 : 0; }
 
@@ -638,7 +684,7 @@ int convect_band_launch(mb_ctx* ctx, const ConvectArgs& a, const mb_grid1d* grid
     const int s = (int)species - 1;
     const int w = ctx->band_w;
     if (w <= 0 || !pia->contiguous[s] || !pia->sorted_layout[s] || pv->n_arrivals != 0 || pv->drop_oob || grid->n_cells != pia->n_cells ||
-        pia->n_cells >= (int64_t)INT_MAX || pv->cap >= (int64_t)INT_MAX)
+        pia->n_cells >= (int64_t)INT_MAX || pv->cap >= (int64_t)INT_MAX || !(grid->L * grid->inv_dx < 2.0e9))
         return MB_OK;
     const int W = 2 * w + 1;
     const int64_t nc = pia->n_cells;
@@ -648,11 +694,19 @@ int convect_band_launch(mb_ctx* ctx, const ConvectArgs& a, const mb_grid1d* grid
     cudaStream_t st = ctx->stream;
     k_clear_cls_flags<<<1, 1, 0, st>>>(ctx->d_flags);
     MB_LAUNCH_CHECK(ctx);
-    const int g = grid_for(nc * 32, 256, 8);
-    if (w == 1) k_convect_band<3><<<g, 256, 0, st>>>(a, S.M, B.seg_lo, B.seg_n, B.lperm, ctx->d_flags);
-    else if (w == 2) k_convect_band<5><<<g, 256, 0, st>>>(a, S.M, B.seg_lo, B.seg_n, B.lperm, ctx->d_flags);
-    else if (w == 4) k_convect_band<9><<<g, 256, 0, st>>>(a, S.M, B.seg_lo, B.seg_n, B.lperm, ctx->d_flags);
-    else k_convect_band<17><<<g, 256, 0, st>>>(a, S.M, B.seg_lo, B.seg_n, B.lperm, ctx->d_flags);
+    const int g = grid_for(nc * 32, 256, MB_CB_MINB);
+    static bool attr_set = false;
+    if (!attr_set) {
+        MB_CUDA(cudaFuncSetAttribute(k_convect_band<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CB_SMEM));
+        MB_CUDA(cudaFuncSetAttribute(k_convect_band<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, CB_SMEM));
+        MB_CUDA(cudaFuncSetAttribute(k_convect_band<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, CB_SMEM));
+        MB_CUDA(cudaFuncSetAttribute(k_convect_band<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, CB_SMEM));
+        attr_set = true;
+    }
+    if (w == 1) k_convect_band<3><<<g, 256, CB_SMEM, st>>>(a, S.M, B.seg_lo, B.seg_n, B.lperm, ctx->d_flags);
+    else if (w == 2) k_convect_band<5><<<g, 256, CB_SMEM, st>>>(a, S.M, B.seg_lo, B.seg_n, B.lperm, ctx->d_flags);
+    else if (w == 4) k_convect_band<9><<<g, 256, CB_SMEM, st>>>(a, S.M, B.seg_lo, B.seg_n, B.lperm, ctx->d_flags);
+    else k_convect_band<17><<<g, 256, CB_SMEM, st>>>(a, S.M, B.seg_lo, B.seg_n, B.lperm, ctx->d_flags);
     MB_LAUNCH_CHECK(ctx);
     // the classification stays valid until something other than a slab exchange touches the particles
     ctx->cls_gen = ctx->state_gen;
@@ -673,11 +727,11 @@ static int launch_band(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pi
     const int wgrid = grid_for(nc * 32, 256, 8);
     {
         ProfScope ps(ctx, PROF_SORT_CLASSIFY);
-        if (!cls_cached) {
-            k_band_classify<W><<<wgrid, 256, 0, st>>>(pv->cur.a[F_X], pv->cell, pv->cell, ix, nc, use_x ? grid->inv_dx : 0.0,
-                                                     use_x ? grid->cell_offset : 0, use_x, B.drop, S.M, B.seg_lo, B.seg_n, B.lperm, S.flags);
-            MB_LAUNCH_CHECK(ctx);
-        }
+        // with a cached classification this is a stub unless a cell was too big for the fused kernel's staging area
+        k_band_classify<W><<<wgrid, 256, 0, st>>>(pv->cur.a[F_X], pv->cell, pv->cell, ix, nc, use_x ? grid->inv_dx : 0.0,
+                                                 use_x ? grid->cell_offset : 0, use_x, B.drop, S.M, B.seg_lo, B.seg_n, B.lperm, S.flags,
+                                                 cls_cached ? S.flags + F_CLS_REDO : nullptr);
+        MB_LAUNCH_CHECK(ctx);
         if (B.n_arr > 0) {
             MB_CUDA(cudaMemsetAsync(B.acnt, 0, (size_t)nc * 4, st));
             k_band_arrivals<<<grid_for(B.n_arr, 256), 256, 0, st>>>(pv->cur.a[F_X], B.n_old, B.n_arr, nc, grid->inv_dx, grid->cell_offset, pv->cell,
