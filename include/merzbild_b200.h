@@ -210,6 +210,12 @@ int mb_comm_init(mb_ctx* ctx, const void* nccl_unique_id128, int rank, int nrank
  * locally; arrivals are appended after n_total.  Call between convect and sort (the sort then places arrivals: they are
  * just more keys).  x coordinates stay global; the slab grid (mb_grid1d_slab) carries the cell offset.
  * n_sent2/n_recv2 (nullable, host, 2 x int64: left, right) report the counts and synchronise. */
+/* mode 0 (default): when the species is in the sorted layout (it was sorted and only moved by convection since) the exchange
+ * only looks at the w cells next to each slab face (w = the sort's band half-width) and swaps fixed-size messages of up to 2048
+ * particles per direction without any host synchronisation; a leaver from any other cell, or more than 2048 per direction, is
+ * reported as an error by the next synchronising call.  Otherwise, and always with mode 1 or when the counts are requested,
+ * every particle is examined and the message sizes are negotiated through the host.  All ranks must use the same mode. */
+int mb_exchange_set_mode(mb_ctx* ctx, int32_t mode);
 int mb_exchange_slab(mb_ctx* ctx, const mb_grid1d* slab, mb_pv* pv, mb_pia* pia, int64_t species, int64_t* n_sent2, int64_t* n_recv2);
 
 #ifdef __cplusplus

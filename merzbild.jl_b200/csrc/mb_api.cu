@@ -256,12 +256,15 @@ int mb_pv_create(mb_ctx* ctx, int64_t np, mb_pv** out) {
     p->ctx = ctx;
     p->cap = np;
     p->has_alt = false;
-    p->drop_oob = false;
+    p->drop_oob = 0;
     p->n_arrivals = 0;
     p->cell = nullptr;
+    p->d_n_arr = nullptr;
     for (int f = 0; f < 7; f++) p->alt.a[f] = nullptr;
     int r = alloc_soa(p->cur, np);
     if (r) { delete p; return r; }
+    MB_CUDA(cudaMalloc(&p->d_n_arr, sizeof(int64_t)));
+    MB_CUDA(cudaMemsetAsync(p->d_n_arr, 0, sizeof(int64_t), ctx->stream));
     if (np > 0) {
         MB_CUDA(cudaMalloc(&p->cell, (size_t)np * sizeof(int32_t)));
         // Particle(0, [0,0,0], [0,0,0]) everywhere (particles.jl:210)
@@ -279,6 +282,7 @@ int mb_pv_destroy(mb_pv* p) {
     free_soa(p->cur);
     if (p->has_alt) free_soa(p->alt);
     if (p->cell) cudaFree(p->cell);
+    if (p->d_n_arr) cudaFree(p->d_n_arr);
     delete p;
     return MB_OK;
 }

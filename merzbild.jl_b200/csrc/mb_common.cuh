@@ -21,6 +21,9 @@ constexpr double EPS = 2.220446049250313e-16;     // Julia eps()
 constexpr int N_SM = 148;                         // B200
 
 // device-side error flag bits (ctx->d_flags[0])
+// other slots of ctx->d_flags: [2] the sort's general path must run, [4..11] per-species "a merge left holes",
+// [12..15] written by the fused convect + classify kernel (mb_sort.cu)
+enum { F_OUTSIDE = 12, F_CLS_BAD = 13, F_FAR = 14, F_CLS_REDO = 15 };
 enum : int { DEVERR_CAPACITY = 1, DEVERR_PRECONDITION = 2, DEVERR_BAND_OVERFLOW = 4, DEVERR_BAD_CELL = 8, DEVERR_OCTREE = 16 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -133,6 +136,7 @@ struct mb_ctx {
     size_t xch_cap;  // particles per direction
     int64_t* d_xch_counts;   // [0..1] send counts, [2..3] recv counts
     int64_t* h_xch_counts;   // pinned
+    int xch_mode;            // 0: edge exchange when the layout allows it, 1: always the full exchange
 };
 
 struct mb_pv {
@@ -141,8 +145,10 @@ struct mb_pv {
     mb::SoA cur, alt;   // alt allocated lazily (sort ping-pong)
     bool has_alt;
     int32_t* cell;      // 1-based cell id per logical position (pv.cell); int32 on device
-    bool drop_oob;      // set by the slab exchange: the next sort drops particles whose cell is outside the slab
-    int64_t n_arrivals; // slab-exchange arrivals appended after the sorted layout (merged by the next sort)
+    int drop_oob;       // set by the slab exchange: the next sort drops particles whose cell is outside the slab
+                        // (1: every leaver was sent; 2: edge exchange -- only leavers from the w cells next to a slab face were sent)
+    int64_t n_arrivals; // host upper bound on the slab-exchange arrivals appended after the sorted layout (merged by the next sort)
+    int64_t* d_n_arr;   // device: exact number of those arrivals (the edge exchange never tells the host)
 };
 
 struct mb_pia {

@@ -174,6 +174,85 @@ static __global__ void __launch_bounds__(256) k_xch_unpack(SoA pv, int64_t* n_to
         for (int f = 0; f < 7; f++) pv.a[f][n0 + t] = src[f];
     }
 }
+// ------------------------------------------------------------------------------------------------ edge exchange
+// On a sorted layout whose particles move at most w cells per step (the sort's band assumption) the leavers to the left can only
+// sit in the first w cells of the slab and the leavers to the right in the last w: two CTAs scan those few thousand particles,
+// pack the leavers (stable, logical order) behind a count header, and the neighbours swap FIXED-size messages -- no host
+// round trip, no scan over all particles.  A leaver from any other cell is a band overflow: the fused convect kernel (F_FAR)
+// or the sort's classify pass reports it as a device error instead of losing the particle silently.
+constexpr int XE_CAP = 2048;             // leavers per direction and step
+constexpr int XE_MSG = 8 + 7 * XE_CAP;   // doubles per message: [0] = count (int64 bits), payload from [8] (64-byte aligned)
+
+static __global__ void __launch_bounds__(256) k_xch_edge_pack(SoA pv, const Indexer* __restrict__ ix, int64_t n_cells, int w, double inv_dx,
+                                                            int64_t cell_offset, double* __restrict__ sendL, double* __restrict__ sendR, int hasL,
+                                                            int hasR, int* flags) {
+    __shared__ int s_w[8];
+    const int side = blockIdx.x;  // 0: left face, 1: right face
+    const int want = side + 1;
+    double* __restrict__ send = side == 0 ? sendL : sendR;
+    const int64_t c_lo = side == 0 ? 0 : (n_cells - w > 0 ? n_cells - w : 0);
+    const int64_t c_hi = side == 0 ? (w < n_cells ? w : n_cells) : n_cells;
+    int64_t lo = INT64_MAX, hi = -1;
+    for (int64_t c = c_lo; c < c_hi; c++) {
+        const Indexer q = ix[c];
+        if (q.n_group1 > 0) {
+            if (q.start1 - 1 < lo) lo = q.start1 - 1;
+            if (q.end1 > hi) hi = q.end1;
+        }
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    int base = 0;
+    for (int64_t i0 = lo; i0 < hi; i0 += 256) {
+        const int64_t i = i0 + threadIdx.x;
+        const bool is = i < hi && xch_dir(pv.a[F_X][i], inv_dx, cell_offset, n_cells) == want;
+        const unsigned bal = __ballot_sync(0xffffffffu, is);
+        if (lane == 0) s_w[wid] = __popc(bal);
+        __syncthreads();
+        int off = 0, tot = 0;
+        for (int k = 0; k < 8; k++) { if (k < wid) off += s_w[k]; tot += s_w[k]; }
+        const int pos = base + off + __popc(bal & lt);
+        if (is && pos < XE_CAP) {
+#pragma unroll
+            for (int f = 0; f < 7; f++) send[8 + 7 * (int64_t)pos + f] = pv.a[f][i];
+        }
+        base += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        send[0] = __longlong_as_double((long long)(base < XE_CAP ? base : XE_CAP));
+        if (base > XE_CAP) { atomicOr(&flags[0], DEVERR_CAPACITY); flags[1] = base; }
+        if (base > 0 && !(side == 0 ? hasL : hasR)) atomicOr(&flags[0], DEVERR_PRECONDITION);  // left the global domain
+        if (side == 0 && flags[F_FAR] != 0) atomicOr(&flags[0], DEVERR_BAND_OVERFLOW);
+    }
+}
+
+static __global__ void __launch_bounds__(256) k_xch_edge_unpack(SoA pv, const int64_t* n_total_p, int64_t cap, const double* __restrict__ recvL,
+                                                              const double* __restrict__ recvR, int hasL, int hasR, int* flags) {
+    int64_t nL = hasL ? (int64_t)__double_as_longlong(recvL[0]) : 0, nR = hasR ? (int64_t)__double_as_longlong(recvR[0]) : 0;
+    nL = nL < 0 ? 0 : (nL > XE_CAP ? XE_CAP : nL);
+    nR = nR < 0 ? 0 : (nR > XE_CAP ? XE_CAP : nR);
+    const int64_t n0 = *n_total_p;
+    if (n0 + nL + nR > cap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) { atomicOr(&flags[0], DEVERR_CAPACITY); flags[1] = (int)(n0 + nL + nR); }
+        return;
+    }
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nL + nR; t += (int64_t)gridDim.x * blockDim.x) {
+        const double* src = t < nL ? recvL + 8 + 7 * t : recvR + 8 + 7 * (t - nL);
+#pragma unroll
+        for (int f = 0; f < 7; f++) pv.a[f][n0 + t] = src[f];
+    }
+}
+// after the unpack (every block of it read the old n_total): n_total += arrivals, and the sort learns their number
+static __global__ void k_xch_edge_commit(int64_t* n_total_p, int64_t cap, const double* recvL, const double* recvR, int hasL, int hasR,
+                                         int64_t* d_n_arr) {
+    int64_t nL = hasL ? (int64_t)__double_as_longlong(recvL[0]) : 0, nR = hasR ? (int64_t)__double_as_longlong(recvR[0]) : 0;
+    nL = nL < 0 ? 0 : (nL > XE_CAP ? XE_CAP : nL);
+    nR = nR < 0 ? 0 : (nR > XE_CAP ? XE_CAP : nR);
+    if (*n_total_p + nL + nR <= cap) { *n_total_p += nL + nR; *d_n_arr += nL + nR; }
+}
+static __global__ void k_add_i64(int64_t* p, int64_t v) { *p += v; }
+
 static __global__ void k_xch_add_total(int64_t* n_total_p, int64_t cap, int64_t add) {
     if (*n_total_p + add <= cap) *n_total_p += add;
 }
@@ -206,6 +285,12 @@ int mb_comm_init(mb_ctx* ctx, const void* id128, int rank, int nranks) {
     ctx->nccl_comm = comm;
     ctx->rank = rank;
     ctx->nranks = nranks;
+    return MB_OK;
+}
+
+int mb_exchange_set_mode(mb_ctx* ctx, int32_t mode) {
+    MB_ARG(ctx && (mode == 0 || mode == 1), "exchange mode must be 0 (edge exchange when possible) or 1 (always the full exchange)");
+    ctx->xch_mode = mode;
     return MB_OK;
 }
 
@@ -242,6 +327,40 @@ int mb_exchange_slab(mb_ctx* ctx, const mb_grid1d* slab, mb_pv* pv, mb_pia* pia,
         }
         ctx->xch_cap = want;
     }
+    const int left = ctx->rank - 1, right = ctx->rank + 1;
+    const bool hasL = ctx->nranks > 1 && left >= 0, hasR = ctx->nranks > 1 && right < ctx->nranks;
+    int64_t* d_nt = pia->d_n_total + s;
+    if (ctx->xch_mode == 0 && pia->sorted_layout[s] && ctx->band_w > 0 && pv->n_arrivals == 0 && !n_sent2 && !n_recv2) {
+        // edge exchange (every rank takes the same decision: it only depends on the operator sequence)
+        double* sL = (double*)ctx->xch_send[0];
+        double* sR = (double*)ctx->xch_send[1];
+        double* rL = (double*)ctx->xch_recv[0];
+        double* rR = (double*)ctx->xch_recv[1];
+        k_xch_edge_pack<<<2, 256, 0, st>>>(pv->cur, pia->d_indexer + (int64_t)s * pia->n_cells, pia->n_cells, ctx->band_w, slab->inv_dx,
+                                         slab->cell_offset, sL, sR, hasL ? 1 : 0, hasR ? 1 : 0, ctx->d_flags);
+        MB_LAUNCH_CHECK(ctx);
+        if (hasL || hasR) {
+            MB_NCCL(g_nccl.GroupStart());
+            if (hasL) {
+                MB_NCCL(g_nccl.Send(sL, XE_MSG, ncclFloat64, left, (ncclComm_t)ctx->nccl_comm, st));
+                MB_NCCL(g_nccl.Recv(rL, XE_MSG, ncclFloat64, left, (ncclComm_t)ctx->nccl_comm, st));
+            }
+            if (hasR) {
+                MB_NCCL(g_nccl.Send(sR, XE_MSG, ncclFloat64, right, (ncclComm_t)ctx->nccl_comm, st));
+                MB_NCCL(g_nccl.Recv(rR, XE_MSG, ncclFloat64, right, (ncclComm_t)ctx->nccl_comm, st));
+            }
+            MB_NCCL(g_nccl.GroupEnd());
+            k_xch_edge_unpack<<<8, 256, 0, st>>>(pv->cur, d_nt, pv->cap, rL, rR, hasL ? 1 : 0, hasR ? 1 : 0, ctx->d_flags);
+            MB_LAUNCH_CHECK(ctx);
+            k_xch_edge_commit<<<1, 1, 0, st>>>(d_nt, pv->cap, rL, rR, hasL ? 1 : 0, hasR ? 1 : 0, pv->d_n_arr);
+            MB_LAUNCH_CHECK(ctx);
+            pv->n_arrivals += 2 * XE_CAP;  // upper bound; the exact number stays on the device
+        }
+        pv->drop_oob = 2;
+        pia->h_valid = false;
+        pia->n_bound[s] = pv->cap;
+        return MB_OK;
+    }
     const int64_t nb_part = pia->n_bound[s] > 0 ? pia->n_bound[s] : pv->cap;
     const int64_t nblocks = (nb_part + XT - 1) / XT;
     int32_t* cnt = (int32_t*)ctx_scratch(ctx, 4, (size_t)(2 * nblocks) * 4);
@@ -250,7 +369,6 @@ int mb_exchange_slab(mb_ctx* ctx, const mb_grid1d* slab, mb_pv* pv, mb_pia* pia,
     int64_t* offL = p64;
     int64_t* offR = p64 + (nblocks + 1);
     int64_t* partial = p64 + 2 * (nblocks + 1);
-    int64_t* d_nt = pia->d_n_total + s;
     k_xch_count<<<(int)nblocks, XB, 0, st>>>(pv->cur.a[F_X], d_nt, slab->inv_dx, slab->cell_offset, slab->n_cells, cnt, cnt + nblocks);
     MB_LAUNCH_CHECK(ctx);
     int r = device_exclusive_scan(ctx, cnt, nblocks, offL, partial);
@@ -260,8 +378,6 @@ int mb_exchange_slab(mb_ctx* ctx, const mb_grid1d* slab, mb_pv* pv, mb_pia* pia,
     k_xch_pack<<<(int)nblocks, XB, 0, st>>>(pv->cur, d_nt, slab->inv_dx, slab->cell_offset, slab->n_cells, offL, offR, (double*)ctx->xch_send[0],
                                             (double*)ctx->xch_send[1], (int64_t)ctx->xch_cap, nblocks, ctx->d_xch_counts, ctx->d_flags);
     MB_LAUNCH_CHECK(ctx);
-    const int left = ctx->rank - 1, right = ctx->rank + 1;
-    const bool hasL = ctx->nranks > 1 && left >= 0, hasR = ctx->nranks > 1 && right < ctx->nranks;
     // counts: send [nL, nR] to the neighbours, receive theirs
     MB_CUDA(cudaMemsetAsync(ctx->d_xch_counts + 2, 0, 2 * 8, st));
     if (hasL || hasR) {
@@ -306,9 +422,11 @@ int mb_exchange_slab(mb_ctx* ctx, const mb_grid1d* slab, mb_pv* pv, mb_pia* pia,
         MB_LAUNCH_CHECK(ctx);
         k_xch_add_total<<<1, 1, 0, st>>>(d_nt, pv->cap, rL + rR);
         MB_LAUNCH_CHECK(ctx);
+        k_add_i64<<<1, 1, 0, st>>>(pv->d_n_arr, rL + rR);
+        MB_LAUNCH_CHECK(ctx);
     }
     // the layout of the own particles is untouched: the next sort drops the leavers and merges the arrivals (band path if sorted)
-    pv->drop_oob = (sL + sR) > 0 || pv->drop_oob;
+    if (sL + sR > 0 && pv->drop_oob == 0) pv->drop_oob = 1;
     pv->n_arrivals += rL + rR;
     pia->h_valid = false;
     pia->n_bound[s] = pv->cap;

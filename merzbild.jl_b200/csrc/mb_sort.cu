@@ -84,6 +84,9 @@ __global__ void __launch_bounds__(256) k_band_classify(const double* __restrict_
             const int64_t dd = (int64_t)nc - c + w;
             const bool inband = inside && dd >= 0 && dd < W;
             if (valid && !inband && !(drop && !inside)) bad = true;
+            // edge exchange: a leaver from a cell further than w from that slab face was never sent
+            if (valid && !inside && drop == 2 && ((nc < 0 && c >= w) || (nc >= n_cells && c < n_cells - w)))
+                atomicOr(&flags[0], DEVERR_BAND_OVERFLOW);
 #pragma unroll
             for (int d = 0; d < W; d++) cnt[d] += __popc(__ballot_sync(0xffffffffu, valid && inband && dd == d));
         }
@@ -112,8 +115,9 @@ __global__ void __launch_bounds__(256) k_band_classify(const double* __restrict_
 }
 
 // arrivals of the slab exchange (appended after the old layout): key + per-cell arrival count
-static __global__ void k_band_arrivals(const double* __restrict__ X, const int64_t* n_total_p, int64_t n_arr, int64_t n_cells, double inv_dx,
+static __global__ void k_band_arrivals(const double* __restrict__ X, const int64_t* n_total_p, const int64_t* n_arr_p, int64_t n_cells, double inv_dx,
                                        int64_t cell_offset, int32_t* cell_out, int32_t* __restrict__ key_arr, int32_t* __restrict__ acnt, int* flags) {
+    const int64_t n_arr = *n_arr_p;
     const int64_t base = *n_total_p - n_arr;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_arr; t += (int64_t)gridDim.x * blockDim.x) {
         const int nc = cell_of(X[base + t], inv_dx, cell_offset);
@@ -250,7 +254,7 @@ template <int W>
 __global__ void __launch_bounds__(256) k_band_gather(SoA in_, SoA out_, const uint16_t* __restrict__ lperm, const int32_t* __restrict__ M,
                                                      const int64_t* __restrict__ seg_lo, const int32_t* __restrict__ seg_n,
                                                      const int64_t* __restrict__ start, int64_t n_cells, const int32_t* __restrict__ acnt,
-                                                     const int32_t* __restrict__ key_arr, int64_t n_arr, const int64_t* n_old_p,
+                                                     const int32_t* __restrict__ key_arr, const int64_t* n_arr_p, const int64_t* n_old_p,
                                                      double* __restrict__ pcache, const int* flags) {
     if (flags[2] != 0) return;  // general path takes over
     constexpr int w = W / 2;
@@ -312,6 +316,7 @@ __global__ void __launch_bounds__(256) k_band_gather(SoA in_, SoA out_, const ui
             dst += cnt;
         }
         if (acnt != nullptr && acnt[c] > 0) {
+            const int64_t n_arr = *n_arr_p;
             const int64_t abase = *n_old_p - n_arr;
             for (int64_t b = 0; b < n_arr; b += 32) {
                 const bool hit = b + lane < n_arr && key_arr[b + lane] == (int32_t)c;
@@ -356,7 +361,6 @@ __global__ void __launch_bounds__(256) k_band_gather(SoA in_, SoA out_, const ui
 // Device flags: F_OUTSIDE = a particle left the slab (legal only if a slab exchange follows), F_CLS_BAD = band overflow
 // (the sort takes the general path), F_FAR = a particle left the slab from a cell further than w from that edge,
 // F_CLS_REDO = a cell could not be classified here (bigger than the staging area): the sort runs k_band_classify after all.
-enum { F_OUTSIDE = 12, F_CLS_BAD = 13, F_FAR = 14, F_CLS_REDO = 15 };
 #ifndef MB_CB_MINB
 #define MB_CB_MINB 2  // resident CTAs per SM the fused kernel is compiled for (register budget)
 #endif
@@ -637,7 +641,8 @@ struct BandBufs {
     uint16_t* lperm;
     int32_t* acnt;     // nullable (no arrivals)
     int32_t* key_arr;
-    int64_t n_arr;
+    int64_t n_arr;     // host upper bound
+    const int64_t* d_n_arr;  // device: exact
     int64_t* n_old;    // device copy of n_total before the sort
     double* pcache;    // nullable
     int drop;
@@ -672,6 +677,7 @@ static int sort_scratch_layout(mb_ctx* ctx, int64_t cap, int64_t nc, int W, Sort
     B.seg_lo = B.n_old + 2;
     B.lperm = (uint16_t*)S.key;
     B.n_arr = 0;
+    B.d_n_arr = nullptr;
     B.drop = 0;
     B.pcache = nullptr;
     B.d_nt_write = nullptr;
@@ -734,7 +740,7 @@ static int launch_band(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pi
         MB_LAUNCH_CHECK(ctx);
         if (B.n_arr > 0) {
             MB_CUDA(cudaMemsetAsync(B.acnt, 0, (size_t)nc * 4, st));
-            k_band_arrivals<<<grid_for(B.n_arr, 256), 256, 0, st>>>(pv->cur.a[F_X], B.n_old, B.n_arr, nc, grid->inv_dx, grid->cell_offset, pv->cell,
+            k_band_arrivals<<<grid_for(B.n_arr, 256), 256, 0, st>>>(pv->cur.a[F_X], B.n_old, B.d_n_arr, nc, grid->inv_dx, grid->cell_offset, pv->cell,
                                                                   B.key_arr, B.acnt, S.flags);
             MB_LAUNCH_CHECK(ctx);
         }
@@ -751,7 +757,7 @@ static int launch_band(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pi
     {
         ProfScope ps(ctx, PROF_SORT_SCATTER);
         k_band_gather<W><<<wgrid, 256, 0, st>>>(pv->cur, pv->alt, B.lperm, S.M, B.seg_lo, B.seg_n, S.start, nc, B.n_arr > 0 ? B.acnt : nullptr,
-                                               B.key_arr, B.n_arr, B.n_old, B.pcache, S.flags);
+                                               B.key_arr, B.d_n_arr, B.n_old, B.pcache, S.flags);
         MB_LAUNCH_CHECK(ctx);
     }
     return MB_OK;
@@ -792,7 +798,7 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
     const int64_t nc = pia->n_cells, cap = pv->cap;
     const int w = ctx->band_w;
     const int W = 2 * w + 1;
-    const bool drop = pv->drop_oob;
+    const int drop = pv->drop_oob;
     const int64_t n_arr = pv->n_arrivals;
     const bool use_x = grid != nullptr;
     // band path: sorted layout; slab-exchange arrivals are merged in as long as they are few (each receiving cell scans the list)
@@ -803,7 +809,8 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
     BandBufs B;
     if (sort_scratch_layout(ctx, cap, nc, W, S, B)) return MB_ERR_CUDA;
     B.n_arr = n_arr;
-    B.drop = drop ? 1 : 0;
+    B.d_n_arr = pv->d_n_arr;
+    B.drop = drop;
     cudaStream_t st = ctx->stream;
     Indexer* ix = pia->d_indexer + (species - 1) * nc;
     int64_t* d_nt = pia->d_n_total + (species - 1);
@@ -855,7 +862,12 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
     SoA t = pv->cur;
     pv->cur = pv->alt;
     pv->alt = t;
-    if (rewrite_total) { pv->drop_oob = false; pv->n_arrivals = 0; pia->h_valid = false; }
+    if (rewrite_total) {
+        pv->drop_oob = 0;
+        pv->n_arrivals = 0;
+        pia->h_valid = false;
+        MB_CUDA(cudaMemsetAsync(pv->d_n_arr, 0, sizeof(int64_t), st));
+    }
     // the cached moments are valid only if the band path ran (device flag 2 == 0): the props kernel checks the flag itself
     ctx->state_gen++;
     ctx->cls_gen = 0;

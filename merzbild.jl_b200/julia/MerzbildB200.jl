@@ -523,6 +523,8 @@ function comm_unique_id()
 end
 comm_init!(ctx::Context, id::Vector{UInt8}, rank::Integer, nranks::Integer) =
     check(ccall((:mb_comm_init, libmb), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint), ctx.h, id, rank, nranks))
+"0: edge exchange when the layout allows it (no host synchronisation), 1: always the full exchange; same on all ranks"
+exchange_set_mode!(ctx::Context, mode::Integer) = check(ccall((:mb_exchange_set_mode, libmb), Cint, (Ptr{Cvoid}, Int32), ctx.h, mode))
 """
     exchange_particles!(ctx, slab, pv, pia, species; counts=false)
 

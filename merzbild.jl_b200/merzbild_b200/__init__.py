@@ -123,6 +123,7 @@ SIGNATURES = {
     "mb_merge_octree_N2": (_int, [_vp, C.POINTER(OctreeParams), _vp, _vp, _i64, _i64, _i64, _i64, _i64, C.POINTER(Grid1D), _u32, _u32]),
     "mb_comm_unique_id": (_int, [_vp]),
     "mb_comm_init": (_int, [_vp, _vp, _int, _int]),
+    "mb_exchange_set_mode": (_int, [_vp, _i32]),
     "mb_exchange_slab": (_int, [_vp, C.POINTER(Grid1D), _vp, _vp, _i64, _vp, _vp]),
 }
 
@@ -588,6 +589,11 @@ def comm_unique_id():
 def comm_init(ctx, unique_id, rank, nranks):
     buf = C.create_string_buffer(unique_id, 128)
     _ck(lib().mb_comm_init(ctx.h, buf, int(rank), int(nranks)))
+
+
+def exchange_set_mode(ctx, mode):
+    """0: edge exchange when the layout allows it (no host synchronisation), 1: always the full exchange."""
+    _ck(lib().mb_exchange_set_mode(ctx.h, int(mode)))
 
 
 def exchange_slab(ctx, slab, pv, pia, species=1, counts=False):

