@@ -1,0 +1,270 @@
+"""Known-answer tests that pin the CPU oracle (part 2): the deterministic vectors of the reference's own tests for indexing,
+squash_pia!, restore_particle_ordering!, octree N:2 merging, the 1-factorisation and the chunk exchange -- restated from
+test/test_indexing.jl, test_pia_contiguous.jl, test_particle_index_sorting.jl, test_octree_merging.jl,
+test_octree_merging_1D.jl, test_1_factorization.jl, test_particle_exchange.jl (file:line in each test).  No GPU."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _rows(n, fn):
+    return np.array([fn(i) for i in range(1, n + 1)], dtype=np.float64)
+
+
+# ------------------------------------------------------------------------------------------------ golden data files
+def test_oracle_constants_match_the_reference_data_files(oracle):
+    """data/particles.toml, data/vhs.toml, data/pseudo_maxwell.toml as captured in tests/golden/reference_vectors.json."""
+    g = json.load(open(os.path.join(GOLDEN, "reference_vectors.json")))
+    assert oracle.MASS["Ar"] == g["particles_toml"]["Ar"]["mass"] and oracle.MASS["He"] == g["particles_toml"]["He"]["mass"]
+    for table, key in ((oracle.VHS, "vhs_toml"), (oracle.PSEUDO_MAXWELL, "pseudo_maxwell_toml")):
+        for (a, b), (d, o, Tref) in table.items():
+            e = g[key].get(f"{a},{b}") or g[key][f"{b},{a}"]
+            assert (d, o, Tref) == (e["vhs_d"], e["vhs_o"], e["vhs_Tref"]), (key, a, b)
+
+
+# ------------------------------------------------------------------------------------------------ indexing
+def test_indexing_new_particles_and_map_cont_index(oracle):
+    """test/test_indexing.jl:1-95"""
+    L = oracle.lib()
+    pia = oracle.OPIA(1, 1)
+    pia.set_single_cell(1, 1, 20)  # ParticleIndexerArray(20)
+    assert tuple(pia.indexer[0, 0]) == (20, 1, 20, 20, 0, -1, 0) and pia.n_total[0] == 20
+    L.mbo_update_particle_indexer_new_particle(pia.h, 1, 1)
+    L.mbo_update_particle_indexer_new_particle(pia.h, 1, 1)
+    assert tuple(pia.indexer[0, 0]) == (22, 1, 20, 20, 21, 22, 2) and pia.n_total[0] == 22
+
+    pia.set_single_cell(1, 1, 10)
+    pia.n_total[0] += 5
+    pia.indexer[0, 0] = (15, 1, 10, 10, 31, 35, 5)
+    for i0 in (1, 4, 10):
+        assert L.mbo_map_cont_index(pia.h, 1, 1, i0 - 1) == 1 + i0 - 1
+    for i0 in (11, 12, 15):
+        assert L.mbo_map_cont_index(pia.h, 1, 1, i0 - 1) == 31 + i0 - 10 - 1
+    pia.n_total[0] = 10
+    pia.indexer[0, 0] = (10, 24, 28, 5, 31, 35, 5)
+    for i0 in (1, 4, 5):
+        assert L.mbo_map_cont_index(pia.h, 1, 1, i0 - 1) == 24 + i0 - 1
+    for i0 in (6, 8, 10):
+        assert L.mbo_map_cont_index(pia.h, 1, 1, i0 - 1) == 31 + i0 - 5 - 1
+    L.mbo_update_particle_indexer_new_lower_count(pia.h, 1, 1, 8)
+    assert tuple(pia.indexer[0, 0]) == (8, 24, 28, 5, 31, 33, 3) and pia.n_total[0] == 8
+    L.mbo_update_particle_indexer_new_lower_count(pia.h, 1, 1, 5)
+    assert tuple(pia.indexer[0, 0]) == (5, 24, 28, 5, 0, -1, 0) and pia.n_total[0] == 5
+    pia.n_total[0] = 10
+    pia.indexer[0, 0] = (10, 24, 28, 5, 31, 35, 5)
+    L.mbo_update_particle_indexer_new_lower_count(pia.h, 1, 1, 2)
+    assert tuple(pia.indexer[0, 0]) == (2, 24, 25, 2, 0, -1, 0) and pia.n_total[0] == 2
+
+
+# ------------------------------------------------------------------------------------------------ squash_pia!
+def test_squash_pia_one_cell(oracle):
+    """test/test_pia_contiguous.jl:9-60 (one group) and :63-110 (two groups): delete at the end, squash, density 55 -> 45."""
+    L = oracle.lib()
+    m = oracle.MASS["Ar"]
+    for two_groups in (False, True):
+        pv, pia = oracle.OPV(10), oracle.OPIA(1, 1)
+        pv.particles[:10] = _rows(10, lambda i: [i, 0, 0, 0, 10.0, 0.0, 1.0])
+        pv.nbuffer = 0
+        pia.indexer[0, 0] = (10, 1, 5, 5, 6, 10, 5) if two_groups else (10, 1, 10, 10, -1, -1, 0)
+        pia.n_total[0] = 10
+        p = oracle.compute_props([pv], pia, [m])
+        assert p.np[0, 0] == 10 and abs(p.n[0, 0] - 55.0) / 55.0 < 1e-15
+        pv.cell[:10] = np.arange(11, 21)
+        L.mbo_delete_particle_end_group1(pv.h, pia.h, 1, 1)
+        pia.contiguous[0] = 0
+        assert pv.nbuffer == 1
+        freed = int(pv.buffer[0])
+        oracle.squash_pia(pv, pia, 1)
+        assert pia.contiguous[0] == 1
+        if two_groups:
+            assert tuple(pia.indexer[0, 0][[1, 2, 3, 4, 5, 6]]) == (1, 4, 4, 5, 9, 5)
+            assert list(pv.cell[:9]) == [11, 12, 13, 14, 16, 17, 18, 19, 20]
+            expect_n = 55.0 - 5.0
+        else:
+            assert pia.indexer[0, 0][3] == 9 and pia.indexer[0, 0][2] == 9 and pia.indexer[0, 0][6] == 0
+            assert list(pv.cell[:9]) == [11, 12, 13, 14, 15, 16, 17, 18, 19]
+            expect_n = 45.0
+        p = oracle.compute_props([pv], pia, [m])
+        assert p.np[0, 0] == 9 and abs(p.n[0, 0] - expect_n) / expect_n < 1e-15
+        assert freed not in list(pv.index[:9])
+
+
+# ------------------------------------------------------------------------------------------------ restore_particle_ordering!
+@pytest.mark.parametrize("index,buffer,n_used", [
+    ([1, 2, 3, 4, 5, 6, 7, 8, 9, 10], [10, 9, 8, 7, 6, 5, 4, 3, 2, 1], 10),
+    ([5, 1, 7, 3, 2, 4, 10, 8, 6, 9], [7, 3, 2, 4, 10, 8, 6, 9, 5, 1], 2),
+    ([10, 9, 5, 6, 1, 8, 3, 7, 2, 4], [4, 7, 2, 10, 9, 5, 6, 1, 8, 3], 7),
+])
+def test_restore_particle_ordering(oracle, index, buffer, n_used):
+    """test/test_particle_index_sorting.jl:9-100: payloads are permuted so that index == 1:n, the buffer becomes descending."""
+    pv = oracle.OPV(10)
+    assert list(pv.index) == list(range(1, 11)) and list(pv.buffer) == list(range(10, 0, -1)) and pv.nbuffer == 10
+    pv.index[:] = index
+    rows = np.zeros((10, 7))
+    rows[:n_used] = _rows(n_used, lambda i: [i, i, 2 * i, 3 * i, -i, -4 * i, -5 * i])
+    pv.set_logical(1, rows)
+    pv.buffer[:] = buffer
+    nb = 10 if n_used == 10 else 10 - n_used
+    pv.nbuffer = nb
+    oracle.restore_particle_ordering(pv)
+    assert list(pv.index) == list(range(1, 11))
+    assert list(pv.buffer[:nb]) == list(range(10, 10 - nb, -1))
+    assert pv.nbuffer == nb
+    np.testing.assert_array_equal(pv.logical(1, n_used), rows[:n_used])
+    np.testing.assert_array_equal(pv.particles[:n_used], rows[:n_used])  # physically in order now
+
+
+# ------------------------------------------------------------------------------------------------ octree N:2 merging
+SIGNS = [(-1, -1, -1), (1, -1, -1), (-1, 1, -1), (1, 1, -1), (-1, -1, 1), (1, -1, 1), (-1, 1, 1), (1, 1, 1)]
+
+
+def _octant_24(weights=(1.0,) * 8):
+    """create_24_3particles_in_octant (test/test_octree_merging.jl:26-44)"""
+    rows = []
+    for o in range(1, 9):
+        for dv in (-0.5, 0.5, 0.0):
+            v = np.array(SIGNS[o - 1], dtype=float) * (9.0 - o + dv)
+            rows.append([o * weights[o - 1], *v, 1.0, -10.0, 3.0])
+    return np.array(rows)
+
+
+def _state(oracle, rows):
+    n = rows.shape[0]
+    pv, pia = oracle.OPV(n), oracle.OPIA(1, 1)
+    for i, r in enumerate(rows):
+        pv.add_particle(i + 1, r[0], r[1:4], r[4:7])
+    pia.set_single_cell(1, 1, n)
+    return pv, pia
+
+
+def test_octree_24_particles_bins_and_merge(oracle):
+    """test/test_octree_merging.jl:66-163: split at v0 = 0 gives 8 bins of 3 particles with w = 3 i, means (9 - i) * sign, x means
+    (1, -10, 3); merging to 16 keeps 8 bins of depth 1, merging to 2 gives one bin, two particles of weight total / 2; n, v, T
+    conserved to 1e-14."""
+    m = oracle.MASS["Ar"]
+    rows = _octant_24()
+    pv, pia = _state(oracle, rows)
+    oc = oracle.Octree(oracle.MID_SPLIT, oracle.INIT_C)
+    oc.init(pv, pia, 1, 1)
+    oc.split_bin(1, pv)
+    assert oc.Nbins == 8
+    for i in range(1, 9):
+        b = oc.bin(i)
+        assert b["np"] == 3 and b["w"] == 3 * i
+        oc.compute_bin_props(i, pv)
+        f = oc.full_bin(i)
+        np.testing.assert_allclose(f["v_mean"], (9.0 - i) * np.array(SIGNS[i - 1]), atol=1e-14)
+        np.testing.assert_allclose(f["x_mean"], [1.0, -10.0, 3.0], atol=1e-14)
+    total_w = sum(3 * i for i in range(1, 9))
+    p0 = oracle.compute_props([pv], pia, [m], Tref=1.0)
+    assert p0.n[0, 0] == total_w
+
+    oc2 = oracle.Octree(oracle.MID_SPLIT, oracle.INIT_C)
+    rng = oracle.Rng.seq(1234)
+    oracle.merge_octree_N2(rng, oc2, pv, pia, 1, 1, 1, 16)
+    assert oc2.Nbins == 8 and pia.n_total[0] == 16 == pia.indexer[0, 0, 0]
+    assert all(oc2.bin(i)["depth"] == 1 for i in range(1, 9))
+    p = oracle.compute_props([pv], pia, [m], Tref=1.0)
+    assert p.np[0, 0] == 16 and abs(p.n[0, 0] - p0.n[0, 0]) < np.finfo(float).eps
+    assert abs(p.T[0, 0] - p0.T[0, 0]) < 1e-14
+    np.testing.assert_allclose(p.v[0, 0], p0.v[0, 0], atol=1e-14)
+
+    oracle.merge_octree_N2(rng, oc2, pv, pia, 1, 1, 1, 2)
+    assert oc2.Nbins == 1 and pia.n_total[0] == 2 and oc2.bin(1)["depth"] == 0
+    p = oracle.compute_props([pv], pia, [m], Tref=1.0)
+    two = pv.logical(1, 2)
+    assert two[0, 0] == 0.5 * total_w == two[1, 0]
+    assert abs(p.n[0, 0] - p0.n[0, 0]) < np.finfo(float).eps and abs(p.T[0, 0] - p0.T[0, 0]) < 1e-14
+    np.testing.assert_allclose(p.v[0, 0], p0.v[0, 0], atol=1e-14)
+
+
+def test_octree_merge_1d_clamps_positions(oracle):
+    """test/test_octree_merging_1D.jl: with a grid the merged particles' x1 is clamped to [min_x, max_x] and the pia of the merged
+    cell shrinks while the species becomes non-contiguous."""
+    rows = _octant_24()
+    rows[:, 4] = np.linspace(1e-9, 4.9e-4, 24)  # spread over the domain so mean +- sigma would leave it
+    pv, pia = oracle.OPV(48), oracle.OPIA(2, 1)
+    for i, r in enumerate(np.concatenate([rows, rows])):
+        pv.add_particle(i + 1, r[0], r[1:4], r[4:7])
+    pia.indexer[0, 0] = (24, 1, 24, 24, 0, -1, 0)
+    pia.indexer[0, 1] = (24, 25, 48, 24, 0, -1, 0)
+    pia.n_total[0] = 48
+    oc = oracle.Octree(oracle.MID_SPLIT, oracle.INIT_C)
+    Lg, nx = 5e-4, 2
+    oracle.merge_octree_N2(oracle.Rng.seq(3), oc, pv, pia, 1, 1, 1, 2, grid=(Lg, nx))
+    assert tuple(pia.indexer[0, 0][:4]) == (2, 1, 2, 2) and tuple(pia.indexer[0, 1][:4]) == (24, 25, 48, 24)
+    assert pia.contiguous[0] == 0 and pia.n_total[0] == 26
+    g = oracle.grid_params(Lg, nx)
+    x = pv.logical(1, 2)[:, 4]
+    assert np.all(x >= g["min_x"]) and np.all(x <= g["max_x"])
+    oracle.squash_pia(pv, pia, 1)
+    assert tuple(pia.indexer[0, 1][:4]) == (24, 3, 26, 24) and pia.contiguous[0] == 1
+
+
+# ------------------------------------------------------------------------------------------------ parallel.jl
+@pytest.mark.parametrize("n", [2, 4, 8, 16, 32, 5, 20, 31])
+def test_1_factorization(oracle, n):
+    """test/test_1_factorization.jl: every pair exactly once, nobody twice in a round, the first rounds are full."""
+    fac = oracle.generate_1_factorization(n)
+    if n == 2:
+        assert len(fac) == 1 and len(fac[0]) == 1 and set(fac[0][0]) == {1, 2}
+        return
+    if n in (4, 8, 16, 32):  # the reference asserts the optimal round count only for these (test_1_factorization.jl:9-13)
+        assert len(fac) == n - 1
+    assert len(fac[0]) == n // 2 and len(fac[1]) == n // 2
+    seen = set()
+    for rnd in fac:
+        used = [x for tp in rnd for x in tp]
+        assert len(used) == len(set(used))
+        for a, b in rnd:
+            assert a != b
+            seen.add(frozenset((a, b)))
+    assert len(seen) == n * (n - 1) // 2
+
+
+def test_chunk_exchange_moves_particles_to_their_owner(oracle):
+    """test/test_particle_exchange.jl + test_particle_resort_after_exchange.jl in miniature: two chunks of a 4-cell grid; after
+    convection-like displacement some particles sit in the other chunk's cells; exchange_particles! + sort_particles_after_exchange!
+    leave every chunk with exactly the particles of its own cells, sorted by cell, nobody lost."""
+    Lg, nx = 4.0, 4
+    chunks = oracle.chunks(nx, 2)
+    assert chunks == [(1, 2), (3, 4)]
+    rng = np.random.default_rng(5)
+    pvs, pias = [], []
+    allrows = []
+    for ci, (lo, hi) in enumerate(chunks):
+        n = 30
+        rows = np.zeros((n, 7))
+        rows[:, 0] = 100 * (ci + 1) + np.arange(n)  # unique ids
+        rows[:, 4] = rng.uniform(lo - 1, hi, n)
+        rows[::5, 4] = rng.uniform(0, Lg, len(rows[::5]))  # some wander into the other chunk
+        pv, pia = oracle.OPV(4 * n), oracle.OPIA(nx, 1)
+        for i, r in enumerate(rows):
+            pv.add_particle(i + 1, r[0], r[1:4], r[4:7])
+        pia.indexer[0, lo - 1] = (n, 1, n, n, 0, -1, 0)
+        pia.n_total[0] = n
+        oracle.sort_particles(pv, pia, 1, grid=(Lg, nx))
+        pvs.append(pv)
+        pias.append(pia)
+        allrows.append(rows)
+    ex = oracle.Exchanger(chunks, nx)
+    ex.reset(1)
+    ex.reset(2)
+    ex.exchange(pvs, pias, 1)
+    got = []
+    for ci, (lo, hi) in enumerate(chunks):
+        ex.sort_after_exchange(pvs[ci], pias[ci], ci + 1, 1)
+        nt = int(pias[ci].n_total[0])
+        rows = pvs[ci].logical(1, nt)
+        cells = np.floor(rows[:, 4] / (Lg / nx)).astype(int) + 1
+        assert np.all((cells >= lo) & (cells <= hi)), (ci, cells)
+        assert np.all(np.diff(cells) >= 0)
+        ok, where = pias[ci].check(1)
+        assert ok, where
+        got.append(rows)
+    ids = np.sort(np.concatenate(got)[:, 0])
+    np.testing.assert_array_equal(ids, np.sort(np.concatenate(allrows)[:, 0]))
