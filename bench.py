@@ -28,7 +28,7 @@ for p in (ROOT, os.path.join(ROOT, "merzbild.jl_b200")):
 AR = 66.3e-27
 K_B = 1.380649e-23
 DX, PPC, NDENS, DT, T_WALL, V_WALL = 1e-5, 1000, 5e22, 2.59e-9, 300.0, 500.0
-BYTES_SCATTER = 116  # sort -- stable scatter (cell id 4 + record 56 read, record 56 write)
+BYTES_SCATTER = 116  # sort -- stable scatter (key 4 + record 56 read, record 56 write)
 BYTES_STEP = 220     # full Couette step (convect + sort + collide + props)
 
 
@@ -308,12 +308,12 @@ def main():
     # particle count it was captured at
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_band_gather"]
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_band_scatter"]
         if sort_path == 1 and abs(tr["particles"] - n_now) <= 0.01 * n_now:
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
     except (OSError, ValueError, KeyError):
         pass
-    roofline = {"bound": "hbm", "kernel": "k_band_gather (sort_particles! stable gather/scatter pass)" if sort_path == 1 else "general sort path",
+    roofline = {"bound": "hbm", "kernel": "k_band_scatter (sort_particles! pass B: stable scatter by source cell)" if sort_path == 1 else "general sort path",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "algorithmic_bytes": BYTES_SCATTER * n_now,
                 "peak_source": peak_src, "algorithmic_bytes_per_particle": BYTES_SCATTER,

@@ -1,0 +1,139 @@
+#!/usr/bin/env python
+"""bench_ops.py -- per-operator device timings of the hot path at BASELINE.json's single-GPU shapes (C2 / C4 / C5), next to the
+algorithmic bytes of SURVEY.md 8(d).  Not the driver's bench (that is bench.py, config C3); prints one JSON line per operator.
+
+    python bench_ops.py [--particles 1e8] [--reps 5]
+"""
+import argparse
+import json
+import math
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "merzbild.jl_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+import numpy as np
+
+import merzbild_b200 as mb
+
+AR, K_B, DX, NDENS, DT = 66.3e-27, 1.380649e-23, 1e-5, 5e22, 2.59e-9
+
+
+def population(n_cells, ppc, seed, vw=False):
+    rng = np.random.default_rng(seed)
+    n = n_cells * ppc
+    sig = math.sqrt(K_B * 300.0 / AR)
+    a = [np.empty(n) for _ in range(7)]
+    a[0][:] = DX * NDENS / ppc
+    if vw:
+        a[0] *= rng.uniform(0.5, 1.5, n)
+    for f in (1, 2, 3):
+        a[f][:] = rng.standard_normal(n) * sig
+    a[4][:] = (np.repeat(np.arange(n_cells, dtype=np.float64), ppc) + rng.uniform(0.001, 0.999, n)) * DX
+    a[5][:] = 0.5
+    a[6][:] = 0.5
+    ix = np.zeros((1, n_cells, 7), dtype=np.int64)
+    c = np.arange(n_cells, dtype=np.int64)
+    ix[0, :, 0] = ppc
+    ix[0, :, 1] = c * ppc + 1
+    ix[0, :, 2] = (c + 1) * ppc
+    ix[0, :, 3] = ppc
+    ix[0, :, 5] = -1
+    return a, ix, n
+
+
+def timed(ctx, fn, reps, setup=None):
+    ts = []
+    for _ in range(reps):
+        if setup:
+            setup()
+        ctx.sync()
+        ctx.timer_start()
+        fn()
+        ts.append(ctx.timer_stop())
+    return min(ts), sorted(ts)[len(ts) // 2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--particles", type=float, default=1e8)
+    ap.add_argument("--reps", type=int, default=5)
+    args = ap.parse_args()
+    peak = 6533.8
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except (OSError, ValueError, KeyError):
+        pass
+    ctx = mb.Context(0, 1234)
+    it = mb.make_interaction(AR, AR, 4.11e-10, 0.81, 273.0)
+
+    def report(name, cfg, n, ms, bytes_per_particle, note=""):
+        gbs = bytes_per_particle * n / (ms * 1e-3) / 1e9
+        print(json.dumps({"op": name, "config": cfg, "particles": n, "ms": ms, "particles_per_s": n / (ms * 1e-3),
+                          "algorithmic_bytes_per_particle": bytes_per_particle, "achieved_GBps": gbs, "frac_of_measured_hbm_peak": gbs / peak, "note": note}),
+              flush=True)
+
+    # ---- C5: fp_linear!, 1e6 cells x 100
+    ppc = 100
+    nc = int(args.particles // ppc)
+    a, ix, n = population(nc, ppc, 1)
+    pv, pia = mb.ParticleVector(n, ctx), mb.ParticleIndexerArray(nc, 1, ctx)
+    pv.upload_soa(1, n, a)
+    pia.upload(ix, np.array([n]), np.array([1], dtype=np.uint8))
+    step = [0]
+
+    def fp():
+        step[0] += 1
+        mb.fp_linear(mb.PhiloxRng(step[0]), None, it, AR, pv, pia, (1, nc), 1, DT, DX)
+
+    fp()
+    best, med = timed(ctx, fp, args.reps)
+    report("fp_linear", "C5: %d cells x %d" % (nc, ppc), n, med, 56, "read w,v 32 B + write v 24 B; 3 normals per particle regenerated from Philox counters")
+
+    # ---- props stand-alone on the same population (two-pass, 32 B/particle)
+    pp = mb.PhysProps(nc, 1, ctx=ctx)
+    best, med = timed(ctx, lambda: mb.compute_props_sorted([pv], pia, [AR], pp), args.reps)
+    report("compute_props_sorted (uncached)", "C5 population", n, med, 32, "two-pass; the second pass re-reads the cell from L1/L2")
+    best, med = timed(ctx, lambda: mb.compute_props([pv], pia, [AR], pp), args.reps)
+    report("compute_props", "C5 population", n, med, 32, "both pia groups")
+    pv.close()
+    pia.close()
+    del a
+
+    # ---- C2 / C4: variable-weight ntc! + octree merge (150 -> 100) + squash, cells of 150
+    ppc = 150
+    nc = int(args.particles * 0.6 // ppc)
+    a, ix, n = population(nc, ppc, 2, vw=True)
+    cap = int(n * 1.3)
+    pv, pia = mb.ParticleVector(cap, ctx), mb.ParticleIndexerArray(nc, 1, ctx)
+    grid = mb.Grid1DUniform(nc * DX, nc)
+    cf = mb.CollisionFactors(nc, mb.estimate_sigma_g_w_max(it, AR, AR, 300.0, 300.0, DX * NDENS / ppc * 1.5), ctx)
+    oc = mb.OctreeN2Merge(mb.OctreeN2Merge.OctreeBinMidSplit, mb.OctreeN2Merge.OctreeInitBinMinMaxVel, max_Nbins=6000)
+
+    def reset():
+        pv.upload_soa(1, n, a)
+        pia.upload(ix, np.array([n]), np.array([1], dtype=np.uint8))
+
+    reset()
+    best, med = timed(ctx, lambda: mb.merge_octree_N2_based(mb.PhiloxRng(1), oc, pv, pia, (1, nc), 1, 100, grid, threshold=130), max(args.reps // 2, 2), setup=reset)
+    report("merge_octree_N2_based (150 -> 100)", "C4: %d cells x %d" % (nc, ppc), n, med, 56 * (150 + 100) / 150.0, "56 (N + N_target) / N bytes per particle of a merged cell")
+    best, med = timed(ctx, lambda: mb.squash_pia(pv, pia, 1), 1)
+    n1 = int(pia.n_total[0])
+    report("squash_pia", "after the merge: %d particles" % n1, n1, best, 112, "payload moves (index indirection is the identity on the device)")
+    best, med = timed(ctx, lambda: mb.sort_particles(None, grid, pv, pia, 1), 1)
+    report("sort_particles (general path)", "after squash", n1, best, 128, "first sort after a merge: general path")
+    step = [0]
+
+    def vw_ntc():
+        step[0] += 1
+        mb.ntc(mb.PhiloxRng(step[0]), cf, None, it, pv, pia, (1, nc), 1, DT * 4, DX)
+
+    best, med = timed(ctx, vw_ntc, 1)
+    report("ntc! variable weight (splits)", "C4 population after merge, dt x 4", n1, best, 64, "candidates only: ~%d new particles" % (int(pia.n_total[0]) - n1))
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
