@@ -202,6 +202,27 @@ int mb_compute_props_sorted(mb_ctx* ctx, mb_pv* const* pvs, mb_pia* pia, const d
 int mb_merge_octree_N2(mb_ctx* ctx, const mb_octree_params* oc, mb_pv* pv, mb_pia* pia, int64_t cell_lo, int64_t cell_hi, int64_t species,
                        int64_t threshold, int64_t target_np, const mb_grid1d* grid, uint32_t timestep, uint32_t substream);
 
+/* ---- initial conditions on the device: 1e8-1e9 particles are not sampled on the host and copied ----
+ * sample_particles_equal_weight!(rng, particles, pia, cell, species, nparticles, m, T, Fnum, xlo, xhi, ylo, yhi, zlo, zhi;
+ *     distribution, vx0, vy0, vz0)                                        distributions_and_sampling.jl:477-509   (grid == NULL, box6 given)
+ * sample_particles_equal_weight!(rng, grid1duniform, particles, pia, species, species_data, ppc::Integer, T, Fnum[, cell_chunk])
+ *                                                                          grids/grid_uniform1D.jl:117-152         (grid given, nparticles >= 0)
+ * sample_particles_equal_weight!(rng, grid1duniform, ..., ndens::Float64, T, Fnum[, cell_chunk])   :154-219       (grid given, nparticles < 0)
+ * for every cell of [cell_lo, cell_hi] in ascending order, appended at n_total + 1 exactly as the reference's loop does.
+ * distribution: 0 Maxwellian (sample_maxwellian! :432-443), 1 BKW at t = 0 (sample_bkw! :195-213).  v0: 3 doubles or NULL.
+ * With a slab grid the x bounds use the GLOBAL cell number (cell_offset + cell).  One Philox stream per cell (entity = cell). */
+int mb_sample_particles_equal_weight(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia, int64_t cell_lo, int64_t cell_hi, int64_t species,
+                                     int64_t nparticles, double ndens, double mass, double T, double Fnum, const double* box6, int32_t distribution,
+                                     const double* v0, uint32_t timestep, uint32_t substream);
+/* sample_on_grid!(rng, vdf_func, particles, nv, m, T, n_total, xlo, xhi, ylo, yhi, zlo, zhi; v_mult, cutoff_mult, noise, v_offset)
+ * distributions_and_sampling.jl:312-346 with evaluate_distribution_on_grid! :253-268 (vdf_kind 0: maxwellian :150-152, 1: bkw at
+ * scaled_time 0 :168-177).  Every cell of [cell_lo, cell_hi] receives the weighted velocity-grid sample (an ensemble of 0-D cells),
+ * appended at n_total + 1, and its indexer is set as ParticleIndexerArray(n_sampled) does (particles.jl:151).
+ * n_sampled (nullable, host): particles per cell (the reference's return value). */
+int mb_sample_on_grid(mb_ctx* ctx, int32_t vdf_kind, mb_pv* pv, mb_pia* pia, int64_t cell_lo, int64_t cell_hi, int64_t species, int64_t nv, double mass,
+                      double T, double n_total, const double* box6, double v_mult, double cutoff_mult, double noise, const double* v_offset,
+                      uint32_t timestep, uint32_t substream, int64_t* n_sampled);
+
 /* ---- slab exchange (replaces ChunkExchanger / exchange_particles! / sort_particles_after_exchange!, parallel.jl:21-581) ----
  * nccl_unique_id: 128 bytes from mb_comm_unique_id on rank 0, distributed by the host (torch.distributed / MPI / files). */
 int mb_comm_unique_id(void* out128);

@@ -25,6 +25,7 @@ export Context, PhiloxRng, DeviceParticleVector, DeviceParticleIndexerArray, Dev
        DeviceGrid1D, slab, sort_particles!, squash_pia!, restore_particle_ordering!, ntc!, ntc_equal_weight!, swpm!, fp_linear!,
        convect_particles!, convect_particles_and_compute_cell!, compute_props!, compute_props_sorted!,
        compute_props_with_total_moments!, avg_props!, clear_props!, merge_octree_N2_based!, exchange_particles!,
+       sample_particles_equal_weight!, sample_on_grid!,
        comm_unique_id, comm_init!, upload!, download, download_indexer, n_total, synchronize, kernel_launches
 
 const libmb = get(ENV, "MERZBILD_B200_LIB", joinpath(@__DIR__, "..", "merzbild_b200", "libmerzbild_b200.so"))
@@ -512,6 +513,60 @@ function merge_octree_N2_based!(rng::PhiloxRng, octree, pv::DeviceParticleVector
     check(ccall((:mb_merge_octree_N2, libmb), Cint,
                 (Ptr{Cvoid}, Ptr{COctreeParams}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int64, Ptr{CGrid1D}, UInt32, UInt32),
                 pv.ctx.h, Ref(oc), pv.h, pia.h, lo, hi, species, threshold, target_np, g, rng.timestep, rng.substream))
+end
+
+# ------------------------------------------------------------------------------------------ initial conditions
+"""
+    sample_particles_equal_weight!(rng, pv, pia, cell, species, nparticles, m, T, Fnum, xlo, xhi, ylo, yhi, zlo, zhi;
+                                   distribution=:Maxwellian, vx0=0.0, vy0=0.0, vz0=0.0)         distributions_and_sampling.jl:477-509
+    sample_particles_equal_weight!(rng, grid, pv, pia, species, species_data, ppc::Integer, T, Fnum[, cell_chunk])   grid_uniform1D.jl:117-152
+    sample_particles_equal_weight!(rng, grid, pv, pia, species, species_data, ndens::Float64, T, Fnum[, cell_chunk]) grid_uniform1D.jl:154-219
+
+Sampled on the device (one Philox stream per cell); `cell` may be a range.
+"""
+function sample_particles_equal_weight!(rng::PhiloxRng, pv::DeviceParticleVector, pia::DeviceParticleIndexerArray, cell, species::Integer,
+                                        nparticles::Integer, m::Real, T::Real, Fnum::Real, xlo, xhi, ylo, yhi, zlo, zhi;
+                                        distribution=:Maxwellian, vx0=0.0, vy0=0.0, vz0=0.0)
+    lo, hi = cellrange(cell)
+    box = Float64[xlo, xhi, ylo, yhi, zlo, zhi]
+    v0 = Float64[vx0, vy0, vz0]
+    check(ccall((:mb_sample_particles_equal_weight, libmb), Cint,
+                (Ptr{Cvoid}, Ptr{CGrid1D}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Float64, Float64, Float64, Float64, Ptr{Float64},
+                 Int32, Ptr{Float64}, UInt32, UInt32),
+                pv.ctx.h, Ptr{CGrid1D}(C_NULL), pv.h, pia.h, lo, hi, species, nparticles, 0.0, m, T, Fnum, box,
+                distribution == :BKW ? 1 : 0, v0, rng.timestep, rng.substream))
+end
+function sample_particles_equal_weight!(rng::PhiloxRng, grid, pv::DeviceParticleVector, pia::DeviceParticleIndexerArray, species::Integer,
+                                        species_data, ppc_or_ndens::Real, T::Real, Fnum::Real, cell_chunk=1:pia.n_cells)
+    lo, hi = cellrange(cell_chunk)
+    np_ = ppc_or_ndens isa Integer ? Int64(ppc_or_ndens) : Int64(-1)
+    nd = ppc_or_ndens isa Integer ? 0.0 : Float64(ppc_or_ndens)
+    check(ccall((:mb_sample_particles_equal_weight, libmb), Cint,
+                (Ptr{Cvoid}, Ptr{CGrid1D}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Float64, Float64, Float64, Float64, Ptr{Float64},
+                 Int32, Ptr{Float64}, UInt32, UInt32),
+                pv.ctx.h, gridref(grid), pv.h, pia.h, lo, hi, species, np_, nd, species_data[species].mass, T, Fnum, Ptr{Float64}(C_NULL),
+                0, Ptr{Float64}(C_NULL), rng.timestep, rng.substream))
+end
+"""
+    sample_on_grid!(rng, vdf::Symbol, pv, pia, cell, species, nv, m, T, n_total, xlo, xhi, ylo, yhi, zlo, zhi;
+                    v_mult=3.5, cutoff_mult=3.5, noise=0.0, v_offset=[0.0, 0.0, 0.0])              distributions_and_sampling.jl:312-346
+
+`vdf` is `:maxwellian` or `:bkw` (the BKW distribution at scaled time 0); every cell of `cell` receives the weighted grid sample
+and its indexer is set as `ParticleIndexerArray(n_sampled)` does.  Returns `n_sampled` per cell.
+"""
+function sample_on_grid!(rng::PhiloxRng, vdf::Symbol, pv::DeviceParticleVector, pia::DeviceParticleIndexerArray, cell, species::Integer,
+                         nv::Integer, m::Real, T::Real, n_total::Real, xlo, xhi, ylo, yhi, zlo, zhi;
+                         v_mult=3.5, cutoff_mult=3.5, noise=0.0, v_offset=[0.0, 0.0, 0.0])
+    lo, hi = cellrange(cell)
+    box = Float64[xlo, xhi, ylo, yhi, zlo, zhi]
+    vo = Float64.(v_offset)
+    n = Ref{Int64}(0)
+    check(ccall((:mb_sample_on_grid, libmb), Cint,
+                (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Float64, Float64, Float64, Ptr{Float64}, Float64, Float64,
+                 Float64, Ptr{Float64}, UInt32, UInt32, Ptr{Int64}),
+                pv.ctx.h, vdf == :bkw ? 1 : 0, pv.h, pia.h, lo, hi, species, nv, m, T, n_total, box, v_mult, cutoff_mult, noise, vo,
+                rng.timestep, rng.substream, n))
+    n[]
 end
 
 # ------------------------------------------------------------------------------------------------- slab exchange

@@ -121,6 +121,8 @@ SIGNATURES = {
     "mb_compute_props": (_int, [_vp, C.POINTER(_vp), _vp, _vp, _vp, _i32]),
     "mb_compute_props_sorted": (_int, [_vp, C.POINTER(_vp), _vp, _vp, _vp, C.POINTER(Grid1D), _i64, _i64]),
     "mb_merge_octree_N2": (_int, [_vp, C.POINTER(OctreeParams), _vp, _vp, _i64, _i64, _i64, _i64, _i64, C.POINTER(Grid1D), _u32, _u32]),
+    "mb_sample_particles_equal_weight": (_int, [_vp, C.POINTER(Grid1D), _vp, _vp, _i64, _i64, _i64, _i64, _f64, _f64, _f64, _f64, _vp, _i32, _vp, _u32, _u32]),
+    "mb_sample_on_grid": (_int, [_vp, _i32, _vp, _vp, _i64, _i64, _i64, _i64, _f64, _f64, _f64, _vp, _f64, _f64, _f64, _vp, _u32, _u32, C.POINTER(_i64)]),
     "mb_comm_unique_id": (_int, [_vp]),
     "mb_comm_init": (_int, [_vp, _vp, _int, _int]),
     "mb_exchange_set_mode": (_int, [_vp, _i32]),
@@ -578,6 +580,46 @@ def merge_octree_N2_based(rng, octree, pv, pia, cell, species, target_np, grid=N
     lo, hi = _range(cell)
     _ck(lib().mb_merge_octree_N2(pv.ctx.h, C.byref(octree.c), pv.h, pia.h, lo, hi, int(species), int(threshold), int(target_np),
                                  grid.ref if grid is not None else None, rng.timestep, rng.substream))
+
+
+def sample_particles_equal_weight(rng, *args, distribution="Maxwellian", vx0=0.0, vy0=0.0, vz0=0.0, cell_chunk=None):
+    """sample_particles_equal_weight!(rng, particles, pia, cell, species, nparticles, m, T, Fnum, xlo, xhi, ylo, yhi, zlo, zhi; ...)
+    (distributions_and_sampling.jl:477) -- ``cell`` may be a range -- or
+    sample_particles_equal_weight!(rng, grid1duniform, particles, pia, species, mass, ppc::Integer | ndens::Float64, T, Fnum[, cell_chunk])
+    (grids/grid_uniform1D.jl:117-219)."""
+    v0 = _f64arr([vx0, vy0, vz0])
+    dist = {"Maxwellian": 0, "BKW": 1}[distribution]
+    if isinstance(args[0], Grid1DUniform):
+        grid, pv, pia, species, mass, ppc_or_ndens, T, Fnum = args[:8]
+        if len(args) > 8:
+            cell_chunk = args[8]
+        lo, hi = (1, pia.n_cells) if cell_chunk is None else _range(cell_chunk)
+        if isinstance(ppc_or_ndens, (int, np.integer)):
+            npart, ndens = int(ppc_or_ndens), 0.0
+        else:
+            npart, ndens = -1, float(ppc_or_ndens)
+        _ck(lib().mb_sample_particles_equal_weight(pv.ctx.h, grid.ref, pv.h, pia.h, lo, hi, int(species), npart, ndens, float(mass), float(T),
+                                                   float(Fnum), None, dist, _p(v0), rng.timestep, rng.substream))
+    else:
+        pv, pia, cell, species, nparticles, m, T, Fnum = args[:8]
+        box = _f64arr(args[8:14])
+        lo, hi = _range(cell)
+        _ck(lib().mb_sample_particles_equal_weight(pv.ctx.h, None, pv.h, pia.h, lo, hi, int(species), int(nparticles), 0.0, float(m), float(T),
+                                                   float(Fnum), _p(box), dist, _p(v0), rng.timestep, rng.substream))
+
+
+def sample_on_grid(rng, vdf, pv, pia, cell, species, nv, m, T, n_total, xlo=0.0, xhi=1.0, ylo=0.0, yhi=1.0, zlo=0.0, zhi=1.0, v_mult=3.5,
+                   cutoff_mult=3.5, noise=0.0, v_offset=(0.0, 0.0, 0.0)):
+    """sample_on_grid!(rng, vdf_func, particles, nv, m, T, n_total, xlo, ..., zhi; v_mult, cutoff_mult, noise, v_offset)
+    (distributions_and_sampling.jl:312) for every cell of ``cell`` (an ensemble of 0-D cells); vdf is "maxwellian" or "bkw".
+    Returns n_sampled (particles per cell) and sets the cells' indexers."""
+    box = _f64arr([xlo, xhi, ylo, yhi, zlo, zhi])
+    vo = _f64arr(v_offset)
+    lo, hi = _range(cell)
+    n = C.c_int64()
+    _ck(lib().mb_sample_on_grid(pv.ctx.h, {"maxwellian": 0, "bkw": 1}[vdf], pv.h, pia.h, lo, hi, int(species), int(nv), float(m), float(T),
+                                float(n_total), _p(box), v_mult, cutoff_mult, noise, _p(vo), rng.timestep, rng.substream, C.byref(n)))
+    return int(n.value)
 
 
 def comm_unique_id():

@@ -1008,7 +1008,7 @@ template <class R>
 inline void sample_particles_equal_weight(R& rng, ParticleVector& pv, ParticleIndexerArray& pia, int64_t cell, int64_t species,
                                           int64_t nparticles, double m, double T, double Fnum, double xlo, double xhi,
                                           double ylo, double yhi, double zlo, double zhi, int distribution,
-                                          const double v0[3]) {
+                                          const double v0[3], bool bkw_use_offset = false) {
     const int64_t start = pia.n_total[species - 1] + 1;
     ParticleIndexer& ix = pia.at(cell, species);
     ix.n_local = nparticles;
@@ -1026,7 +1026,9 @@ inline void sample_particles_equal_weight(R& rng, ParticleVector& pv, ParticleIn
         pv.cell[i + offset - 1] = cell;
     }
     if (distribution == 0) sample_maxwellian(rng, pv, nparticles, offset, m, T, v0);
-    else sample_bkw(rng, pv, nparticles, 0, m, T, v0);  // reference passes no offset for BKW (:507)
+    // the reference passes no offset for BKW (:507), which is only right for the first cell sampled; the device follows the
+    // evident intent (bkw_use_offset) when a range of cells is sampled
+    else sample_bkw(rng, pv, nparticles, bkw_use_offset ? offset : 0, m, T, v0);
 }
 // grid_uniform1D.jl:198-219 (ndens version) over cells [cell_lo, cell_hi]
 template <class R>
@@ -1056,10 +1058,11 @@ inline double maxwellian_vdf(double vx, double vy, double vz, double m, double T
 template <class R>
 inline int64_t sample_on_grid(R& rng, int vdf_kind, ParticleVector& pv, int64_t nv, double m, double T, double n_total,
                               double xlo, double xhi, double ylo, double yhi, double zlo, double zhi, double v_mult,
-                              double cutoff_mult, double noise, const double v_offset[3]) {
+                              double cutoff_mult, double noise, const double v_offset[3], int64_t offset = 0) {
     const double v_thermal = std::sqrt(2 * k_B * T / m);
     std::vector<double> g(nv);
-    for (int64_t i = 0; i < nv; i++) g[i] = (-1.0 + 2.0 * (double)i / (double)(nv - 1));  // LinRange(-1,1,nv)
+    // LinRange(-1.0, 1.0, nv)[i + 1] = lerpi(i, nv - 1, -1.0, 1.0) = (1 - t) * a + t * b with t = i / (nv - 1) (Julia Base range.jl)
+    for (int64_t i = 0; i < nv; i++) { const double t = (double)i / (double)(nv - 1); g[i] = (1.0 - t) * -1.0 + t * 1.0; }
     const double dxu = g[1] - g[0];
     const double vmax = v_thermal * v_mult;
     std::vector<double> vg(nv);
@@ -1091,7 +1094,7 @@ inline int64_t sample_on_grid(R& rng, int vdf_kind, ParticleVector& pv, int64_t 
                     x[0] = xlo + rng.rand() * (xhi - xlo);
                     x[1] = ylo + rng.rand() * (yhi - ylo);
                     x[2] = zlo + rng.rand() * (zhi - zlo);
-                    add_particle(pv, pid, f, v, x);
+                    add_particle(pv, pid + offset, f, v, x);
                 }
             }
     return pid;

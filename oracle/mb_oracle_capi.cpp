@@ -282,6 +282,53 @@ int64_t mbo_sample_on_grid(void* rng, int vdf_kind, void* pv, int64_t nv, double
                           v_mult, cutoff_mult, noise, v_offset);
 }
 
+// per-cell variants: with Philox one stream per cell (entity = cell), the convention of merzbild.jl_b200/csrc/mb_sample.cu;
+// grid2 = (L, nx) or NULL (then box6); nparticles < 0: the number-density variant of grid_uniform1D.jl:198-219
+void mbo_sample_equal_weight_cells(const mbo_rng_spec* rs, const double* grid2, void* pv_, void* pia_, int64_t cell_lo, int64_t cell_hi, int64_t species,
+                                   int64_t nparticles, double ndens, double m, double T, double Fnum, const double* box6, int distribution,
+                                   const double* v0) {
+    ParticleVector& pv = *(ParticleVector*)pv_;
+    ParticleIndexerArray& pia = *(ParticleIndexerArray*)pia_;
+    for (int64_t cell = cell_lo; cell <= cell_hi; cell++) {
+        auto one = [&](auto& rng) {
+            double b[6] = {0, 0, 0.0, 1.0, 0.0, 1.0};
+            if (grid2) {
+                Grid1DUniform g(grid2[0], (int64_t)grid2[1]);
+                b[0] = g.cell_xlo(cell); b[1] = g.cell_xhi(cell);
+                if (nparticles < 0) { sample_particles_equal_weight_grid(rng, g, pv, pia, species, m, ndens, T, Fnum, cell, cell); return; }
+            } else {
+                for (int d = 0; d < 6; d++) b[d] = box6[d];
+            }
+            sample_particles_equal_weight(rng, pv, pia, cell, species, nparticles, m, T, Fnum, b[0], b[1], b[2], b[3], b[4], b[5], distribution, v0, true);
+        };
+        if (rs->kind == 0) one(*(Xoshiro256pp*)rs->seq);
+        else { PhiloxStream s(rs->seed, OP_SAMPLE, rs->substream, rs->timestep, (uint32_t)cell); one(s); }
+    }
+}
+// ensemble of 0-D cells, each the sample_on_grid! population appended at n_total + 1 with the cell's indexer set as
+// ParticleIndexerArray(n_sampled) does (particles.jl:151)
+int64_t mbo_sample_on_grid_cells(const mbo_rng_spec* rs, int vdf_kind, void* pv_, void* pia_, int64_t cell_lo, int64_t cell_hi, int64_t species, int64_t nv,
+                                 double m, double T, double n_total, const double* box6, double v_mult, double cutoff_mult, double noise,
+                                 const double* v_offset) {
+    ParticleVector& pv = *(ParticleVector*)pv_;
+    ParticleIndexerArray& pia = *(ParticleIndexerArray*)pia_;
+    int64_t n = 0;
+    for (int64_t cell = cell_lo; cell <= cell_hi; cell++) {
+        const int64_t off = pia.n_total[species - 1];
+        auto one = [&](auto& rng) {
+            n = sample_on_grid(rng, vdf_kind, pv, nv, m, T, n_total, box6[0], box6[1], box6[2], box6[3], box6[4], box6[5], v_mult, cutoff_mult, noise,
+                               v_offset, off);
+        };
+        if (rs->kind == 0) one(*(Xoshiro256pp*)rs->seq);
+        else { PhiloxStream s(rs->seed, OP_SAMPLE, rs->substream, rs->timestep, (uint32_t)cell); one(s); }
+        ParticleIndexer& ix = pia.at(cell, species);
+        ix.n_local = n; ix.start1 = off + 1; ix.end1 = off + n; ix.n_group1 = n; ix.start2 = 0; ix.end2 = -1; ix.n_group2 = 0;
+        pia.n_total[species - 1] += n;
+        for (int64_t i = 1; i <= n; i++) pv.cell[off + i - 1] = cell;
+    }
+    return n;
+}
+
 // ---- octree ----
 void* mbo_octree_create(int split, int init_bounds, int bounds_compute, int64_t max_Nbins, int64_t max_depth) {
     return new OctreeN2Merge((OctreeBinSplit)split, (OctreeInitBin)init_bounds, (OctreeBinBounds)bounds_compute, max_Nbins, max_depth);

@@ -106,6 +106,8 @@ def lib():
     sig("mbo_sample_equal_weight_grid", None, vp, f64, i64, vp, vp, i64, f64, f64, f64, f64, i64, i64)
     sig("mbo_sample_equal_weight_cell", None, vp, vp, vp, i64, i64, i64, f64, f64, f64, vp, C.c_int, vp)
     sig("mbo_sample_on_grid", i64, vp, C.c_int, vp, i64, f64, f64, f64, vp, f64, f64, f64, vp)
+    sig("mbo_sample_equal_weight_cells", None, vp, vp, vp, vp, i64, i64, i64, i64, f64, f64, f64, f64, vp, C.c_int, vp)
+    sig("mbo_sample_on_grid_cells", i64, vp, C.c_int, vp, vp, i64, i64, i64, i64, f64, f64, f64, vp, f64, f64, f64, vp)
     sig("mbo_octree_create", vp, C.c_int, C.c_int, C.c_int, i64, i64)
     sig("mbo_octree_free", None, vp)
     sig("mbo_octree_nbins", i64, vp)
@@ -434,6 +436,23 @@ def sample_on_grid(rng, vdf, pv, nv, m, T, n_total, box=(0, 1, 0, 1, 0, 1), v_mu
     box = _f64(box)
     vo = _f64(v_offset)
     return lib().mbo_sample_on_grid(rng._h, 0 if vdf == "maxwellian" else 1, pv.h, nv, m, T, n_total, _p(box), v_mult, cutoff_mult, noise, _p(vo))
+
+
+def sample_equal_weight_cells(rng, pv, pia, cell_lo, cell_hi, species, nparticles, m, T, Fnum, grid=None, ndens=0.0, box=(0, 1, 0, 1, 0, 1),
+                              distribution="Maxwellian", v0=(0, 0, 0)):
+    """sample_particles_equal_weight! for cells cell_lo..cell_hi; with ``Rng.philox`` one stream per cell (the device convention).
+    grid = (L, nx): the 1-D grid variants (nparticles < 0: number-density variant)."""
+    box, v0 = _f64(box), _f64(v0)
+    g = None if grid is None else _f64([grid[0], grid[1]])
+    lib().mbo_sample_equal_weight_cells(rng.ref, _p(g), pv.h, pia.h, cell_lo, cell_hi, species, nparticles, ndens, m, T, Fnum, _p(box),
+                                        0 if distribution == "Maxwellian" else 1, _p(v0))
+
+
+def sample_on_grid_cells(rng, vdf, pv, pia, cell_lo, cell_hi, species, nv, m, T, n_total, box=(0, 1, 0, 1, 0, 1), v_mult=3.5, cutoff_mult=3.5, noise=0.0,
+                         v_offset=(0, 0, 0)):
+    box, vo = _f64(box), _f64(v_offset)
+    return lib().mbo_sample_on_grid_cells(rng.ref, 0 if vdf == "maxwellian" else 1, pv.h, pia.h, cell_lo, cell_hi, species, nv, m, T, n_total, _p(box),
+                                          v_mult, cutoff_mult, noise, _p(vo))
 
 
 MID_SPLIT, MEAN_SPLIT = 1, 2

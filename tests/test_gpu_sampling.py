@@ -1,0 +1,126 @@
+"""GPU parity: device-side initial conditions (mb_sample_particles_equal_weight, mb_sample_on_grid) against the CPU oracle,
+draw for draw (same per-cell Philox streams): pia bit-exact, weights / grid velocities bit-exact, sampled positions and
+velocities to 1e-13 relative (log / sincos differ in the last ulp between libm and CUDA).  Plus the reference's own
+distribution-level pins of test/test_sampling.jl on the device sample."""
+import numpy as np
+import pytest
+
+from parity_util import AR, assert_rows_close, assert_same_pia
+
+pytestmark = pytest.mark.gpu
+K_B = 1.380649e-23
+
+
+@pytest.fixture(scope="module")
+def ctx(mb):
+    c = mb.Context(0, 1234)
+    yield c
+    c.close()
+
+
+def _cmp(pv, opv, n, rtol=1e-13):
+    a, b = pv.logical(1, n), opv.logical(1, n)
+    assert np.array_equal(a[:, 0], b[:, 0]), "weights differ"
+    assert_rows_close(a, b, rtol, "sampled particles")
+    np.testing.assert_array_equal(pv.cell(1, n), opv.cell[:n])
+    return a
+
+
+@pytest.mark.parametrize("ppc", [1, 37, 300])
+def test_sample_grid_fixed_ppc_parity(mb, oracle, ctx, ppc):
+    nx, L, Fnum, T = 23, 23e-5, 5e14, 300.0
+    opv, opia = oracle.OPV(nx * ppc + 5), oracle.OPIA(nx, 1)
+    oracle.sample_equal_weight_cells(oracle.Rng.philox(1234, 3, 1), opv, opia, 1, nx, 1, ppc, AR, T, Fnum, grid=(L, nx))
+    pv, pia = mb.ParticleVector(nx * ppc + 5, ctx), mb.ParticleIndexerArray(nx, 1, ctx)
+    mb.sample_particles_equal_weight(mb.PhiloxRng(3, 1), mb.Grid1DUniform(L, nx), pv, pia, 1, AR, ppc, T, Fnum)
+    assert_same_pia(opia, pia)
+    _cmp(pv, opv, nx * ppc)
+    # the sampled layout is sorted: the band path of the first sort needs no general pass and changes nothing
+    mb.sort_particles(None, mb.Grid1DUniform(L, nx), pv, pia, 1)
+    assert_same_pia(opia, pia)
+
+
+def test_sample_grid_number_density_parity(mb, oracle, ctx):
+    """grid_uniform1D.jl:198-219: 41.37 particles per cell on average -> 41 or 42, decided by the first draw of the cell's stream."""
+    nx, L, Fnum, T = 200, 2e-3, 1e12, 450.0
+    ndens = 41.37 * Fnum / (L / nx)
+    opv, opia = oracle.OPV(nx * 43), oracle.OPIA(nx, 1)
+    oracle.sample_equal_weight_cells(oracle.Rng.philox(1234, 0, 0), opv, opia, 1, nx, 1, -1, AR, T, Fnum, grid=(L, nx), ndens=ndens)
+    pv, pia = mb.ParticleVector(nx * 43, ctx), mb.ParticleIndexerArray(nx, 1, ctx)
+    mb.sample_particles_equal_weight(mb.PhiloxRng(0, 0), mb.Grid1DUniform(L, nx), pv, pia, 1, AR, float(ndens), T, Fnum)
+    assert_same_pia(opia, pia)
+    counts = opia.indexer[0, :, 0]
+    assert set(counts.tolist()) == {41, 42}
+    _cmp(pv, opv, int(opia.n_total[0]))
+
+
+def test_sample_cell_chunk_appends(mb, oracle, ctx):
+    """two cell chunks sampled one after the other (the multithreaded drivers' per-chunk calls): the second appends at n_total + 1"""
+    nx, L, ppc = 10, 1e-4, 16
+    opv, opia = oracle.OPV(nx * ppc), oracle.OPIA(nx, 1)
+    pv, pia = mb.ParticleVector(nx * ppc, ctx), mb.ParticleIndexerArray(nx, 1, ctx)
+    g = mb.Grid1DUniform(L, nx)
+    for lo, hi in ((1, 4), (5, 10)):
+        oracle.sample_equal_weight_cells(oracle.Rng.philox(1234, 0), opv, opia, lo, hi, 1, ppc, AR, 300.0, 1e10, grid=(L, nx))
+        mb.sample_particles_equal_weight(mb.PhiloxRng(0), g, pv, pia, 1, AR, ppc, 300.0, 1e10, (lo, hi))
+    assert_same_pia(opia, pia)
+    _cmp(pv, opv, nx * ppc)
+
+
+@pytest.mark.parametrize("dist", ["Maxwellian", "BKW"])
+def test_sample_box_parity_and_reference_pins(mb, oracle, ctx, dist):
+    """0-D box variant with a velocity offset (test/test_sampling.jl:17-63) for both distributions; 3 cells = 3 ensemble members."""
+    n, n_dens, T0, v0 = 20000, 1e20, 1000.0, (20.0, -10.0, 30.0)
+    Fnum = n_dens / n
+    box = (0.0, 0.5, 0.0, 1.0, 0.0, 2.0)
+    opv, opia = oracle.OPV(3 * n), oracle.OPIA(3, 1)
+    oracle.sample_equal_weight_cells(oracle.Rng.philox(1234, 0), opv, opia, 1, 3, 1, n, AR, T0, Fnum, box=box, distribution=dist, v0=v0)
+    pv, pia = mb.ParticleVector(3 * n, ctx), mb.ParticleIndexerArray(3, 1, ctx)
+    mb.sample_particles_equal_weight(mb.PhiloxRng(0), pv, pia, (1, 3), 1, n, AR, T0, Fnum, *box, distribution=dist, vx0=v0[0], vy0=v0[1], vz0=v0[2])
+    assert_same_pia(opia, pia)
+    a = _cmp(pv, opv, 3 * n, rtol=1e-12)
+    assert a[:, 4].min() >= 0 and a[:, 4].max() <= 0.5 and a[:, 5].max() <= 1.0 and a[:, 6].max() <= 2.0
+    pp = mb.PhysProps(3, 1, (4, 6, 8), Tref=T0, ctx=ctx)
+    mb.compute_props_with_total_moments([pv], pia, [AR], pp)
+    d = pp.download()
+    for c in range(3):
+        assert abs(d["n"][0, c] / n_dens - 1) < 1e-14
+        assert np.all(np.abs(d["v"][0, c] - np.array(v0)) < 10.0)
+        assert abs(d["T"][0, c] / T0 - 1) < (1e-2 if dist == "Maxwellian" else 2e-2)
+        if dist == "Maxwellian":
+            m = d["moments"][0, c]
+            assert abs(m[0] - 1) < 0.05 and abs(m[1] - 1) < 0.05 and abs(m[2] - 1) < 0.12
+
+
+@pytest.mark.parametrize("vdf,noise", [("bkw", 0.0), ("maxwellian", 0.7)])
+def test_sample_on_grid_parity(mb, oracle, ctx, vdf, noise):
+    """sample_on_grid! ensemble (the C2 initial condition, bkw_varweight_octree.jl:62-66): weights bit-exact (host table summed in
+    the reference's order), velocities / positions against the oracle."""
+    nv, T0, n_dens, cells = 16, 273.0, 1e23, 5
+    opv, opia = oracle.OPV(cells * nv ** 3), oracle.OPIA(cells, 1)
+    n = oracle.sample_on_grid_cells(oracle.Rng.philox(1234, 2), vdf, opv, opia, 1, cells, 1, nv, AR, T0, n_dens, noise=noise, v_offset=(1.0, 2.0, 3.0))
+    pv, pia = mb.ParticleVector(cells * nv ** 3, ctx), mb.ParticleIndexerArray(cells, 1, ctx)
+    n_dev = mb.sample_on_grid(mb.PhiloxRng(2), vdf, pv, pia, (1, cells), 1, nv, AR, T0, n_dens, noise=noise, v_offset=(1.0, 2.0, 3.0))
+    assert n_dev == n
+    assert_same_pia(opia, pia)
+    a = _cmp(pv, opv, cells * n, rtol=1e-14)
+    assert abs(a[:n, 0].sum() / n_dens - 1) < 1e-13
+
+
+def test_sample_capacity_error(mb, ctx):
+    pv, pia = mb.ParticleVector(100, ctx), mb.ParticleIndexerArray(4, 1, ctx)
+    mb.sample_particles_equal_weight(mb.PhiloxRng(0), mb.Grid1DUniform(4e-5, 4), pv, pia, 1, AR, 26, 300.0, 1e10)
+    with pytest.raises(mb.CapacityError):
+        ctx.sync()
+    assert int(pia.n_total[0]) == 0  # nothing was sampled
+
+
+def test_sample_slab_uses_global_cells(mb, ctx):
+    """a slab grid samples x in the slab's global cells"""
+    G = mb.Grid1DUniform(1e-3, 100)
+    slab = G.slab(2, 4)
+    pv, pia = mb.ParticleVector(25 * 8, ctx), mb.ParticleIndexerArray(slab.n_cells, 1, ctx)
+    mb.sample_particles_equal_weight(mb.PhiloxRng(0), slab, pv, pia, 1, AR, 8, 300.0, 1e10)
+    a = pv.logical(1, 25 * 8)
+    gc = np.floor(a[:, 4] * G.inv_dx).astype(int)
+    assert np.array_equal(gc, np.repeat(np.arange(50, 75), 8))
