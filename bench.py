@@ -164,32 +164,11 @@ def main():
     n = nx * PPC
     Fnum = DX * NDENS / PPC
     cap = int(n * 1.05) + 4096
-    rng = np.random.default_rng(1234 + rank)
-    pin = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(7)]
-    host = [p.numpy() for p in pin]
-    host[0][:] = Fnum
-    sig = np.sqrt(K_B * T_WALL / AR)
-    chunk = 1 << 24
-    for f in (1, 2, 3):
-        for s in range(0, n, chunk):
-            e = min(n, s + chunk)
-            host[f][s:e] = rng.standard_normal(e - s) * sig
-    for s in range(0, n, chunk):
-        e = min(n, s + chunk)
-        idx = np.arange(s, e, dtype=np.int64)
-        host[4][s:e] = ((idx // PPC) + slab.cell_offset + rng.random(e - s)) * DX
-        host[5][s:e] = rng.random(e - s)
-        host[6][s:e] = rng.random(e - s)
-    np.clip(host[4], slab.min_x, slab.max_x, out=host[4])
     indexer = np.zeros((1, nx, 7), dtype=np.int64)
-    c = np.arange(nx, dtype=np.int64)
-    indexer[0, :, 0] = PPC
-    indexer[0, :, 1] = c * PPC + 1
-    indexer[0, :, 2] = (c + 1) * PPC
-    indexer[0, :, 3] = PPC
-    indexer[0, :, 5] = -1
     n_total = np.array([n], dtype=np.int64)
     contiguous = np.array([1], dtype=np.uint8)
+    pin = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(7)]
+    host = [p.numpy() for p in pin]
 
     pv = mb.ParticleVector(cap, ctx)
     pia = mb.ParticleIndexerArray(nx, 1, ctx)
@@ -203,6 +182,13 @@ def main():
         uid = [mb.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         mb.comm_init(ctx, uid[0], rank, world)
+
+    # initial condition sampled on the device (sample_particles_equal_weight!(rng, grid, ..., ppc, T, Fnum), grid_uniform1D.jl:117-152),
+    # then copied once to pinned host memory: the end-to-end leg uploads it from there every step
+    mb.sample_particles_equal_weight(mb.PhiloxRng(0, 0), slab, pv, pia, 1, AR, PPC, T_WALL, Fnum)
+    ctx.sync()
+    pv.download_soa(1, n, host)
+    indexer[:] = pia.indexer
 
     def upload():
         pv.upload_soa(1, n, host)

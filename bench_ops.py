@@ -108,30 +108,53 @@ def main():
     a, ix, n = population(nc, ppc, 2, vw=True)
     cap = int(n * 1.3)
     pv, pia = mb.ParticleVector(cap, ctx), mb.ParticleIndexerArray(nc, 1, ctx)
-    grid = mb.Grid1DUniform(nc * DX, nc)
+    # wall_offset 1e-6: with L = nc dx ~ 1 m the default offset dx * 1e-12 is below ulp(L), so a merged particle clamped to max_x would sit exactly on L
+    grid = mb.Grid1DUniform(nc * DX, nc, wall_offset=1e-6)
     cf = mb.CollisionFactors(nc, mb.estimate_sigma_g_w_max(it, AR, AR, 300.0, 300.0, DX * NDENS / ppc * 1.5), ctx)
     oc = mb.OctreeN2Merge(mb.OctreeN2Merge.OctreeBinMidSplit, mb.OctreeN2Merge.OctreeInitBinMinMaxVel, max_Nbins=6000)
+
+    pp2 = mb.PhysProps(nc, 1, ctx=ctx)
 
     def reset():
         pv.upload_soa(1, n, a)
         pia.upload(ix, np.array([n]), np.array([1], dtype=np.uint8))
 
-    reset()
-    best, med = timed(ctx, lambda: mb.merge_octree_N2_based(mb.PhiloxRng(1), oc, pv, pia, (1, nc), 1, 100, grid, threshold=130), max(args.reps // 2, 2), setup=reset)
-    report("merge_octree_N2_based (150 -> 100)", "C4: %d cells x %d" % (nc, ppc), n, med, 56 * (150 + 100) / 150.0, "56 (N + N_target) / N bytes per particle of a merged cell")
-    best, med = timed(ctx, lambda: mb.squash_pia(pv, pia, 1), 1)
-    n1 = int(pia.n_total[0])
-    report("squash_pia", "after the merge: %d particles" % n1, n1, best, 112, "payload moves (index indirection is the identity on the device)")
-    best, med = timed(ctx, lambda: mb.sort_particles(None, grid, pv, pia, 1), 1)
-    report("sort_particles (general path)", "after squash", n1, best, 128, "first sort after a merge: general path")
     step = [0]
+
+    def merge():
+        mb.merge_octree_N2_based(mb.PhiloxRng(1), oc, pv, pia, (1, nc), 1, 100, grid, threshold=130)
 
     def vw_ntc():
         step[0] += 1
         mb.ntc(mb.PhiloxRng(step[0]), cf, None, it, pv, pia, (1, nc), 1, DT * 4, DX)
 
-    best, med = timed(ctx, vw_ntc, 1)
-    report("ntc! variable weight (splits)", "C4 population after merge, dt x 4", n1, best, 64, "candidates only: ~%d new particles" % (int(pia.n_total[0]) - n1))
+    def one(fn):
+        ctx.sync()
+        ctx.timer_start()
+        fn()
+        return ctx.timer_stop()
+
+    # one untimed cycle first: lazy allocations (sort ping-pong buffer, scratch arena) must not be inside a timed region
+    res = {}
+    for rep in range(max(args.reps, 2)):
+        reset()
+        t_merge = one(merge)
+        t_squash = one(lambda: mb.squash_pia(pv, pia, 1))
+        n1 = int(pia.n_total[0])
+        t_sort = one(lambda: mb.sort_particles(None, grid, pv, pia, 1))
+        t_ntc = one(vw_ntc)
+        n2 = int(pia.n_total[0])
+        t_props = one(lambda: mb.compute_props([pv], pia, [AR], pp2))
+        if rep > 0:
+            for k, v in (("merge", t_merge), ("squash", t_squash), ("sort", t_sort), ("ntc", t_ntc), ("props", t_props)):
+                res.setdefault(k, []).append(v)
+    med = {k: sorted(v)[len(v) // 2] for k, v in res.items()}
+    report("merge_octree_N2_based (150 -> 100)", "C4: %d cells x %d" % (nc, ppc), n, med["merge"], 56 * (150 + 100) / 150.0,
+           "56 (N + N_target) / N bytes per particle of a merged cell")
+    report("squash_pia", "after the merge: %d particles" % n1, n1, med["squash"], 112, "payload moves (index indirection is the identity on the device)")
+    report("sort_particles (general path)", "after squash", n1, med["sort"], 128, "first sort after a merge: general path")
+    report("ntc! variable weight (splits)", "C4 population after merge, dt x 4", n1, med["ntc"], 64, "candidates only: ~%d new particles" % (n2 - n1))
+    report("compute_props (both groups)", "C4 population after ntc", n2, med["props"], 32, "group 2 at the tail")
     ctx.close()
 
 

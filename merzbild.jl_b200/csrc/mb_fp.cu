@@ -41,7 +41,7 @@ __device__ __forceinline__ double wsum(double x) {
     return x;
 }
 
-static __global__ void __launch_bounds__(256) k_fp_linear(FpArgs a) {
+static __global__ void __launch_bounds__(256) k_fp_linear(FpArgs a, int n_lo) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -50,11 +50,17 @@ static __global__ void __launch_bounds__(256) k_fp_linear(FpArgs a) {
     double* __restrict__ VY = a.pv.a[F_VY];
     double* __restrict__ VZ = a.pv.a[F_VZ];
     const double* __restrict__ W = a.pv.a[F_W];
-    for (int64_t r = warp0; r < nr; r += nwarps) {
+    // a warp takes 32 consecutive cells at a time: one read of their sizes, then only the cells of this kernel's size class
+    for (int64_t r0 = warp0 * 32; r0 < nr; r0 += nwarps * 32) {
+      const int64_t myr = r0 + lane;
+      const int64_t my_n = myr < nr ? a.ix[a.cell_lo - 1 + myr].n_local : 0;
+      unsigned todo = __ballot_sync(0xffffffffu, my_n >= 7 && my_n > n_lo);  // :35-37; smaller cells are handled by k_fp_linear_reg
+      while (todo) {
+        const int64_t r = r0 + (__ffs(todo) - 1);
+        todo &= todo - 1;
         const int64_t cell = a.cell_lo + r;
         const Indexer q = a.ix[cell - 1];
         const int64_t n = q.n_local, lo = q.start1 - 1;
-        if (n < 7) continue;  // :35-37
         // scale_norm_rands!: exact standardisation over the n draws of each component
         double m[3] = {0, 0, 0}, s2[3] = {0, 0, 0};
         for (int64_t j = lane; j < n; j += 32) {
@@ -110,6 +116,108 @@ static __global__ void __launch_bounds__(256) k_fp_linear(FpArgs a) {
             VY[lo + j] = alpha * VY[lo + j] + uy;
             VZ[lo + j] = alpha * VZ[lo + j] + uz;
         }
+      }
+    }
+}
+
+// Small cells (n <= 32 K): the whole cell lives in registers -- K particles per lane, the normals are generated ONCE, the cell is
+// read once and written once.  The arithmetic (per-lane accumulation in ascending j, then the xor butterfly) is the same as in
+// k_fp_linear, so both kernels give bit-identical results.  Handles the cells with n_lo < n_local <= 32 K; the others are skipped.
+template <int K>
+static __global__ void __launch_bounds__(128) k_fp_linear_reg(FpArgs a, int n_lo) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t nr = a.cell_hi - a.cell_lo + 1;
+    double* __restrict__ VX = a.pv.a[F_VX];
+    double* __restrict__ VY = a.pv.a[F_VY];
+    double* __restrict__ VZ = a.pv.a[F_VZ];
+    const double* __restrict__ W = a.pv.a[F_W];
+    for (int64_t r0 = warp0 * 32; r0 < nr; r0 += nwarps * 32) {
+      const int64_t myr = r0 + lane;
+      const int64_t my_n = myr < nr ? a.ix[a.cell_lo - 1 + myr].n_local : 0;
+      unsigned todo = __ballot_sync(0xffffffffu, my_n >= 7 && my_n > n_lo && my_n <= 32 * K);
+      while (todo) {
+        const int64_t r = r0 + (__ffs(todo) - 1);
+        todo &= todo - 1;
+        const int64_t cell = a.cell_lo + r;
+        const Indexer q = a.ix[cell - 1];
+        const int n = (int)q.n_local;
+        const int64_t lo = q.start1 - 1;
+        double w[K], vx[K], vy[K], vz[K], o0[K], o1[K], o2[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const int j = lane + 32 * k;
+            const bool valid = j < n;
+            w[k] = valid ? W[lo + j] : 0.0;
+            vx[k] = valid ? VX[lo + j] : 0.0;
+            vy[k] = valid ? VY[lo + j] : 0.0;
+            vz[k] = valid ? VZ[lo + j] : 0.0;
+        }
+        double m[3] = {0, 0, 0}, s2[3] = {0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const int j = lane + 32 * k;
+            o0[k] = o1[k] = o2[k] = 0.0;
+            if (j < n) {
+                double o[3];
+                fp_normals(a, (uint32_t)cell, j, o);
+                o0[k] = o[0]; o1[k] = o[1]; o2[k] = o[2];
+                m[0] += o[0]; m[1] += o[1]; m[2] += o[2];
+            }
+        }
+        for (int d = 0; d < 3; d++) m[d] = wsum(m[d]) / (double)n;
+#pragma unroll
+        for (int k = 0; k < K; k++)
+            if (lane + 32 * k < n) {
+                const double x0 = o0[k] - m[0], x1 = o1[k] - m[1], x2 = o2[k] - m[2];
+                s2[0] += x0 * x0; s2[1] += x1 * x1; s2[2] += x2 * x2;
+            }
+        for (int d = 0; d < 3; d++) s2[d] = sqrt((double)n / wsum(s2[d]));
+        double lw = 0, ux = 0, uy = 0, uz = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++)
+            if (lane + 32 * k < n) {
+                lw += w[k];
+                ux += vx[k] * w[k]; uy += vy[k] * w[k]; uz += vz[k] * w[k];
+            }
+        lw = wsum(lw);
+        ux = wsum(ux) / lw; uy = wsum(uy) / lw; uz = wsum(uz) / lw;
+        double es_old = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++)
+            if (lane + 32 * k < n) {
+                const double cx = vx[k] - ux, cy = vy[k] - uy, cz = vz[k] - uz;
+                es_old += (cx * cx + cy * cy + cz * cz) * w[k];
+            }
+        es_old = 0.5 * wsum(es_old) / lw;
+        const double T = es_old * a.mass / ((3.0 / 2.0) * k_B);
+        const double p = (lw / a.V) * k_B * T;
+        const double mu = a.it.vhs_muref * pow(T / a.it.vhs_Tref, a.it.vhs_o);
+        const double tau = 2.0 * mu / p;
+        const double A = exp(-a.dt / tau);
+        const double C = sqrt(((2.0 / 3.0) * es_old) * (1.0 - exp(-2.0 * a.dt / tau)));
+        double es_new = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++)
+            if (lane + 32 * k < n) {
+                vx[k] = (vx[k] - ux) * A + C * ((o0[k] - m[0]) * s2[0]);
+                vy[k] = (vy[k] - uy) * A + C * ((o1[k] - m[1]) * s2[1]);
+                vz[k] = (vz[k] - uz) * A + C * ((o2[k] - m[2]) * s2[2]);
+                es_new += (vx[k] * vx[k] + vy[k] * vy[k] + vz[k] * vz[k]) * w[k];
+            }
+        es_new = 0.5 * wsum(es_new) / lw;
+        const double alpha = sqrt(es_old / es_new);
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const int j = lane + 32 * k;
+            if (j < n) {
+                VX[lo + j] = alpha * vx[k] + ux;
+                VY[lo + j] = alpha * vy[k] + uy;
+                VZ[lo + j] = alpha * vz[k] + uz;
+            }
+        }
+      }
     }
 }
 
@@ -133,7 +241,13 @@ extern "C" int mb_fp_linear(mb_ctx* ctx, const mb_interaction* it, double mass, 
     a.seed = ctx->seed; a.timestep = timestep; a.substream = substream;
     ProfScope ps(ctx, PROF_FP);
     ctx->state_gen++;
-    k_fp_linear<<<grid_for((cell_hi - cell_lo + 1) * 32, 256, 8), 256, 0, ctx->stream>>>(a);
+    // three size classes, each kernel skips the cells of the others: n <= 128 and n <= 256 in registers, larger cells streamed
+    const int64_t nr = cell_hi - cell_lo + 1;
+    k_fp_linear_reg<4><<<grid_for(nr * 32, 128, 12), 128, 0, ctx->stream>>>(a, 0);
+    MB_LAUNCH_CHECK(ctx);
+    k_fp_linear_reg<8><<<grid_for(nr * 32, 128, 8), 128, 0, ctx->stream>>>(a, 128);
+    MB_LAUNCH_CHECK(ctx);
+    k_fp_linear<<<grid_for(nr * 32, 256, 8), 256, 0, ctx->stream>>>(a, 256);
     MB_LAUNCH_CHECK(ctx);
     return MB_OK;
 }

@@ -42,6 +42,7 @@ struct MergeArgs {
     double* outbuf;                                      // [nCTA][2 * Bmax][7]
     int* flags;
     int* noncontig;
+    int small_max;  // cells with n_local <= small_max are merged by k_merge_warp
 };
 
 static __global__ void k_merge_counts(const Indexer* __restrict__ ix, int64_t cell_lo, int64_t nr, int64_t threshold, int32_t* __restrict__ cnt) {
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(MT) k_merge(MergeArgs a) {
         const int64_t cell = a.cell_lo + r;
         const Indexer q = a.ix[cell - 1];
         const int N = (int)q.n_local;
-        if (N <= 0 || !(a.threshold < 0 || N > a.threshold)) continue;  // block-uniform
+        if (N <= 0 || !(a.threshold < 0 || N > a.threshold) || N <= a.small_max) continue;  // block-uniform; small cells: k_merge_warp
         int32_t* idx = a.idx + a.slice[r];
         int32_t* tmp = a.tmp + a.slice[r];
         uint8_t* oct = a.oct + a.slice[r];
@@ -427,6 +428,352 @@ __global__ void __launch_bounds__(MT) k_merge(MergeArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Small cells (N <= NS particles; the C4 / small-cell C2 shapes: 130-500 sampled, threshold 130-150, target 100): ONE WARP per
+// merging cell, the cell staged once in shared memory (w, v, x: 56 B/particle read once from HBM), every step of the octree
+// refinement done by the warp with ballots / shuffles and __syncwarp only -- no block barrier, no global index arrays.
+// Summation orders follow the reference's sequential loops wherever one lane does the sum (child weights: forward slice order;
+// bin means / variances of bins of <= 32 particles: slice order), so those results are bit-identical to the CPU oracle.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int NS = 256;        // largest cell handled by the warp kernel
+constexpr int MW_WARPS = 4;    // warps (= concurrent cells) per CTA
+
+__host__ __device__ inline size_t merge_warp_smem(int BC) {
+    size_t b = (size_t)7 * NS * 8 + (size_t)BC * 8 + (size_t)NS * 2 * 2 + (size_t)BC * 2 * 5 + (size_t)NS;
+    return (b + 15) / 16 * 16;
+}
+
+__global__ void __launch_bounds__(32 * MW_WARPS) k_merge_warp(MergeArgs a, int BC, double* __restrict__ gbounds) {
+    extern __shared__ __align__(16) unsigned char mw_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1u;
+    unsigned char* base = mw_smem + (size_t)wid * merge_warp_smem(BC);
+    double* P = (double*)base;                 // [7][NS]: field f of local particle j at P[f * NS + j]
+    double* bw = P + 7 * NS;                   // [BC] bin weight
+    int16_t* idx = (int16_t*)(bw + BC);        // [NS] local particle index per slice position
+    int16_t* tmp = idx + NS;                   // [NS]
+    int16_t* bnp = tmp + NS;                   // [BC]
+    int16_t* bstart = bnp + BC;
+    int16_t* bend = bstart + BC;
+    int16_t* bdepth = bend + BC;
+    int16_t* bout = bdepth + BC;
+    uint8_t* oct = (uint8_t*)(bout + BC);      // [NS]
+    const int64_t gw = (int64_t)blockIdx.x * MW_WARPS + wid, nwarps = (int64_t)gridDim.x * MW_WARPS;
+    double* bvmin = gbounds + gw * 6 * BC;     // [3 * BC] (global, L1/L2 resident: touched once per split)
+    double* bvmax = bvmin + 3 * BC;
+    const int64_t nr = a.cell_hi - a.cell_lo + 1;
+    const double* Pw = P;
+
+    // a warp takes 32 consecutive cells at a time (one read of their sizes) and merges the ones that need it
+    for (int64_t r0 = gw * 32; r0 < nr; r0 += nwarps * 32) {
+      const int64_t myr = r0 + lane;
+      const int64_t my_n = myr < nr ? a.ix[a.cell_lo - 1 + myr].n_local : 0;
+      unsigned todo = __ballot_sync(FULL, my_n > 0 && my_n <= NS && (a.threshold < 0 || my_n > a.threshold));
+      while (todo) {
+        const int64_t r = r0 + (__ffs(todo) - 1);
+        todo &= todo - 1;
+        const int64_t cell = a.cell_lo + r;
+        const Indexer q = a.ix[cell - 1];
+        const int N = (int)q.n_local;
+        __syncwarp();
+        // ---- stage the cell; init_octree! (:947-984)
+        for (int j = lane; j < N; j += 32) {
+            const int64_t p = mpos(q, j);
+#pragma unroll
+            for (int f = 0; f < 7; f++) P[f * NS + j] = a.pv.a[f][p];
+            idx[j] = (int16_t)j;
+        }
+        __syncwarp();
+        {
+            double mn[3], mx[3];
+            if (a.oc.init_bin_bounds == 3) {
+                for (int d = 0; d < 3; d++) { mn[d] = -c_light; mx[d] = c_light; }
+            } else {
+                for (int d = 0; d < 3; d++) { mn[d] = 9299792458.0; mx[d] = -9299792458.0; }
+                for (int j = lane; j < N; j += 32)
+#pragma unroll
+                    for (int d = 0; d < 3; d++) { const double v = P[(1 + d) * NS + j]; mn[d] = fmin(mn[d], v); mx[d] = fmax(mx[d], v); }
+#pragma unroll
+                for (int d = 0; d < 3; d++)
+                    for (int o = 16; o > 0; o >>= 1) { mn[d] = fmin(mn[d], __shfl_xor_sync(FULL, mn[d], o)); mx[d] = fmax(mx[d], __shfl_xor_sync(FULL, mx[d], o)); }
+                if (a.oc.init_bin_bounds == 2)
+                    for (int d = 0; d < 3; d++) { const double m = fmax(fabs(mn[d]), fabs(mx[d])); mn[d] = -m; mx[d] = m; }
+            }
+            if (lane == 0) {
+                bnp[0] = (int16_t)N; bw[0] = 1e50; bdepth[0] = 0; bstart[0] = 0; bend[0] = (int16_t)(N - 1);
+                for (int d = 0; d < 3; d++) { bvmin[d] = mn[d]; bvmax[d] = mx[d]; }
+            }
+        }
+        int Nbins = 1, total_post = N >= 2 ? 2 : N;
+        __syncwarp();
+        // ---- compute_octree! (:998-1039)
+        while (true) {
+            double bwm = -1.0;
+            int bid = -1;
+            for (int b = lane; b < Nbins; b += 32) {
+                const double w = bw[b];
+                if (w > bwm && bnp[b] > 2 && bdepth[b] < a.oc.max_depth) { bwm = w; bid = b; }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ow = __shfl_xor_sync(FULL, bwm, o);
+                const int oid = __shfl_xor_sync(FULL, bid, o);
+                if (oid >= 0 && (bid < 0 || ow > bwm || (ow == bwm && oid < bid))) { bwm = ow; bid = oid; }
+            }
+            if (bid < 0 || total_post + 14 > a.target) break;
+            // ---- split_bin! (:503-633)
+            const int bin = bid;
+            const int bs = bstart[bin], be = bend[bin], depth = bdepth[bin];
+            double pmn[3], pmx[3];
+            if (a.oc.bin_bounds_compute == 2) {  // bin_bounds_recompute! (:382-418)
+                for (int d = 0; d < 3; d++) { pmn[d] = 9299792458.0; pmx[d] = -9299792458.0; }
+                for (int j = bs + lane; j <= be; j += 32) {
+                    const int pj = idx[j];
+#pragma unroll
+                    for (int d = 0; d < 3; d++) { const double v = P[(1 + d) * NS + pj]; pmn[d] = fmin(pmn[d], v); pmx[d] = fmax(pmx[d], v); }
+                }
+#pragma unroll
+                for (int d = 0; d < 3; d++)
+                    for (int o = 16; o > 0; o >>= 1) { pmn[d] = fmin(pmn[d], __shfl_xor_sync(FULL, pmn[d], o)); pmx[d] = fmax(pmx[d], __shfl_xor_sync(FULL, pmx[d], o)); }
+            } else {
+                for (int d = 0; d < 3; d++) { pmn[d] = bvmin[3 * bin + d]; pmx[d] = bvmax[3 * bin + d]; }
+            }
+            double mid[3];
+            if (a.oc.split == 1) {
+                for (int d = 0; d < 3; d++) mid[d] = 0.5 * (pmn[d] + pmx[d]);
+            } else {  // OctreeBinMeanSplit
+                double sw = 0, sv[3] = {0, 0, 0};
+                for (int j = bs + lane; j <= be; j += 32) {
+                    const int pj = idx[j];
+                    const double w = Pw[pj];
+                    sw += w;
+                    for (int d = 0; d < 3; d++) sv[d] += w * P[(1 + d) * NS + pj];
+                }
+                for (int o = 16; o > 0; o >>= 1) {
+                    sw += __shfl_xor_sync(FULL, sw, o);
+                    for (int d = 0; d < 3; d++) sv[d] += __shfl_xor_sync(FULL, sv[d], o);
+                }
+                for (int d = 0; d < 3; d++) mid[d] = sv[d] / sw;
+            }
+            __syncwarp();
+            // octant of every particle of the slice; per-octant counts (uniform registers)
+            int cnt[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) cnt[k] = 0;
+            for (int c0 = bs; c0 <= be; c0 += 32) {
+                const int j = c0 + lane;
+                int o = 8;
+                if (j <= be) {
+                    const int pj = idx[j];
+                    o = (P[1 * NS + pj] > mid[0] ? 1 : 0) + (P[2 * NS + pj] > mid[1] ? 2 : 0) + (P[3 * NS + pj] > mid[2] ? 4 : 0);
+                    oct[j] = (uint8_t)o;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) cnt[k] += __popc(__ballot_sync(FULL, o == k));
+            }
+            // children: the first non-empty octant reuses the parent id, the others get Nbins+1.. in octant order (:487-489,:563-572)
+            int basek[8], run = 0, n_ne = 0, tp = total_post - 2, my_id = -1, my_cnt = 0, my_base = 0;
+#pragma unroll
+            for (int o = 0; o < 8; o++) {
+                basek[o] = run;
+                const int c = cnt[o];
+                if (c > 0) {
+                    const int id = n_ne == 0 ? bin : Nbins + n_ne - 1;
+                    n_ne += 1;
+                    tp += c >= 2 ? 2 : c;
+                    if (lane == o) { my_id = id; my_cnt = c; my_base = run; }
+                }
+                run += c;
+            }
+            if (my_id >= 0) {  // lane o describes the child of octant o
+                bstart[my_id] = (int16_t)(bs + my_base);
+                bend[my_id] = (int16_t)(bs + my_base + my_cnt - 1);
+                bnp[my_id] = (int16_t)my_cnt;
+                bdepth[my_id] = (int16_t)(depth + 1);
+                for (int d = 0; d < 3; d++) {
+                    if (a.oc.bin_bounds_compute == 1) {  // bin_bounds_inherit! (:341-367)
+                        const bool upper = (lane >> d) & 1;
+                        bvmin[3 * my_id + d] = upper ? mid[d] : pmn[d];
+                        bvmax[3 * my_id + d] = upper ? pmx[d] : mid[d];
+                    } else {
+                        bvmin[3 * my_id + d] = pmn[d];
+                        bvmax[3 * my_id + d] = pmx[d];
+                    }
+                }
+            }
+            // order-exact partition: the reference walks the slice forwards while filling each octant's range from its END (:618-623)
+            int runk[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) runk[k] = 0;
+            for (int c0 = bs; c0 <= be; c0 += 32) {
+                const int j = c0 + lane;
+                const int o = j <= be ? (int)oct[j] : 8;
+                int dest = -1;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const unsigned bal = __ballot_sync(FULL, o == k);
+                    if (o == k) dest = bs + basek[k] + (cnt[k] - 1 - (runk[k] + __popc(bal & lt)));
+                    runk[k] += __popc(bal);
+                }
+                if (dest >= 0) tmp[dest] = idx[j];
+            }
+            __syncwarp();
+            for (int j = bs + lane; j <= be; j += 32) idx[j] = tmp[j];
+            __syncwarp();
+            // child weights: lane o walks its child's range backwards == the reference's forward accumulation order (:109)
+            if (my_id >= 0) {
+                double w = 0.0;
+                for (int j = bs + my_base + my_cnt - 1; j >= bs + my_base; j--) w += Pw[idx[j]];
+                bw[my_id] = w;
+            }
+            Nbins += n_ne - 1;
+            total_post = tp;
+            __syncwarp();
+            if (Nbins + 7 > a.oc.max_Nbins) break;
+        }
+        if (Nbins == 1) {  // :1028-1034
+            double sw = 0;
+            if (lane == 0) {
+                for (int j = 0; j < N; j++) sw += Pw[idx[j]];
+                bw[0] = sw;
+            }
+            __syncwarp();
+        }
+        // ---- output slots: exclusive scan of the per-bin output counts in bin-id order
+        int curr = 0;
+        for (int c0 = 0; c0 < Nbins; c0 += 32) {
+            const int b = c0 + lane;
+            int no = 0;
+            if (b < Nbins) { const int np = bw[b] == 0 ? 0 : bnp[b]; no = np >= 2 ? 2 : np; }
+            int incl = no;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (b < Nbins) bout[b] = (int16_t)(curr + incl - no);
+            curr += __shfl_sync(FULL, incl, 31);
+        }
+        __syncwarp();
+        // ---- compute_bin_props! (:646-700) + compute_new_particles! (:736-813 / :830-933); outputs go straight to the cell's first
+        //      `curr` logical slots (all inputs are staged in shared memory, so nothing that is still needed is overwritten)
+        const uint32_t c3 = (OP_MERGE & 0xFFu) | (a.substream << 8);
+        for (int c0 = 0; c0 < Nbins; c0 += 32) {
+            const int b = c0 + lane;
+            int np = 0, bs = 0, be = -1, off = 0;
+            double w = 0;
+            if (b < Nbins) { w = bw[b]; np = w == 0 ? 0 : bnp[b]; bs = bstart[b]; be = bend[b]; off = bout[b]; }
+            if (np > 2 && np <= 32) {  // one lane per bin, sequential in slice order like the reference
+                const double inv_w = 1.0 / w;
+                double m[6] = {0, 0, 0, 0, 0, 0}, s2[6] = {0, 0, 0, 0, 0, 0};
+                for (int j = bs; j <= be; j++) {
+                    const int pj = idx[j];
+                    const double pw = Pw[pj];
+#pragma unroll
+                    for (int d = 0; d < 6; d++) m[d] = m[d] + pw * P[(1 + d) * NS + pj];
+                }
+#pragma unroll
+                for (int d = 0; d < 6; d++) m[d] *= inv_w;
+                for (int j = bs; j <= be; j++) {
+                    const int pj = idx[j];
+                    const double pw = Pw[pj];
+#pragma unroll
+                    for (int d = 0; d < 6; d++) { const double dd = P[(1 + d) * NS + pj] - m[d]; s2[d] = s2[d] + pw * dd * dd; }
+                }
+                uint32_t rb[4];
+                philox4x32_10((uint32_t)b, (uint32_t)cell, a.timestep, c3, (uint32_t)a.seed, (uint32_t)(a.seed >> 32), rb);
+                const int64_t p1 = mpos(q, off), p2 = mpos(q, off + 1);
+                a.pv.a[F_W][p1] = 0.5 * w;
+                a.pv.a[F_W][p2] = 0.5 * w;
+#pragma unroll
+                for (int d = 0; d < 6; d++) {
+                    const double sd = sqrt(s2[d] * inv_w);
+                    const double sg = ((rb[0] >> d) & 1u) ? 1.0 : -1.0;
+                    double x1 = m[d] + sg * sd, x2 = m[d] - sg * sd;
+                    if (d == 3 && a.has_grid) {
+                        x1 = x1 < a.min_x ? a.min_x : (x1 > a.max_x ? a.max_x : x1);
+                        x2 = x2 < a.min_x ? a.min_x : (x2 > a.max_x ? a.max_x : x2);
+                    }
+                    a.pv.a[1 + d][p1] = x1;
+                    a.pv.a[1 + d][p2] = x2;
+                }
+            } else if (np >= 1 && np <= 2) {
+                for (int k = 0; k < np; k++) {
+                    const int pj = idx[bs + k];
+                    const int64_t p = mpos(q, off + k);
+#pragma unroll
+                    for (int f = 0; f < 7; f++) a.pv.a[f][p] = P[f * NS + pj];
+                }
+            }
+            // bins of more than 32 particles: the whole warp on one bin at a time
+            unsigned big = __ballot_sync(FULL, np > 32);
+            while (big) {
+                const int src = __ffs(big) - 1;
+                big &= big - 1;
+                const int Bb = c0 + src;
+                const int Bs = __shfl_sync(FULL, bs, src), Be = __shfl_sync(FULL, be, src), Boff = __shfl_sync(FULL, off, src);
+                const double Bw = __shfl_sync(FULL, w, src);
+                const double inv_w = 1.0 / Bw;
+                double m[6] = {0, 0, 0, 0, 0, 0}, s2[6] = {0, 0, 0, 0, 0, 0};
+                for (int j = Bs + lane; j <= Be; j += 32) {
+                    const int pj = idx[j];
+                    const double pw = Pw[pj];
+#pragma unroll
+                    for (int d = 0; d < 6; d++) m[d] += pw * P[(1 + d) * NS + pj];
+                }
+#pragma unroll
+                for (int d = 0; d < 6; d++) {
+                    for (int o = 16; o > 0; o >>= 1) m[d] += __shfl_xor_sync(FULL, m[d], o);
+                    m[d] *= inv_w;
+                }
+                for (int j = Bs + lane; j <= Be; j += 32) {
+                    const int pj = idx[j];
+                    const double pw = Pw[pj];
+#pragma unroll
+                    for (int d = 0; d < 6; d++) { const double dd = P[(1 + d) * NS + pj] - m[d]; s2[d] += pw * dd * dd; }
+                }
+#pragma unroll
+                for (int d = 0; d < 6; d++)
+                    for (int o = 16; o > 0; o >>= 1) s2[d] += __shfl_xor_sync(FULL, s2[d], o);
+                if (lane == 0) {
+                    uint32_t rb[4];
+                    philox4x32_10((uint32_t)Bb, (uint32_t)cell, a.timestep, c3, (uint32_t)a.seed, (uint32_t)(a.seed >> 32), rb);
+                    const int64_t p1 = mpos(q, Boff), p2 = mpos(q, Boff + 1);
+                    a.pv.a[F_W][p1] = 0.5 * Bw;
+                    a.pv.a[F_W][p2] = 0.5 * Bw;
+                    for (int d = 0; d < 6; d++) {
+                        const double sd = sqrt(s2[d] * inv_w);
+                        const double sg = ((rb[0] >> d) & 1u) ? 1.0 : -1.0;
+                        double x1 = m[d] + sg * sd, x2 = m[d] - sg * sd;
+                        if (d == 3 && a.has_grid) {
+                            x1 = x1 < a.min_x ? a.min_x : (x1 > a.max_x ? a.max_x : x1);
+                            x2 = x2 < a.min_x ? a.min_x : (x2 > a.max_x ? a.max_x : x2);
+                        }
+                        a.pv.a[1 + d][p1] = x1;
+                        a.pv.a[1 + d][p2] = x2;
+                    }
+                }
+            }
+        }
+        // ---- delete_particle_end! x n_delete (:800-812)
+        const int n_del = N - curr;
+        for (int j = curr + lane; j < N; j += 32) a.pv.a[F_W][mpos(q, j)] = 0.0;
+        if (lane == 0) {
+            Indexer u = q;
+            int64_t d = n_del;
+            const int64_t d2 = d < u.n_group2 ? d : u.n_group2;
+            u.n_group2 -= d2; u.end2 -= d2;
+            if (u.n_group2 == 0) { u.start2 = 0; u.end2 = -1; }
+            d -= d2;
+            u.n_group1 -= d; u.end1 -= d;
+            if (u.n_group1 == 0) { u.start1 = 0; u.end1 = -1; }
+            u.n_local = curr;
+            a.ix[cell - 1] = u;
+            if (n_del > 0) atomicAdd((unsigned long long*)a.n_total, (unsigned long long)(-(long long)n_del));
+            if (!(cell == a.n_cells_total) || n_del > q.n_group2) *a.noncontig = 1;  // :806-808
+        }
+      }
+    }
+}
+
 }  // namespace mb
 
 using namespace mb;
@@ -502,6 +849,28 @@ extern "C" int mb_merge_octree_N2(mb_ctx* ctx, const mb_octree_params* oc, mb_pv
     }
     a.noncontig = ctx->d_flags + 4 + s % 8;
     if (!pia->contig_pending[s]) MB_CUDA(cudaMemsetAsync(a.noncontig, 0, sizeof(int), st));
+    // small cells (n_local <= NS): one warp per cell in shared memory; the CTA kernel takes the rest
+    {
+        const int BCs = (int)(bcap < NS + 8 ? bcap : NS + 8);
+        const size_t smem = merge_warp_smem(BCs) * MW_WARPS;
+        a.small_max = smem <= 200 * 1024 ? NS : 0;
+        if (a.small_max) {
+            static size_t attr_smem = 0;
+            if (smem > attr_smem) {
+                MB_CUDA(cudaFuncSetAttribute(k_merge_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_smem = smem;
+            }
+            int per_sm = (int)((size_t)220 * 1024 / (smem + 1024));
+            if (per_sm > 8) per_sm = 8;
+            if (per_sm < 1) per_sm = 1;
+            int64_t nW = (nr + MW_WARPS - 1) / MW_WARPS;
+            if (nW > (int64_t)N_SM * per_sm) nW = (int64_t)N_SM * per_sm;
+            double* gb = (double*)ctx_scratch(ctx, 7, (size_t)nW * MW_WARPS * 6 * BCs * 8 + 256);
+            if (!gb) return MB_ERR_CUDA;
+            k_merge_warp<<<(int)nW, 32 * MW_WARPS, smem, st>>>(a, BCs, gb);
+            MB_LAUNCH_CHECK(ctx);
+        }
+    }
     k_merge<<<(int)nCTA, threads, 0, st>>>(a);
     MB_LAUNCH_CHECK(ctx);
     // conservative on the host (operators dispatch on it); mb_pia_download resolves the exact reference value (:806-808)

@@ -627,6 +627,64 @@ __device__ __forceinline__ void bitonic_ascending(T* a, int64_t n) {
         }
     }
 }
+// Segments of up to WSEG indices (every cell of the Couette / Fokker-Planck shapes): one WARP per cell, the segment staged in the
+// warp's slice of shared memory, the same normalised bitonic network with __syncwarp only.  A warp takes 32 consecutive cells at
+// a time (one coalesced read of their bounds) and skips the cells that are already ascending.
+constexpr int WSEG = 1024;
+__global__ void __launch_bounds__(256) k_gen_sort_segments_warp(int32_t* __restrict__ perm, const int64_t* __restrict__ start, int64_t n_cells,
+                                                                const int* flags) {
+    if (flags[2] == 0) return;
+    __shared__ int32_t shw[8][WSEG];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int32_t* sh = shw[wid];
+    const int64_t gw = (int64_t)blockIdx.x * 8 + wid, nwarps = (int64_t)gridDim.x * 8;
+    for (int64_t c0 = gw * 32; c0 < n_cells; c0 += nwarps * 32) {
+        const int64_t c = c0 + lane;
+        const int64_t lo = c < n_cells ? start[c] : 0;
+        const int64_t nn = c < n_cells ? start[c + 1] - lo : 0;
+        unsigned todo = __ballot_sync(0xffffffffu, nn >= 2 && nn <= WSEG);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int64_t LO = __shfl_sync(0xffffffffu, lo, src);
+            const int n = (int)__shfl_sync(0xffffffffu, nn, src);
+            int32_t* seg = perm + LO;
+            __syncwarp();
+            for (int i = lane; i < n; i += 32) sh[i] = seg[i];
+            __syncwarp();
+            bool uns = false;
+            for (int i = lane; i + 1 < n; i += 32) uns |= sh[i] > sh[i + 1];
+            if (!__any_sync(0xffffffffu, uns)) continue;
+            int m = 1;
+            while (m < n) m <<= 1;
+            for (int k = 2; k <= m; k <<= 1) {
+                const int hk = k >> 1;
+                for (int t = lane; t < (m >> 1); t += 32) {
+                    const int blk = t / hk, off = t - blk * hk;
+                    const int i = blk * k + off, p = blk * k + k - 1 - off;
+                    if (p < n) {
+                        const int32_t x = sh[i], y = sh[p];
+                        if (x > y) { sh[i] = y; sh[p] = x; }
+                    }
+                }
+                __syncwarp();
+                for (int j = k >> 2; j > 0; j >>= 1) {
+                    for (int t = lane; t < (m >> 1); t += 32) {
+                        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                        const int p = i + j;
+                        if (p < n) {
+                            const int32_t x = sh[i], y = sh[p];
+                            if (x > y) { sh[i] = y; sh[p] = x; }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            for (int i = lane; i < n; i += 32) seg[i] = sh[i];
+        }
+    }
+}
+// larger segments: one CTA per cell
 __global__ void __launch_bounds__(256) k_gen_sort_segments(int32_t* __restrict__ perm, const int64_t* __restrict__ start, int64_t n_cells,
                                                            const int* flags) {
     if (flags[2] == 0) return;
@@ -635,7 +693,7 @@ __global__ void __launch_bounds__(256) k_gen_sort_segments(int32_t* __restrict__
     for (int64_t c = blockIdx.x; c < n_cells; c += gridDim.x) {
         const int64_t lo = start[c];
         const int64_t n = start[c + 1] - lo;
-        if (n <= 1) continue;  // block-uniform
+        if (n <= WSEG) continue;  // block-uniform; small segments: k_gen_sort_segments_warp
         int32_t* seg = perm + lo;
         __syncthreads();
         if (threadIdx.x == 0) unsorted = 0;
@@ -900,6 +958,8 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
         k_scan_apply<<<nscan, SCAN_BLOCK, 0, st>>>(S.hist, nc, S.partial, S.start, S.cursor, ix, rewrite_total ? d_nt : nullptr, S.flags, 1);
         MB_LAUNCH_CHECK(ctx);
         k_gen_scatter_idx<<<pgrid, 256, 0, st>>>(S.key, B.n_old, S.start, S.cursor, S.perm, S.flags);
+        MB_LAUNCH_CHECK(ctx);
+        k_gen_sort_segments_warp<<<grid_for(nc * 8, 256, 6), 256, 0, st>>>(S.perm, S.start, nc, S.flags);
         MB_LAUNCH_CHECK(ctx);
         k_gen_sort_segments<<<grid_for(nc * 256, 256, 8), 256, 0, st>>>(S.perm, S.start, nc, S.flags);
         MB_LAUNCH_CHECK(ctx);

@@ -86,10 +86,14 @@ def test_sample_box_parity_and_reference_pins(mb, oracle, ctx, dist):
     for c in range(3):
         assert abs(d["n"][0, c] / n_dens - 1) < 1e-14
         assert np.all(np.abs(d["v"][0, c] - np.array(v0)) < 10.0)
-        assert abs(d["T"][0, c] / T0 - 1) < (1e-2 if dist == "Maxwellian" else 2e-2)
+        # test_sampling.jl:35 asks 1e-2 of its one fixed seed; the standard error of T over 20000 particles is sqrt(2 / (3 N)) = 0.58 %,
+        # so each of the three ensemble members is held to 3.5 sigma
+        assert abs(d["T"][0, c] / T0 - 1) < 2e-2
         if dist == "Maxwellian":
             m = d["moments"][0, c]
-            assert abs(m[0] - 1) < 0.05 and abs(m[1] - 1) < 0.05 and abs(m[2] - 1) < 0.12
+            # test_sampling.jl:36-38 asks 0.05 / 0.05 / 0.12 of its one fixed seed; the standard errors of the 4th / 6th / 8th moments
+            # over 20000 Maxwellian particles are 1.3 % / 2.4 % / 4.3 %, so each ensemble member is held to 3.5 sigma
+            assert abs(m[0] - 1) < 0.05 and abs(m[1] - 1) < 0.085 and abs(m[2] - 1) < 0.16
 
 
 @pytest.mark.parametrize("vdf,noise", [("bkw", 0.0), ("maxwellian", 0.7)])
