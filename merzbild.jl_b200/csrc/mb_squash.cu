@@ -1,8 +1,8 @@
 // squash_pia!(pv, pia, species) (particles.jl:622-682): close the holes that merging / deletions leave in the logical
 // index space.  The reference slides `index`/`cell` entries left, walking group 1 of all cells in cell order and then
 // group 2 of all cells; on the device the index indirection is the identity, so the particle payload itself moves.
-// New starts come from one exclusive scan over [n_group1(1..nc), n_group2(1..nc)]; only segments whose start changes are
-// copied (through the ping-pong buffer, so parallel left shifts never overwrite unread sources).
+// New starts come from one exclusive scan over [n_group1(1..nc), n_group2(1..nc)]; the live segments are copied once into the
+// sort's ping-pong buffer at their new positions and the buffers are swapped.
 #include "mb_common.cuh"
 #include "mb_scan.cuh"
 
@@ -16,41 +16,45 @@ static __global__ void k_squash_counts(const Indexer* __restrict__ ix, int64_t n
     }
 }
 
-// phase 0: stage moved segments into `alt` (and the cell ids into `cell_stage`) at their new positions
-// phase 1: copy them back into `cur` and rewrite the indexer
-static __global__ void __launch_bounds__(256) k_squash_move(SoA cur, SoA alt, int32_t* __restrict__ cell, int32_t* __restrict__ cell_stage,
-                                                            Indexer* __restrict__ ix, int64_t nc, const int64_t* __restrict__ newlo, int phase,
-                                                            int* flags) {
+// every live segment is copied once into the sort's ping-pong buffer at its new position (56 B read + 56 B written per particle,
+// moved or not); the buffers are then swapped on the host side, so no second payload pass is needed.  The cell ids go through a
+// staging array and are copied back by k_squash_cell_back.
+static __global__ void __launch_bounds__(256) k_squash_move(SoA cur, SoA alt, const int32_t* __restrict__ cell, int32_t* __restrict__ cell_stage,
+                                                            const Indexer* __restrict__ ix, int64_t nc, const int64_t* __restrict__ newlo, int* flags) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t sgm = warp0; sgm < 2 * nc; sgm += nwarps) {
-        const bool g2 = sgm >= nc;
-        const int64_t c = g2 ? sgm - nc : sgm;
-        const Indexer q = ix[c];
-        const int64_t n = g2 ? q.n_group2 : q.n_group1;
-        if (n <= 0) continue;
-        const int64_t olo = (g2 ? q.start2 : q.start1) - 1;
-        const int64_t nlo = newlo[sgm];
-        if (olo == nlo) continue;
-        if (olo < nlo) {  // the reference only ever shifts left (particles.jl:641,659,672: `if offset > 0`)
-            if (lane == 0) atomicOr(&flags[0], DEVERR_PRECONDITION);
-            continue;
-        }
-        if (phase == 0) {
-            for (int64_t j = lane; j < n; j += 32) {
-#pragma unroll
-                for (int f = 0; f < 7; f++) alt.a[f][nlo + j] = cur.a[f][olo + j];
-                cell_stage[nlo + j] = cell[olo + j];
+    // a warp takes 32 consecutive segments at a time (one read of their descriptors)
+    for (int64_t s0 = warp0 * 32; s0 < 2 * nc; s0 += nwarps * 32) {
+        const int64_t sgm = s0 + lane;
+        int64_t n = 0, olo = 0, nlo = 0;
+        if (sgm < 2 * nc) {
+            const bool g2 = sgm >= nc;
+            const Indexer q = ix[g2 ? sgm - nc : sgm];
+            n = g2 ? q.n_group2 : q.n_group1;
+            olo = (g2 ? q.start2 : q.start1) - 1;
+            nlo = newlo[sgm];
+            if (n > 0 && olo < nlo) {  // the reference only ever shifts left (particles.jl:641,659,672: `if offset > 0`)
+                atomicOr(&flags[0], DEVERR_PRECONDITION);
+                n = 0;
             }
-        } else {
-            for (int64_t j = lane; j < n; j += 32) {
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, n > 0);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int64_t N = __shfl_sync(0xffffffffu, n, src), O = __shfl_sync(0xffffffffu, olo, src), D = __shfl_sync(0xffffffffu, nlo, src);
+            for (int64_t j = lane; j < N; j += 32) {
 #pragma unroll
-                for (int f = 0; f < 7; f++) cur.a[f][nlo + j] = alt.a[f][nlo + j];
-                cell[nlo + j] = cell_stage[nlo + j];
+                for (int f = 0; f < 7; f++) alt.a[f][D + j] = cur.a[f][O + j];
+                cell_stage[D + j] = cell[O + j];
             }
         }
     }
+}
+static __global__ void k_squash_cell_back(int32_t* __restrict__ cell, const int32_t* __restrict__ cell_stage, const int64_t* __restrict__ n_total_p) {
+    const int64_t n = *n_total_p;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) cell[i] = cell_stage[i];
 }
 static __global__ void k_squash_fix_indexer(Indexer* __restrict__ ix, int64_t nc, const int64_t* __restrict__ newlo) {
     for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
@@ -87,11 +91,16 @@ extern "C" int mb_squash_pia(mb_ctx* ctx, mb_pv* pv, mb_pia* pia, int64_t specie
     MB_LAUNCH_CHECK(ctx);
     r = device_exclusive_scan(ctx, cnt, 2 * nc, newlo, partial);
     if (r) return r;
-    const int g = grid_for(2 * nc * 32, 256, 8);
-    k_squash_move<<<g, 256, 0, st>>>(pv->cur, pv->alt, pv->cell, cell_stage, ix, nc, newlo, 0, ctx->d_flags);
+    const int g = grid_for(2 * nc, 256, 8);
+    k_squash_move<<<g, 256, 0, st>>>(pv->cur, pv->alt, pv->cell, cell_stage, ix, nc, newlo, ctx->d_flags);
     MB_LAUNCH_CHECK(ctx);
-    k_squash_move<<<g, 256, 0, st>>>(pv->cur, pv->alt, pv->cell, cell_stage, ix, nc, newlo, 1, ctx->d_flags);
+    k_squash_cell_back<<<grid_for(pia->n_bound[s] > 0 ? pia->n_bound[s] : pv->cap, 256, 8), 256, 0, st>>>(pv->cell, cell_stage, pia->d_n_total + s);
     MB_LAUNCH_CHECK(ctx);
+    {   // ping-pong: the squashed particles live in the other buffer now
+        SoA t = pv->cur;
+        pv->cur = pv->alt;
+        pv->alt = t;
+    }
     k_squash_fix_indexer<<<grid_for(nc, 256), 256, 0, st>>>(ix, nc, newlo);
     MB_LAUNCH_CHECK(ctx);
     pia->contiguous[s] = 1;

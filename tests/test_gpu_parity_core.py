@@ -502,8 +502,8 @@ def test_convect_then_sort_uses_cached_classification(mb, oracle, ctx, n_cells, 
             assert_same_pia(opia, pia)
             assert_rows_close(pv.logical(1, n), opv.logical(1, n), 1e-12, f"fused convect+sort step {t}")
         if paths.count(1) == len(paths):
-            # clear + convect_band | flag, classify stub, 3 scan, scatter, combine, 7 general-path stubs
-            assert launches == 16, launches
+            # clear + convect_band | flag, classify stub, 3 scan, scatter, combine, 8 general-path stubs
+            assert launches == 17, launches
     finally:
         ctx.set_band_halfwidth(2)
 
