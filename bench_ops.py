@@ -21,6 +21,7 @@ import merzbild_b200 as mb
 AR, K_B, DX, NDENS, DT = 66.3e-27, 1.380649e-23, 1e-5, 5e22, 2.59e-9
 
 
+
 def population(n_cells, ppc, seed, vw=False):
     rng = np.random.default_rng(seed)
     n = n_cells * ppc
@@ -155,6 +156,55 @@ def main():
     report("sort_particles (general path)", "after squash", n1, med["sort"], 128, "first sort after a merge: general path")
     report("ntc! variable weight (splits)", "C4 population after merge, dt x 4", n1, med["ntc"], 64, "candidates only: ~%d new particles" % (n2 - n1))
     report("compute_props (both groups)", "C4 population after ntc", n2, med["props"], 32, "group 2 at the tail")
+    pv.close()
+    pia.close()
+    del a
+
+    # ---- C2: 0-D BKW variable-weight relaxation with octree N:2 merging (bkw_varweight_octree.jl / test_bkw_varweight_octree.jl:43-47):
+    #      an ensemble of independent cells, each the nv = 40 grid sample (~33.5k particles) merged to 8000 at t = 0, then per step
+    #      ntc! -> merge if n_local > 10000 -> squash_pia! / re-sort by cell id -> compute_props_with_total_moments!.  Sampled on the device.
+    itm = mb.make_interaction(AR, AR, 4.11e-10, 1.0, 273.0)  # data/pseudo_maxwell.toml
+    T0, n_dens, nv = 273.0, 1e23, 40
+    probe_pv, probe_pia = mb.ParticleVector(nv ** 3, ctx), mb.ParticleIndexerArray(1, 1, ctx)
+    n_s = mb.sample_on_grid(mb.PhiloxRng(0), "bkw", probe_pv, probe_pia, 1, 1, nv, AR, T0, n_dens)
+    probe_pv.close()
+    probe_pia.close()
+    ncell = max(int(args.particles // n_s), 1)
+    n = ncell * n_s
+    pv, pia = mb.ParticleVector(n, ctx), mb.ParticleIndexerArray(ncell, 1, ctx)
+    t_sample = one(lambda: mb.sample_on_grid(mb.PhiloxRng(0), "bkw", pv, pia, (1, ncell), 1, nv, AR, T0, n_dens))
+    report("sample_on_grid! (BKW, nv = 40)", "C2: %d cells x %d" % (ncell, n_s), n, t_sample, 60, "write 56 B + cell id 4 B per particle (includes the host weight table)")
+    ppm = mb.PhysProps(ncell, 1, (4, 6, 8, 10), Tref=T0, ctx=ctx)
+    oc2 = mb.OctreeN2Merge(mb.OctreeN2Merge.OctreeBinMidSplit, mb.OctreeN2Merge.OctreeInitBinMinMaxVel, max_Nbins=6000)
+    t_m0 = one(lambda: mb.merge_octree_N2_based(mb.PhiloxRng(0), oc2, pv, pia, (1, ncell), 1, 8000, threshold=10000))
+    report("merge_octree_N2_based (%d -> 8000)" % n_s, "C2 initial merge", n, t_m0, 56 * (n_s + 8000) / n_s, "CTA per cell")
+    mb.sort_particles(None, pv, pia, 1)
+    n1 = int(pia.n_total[0])
+    Fnum = n_dens / 8000.0
+    cf2 = mb.CollisionFactors(ncell, mb.estimate_sigma_g_w_max(itm, AR, AR, T0, T0, Fnum), ctx)
+    sigma_ref = math.pi * 4.11e-10 ** 2
+    tref = 1.0 / (n_dens * sigma_ref) / math.sqrt(2 * K_B * T0 / AR)
+    dt2 = 0.025 * tref
+    acc = {}
+    n_steps = 12
+    for t in range(1, n_steps + 1):
+        tt = {"ntc": one(lambda: mb.ntc(mb.PhiloxRng(t), cf2, None, itm, pv, pia, (1, ncell), 1, dt2, 1.0)),
+              "merge": one(lambda: mb.merge_octree_N2_based(mb.PhiloxRng(t), oc2, pv, pia, (1, ncell), 1, 8000, threshold=10000)),
+              # an ensemble of 0-D cells shares one ParticleVector: the split particles appended at the tail are folded back into
+              # their cells by the cell-id sort (which squashes first when a merge left holes)
+              "sort": one(lambda: mb.sort_particles(None, pv, pia, 1)),
+              "props": one(lambda: mb.compute_props_with_total_moments([pv], pia, [AR], ppm))}
+        if t > 2:
+            for k, v in tt.items():
+                acc.setdefault(k, []).append(v)
+    n2 = int(pia.n_total[0])
+    d = ppm.download()
+    tot = sum(sum(v) / len(v) for v in acc.values())
+    for k, bpp in (("ntc", 64), ("merge", 112), ("sort", 128), ("props", 32 * 6)):
+        v = acc[k]
+        report("C2 step: " + k, "%d cells, %d..%d particles, mean of steps 3-%d (max %.2f ms)" % (ncell, n1, n2, n_steps, max(v)), n2, sum(v) / len(v), bpp,
+               "T = %.2f K (T0 %.0f), M4 = %.4f" % (d["T"].mean(), T0, d["moments"][0, :, 0].mean()))
+    print(json.dumps({"op": "C2 step total", "ms": tot, "particle_steps_per_s": n2 / (tot * 1e-3)}), flush=True)
     ctx.close()
 
 

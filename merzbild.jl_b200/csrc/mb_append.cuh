@@ -33,28 +33,44 @@ __device__ __forceinline__ void append_split(const SoA& s, Indexer& q, int64_t w
 // pack the per-cell windows to the left (cell order) so the layout equals the reference's sequential appends
 static __global__ void __launch_bounds__(256) k_ntc_pack(SoA cur, SoA alt, Indexer* __restrict__ ix, int64_t cell_lo, int64_t nr,
                                                          const int64_t* __restrict__ win, const int64_t* __restrict__ packed,
-                                                         const int32_t* __restrict__ nsplit, const int64_t* n_total, int phase) {
+                                                         const int32_t* __restrict__ nsplit, const int64_t* n_total, int phase,
+                                                         int32_t* __restrict__ cell_id) {
     const int64_t nt = *n_total;
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = warp0; r < nr; r += nwarps) {
-        const int n = nsplit[r];
-        if (n <= 0 || win[r] == packed[r]) continue;
-        const int64_t olo = nt + win[r], nlo = nt + packed[r];
-        if (phase == 0) {
-            for (int j = lane; j < n; j += 32)
+    // a warp takes 32 consecutive cells at a time (one read of their split counts)
+    for (int64_t r0 = warp0 * 32; r0 < nr; r0 += nwarps * 32) {
+        const int64_t myr = r0 + lane;
+        const int my_n = myr < nr ? nsplit[myr] : 0;
+        unsigned todo = __ballot_sync(0xffffffffu, my_n > 0);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int64_t r = r0 + src;
+            const int n = __shfl_sync(0xffffffffu, my_n, src);
+            const int64_t olo = nt + win[r], nlo = nt + packed[r];
+            const bool moved = olo != nlo;
+            if (phase == 0) {
+                if (moved)
+                    for (int j = lane; j < n; j += 32)
 #pragma unroll
-                for (int f = 0; f < 7; f++) alt.a[f][nlo + j] = cur.a[f][olo + j];
-        } else {
-            for (int j = lane; j < n; j += 32)
+                        for (int f = 0; f < 7; f++) alt.a[f][nlo + j] = cur.a[f][olo + j];
+            } else {
+                for (int j = lane; j < n; j += 32) {
+                    if (moved)
 #pragma unroll
-                for (int f = 0; f < 7; f++) cur.a[f][nlo + j] = alt.a[f][nlo + j];
-            if (lane == 0) {
-                Indexer q = ix[cell_lo - 1 + r];
-                q.start2 = nlo + 1;
-                q.end2 = nlo + n;
-                ix[cell_lo - 1 + r] = q;
+                        for (int f = 0; f < 7; f++) cur.a[f][nlo + j] = alt.a[f][nlo + j];
+                    // device-side extension: the new particles carry their cell id, so that an ensemble of 0-D cells can be re-sorted
+                    // by sort_particles!(gridsort, particles, pia, species) (grid_sorting.jl:128) without a grid
+                    cell_id[nlo + j] = (int32_t)(cell_lo + r);
+                }
+                if (lane == 0 && moved) {
+                    Indexer q = ix[cell_lo - 1 + r];
+                    q.start2 = nlo + 1;
+                    q.end2 = nlo + n;
+                    ix[cell_lo - 1 + r] = q;
+                }
             }
         }
     }
@@ -69,13 +85,13 @@ static inline int pack_windows(mb_ctx* ctx, mb_pv* pv, Indexer* ix, int64_t cell
                                int64_t* packed, int64_t* partial, int64_t* n_total) {
     int r = device_exclusive_scan(ctx, nsplit, nr, packed, partial);
     if (r) return r;
+    const int gw = grid_for(nr, 256, 8);
     if (nr > 1) {
-        const int gw = grid_for(nr * 32, 256, 8);
-        k_ntc_pack<<<gw, 256, 0, ctx->stream>>>(pv->cur, pv->alt, ix, cell_lo, nr, win, packed, nsplit, n_total, 0);
-        MB_LAUNCH_CHECK(ctx);
-        k_ntc_pack<<<gw, 256, 0, ctx->stream>>>(pv->cur, pv->alt, ix, cell_lo, nr, win, packed, nsplit, n_total, 1);
+        k_ntc_pack<<<gw, 256, 0, ctx->stream>>>(pv->cur, pv->alt, ix, cell_lo, nr, win, packed, nsplit, n_total, 0, pv->cell);
         MB_LAUNCH_CHECK(ctx);
     }
+    k_ntc_pack<<<gw, 256, 0, ctx->stream>>>(pv->cur, pv->alt, ix, cell_lo, nr, win, packed, nsplit, n_total, 1, pv->cell);
+    MB_LAUNCH_CHECK(ctx);
     k_add_total<<<1, 1, 0, ctx->stream>>>(n_total, packed, nr);
     MB_LAUNCH_CHECK(ctx);
     return MB_OK;

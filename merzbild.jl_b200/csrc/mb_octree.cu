@@ -435,19 +435,21 @@ __global__ void __launch_bounds__(MT) k_merge(MergeArgs a) {
 // Summation orders follow the reference's sequential loops wherever one lane does the sum (child weights: forward slice order;
 // bin means / variances of bins of <= 32 particles: slice order), so those results are bit-identical to the CPU oracle.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int NS = 256;        // largest cell handled by the warp kernel
+constexpr int NS_MAX = 256;    // largest cell handled by the warp kernel (instantiated for NS = 160 and 256)
 constexpr int MW_WARPS = 4;    // warps (= concurrent cells) per CTA
 
+template <int NS>
 __host__ __device__ inline size_t merge_warp_smem(int BC) {
     size_t b = (size_t)7 * NS * 8 + (size_t)BC * 8 + (size_t)NS * 2 * 2 + (size_t)BC * 2 * 5 + (size_t)NS;
     return (b + 15) / 16 * 16;
 }
 
-__global__ void __launch_bounds__(32 * MW_WARPS) k_merge_warp(MergeArgs a, int BC, double* __restrict__ gbounds) {
+template <int NS>
+__global__ void __launch_bounds__(32 * MW_WARPS) k_merge_warp(MergeArgs a, int BC, double* __restrict__ gbounds, int ch) {
     extern __shared__ __align__(16) unsigned char mw_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1u;
-    unsigned char* base = mw_smem + (size_t)wid * merge_warp_smem(BC);
+    unsigned char* base = mw_smem + (size_t)wid * merge_warp_smem<NS>(BC);
     double* P = (double*)base;                 // [7][NS]: field f of local particle j at P[f * NS + j]
     double* bw = P + 7 * NS;                   // [BC] bin weight
     int16_t* idx = (int16_t*)(bw + BC);        // [NS] local particle index per slice position
@@ -464,10 +466,10 @@ __global__ void __launch_bounds__(32 * MW_WARPS) k_merge_warp(MergeArgs a, int B
     const int64_t nr = a.cell_hi - a.cell_lo + 1;
     const double* Pw = P;
 
-    // a warp takes 32 consecutive cells at a time (one read of their sizes) and merges the ones that need it
-    for (int64_t r0 = gw * 32; r0 < nr; r0 += nwarps * 32) {
+    // a warp takes ch (<= 32) consecutive cells at a time (one read of their sizes) and merges the ones that need it
+    for (int64_t r0 = gw * ch; r0 < nr; r0 += nwarps * ch) {
       const int64_t myr = r0 + lane;
-      const int64_t my_n = myr < nr ? a.ix[a.cell_lo - 1 + myr].n_local : 0;
+      const int64_t my_n = (lane < ch && myr < nr) ? a.ix[a.cell_lo - 1 + myr].n_local : 0;
       unsigned todo = __ballot_sync(FULL, my_n > 0 && my_n <= NS && (a.threshold < 0 || my_n > a.threshold));
       while (todo) {
         const int64_t r = r0 + (__ffs(todo) - 1);
@@ -514,10 +516,15 @@ __global__ void __launch_bounds__(32 * MW_WARPS) k_merge_warp(MergeArgs a, int B
                 const double w = bw[b];
                 if (w > bwm && bnp[b] > 2 && bdepth[b] < a.oc.max_depth) { bwm = w; bid = b; }
             }
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ow = __shfl_xor_sync(FULL, bwm, o);
-                const int oid = __shfl_xor_sync(FULL, bid, o);
-                if (oid >= 0 && (bid < 0 || ow > bwm || (ow == bwm && oid < bid))) { bwm = ow; bid = oid; }
+            {   // first bin with the strictly largest weight: weights are >= 0, so their bit patterns order like integers and the
+                // hardware warp reductions (redux.sync) replace a 5-round shuffle tournament
+                const unsigned long long key = bid >= 0 ? (unsigned long long)__double_as_longlong(bwm) + 1ull : 0ull;
+                const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+                const unsigned mhi = __reduce_max_sync(FULL, hi);
+                const unsigned mlo = __reduce_max_sync(FULL, hi == mhi ? lo : 0u);
+                const bool win = key != 0ull && hi == mhi && lo == mlo;
+                const unsigned mid_id = __reduce_min_sync(FULL, win ? (unsigned)bid : 0xffffffffu);
+                bid = mid_id == 0xffffffffu ? -1 : (int)mid_id;
             }
             if (bid < 0 || total_post + 14 > a.target) break;
             // ---- split_bin! (:503-633)
@@ -571,7 +578,7 @@ __global__ void __launch_bounds__(32 * MW_WARPS) k_merge_warp(MergeArgs a, int B
                 for (int k = 0; k < 8; k++) cnt[k] += __popc(__ballot_sync(FULL, o == k));
             }
             // children: the first non-empty octant reuses the parent id, the others get Nbins+1.. in octant order (:487-489,:563-572)
-            int basek[8], run = 0, n_ne = 0, tp = total_post - 2, my_id = -1, my_cnt = 0, my_base = 0;
+            int basek[8], run = 0, n_ne = 0, tp = total_post - 2, my_id = -1, my_cnt = 0, my_base = 0, w_id = -1, w_cnt = 0, w_base = 0;
 #pragma unroll
             for (int o = 0; o < 8; o++) {
                 basek[o] = run;
@@ -581,6 +588,7 @@ __global__ void __launch_bounds__(32 * MW_WARPS) k_merge_warp(MergeArgs a, int B
                     n_ne += 1;
                     tp += c >= 2 ? 2 : c;
                     if (lane == o) { my_id = id; my_cnt = c; my_base = run; }
+                    if ((lane >> 2) == o) { w_id = id; w_cnt = c; w_base = run; }  // lanes 4o .. 4o+3 sum the weights of octant o
                 }
                 run += c;
             }
@@ -619,11 +627,20 @@ __global__ void __launch_bounds__(32 * MW_WARPS) k_merge_warp(MergeArgs a, int B
             __syncwarp();
             for (int j = bs + lane; j <= be; j += 32) idx[j] = tmp[j];
             __syncwarp();
-            // child weights: lane o walks its child's range backwards == the reference's forward accumulation order (:109)
-            if (my_id >= 0) {
+            // child weights (:109): four lanes per octant, each a quarter of the child's range walked backwards (== the reference's
+            // forward order inside the quarter), combined as (q0 + q1) + (q2 + q3)
+            {
                 double w = 0.0;
-                for (int j = bs + my_base + my_cnt - 1; j >= bs + my_base; j--) w += Pw[idx[j]];
-                bw[my_id] = w;
+                if (w_id >= 0) {
+                    const int chunk = (w_cnt + 3) >> 2, part = lane & 3;
+                    const int hi_j = bs + w_base + w_cnt - 1 - part * chunk;
+                    int lo_j = hi_j - chunk + 1;
+                    if (lo_j < bs + w_base) lo_j = bs + w_base;
+                    for (int j = hi_j; j >= lo_j; j--) w += Pw[idx[j]];
+                }
+                w += __shfl_xor_sync(FULL, w, 1);
+                w += __shfl_xor_sync(FULL, w, 2);
+                if (w_id >= 0 && (lane & 3) == 0) bw[w_id] = w;
             }
             Nbins += n_ne - 1;
             total_post = tp;
@@ -849,25 +866,35 @@ extern "C" int mb_merge_octree_N2(mb_ctx* ctx, const mb_octree_params* oc, mb_pv
     }
     a.noncontig = ctx->d_flags + 4 + s % 8;
     if (!pia->contig_pending[s]) MB_CUDA(cudaMemsetAsync(a.noncontig, 0, sizeof(int), st));
-    // small cells (n_local <= NS): one warp per cell in shared memory; the CTA kernel takes the rest
+    // small cells: one warp per cell in shared memory; the CTA kernel takes the rest.  The staging area is sized for 160 particles
+    // when the threshold says that cells are merged long before they reach that size (a cell is merged as soon as it exceeds the
+    // threshold, so it rarely exceeds it by much), else for 256; larger cells simply fall through to the CTA kernel.
     {
-        const int BCs = (int)(bcap < NS + 8 ? bcap : NS + 8);
-        const size_t smem = merge_warp_smem(BCs) * MW_WARPS;
-        a.small_max = smem <= 200 * 1024 ? NS : 0;
+        const int ns = (threshold > 0 && threshold + 24 <= 160) ? 160 : NS_MAX;
+        const int BCs = (int)(bcap < ns + 8 ? bcap : ns + 8);
+        const size_t smem = (ns == 160 ? merge_warp_smem<160>(BCs) : merge_warp_smem<NS_MAX>(BCs)) * MW_WARPS;
+        a.small_max = smem <= 200 * 1024 ? ns : 0;
         if (a.small_max) {
-            static size_t attr_smem = 0;
-            if (smem > attr_smem) {
-                MB_CUDA(cudaFuncSetAttribute(k_merge_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                attr_smem = smem;
+            static size_t attr_smem[2] = {0, 0};
+            size_t& as = attr_smem[ns == 160 ? 0 : 1];
+            if (smem > as) {
+                if (ns == 160) MB_CUDA(cudaFuncSetAttribute(k_merge_warp<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                else MB_CUDA(cudaFuncSetAttribute(k_merge_warp<NS_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                as = smem;
             }
             int per_sm = (int)((size_t)220 * 1024 / (smem + 1024));
-            if (per_sm > 8) per_sm = 8;
+            if (per_sm > 4) per_sm = 4;  // 128 registers x 128 threads
             if (per_sm < 1) per_sm = 1;
-            int64_t nW = (nr + MW_WARPS - 1) / MW_WARPS;
-            if (nW > (int64_t)N_SM * per_sm) nW = (int64_t)N_SM * per_sm;
+            // a warp takes ch cells at a time: 32 when there are enough cells to keep every warp busy, fewer for short ranges
+            const int64_t max_ctas = (int64_t)N_SM * per_sm;
+            int ch = 32;
+            while (ch > 1 && nr < max_ctas * MW_WARPS * ch) ch >>= 1;
+            int64_t nW = (nr + (int64_t)ch * MW_WARPS - 1) / ((int64_t)ch * MW_WARPS);
+            if (nW > max_ctas) nW = max_ctas;
             double* gb = (double*)ctx_scratch(ctx, 7, (size_t)nW * MW_WARPS * 6 * BCs * 8 + 256);
             if (!gb) return MB_ERR_CUDA;
-            k_merge_warp<<<(int)nW, 32 * MW_WARPS, smem, st>>>(a, BCs, gb);
+            if (ns == 160) k_merge_warp<160><<<(int)nW, 32 * MW_WARPS, smem, st>>>(a, BCs, gb, ch);
+            else k_merge_warp<NS_MAX><<<(int)nW, 32 * MW_WARPS, smem, st>>>(a, BCs, gb, ch);
             MB_LAUNCH_CHECK(ctx);
         }
     }
