@@ -61,6 +61,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--particles", type=float, default=1e8)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--only", default="", help="c2: only the BKW variable-weight 0-D ensemble section")
     args = ap.parse_args()
     peak = 6533.8
     try:
@@ -70,95 +71,102 @@ def main():
     ctx = mb.Context(0, 1234)
     it = mb.make_interaction(AR, AR, 4.11e-10, 0.81, 273.0)
 
-    def report(name, cfg, n, ms, bytes_per_particle, note=""):
-        gbs = bytes_per_particle * n / (ms * 1e-3) / 1e9
-        print(json.dumps({"op": name, "config": cfg, "particles": n, "ms": ms, "particles_per_s": n / (ms * 1e-3),
-                          "algorithmic_bytes_per_particle": bytes_per_particle, "achieved_GBps": gbs, "frac_of_measured_hbm_peak": gbs / peak, "note": note}),
-              flush=True)
-
-    # ---- C5: fp_linear!, 1e6 cells x 100
-    ppc = 100
-    nc = int(args.particles // ppc)
-    a, ix, n = population(nc, ppc, 1)
-    pv, pia = mb.ParticleVector(n, ctx), mb.ParticleIndexerArray(nc, 1, ctx)
-    pv.upload_soa(1, n, a)
-    pia.upload(ix, np.array([n]), np.array([1], dtype=np.uint8))
-    step = [0]
-
-    def fp():
-        step[0] += 1
-        mb.fp_linear(mb.PhiloxRng(step[0]), None, it, AR, pv, pia, (1, nc), 1, DT, DX)
-
-    fp()
-    best, med = timed(ctx, fp, args.reps)
-    report("fp_linear", "C5: %d cells x %d" % (nc, ppc), n, med, 56, "read w,v 32 B + write v 24 B; 3 normals per particle regenerated from Philox counters")
-
-    # ---- props stand-alone on the same population (two-pass, 32 B/particle)
-    pp = mb.PhysProps(nc, 1, ctx=ctx)
-    best, med = timed(ctx, lambda: mb.compute_props_sorted([pv], pia, [AR], pp), args.reps)
-    report("compute_props_sorted (uncached)", "C5 population", n, med, 32, "two-pass; the second pass re-reads the cell from L1/L2")
-    best, med = timed(ctx, lambda: mb.compute_props([pv], pia, [AR], pp), args.reps)
-    report("compute_props", "C5 population", n, med, 32, "both pia groups")
-    pv.close()
-    pia.close()
-    del a
-
-    # ---- C2 / C4: variable-weight ntc! + octree merge (150 -> 100) + squash, cells of 150
-    ppc = 150
-    nc = int(args.particles * 0.6 // ppc)
-    a, ix, n = population(nc, ppc, 2, vw=True)
-    cap = int(n * 1.3)
-    pv, pia = mb.ParticleVector(cap, ctx), mb.ParticleIndexerArray(nc, 1, ctx)
-    # wall_offset 1e-6: with L = nc dx ~ 1 m the default offset dx * 1e-12 is below ulp(L), so a merged particle clamped to max_x would sit exactly on L
-    grid = mb.Grid1DUniform(nc * DX, nc, wall_offset=1e-6)
-    cf = mb.CollisionFactors(nc, mb.estimate_sigma_g_w_max(it, AR, AR, 300.0, 300.0, DX * NDENS / ppc * 1.5), ctx)
-    oc = mb.OctreeN2Merge(mb.OctreeN2Merge.OctreeBinMidSplit, mb.OctreeN2Merge.OctreeInitBinMinMaxVel, max_Nbins=6000)
-
-    pp2 = mb.PhysProps(nc, 1, ctx=ctx)
-
-    def reset():
-        pv.upload_soa(1, n, a)
-        pia.upload(ix, np.array([n]), np.array([1], dtype=np.uint8))
-
-    step = [0]
-
-    def merge():
-        mb.merge_octree_N2_based(mb.PhiloxRng(1), oc, pv, pia, (1, nc), 1, 100, grid, threshold=130)
-
-    def vw_ntc():
-        step[0] += 1
-        mb.ntc(mb.PhiloxRng(step[0]), cf, None, it, pv, pia, (1, nc), 1, DT * 4, DX)
-
     def one(fn):
         ctx.sync()
         ctx.timer_start()
         fn()
         return ctx.timer_stop()
 
-    # one untimed cycle first: lazy allocations (sort ping-pong buffer, scratch arena) must not be inside a timed region
-    res = {}
-    for rep in range(max(args.reps, 2)):
-        reset()
-        t_merge = one(merge)
-        t_squash = one(lambda: mb.squash_pia(pv, pia, 1))
-        n1 = int(pia.n_total[0])
-        t_sort = one(lambda: mb.sort_particles(None, grid, pv, pia, 1))
-        t_ntc = one(vw_ntc)
-        n2 = int(pia.n_total[0])
-        t_props = one(lambda: mb.compute_props([pv], pia, [AR], pp2))
-        if rep > 0:
-            for k, v in (("merge", t_merge), ("squash", t_squash), ("sort", t_sort), ("ntc", t_ntc), ("props", t_props)):
-                res.setdefault(k, []).append(v)
-    med = {k: sorted(v)[len(v) // 2] for k, v in res.items()}
-    report("merge_octree_N2_based (150 -> 100)", "C4: %d cells x %d" % (nc, ppc), n, med["merge"], 56 * (150 + 100) / 150.0,
-           "56 (N + N_target) / N bytes per particle of a merged cell")
-    report("squash_pia", "after the merge: %d particles" % n1, n1, med["squash"], 112, "payload moves (index indirection is the identity on the device)")
-    report("sort_particles (general path)", "after squash", n1, med["sort"], 128, "first sort after a merge: general path")
-    report("ntc! variable weight (splits)", "C4 population after merge, dt x 4", n1, med["ntc"], 64, "candidates only: ~%d new particles" % (n2 - n1))
-    report("compute_props (both groups)", "C4 population after ntc", n2, med["props"], 32, "group 2 at the tail")
-    pv.close()
-    pia.close()
-    del a
+    def report(name, cfg, n, ms, bytes_per_particle, note=""):
+        gbs = bytes_per_particle * n / (ms * 1e-3) / 1e9
+        print(json.dumps({"op": name, "config": cfg, "particles": n, "ms": ms, "particles_per_s": n / (ms * 1e-3),
+                          "algorithmic_bytes_per_particle": bytes_per_particle, "achieved_GBps": gbs, "frac_of_measured_hbm_peak": gbs / peak, "note": note}),
+              flush=True)
+
+    if args.only != "c2":
+        # ---- C5: fp_linear!, 1e6 cells x 100
+        ppc = 100
+        nc = int(args.particles // ppc)
+        a, ix, n = population(nc, ppc, 1)
+        pv, pia = mb.ParticleVector(n, ctx), mb.ParticleIndexerArray(nc, 1, ctx)
+        pv.upload_soa(1, n, a)
+        pia.upload(ix, np.array([n]), np.array([1], dtype=np.uint8))
+        step = [0]
+
+        def fp():
+            step[0] += 1
+            mb.fp_linear(mb.PhiloxRng(step[0]), None, it, AR, pv, pia, (1, nc), 1, DT, DX)
+
+        fp()
+        best, med = timed(ctx, fp, args.reps)
+        report("fp_linear", "C5: %d cells x %d" % (nc, ppc), n, med, 56, "read w,v 32 B + write v 24 B; 3 normals per particle regenerated from Philox counters")
+
+        # ---- props stand-alone on the same population (two-pass, 32 B/particle)
+        pp = mb.PhysProps(nc, 1, ctx=ctx)
+        best, med = timed(ctx, lambda: mb.compute_props_sorted([pv], pia, [AR], pp), args.reps)
+        report("compute_props_sorted (uncached)", "C5 population", n, med, 32, "two-pass; the second pass re-reads the cell from L1/L2")
+        best, med = timed(ctx, lambda: mb.compute_props([pv], pia, [AR], pp), args.reps)
+        report("compute_props", "C5 population", n, med, 32, "both pia groups")
+        pv.close()
+        pia.close()
+        del a
+
+        # ---- C2 / C4: variable-weight ntc! + octree merge (150 -> 100) + squash, cells of 150
+        ppc = 150
+        nc = int(args.particles * 0.6 // ppc)
+        a, ix, n = population(nc, ppc, 2, vw=True)
+        cap = int(n * 1.3)
+        pv, pia = mb.ParticleVector(cap, ctx), mb.ParticleIndexerArray(nc, 1, ctx)
+        # wall_offset 1e-6: with L = nc dx ~ 1 m the default offset dx * 1e-12 is below ulp(L), so a merged particle clamped to max_x would sit exactly on L
+        grid = mb.Grid1DUniform(nc * DX, nc, wall_offset=1e-6)
+        cf = mb.CollisionFactors(nc, mb.estimate_sigma_g_w_max(it, AR, AR, 300.0, 300.0, DX * NDENS / ppc * 1.5), ctx)
+        oc = mb.OctreeN2Merge(mb.OctreeN2Merge.OctreeBinMidSplit, mb.OctreeN2Merge.OctreeInitBinMinMaxVel, max_Nbins=6000)
+
+        pp2 = mb.PhysProps(nc, 1, ctx=ctx)
+
+        def reset():
+            pv.upload_soa(1, n, a)
+            pia.upload(ix, np.array([n]), np.array([1], dtype=np.uint8))
+
+        step = [0]
+
+        def merge():
+            mb.merge_octree_N2_based(mb.PhiloxRng(1), oc, pv, pia, (1, nc), 1, 100, grid, threshold=130)
+
+        def vw_ntc():
+            step[0] += 1
+            mb.ntc(mb.PhiloxRng(step[0]), cf, None, it, pv, pia, (1, nc), 1, DT * 4, DX)
+
+        def one(fn):
+            ctx.sync()
+            ctx.timer_start()
+            fn()
+            return ctx.timer_stop()
+
+        # one untimed cycle first: lazy allocations (sort ping-pong buffer, scratch arena) must not be inside a timed region
+        res = {}
+        for rep in range(max(args.reps, 2)):
+            reset()
+            t_merge = one(merge)
+            t_squash = one(lambda: mb.squash_pia(pv, pia, 1))
+            n1 = int(pia.n_total[0])
+            t_sort = one(lambda: mb.sort_particles(None, grid, pv, pia, 1))
+            t_ntc = one(vw_ntc)
+            n2 = int(pia.n_total[0])
+            t_props = one(lambda: mb.compute_props([pv], pia, [AR], pp2))
+            if rep > 0:
+                for k, v in (("merge", t_merge), ("squash", t_squash), ("sort", t_sort), ("ntc", t_ntc), ("props", t_props)):
+                    res.setdefault(k, []).append(v)
+        med = {k: sorted(v)[len(v) // 2] for k, v in res.items()}
+        report("merge_octree_N2_based (150 -> 100)", "C4: %d cells x %d" % (nc, ppc), n, med["merge"], 56 * (150 + 100) / 150.0,
+               "56 (N + N_target) / N bytes per particle of a merged cell")
+        report("squash_pia", "after the merge: %d particles" % n1, n1, med["squash"], 112, "payload moves (index indirection is the identity on the device)")
+        report("sort_particles (general path)", "after squash", n1, med["sort"], 128, "first sort after a merge: general path")
+        report("ntc! variable weight (splits)", "C4 population after merge, dt x 4", n1, med["ntc"], 64, "candidates only: ~%d new particles" % (n2 - n1))
+        report("compute_props (both groups)", "C4 population after ntc", n2, med["props"], 32, "group 2 at the tail")
+        pv.close()
+        pia.close()
+        del a
 
     # ---- C2: 0-D BKW variable-weight relaxation with octree N:2 merging (bkw_varweight_octree.jl / test_bkw_varweight_octree.jl:43-47):
     #      an ensemble of independent cells, each the nv = 40 grid sample (~33.5k particles) merged to 8000 at t = 0, then per step

@@ -95,12 +95,37 @@ __device__ void slice_bounds(const MergeArgs& a, const int32_t* idx, int bs, int
     for (int d = 0; d < 3; d++) { mn[d] = block_min(lmn[d], sh); mx[d] = block_max(lmx[d], sh); }
 }
 
+constexpr int SMALL_NP = 1024;  // bins of up to SMALL_NP particles are split by warp 0 alone
+
+// level 1 of the two-level arg-max: group g covers bins 32 g .. 32 g + 31; key = bit pattern of the weight + 1 for a refinable bin
+// (weights are >= 0, so the patterns order like integers), 0 otherwise; gid = the first bin of the group with the largest key
+__device__ __forceinline__ void merge_group_update(int g, int Nbins, const double* b_w, const int32_t* b_np, const int32_t* b_depth, int max_depth,
+                                                   unsigned long long* s_gkey, int* s_gid) {
+    const int lane = threadIdx.x & 31;
+    const int b = 32 * g + lane;
+    unsigned long long key = 0ull;
+    if (b < Nbins && b_np[b] > 2 && b_depth[b] < max_depth) key = (unsigned long long)__double_as_longlong(b_w[b]) + 1ull;
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+    const bool win = key != 0ull && hi == mhi && lo == mlo;
+    const unsigned bmin = __reduce_min_sync(0xffffffffu, win ? (unsigned)b : 0xffffffffu);
+    if (lane == 0) {
+        s_gkey[g] = ((unsigned long long)mhi << 32) | mlo;
+        s_gid[g] = bmin == 0xffffffffu ? -1 : (int)bmin;
+    }
+}
+
 __global__ void __launch_bounds__(MT) k_merge(MergeArgs a) {
+    extern __shared__ __align__(16) unsigned char mg_dyn[];  // group maxima: (Bmax + 31) / 32 keys + ids
+    unsigned long long* s_gkey = (unsigned long long*)mg_dyn;
+    int* s_gid = (int*)(s_gkey + ((a.Bmax + 31) >> 5) + 1);
+    __shared__ int32_t s_p[SMALL_NP], s_q[SMALL_NP];
+    __shared__ uint8_t s_oct[SMALL_NP];
+    __shared__ int s_mode, s_prevN;
     __shared__ double sh[MT / 32];
     __shared__ double sh_w[MT / 32][8];
     __shared__ int sh_c[MT / 32][8];
-    __shared__ double s_best_w[MT / 32];
-    __shared__ int s_best_id[MT / 32];
     __shared__ int s_Nbins, s_total_post, s_refine, s_stop;
     __shared__ int s_cnt[8], s_base[8], s_run[8];
     __shared__ double s_wsum[8];
@@ -152,36 +177,164 @@ __global__ void __launch_bounds__(MT) k_merge(MergeArgs a) {
             }
         }
         __syncthreads();
-        // ---- compute_octree! (:998-1039)
+        // ---- compute_octree! (:998-1039).  The greedy refinement is sequential; most of its ~target/7 splits act on bins of a few
+        //      dozen particles, so warp 0 runs the loop alone without block barriers -- two-level arg-max (group maxima in shared
+        //      memory, hardware redux), octant classification and the order-exact partition staged in shared memory -- and calls in
+        //      the whole CTA only for bins of more than SMALL_NP particles (the first few levels of the tree).
+        if (wid == 0) merge_group_update(0, 1, b_w, b_np, b_depth, a.oc.max_depth, s_gkey, s_gid);
+        __syncthreads();
         while (true) {
-            const int Nbins = s_Nbins;
-            double bw = -1.0;
-            int bid = -1;
-            for (int b = tid; b < Nbins; b += nt) {
-                const double w = b_w[b];
-                if (w > bw && b_np[b] > 2 && b_depth[b] < a.oc.max_depth) { bw = w; bid = b; }
-            }
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ow = __shfl_xor_sync(0xffffffffu, bw, o);
-                const int oid = __shfl_xor_sync(0xffffffffu, bid, o);
-                if (oid >= 0 && (bid < 0 || ow > bw || (ow == bw && oid < bid))) { bw = ow; bid = oid; }
-            }
-            if (lane == 0) { s_best_w[wid] = bw; s_best_id[wid] = bid; }
-            __syncthreads();
-            if (tid == 0) {
-                double w0 = -1.0;
-                int i0 = -1;
-                for (int i = 0; i < nw; i++) {
-                    const int oid = s_best_id[i];
-                    const double ow = s_best_w[i];
-                    if (oid >= 0 && (i0 < 0 || ow > w0 || (ow == w0 && oid < i0))) { w0 = ow; i0 = oid; }
+            if (wid == 0) {
+                int Nbins = s_Nbins, total_post = s_total_post, mode = 0;
+                while (!s_stop) {
+                    // first bin with the strictly largest weight among the refinable ones
+                    int bin;
+                    {
+                        const int ng = (Nbins + 31) >> 5;
+                        unsigned long long key = 0ull;
+                        int g_best = 0x7fffffff;
+                        for (int g = lane; g < ng; g += 32) {
+                            const unsigned long long k = s_gkey[g];
+                            if (k > key) { key = k; g_best = g; }
+                        }
+                        const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+                        const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+                        const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+                        const bool win = key != 0ull && hi == mhi && lo == mlo;
+                        const unsigned g_min = __reduce_min_sync(0xffffffffu, win ? (unsigned)g_best : 0xffffffffu);
+                        bin = g_min == 0xffffffffu ? -1 : s_gid[g_min];
+                    }
+                    if (bin < 0 || total_post + 14 > a.target) break;
+                    const int bs = b_start[bin], be = b_end[bin], depth = b_depth[bin];
+                    const int n = be - bs + 1;
+                    if (n > SMALL_NP) { if (lane == 0) s_refine = bin; mode = 1; break; }
+                    // ---- split_bin! (:503-633) by one warp
+                    double pmn[3], pmx[3];
+                    if (a.oc.bin_bounds_compute == 2) {
+                        for (int d = 0; d < 3; d++) { pmn[d] = 9299792458.0; pmx[d] = -9299792458.0; }
+                        for (int j = lane; j < n; j += 32) {
+                            const int64_t pj = idx[bs + j];
+#pragma unroll
+                            for (int d = 0; d < 3; d++) { const double v = a.pv.a[F_VX + d][pj]; pmn[d] = fmin(pmn[d], v); pmx[d] = fmax(pmx[d], v); }
+                        }
+#pragma unroll
+                        for (int d = 0; d < 3; d++)
+                            for (int o = 16; o > 0; o >>= 1) {
+                                pmn[d] = fmin(pmn[d], __shfl_xor_sync(0xffffffffu, pmn[d], o));
+                                pmx[d] = fmax(pmx[d], __shfl_xor_sync(0xffffffffu, pmx[d], o));
+                            }
+                    } else {
+                        for (int d = 0; d < 3; d++) { pmn[d] = b_vmin[3 * bin + d]; pmx[d] = b_vmax[3 * bin + d]; }
+                    }
+                    double mid[3];
+                    if (a.oc.split == 1) {
+                        for (int d = 0; d < 3; d++) mid[d] = 0.5 * (pmn[d] + pmx[d]);
+                    } else {
+                        double sw = 0, sv[3] = {0, 0, 0};
+                        for (int j = lane; j < n; j += 32) {
+                            const int64_t pj = idx[bs + j];
+                            const double w = PW[pj];
+                            sw += w;
+                            for (int d = 0; d < 3; d++) sv[d] += w * a.pv.a[F_VX + d][pj];
+                        }
+                        for (int o = 16; o > 0; o >>= 1) {
+                            sw += __shfl_xor_sync(0xffffffffu, sw, o);
+                            for (int d = 0; d < 3; d++) sv[d] += __shfl_xor_sync(0xffffffffu, sv[d], o);
+                        }
+                        for (int d = 0; d < 3; d++) mid[d] = sv[d] / sw;
+                    }
+                    int cnt[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) cnt[k] = 0;
+                    for (int c0 = 0; c0 < n; c0 += 32) {
+                        const int j = c0 + lane;
+                        int o = 8;
+                        if (j < n) {
+                            const int32_t pj = idx[bs + j];
+                            s_p[j] = pj;
+                            o = (a.pv.a[F_VX][pj] > mid[0] ? 1 : 0) + (a.pv.a[F_VY][pj] > mid[1] ? 2 : 0) + (a.pv.a[F_VZ][pj] > mid[2] ? 4 : 0);
+                            s_oct[j] = (uint8_t)o;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; k++) cnt[k] += __popc(__ballot_sync(0xffffffffu, o == k));
+                    }
+                    int basek[8], run = 0, n_ne = 0, tp = total_post - 2, my_id = -1, my_cnt = 0, my_base = 0, w_id = -1, w_cnt = 0, w_base = 0;
+#pragma unroll
+                    for (int o = 0; o < 8; o++) {
+                        basek[o] = run;
+                        const int c = cnt[o];
+                        if (c > 0) {
+                            const int id = n_ne == 0 ? bin : Nbins + n_ne - 1;
+                            n_ne += 1;
+                            tp += c >= 2 ? 2 : c;
+                            if (lane == o) { my_id = id; my_cnt = c; my_base = run; }
+                            if ((lane >> 2) == o) { w_id = id; w_cnt = c; w_base = run; }
+                        }
+                        run += c;
+                    }
+                    __syncwarp();  // every lane has read the parent's descriptors and bounds
+                    if (my_id >= 0) {
+                        b_start[my_id] = bs + my_base;
+                        b_end[my_id] = bs + my_base + my_cnt - 1;
+                        b_np[my_id] = my_cnt;
+                        b_depth[my_id] = depth + 1;
+                        for (int d = 0; d < 3; d++) {
+                            if (a.oc.bin_bounds_compute == 1) {
+                                const bool upper = (lane >> d) & 1;
+                                b_vmin[3 * my_id + d] = upper ? mid[d] : pmn[d];
+                                b_vmax[3 * my_id + d] = upper ? pmx[d] : mid[d];
+                            } else {
+                                b_vmin[3 * my_id + d] = pmn[d];
+                                b_vmax[3 * my_id + d] = pmx[d];
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    int runk[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) runk[k] = 0;
+                    for (int c0 = 0; c0 < n; c0 += 32) {
+                        const int j = c0 + lane;
+                        const int o = j < n ? (int)s_oct[j] : 8;
+                        int dest = -1;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            const unsigned bal = __ballot_sync(0xffffffffu, o == k);
+                            if (o == k) dest = basek[k] + (cnt[k] - 1 - (runk[k] + __popc(bal & lt)));
+                            runk[k] += __popc(bal);
+                        }
+                        if (dest >= 0) s_q[dest] = s_p[j];
+                    }
+                    __syncwarp();
+                    for (int j = lane; j < n; j += 32) idx[bs + j] = s_q[j];
+                    {
+                        double w = 0.0;
+                        if (w_id >= 0) {
+                            const int chunk = (w_cnt + 3) >> 2, part = lane & 3;
+                            const int hi_j = w_base + w_cnt - 1 - part * chunk;
+                            int lo_j = hi_j - chunk + 1;
+                            if (lo_j < w_base) lo_j = w_base;
+                            for (int j = hi_j; j >= lo_j; j--) w += PW[s_q[j]];
+                        }
+                        w += __shfl_xor_sync(0xffffffffu, w, 1);
+                        w += __shfl_xor_sync(0xffffffffu, w, 2);
+                        if (w_id >= 0 && (lane & 3) == 0) b_w[w_id] = w;
+                    }
+                    const int Nb0 = Nbins;
+                    Nbins += n_ne - 1;
+                    total_post = tp;
+                    __syncwarp();
+                    merge_group_update(bin >> 5, Nbins, b_w, b_np, b_depth, a.oc.max_depth, s_gkey, s_gid);
+                    for (int g = Nb0 >> 5; g <= (Nbins - 1) >> 5; g++)
+                        if (g != (bin >> 5)) merge_group_update(g, Nbins, b_w, b_np, b_depth, a.oc.max_depth, s_gkey, s_gid);
+                    __syncwarp();
+                    if (Nbins + 7 > a.oc.max_Nbins) break;
                 }
-                s_refine = i0;
-                if (i0 < 0 || s_total_post + 14 > a.target) s_stop = 1;
+                if (lane == 0) { s_mode = mode; s_Nbins = Nbins; s_total_post = total_post; s_prevN = Nbins; }
             }
             __syncthreads();
-            if (s_stop) break;
-            // ---- split_bin! (:503-633)
+            if (s_mode == 0) break;
+            // ---- split_bin! (:503-633) by the whole CTA (bins of more than SMALL_NP particles)
             const int bin = s_refine;
             const int bs = b_start[bin], be = b_end[bin];
             const int depth = b_depth[bin];
@@ -302,7 +455,13 @@ __global__ void __launch_bounds__(MT) k_merge(MergeArgs a) {
             }
             for (int j = tid; j < n; j += nt) idx[bs + j] = tmp[bs + j];
             __syncthreads();
-            if (s_stop) break;
+            if (wid == 0) {  // refresh the group maxima the split touched
+                const int Nb0 = s_prevN, Nb1 = s_Nbins, bin0 = s_refine;
+                merge_group_update(bin0 >> 5, Nb1, b_w, b_np, b_depth, a.oc.max_depth, s_gkey, s_gid);
+                for (int g = Nb0 >> 5; g <= (Nb1 - 1) >> 5; g++)
+                    if (g != (bin0 >> 5)) merge_group_update(g, Nb1, b_w, b_np, b_depth, a.oc.max_depth, s_gkey, s_gid);
+            }
+            __syncthreads();
         }
         __syncthreads();
         const int Nbins = s_Nbins;
@@ -313,15 +472,70 @@ __global__ void __launch_bounds__(MT) k_merge(MergeArgs a) {
             if (tid == 0) b_w[0] = sw;
             __syncthreads();
         }
-        // ---- compute_bin_props! (:646-700) + the per-bin part of compute_new_particles! (:742-784): a warp per bin
-        for (int b = wid; b < Nbins; b += nw) {
+        // ---- compute_bin_props! (:646-700) + the per-bin part of compute_new_particles! (:742-784): one THREAD per bin of up to 32
+        //      particles (sequential in slice order, like the reference), one warp per larger bin
+        for (int b = tid; b < Nbins; b += nt) {
             int np = b_np[b];
             const double w = b_w[b];
             if (w == 0) np = 0;
             const int bs = b_start[b], be = b_end[b];
             double* o1 = outbuf + (int64_t)(2 * b) * 7;
             double* o2 = o1 + 7;
-            if (np > 2) {
+            if (np > 2 && np <= 32) {
+                const double inv_w = 1.0 / w;
+                double m[6] = {0, 0, 0, 0, 0, 0}, s2[6] = {0, 0, 0, 0, 0, 0};
+                for (int j = bs; j <= be; j++) {
+                    const int64_t p = idx[j];
+                    const double pw = PW[p];
+#pragma unroll
+                    for (int d = 0; d < 6; d++) m[d] = m[d] + pw * a.pv.a[F_VX + d][p];
+                }
+#pragma unroll
+                for (int d = 0; d < 6; d++) m[d] *= inv_w;
+                for (int j = bs; j <= be; j++) {
+                    const int64_t p = idx[j];
+                    const double pw = PW[p];
+#pragma unroll
+                    for (int d = 0; d < 6; d++) { const double dd = a.pv.a[F_VX + d][p] - m[d]; s2[d] = s2[d] + pw * dd * dd; }
+                }
+                uint32_t rb[4];
+                philox4x32_10((uint32_t)b, (uint32_t)cell, a.timestep, (OP_MERGE & 0xFFu) | (a.substream << 8), (uint32_t)a.seed,
+                              (uint32_t)(a.seed >> 32), rb);
+                o1[0] = 0.5 * w; o2[0] = 0.5 * w;
+#pragma unroll
+                for (int d = 0; d < 6; d++) {
+                    const double sd = sqrt(s2[d] * inv_w);
+                    const double sg = ((rb[0] >> d) & 1u) ? 1.0 : -1.0;
+                    double x1 = m[d] + sg * sd, x2 = m[d] - sg * sd;
+                    if (d == 3 && a.has_grid) {  // :878-897: clamp x1 of the np > 2 outputs into [min_x, max_x]
+                        x1 = x1 < a.min_x ? a.min_x : (x1 > a.max_x ? a.max_x : x1);
+                        x2 = x2 < a.min_x ? a.min_x : (x2 > a.max_x ? a.max_x : x2);
+                    }
+                    o1[1 + d] = x1;
+                    o2[1 + d] = x2;
+                }
+            } else if (np >= 1 && np <= 2) {
+                const int64_t p1 = idx[bs];
+#pragma unroll
+                for (int f = 0; f < 7; f++) o1[f] = a.pv.a[f][p1];
+                if (np == 2) {
+                    const int64_t p2 = idx[bs + 1];
+#pragma unroll
+                    for (int f = 0; f < 7; f++) o2[f] = a.pv.a[f][p2];
+                }
+            }
+            b_out[b] = np >= 2 ? 2 : np;
+        }
+        for (int b0 = wid * 32; b0 < Nbins; b0 += nw * 32) {
+            const int mb_ = b0 + lane;
+            unsigned big = __ballot_sync(0xffffffffu, mb_ < Nbins && b_np[mb_] > 32 && b_w[mb_] != 0);
+            while (big) {
+                const int b = b0 + (__ffs(big) - 1);
+                big &= big - 1;
+                const double w = b_w[b];
+                const int bs = b_start[b], be = b_end[b];
+                double* o1 = outbuf + (int64_t)(2 * b) * 7;
+                double* o2 = o1 + 7;
                 const double inv_w = 1.0 / w;
                 double m[6] = {0, 0, 0, 0, 0, 0};
                 for (int j = bs + lane; j <= be; j += 32) {
@@ -357,7 +571,7 @@ __global__ void __launch_bounds__(MT) k_merge(MergeArgs a) {
                     for (int d = 0; d < 6; d++) {
                         const double sg = ((rb[0] >> d) & 1u) ? 1.0 : -1.0;
                         double x1 = m[d] + sg * s2[d], x2 = m[d] - sg * s2[d];
-                        if (d == 3 && a.has_grid) {  // :878-897: clamp x1 of the np > 2 outputs into [min_x, max_x]
+                        if (d == 3 && a.has_grid) {
                             x1 = x1 < a.min_x ? a.min_x : (x1 > a.max_x ? a.max_x : x1);
                             x2 = x2 < a.min_x ? a.min_x : (x2 > a.max_x ? a.max_x : x2);
                         }
@@ -365,13 +579,7 @@ __global__ void __launch_bounds__(MT) k_merge(MergeArgs a) {
                         o2[1 + d] = x2;
                     }
                 }
-            } else if (np >= 1) {
-                if (lane < 7) {
-                    o1[lane] = a.pv.a[lane][idx[bs]];
-                    if (np == 2) o2[lane] = a.pv.a[lane][idx[bs + 1]];
-                }
             }
-            if (lane == 0) b_out[b] = np >= 2 ? 2 : np;
         }
         __syncthreads();
         // exclusive scan of the per-bin output counts (bins in id order)
@@ -592,6 +800,7 @@ __global__ void __launch_bounds__(32 * MW_WARPS) k_merge_warp(MergeArgs a, int B
                 }
                 run += c;
             }
+            __syncwarp();  // every lane has read the parent's descriptors and bounds
             if (my_id >= 0) {  // lane o describes the child of octant o
                 bstart[my_id] = (int16_t)(bs + my_base);
                 bend[my_id] = (int16_t)(bs + my_base + my_cnt - 1);
@@ -842,8 +1051,10 @@ extern "C" int mb_merge_octree_N2(mb_ctx* ctx, const mb_octree_params* oc, mb_pv
     const int64_t bcap = (oc->max_Nbins < target_np ? oc->max_Nbins : target_np) + 8;
     a.Bmax = (int)bcap;
     const int64_t avg = (pia->n_bound[s] > 0 ? pia->n_bound[s] : cap) / nc;
-    const int threads = avg > 2048 ? 256 : 128;
-    int64_t nCTA = nr < (int64_t)N_SM * (threads == 256 ? 4 : 8) ? nr : (int64_t)N_SM * (threads == 256 ? 4 : 8);
+    // the refinement loop is run by warp 0 of each CTA, so many small CTAs (= concurrent cells) beat few large ones
+    (void)avg;
+    const int threads = 128;
+    int64_t nCTA = nr < (int64_t)N_SM * 4 ? nr : (int64_t)N_SM * 4;
     const size_t per = (size_t)bcap * (5 * 4 + 8 + 24 + 24 + 2 * 7 * 8) + 64;
     char* ws = (char*)ctx_scratch(ctx, 9, per * (size_t)nCTA + 4096);
     if (!ws) return MB_ERR_CUDA;
@@ -898,7 +1109,19 @@ extern "C" int mb_merge_octree_N2(mb_ctx* ctx, const mb_octree_params* oc, mb_pv
             MB_LAUNCH_CHECK(ctx);
         }
     }
-    k_merge<<<(int)nCTA, threads, 0, st>>>(a);
+    {
+        const size_t gsm = ((size_t)((bcap + 31) / 32) + 2) * 12 + 16;
+        if (gsm > 160 * 1024) {
+            set_error("merge_octree_N2_based!: max_Nbins / target_np too large for the arg-max group table");
+            return MB_ERR_UNSUPPORTED;
+        }
+        static size_t attr_gsm = 0;
+        if (gsm > 40 * 1024 && gsm > attr_gsm) {
+            MB_CUDA(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+            attr_gsm = gsm;
+        }
+        k_merge<<<(int)nCTA, threads, gsm, st>>>(a);
+    }
     MB_LAUNCH_CHECK(ctx);
     // conservative on the host (operators dispatch on it); mb_pia_download resolves the exact reference value (:806-808)
     if (pia->contiguous[s]) pia->contig_pending[s] = 1;
