@@ -41,6 +41,7 @@ struct NtcArgs {
     int32_t* nsplit2;
     int* flags;
     int single_cell_tail;  // VW: one cell whose existing group 2 ends at n_total (0-D usage)
+    int64_t warp_min;      // one species: cells with n_local >= warp_min are collided by k_ntc_warp (0: never)
 };
 
 __device__ __forceinline__ int64_t ncoll_of(double dt, double V, double sgwm, int64_t n1, int64_t n2, bool two, double R) {
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(128) k_ntc(NtcArgs a) {
     for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nr; r += (int64_t)gridDim.x * blockDim.x) {
         const int64_t cell = a.cell_lo + r;
         Indexer q1 = a.ix1[cell - 1];
+        if (!TWO && a.warp_min > 0 && q1.n_local >= a.warp_min) continue;  // large cells: k_ntc_warp
         Indexer q2 = TWO ? a.ix2[cell - 1] : q1;
         int64_t win1 = 0, win2 = 0;
         const int64_t g2_before1 = q1.n_group2, g2_before2 = q2.n_group2;
@@ -165,6 +167,164 @@ __global__ void __launch_bounds__(128) k_ntc(NtcArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Large cells (0-D ensembles: 1e3 - 1e5 particles per cell, thousands of candidates per step, few accepted when the weights span
+// orders of magnitude): ONE WARP per cell, still the reference's exact sequential candidate loop.  The 32 lanes evaluate the next
+// 32 candidates speculatively -- lane L assumes that the candidates before it in the batch were plain rejections (3 draws each,
+// nothing modified), so its draws are draws d + 3 L .. d + 3 L + 2 of the cell's counter-based stream.  A candidate is an EVENT if
+// it is anything else: i == k (a retry draw), g <= eps, sigma g w above the running maximum, or accepted.  The lanes before the
+// first event were indeed plain rejections; the event lane then runs its candidate for real (retry draws, maximum update, split,
+// scattering) from its stream position, and the next batch starts after it.  Results are identical, draw for draw, to the one-thread
+// loop (and to the CPU oracle); the gathers of a batch are in flight together instead of one pair at a time.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double stream_draw(uint32_t k0, uint32_t k1, uint32_t c1, uint32_t c2, uint32_t c3, int64_t d) {
+    uint32_t o[4];
+    philox4x32_10((uint32_t)(d >> 1), c1, c2, c3, k0, k1, o);
+    return (d & 1) ? u64_to_unit_double(o[2], o[3]) : u64_to_unit_double(o[0], o[1]);
+}
+
+__global__ void __launch_bounds__(128) k_ntc_warp(NtcArgs a) {
+    const int64_t nr = a.cell_hi - a.cell_lo + 1;
+    const bool vw = !a.equal_weight;
+    const unsigned FULL = 0xffffffffu;
+    int64_t nt1 = 0;
+    if (vw) {
+        nt1 = *a.n_total1;
+        if (nt1 + a.win[nr] > a.cap1) return;  // k_ntc reports MB_ERR_CAPACITY
+    }
+    const mb_interaction it = a.it;
+    const double pw = 1.0 - 2 * it.vhs_o;
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32), c3 = (OP_NTC & 0xFFu) | (a.substream << 8);
+    for (int64_t r0 = gw * 32; r0 < nr; r0 += nwarps * 32) {
+      const int64_t myr = r0 + lane;
+      const int64_t my_n = myr < nr ? a.ix1[a.cell_lo - 1 + myr].n_local : 0;
+      unsigned todo = __ballot_sync(FULL, my_n >= a.warp_min);
+      while (todo) {
+        const int64_t r = r0 + (__ffs(todo) - 1);
+        todo &= todo - 1;
+        const int64_t cell = a.cell_lo + r;
+        Indexer q = a.ix1[cell - 1];
+        const int64_t g2_before = q.n_group2;
+        int64_t win1 = 0;
+        if (vw) {
+            win1 = nt1 + a.win[r];
+            if (!(q.n_group2 == 0 || (a.single_cell_tail && q.end2 == nt1))) {  // same precondition as k_ntc
+                if (lane == 0) { atomicOr(&a.flags[0], DEVERR_PRECONDITION); a.nsplit1[r] = 0; }
+                continue;
+            }
+        }
+        double sgwm = a.sgwm[cell - 1];
+        const int64_t n_coll = ncoll_of(a.dt, a.V, sgwm, q.n_local, q.n_local, false, stream_draw(k0, k1, (uint32_t)cell, a.timestep, c3, 0));
+        int64_t d = 1, c = 0, n_perf = 0, n_eqw = 0;
+        while (c < n_coll) {
+            const bool active = c + lane < n_coll;
+            bool ev = false;
+            if (active) {
+                const int64_t p0 = d + 3 * lane;
+                const double Nd = (double)q.n_local;
+                const int64_t i = (int64_t)floor(stream_draw(k0, k1, (uint32_t)cell, a.timestep, c3, p0) * Nd);
+                const int64_t k = (int64_t)floor(stream_draw(k0, k1, (uint32_t)cell, a.timestep, c3, p0 + 1) * Nd);
+                if (i == k) {
+                    ev = true;
+                } else {
+                    PRef pi, pk;
+                    load_p(a.p1, map_cont(q, i), pi);
+                    load_p(a.p1, map_cont(q, k), pk);
+                    const double gx = pi.vx - pk.vx, gy = pi.vy - pk.vy, gz = pi.vz - pk.vz;
+                    const double g = sqrt(gx * gx + gy * gy + gz * gz);
+                    if (!(g > EPS)) {
+                        ev = true;
+                    } else {
+                        const double sigma = it.vhs_factor * pow(g, pw);
+                        const double sgw = sigma * g * fmax(pi.w, pk.w);
+                        ev = sgw > sgwm || stream_draw(k0, k1, (uint32_t)cell, a.timestep, c3, p0 + 2) < sgw / sgwm;
+                    }
+                }
+            }
+            const unsigned m = __ballot_sync(FULL, ev);
+            if (m == 0) {
+                const int64_t nact = n_coll - c < 32 ? n_coll - c : 32;
+                c += nact;
+                d += 3 * nact;
+                continue;
+            }
+            const int al = __ffs(m) - 1;
+            if (lane == al) {  // the reference's candidate, for real, from stream position d + 3 al
+                const int64_t p0 = d + 3 * al;
+                PhiloxStream rng(a.seed, OP_NTC, a.substream, a.timestep, (uint32_t)cell);
+                rng.c0 = (uint32_t)(p0 >> 1);
+                if (p0 & 1) (void)rng.rand();
+                int64_t i = (int64_t)floor(rng.rand() * (double)q.n_local);
+                int64_t k = (int64_t)floor(rng.rand() * (double)q.n_local);
+                while (i == k) k = (int64_t)floor(rng.rand() * (double)q.n_local);
+                PRef pi, pk;
+                load_p(a.p1, map_cont(q, i), pi);
+                load_p(a.p1, map_cont(q, k), pk);
+                const double gx = pi.vx - pk.vx, gy = pi.vy - pk.vy, gz = pi.vz - pk.vz;
+                const double g = sqrt(gx * gx + gy * gy + gz * gz);
+                if (g > EPS) {
+                    const double sigma = it.vhs_factor * pow(g, pw);
+                    const double sgw = sigma * g * fmax(pi.w, pk.w);
+                    sgwm = fmax(sgw, sgwm);
+                    if (rng.rand() < sgw / sgwm) {
+                        n_perf += 1;
+                        const double cx = it.mu1 * pi.vx + it.mu2 * pk.vx, cy = it.mu1 * pi.vy + it.mu2 * pk.vy,
+                                     cz = it.mu1 * pi.vz + it.mu2 * pk.vz;
+                        if (!vw) {
+                            n_eqw += 1;
+                        } else if (fabs(pi.w - pk.w) < a.dw_tol) {
+                            n_eqw += 1;
+                        } else if (pi.w > pk.w) {
+                            append_split(a.p1, q, win1, pi.pos, pi.w - pk.w, pi.vx, pi.vy, pi.vz);
+                            a.p1.a[F_W][pi.pos] = pk.w;
+                        } else {
+                            append_split(a.p1, q, win1, pk.pos, pk.w - pi.w, pk.vx, pk.vy, pk.vz);
+                            a.p1.a[F_W][pk.pos] = pi.w;
+                        }
+                        const double phi = twopi * rng.rand();
+                        double sphi, cphi;
+                        sincos(phi, &sphi, &cphi);
+                        const double ctheta = 2.0 * rng.rand() - 1.0;
+                        const double stheta = sqrt(1.0 - ctheta * ctheta);
+                        const double nx = g * (stheta * cphi), ny = g * (stheta * sphi), nz = g * ctheta;
+                        a.p1.a[F_VX][pi.pos] = cx + it.mu2 * nx;
+                        a.p1.a[F_VY][pi.pos] = cy + it.mu2 * ny;
+                        a.p1.a[F_VZ][pi.pos] = cz + it.mu2 * nz;
+                        a.p1.a[F_VX][pk.pos] = cx - it.mu1 * nx;
+                        a.p1.a[F_VY][pk.pos] = cy - it.mu1 * ny;
+                        a.p1.a[F_VZ][pk.pos] = cz - it.mu1 * nz;
+                    }
+                }
+                d = 2 * (int64_t)rng.c0 - rng.have;  // draws consumed so far
+            }
+            // everybody continues from the event lane's state
+            d = __shfl_sync(FULL, d, al);
+            sgwm = __shfl_sync(FULL, sgwm, al);
+            n_perf = __shfl_sync(FULL, n_perf, al);
+            n_eqw = __shfl_sync(FULL, n_eqw, al);
+            q.n_local = __shfl_sync(FULL, q.n_local, al);
+            q.n_group2 = __shfl_sync(FULL, q.n_group2, al);
+            q.start2 = __shfl_sync(FULL, q.start2, al);
+            q.end2 = __shfl_sync(FULL, q.end2, al);
+            c += al + 1;
+            __syncwarp();  // the event lane's stores are ordered before the next batch's gathers
+        }
+        if (lane == 0) {
+            a.sgwm[cell - 1] = sgwm;
+            a.n_coll[cell - 1] = n_coll;
+            a.n_perf[cell - 1] = n_perf;
+            a.n_eqw[cell - 1] = n_eqw;
+            if (vw) {
+                a.ix1[cell - 1] = q;
+                a.nsplit1[r] = (int32_t)(q.n_group2 - g2_before);
+            }
+        }
+      }
+    }
+}
+
 static int ntc_impl(mb_ctx* ctx, mb_cf* cf, const mb_interaction* it, mb_pv* pv1, mb_pv* pv2, mb_pia* pia, int64_t cell_lo, int64_t cell_hi,
                     int64_t s1, int64_t s2, double dt, double V, double dw_tol, int equal_weight, uint32_t timestep, uint32_t substream,
                     bool two) {
@@ -197,10 +357,16 @@ static int ntc_impl(mb_ctx* ctx, mb_cf* cf, const mb_interaction* it, mb_pv* pv1
     const int g = grid_for(nr, 128, 16);
     ProfScope ps(ctx, PROF_NTC);
     ctx->state_gen++;
+    a.warp_min = two ? 0 : 2048;
+    const int gwarp = grid_for(nr, 128, 8);  // a warp takes 32 cells at a time
     if (equal_weight) {
         if (two) k_ntc<true><<<g, 128, 0, st>>>(a);
         else k_ntc<false><<<g, 128, 0, st>>>(a);
         MB_LAUNCH_CHECK(ctx);
+        if (!two) {
+            k_ntc_warp<<<gwarp, 128, 0, st>>>(a);
+            MB_LAUNCH_CHECK(ctx);
+        }
         return MB_OK;
     }
     // variable weight
@@ -224,6 +390,10 @@ static int ntc_impl(mb_ctx* ctx, mb_cf* cf, const mb_interaction* it, mb_pv* pv1
     if (two) k_ntc<true><<<g, 128, 0, st>>>(a);
     else k_ntc<false><<<g, 128, 0, st>>>(a);
     MB_LAUNCH_CHECK(ctx);
+    if (!two) {
+        k_ntc_warp<<<gwarp, 128, 0, st>>>(a);
+        MB_LAUNCH_CHECK(ctx);
+    }
     for (int sp = 0; sp < (two ? 2 : 1); sp++) {
         mb_pv* pv = sp == 0 ? pv1 : pv2;
         r = pack_windows(ctx, pv, sp == 0 ? a.ix1 : a.ix2, cell_lo, nr, a.win, sp == 0 ? a.nsplit1 : a.nsplit2, sp == 0 ? packed1 : packed2, partial,

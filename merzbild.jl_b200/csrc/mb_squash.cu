@@ -16,39 +16,48 @@ static __global__ void k_squash_counts(const Indexer* __restrict__ ix, int64_t n
     }
 }
 
-// every live segment is copied once into the sort's ping-pong buffer at its new position (56 B read + 56 B written per particle,
+// every live particle is copied once into the sort's ping-pong buffer at its new position (56 B read + 56 B written per particle,
 // moved or not); the buffers are then swapped on the host side, so no second payload pass is needed.  The cell ids go through a
 // staging array and are copied back by k_squash_cell_back.
+// Load balance: the OUTPUT range [0, n_total) is cut into tiles of SQ_TILE positions, one warp per tile; the warp finds the segment
+// that holds the tile's first position by bisection over the new starts and walks on from there, so a 0-D cell of 1e4 particles and a
+// Couette cell of 1e2 cost the same per particle.
+constexpr int SQ_TILE = 2048;
 static __global__ void __launch_bounds__(256) k_squash_move(SoA cur, SoA alt, const int32_t* __restrict__ cell, int32_t* __restrict__ cell_stage,
                                                             const Indexer* __restrict__ ix, int64_t nc, const int64_t* __restrict__ newlo, int* flags) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    // a warp takes 32 consecutive segments at a time (one read of their descriptors)
-    for (int64_t s0 = warp0 * 32; s0 < 2 * nc; s0 += nwarps * 32) {
-        const int64_t sgm = s0 + lane;
-        int64_t n = 0, olo = 0, nlo = 0;
-        if (sgm < 2 * nc) {
-            const bool g2 = sgm >= nc;
-            const Indexer q = ix[g2 ? sgm - nc : sgm];
-            n = g2 ? q.n_group2 : q.n_group1;
-            olo = (g2 ? q.start2 : q.start1) - 1;
-            nlo = newlo[sgm];
-            if (n > 0 && olo < nlo) {  // the reference only ever shifts left (particles.jl:641,659,672: `if offset > 0`)
-                atomicOr(&flags[0], DEVERR_PRECONDITION);
-                n = 0;
-            }
+    const int64_t nseg = 2 * nc, total = newlo[nseg];
+    for (int64_t d0 = warp0 * SQ_TILE; d0 < total; d0 += nwarps * SQ_TILE) {
+        const int64_t d1 = d0 + SQ_TILE < total ? d0 + SQ_TILE : total;
+        // last segment whose new start is <= d0 (empty segments share their successor's start, so this one is not empty)
+        int64_t lo = 0, hi = nseg - 1;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi + 1) >> 1;
+            if (newlo[mid] <= d0) lo = mid; else hi = mid - 1;
         }
-        unsigned todo = __ballot_sync(0xffffffffu, n > 0);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int64_t N = __shfl_sync(0xffffffffu, n, src), O = __shfl_sync(0xffffffffu, olo, src), D = __shfl_sync(0xffffffffu, nlo, src);
-            for (int64_t j = lane; j < N; j += 32) {
+        int64_t sgm = lo, d = d0;
+        while (d < d1) {
+            const int64_t s_lo = newlo[sgm], s_hi = newlo[sgm + 1];
+            if (s_hi > d) {
+                const bool g2 = sgm >= nc;
+                const Indexer q = ix[g2 ? sgm - nc : sgm];
+                const int64_t olo = (g2 ? q.start2 : q.start1) - 1;
+                if (olo < s_lo) {  // the reference only ever shifts left (particles.jl:641,659,672: `if offset > 0`)
+                    if (lane == 0) atomicOr(&flags[0], DEVERR_PRECONDITION);
+                } else {
+                    const int64_t e = s_hi < d1 ? s_hi : d1;
+                    const int64_t src0 = olo + (d - s_lo);
+                    for (int64_t j = lane; j < e - d; j += 32) {
 #pragma unroll
-                for (int f = 0; f < 7; f++) alt.a[f][D + j] = cur.a[f][O + j];
-                cell_stage[D + j] = cell[O + j];
+                        for (int f = 0; f < 7; f++) alt.a[f][d + j] = cur.a[f][src0 + j];
+                        cell_stage[d + j] = cell[src0 + j];
+                    }
+                }
+                d = s_hi < d1 ? s_hi : d1;
             }
+            sgm++;
         }
     }
 }
@@ -91,7 +100,8 @@ extern "C" int mb_squash_pia(mb_ctx* ctx, mb_pv* pv, mb_pia* pia, int64_t specie
     MB_LAUNCH_CHECK(ctx);
     r = device_exclusive_scan(ctx, cnt, 2 * nc, newlo, partial);
     if (r) return r;
-    const int g = grid_for(2 * nc, 256, 8);
+    const int64_t nb = pia->n_bound[s] > 0 ? pia->n_bound[s] : pv->cap;
+    const int g = grid_for((nb + SQ_TILE - 1) / SQ_TILE * 32, 256, 8);
     k_squash_move<<<g, 256, 0, st>>>(pv->cur, pv->alt, pv->cell, cell_stage, ix, nc, newlo, ctx->d_flags);
     MB_LAUNCH_CHECK(ctx);
     k_squash_cell_back<<<grid_for(pia->n_bound[s] > 0 ? pia->n_bound[s] : pv->cap, 256, 8), 256, 0, st>>>(pv->cell, cell_stage, pia->d_n_total + s);
