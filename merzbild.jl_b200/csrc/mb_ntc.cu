@@ -183,7 +183,7 @@ __device__ __forceinline__ double stream_draw(uint32_t k0, uint32_t k1, uint32_t
     return (d & 1) ? u64_to_unit_double(o[2], o[3]) : u64_to_unit_double(o[0], o[1]);
 }
 
-__global__ void __launch_bounds__(128) k_ntc_warp(NtcArgs a) {
+__global__ void __launch_bounds__(128) k_ntc_warp(NtcArgs a, int ch) {
     const int64_t nr = a.cell_hi - a.cell_lo + 1;
     const bool vw = !a.equal_weight;
     const unsigned FULL = 0xffffffffu;
@@ -197,9 +197,10 @@ __global__ void __launch_bounds__(128) k_ntc_warp(NtcArgs a) {
     const int lane = threadIdx.x & 31;
     const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32), c3 = (OP_NTC & 0xFFu) | (a.substream << 8);
-    for (int64_t r0 = gw * 32; r0 < nr; r0 += nwarps * 32) {
+    // a warp takes ch (<= 32) consecutive cells at a time: one read of their sizes, then the large ones
+    for (int64_t r0 = gw * ch; r0 < nr; r0 += nwarps * ch) {
       const int64_t myr = r0 + lane;
-      const int64_t my_n = myr < nr ? a.ix1[a.cell_lo - 1 + myr].n_local : 0;
+      const int64_t my_n = (lane < ch && myr < nr) ? a.ix1[a.cell_lo - 1 + myr].n_local : 0;
       unsigned todo = __ballot_sync(FULL, my_n >= a.warp_min);
       while (todo) {
         const int64_t r = r0 + (__ffs(todo) - 1);
@@ -358,13 +359,16 @@ static int ntc_impl(mb_ctx* ctx, mb_cf* cf, const mb_interaction* it, mb_pv* pv1
     ProfScope ps(ctx, PROF_NTC);
     ctx->state_gen++;
     a.warp_min = two ? 0 : 2048;
-    const int gwarp = grid_for(nr, 128, 8);  // a warp takes 32 cells at a time
+    // k_ntc_warp: a warp takes ch cells at a time -- 32 when the range is long enough to keep every warp busy, fewer otherwise
+    int ch = 32;
+    while (ch > 1 && nr < (int64_t)N_SM * 8 * 4 * ch) ch >>= 1;
+    const int gwarp = grid_for((nr + ch - 1) / ch * 32, 128, 8);
     if (equal_weight) {
         if (two) k_ntc<true><<<g, 128, 0, st>>>(a);
         else k_ntc<false><<<g, 128, 0, st>>>(a);
         MB_LAUNCH_CHECK(ctx);
         if (!two) {
-            k_ntc_warp<<<gwarp, 128, 0, st>>>(a);
+            k_ntc_warp<<<gwarp, 128, 0, st>>>(a, ch);
             MB_LAUNCH_CHECK(ctx);
         }
         return MB_OK;
@@ -391,7 +395,7 @@ static int ntc_impl(mb_ctx* ctx, mb_cf* cf, const mb_interaction* it, mb_pv* pv1
     else k_ntc<false><<<g, 128, 0, st>>>(a);
     MB_LAUNCH_CHECK(ctx);
     if (!two) {
-        k_ntc_warp<<<gwarp, 128, 0, st>>>(a);
+        k_ntc_warp<<<gwarp, 128, 0, st>>>(a, ch);
         MB_LAUNCH_CHECK(ctx);
     }
     for (int sp = 0; sp < (two ? 2 : 1); sp++) {

@@ -374,6 +374,53 @@ def test_ntc_variable_weight_parity(mb, oracle, ctx):
     assert abs(pv.logical(1, n)[:, 0].sum() - opv.logical(1, n)[:, 0].sum()) == 0.0
 
 
+@pytest.mark.parametrize("vw", [True, False])
+@pytest.mark.parametrize("sizes", [(5000,), (3000, 150, 2600, 40, 2048)])
+def test_ntc_large_cells_parity(mb, oracle, ctx, vw, sizes):
+    """Cells of >= 2048 particles are collided by the speculative warp kernel (one warp per cell, 32 candidates evaluated at a time,
+    the first non-trivial one executed for real): it must replay the reference's sequential loop draw for draw -- candidate and
+    collision counters, sigma_g_w_max, split particles, pia identical to the oracle -- also next to small cells in the same range."""
+    rng = np.random.default_rng(4242 + len(sizes))
+    n_cells, n = len(sizes), sum(sizes)
+    L = n_cells * 1e-5
+    Fnum = 1e-5 * 5e22 / 300
+    rows = maxwellian_rows(rng, n, L, w=Fnum, vw=False)
+    if vw:
+        rows[:, 0] *= 10.0 ** rng.uniform(-2.0, 1.0, n)  # weights over three decades: low acceptance, long rejection runs
+    rows[:, 4] = (np.repeat(np.arange(n_cells), sizes) + rng.uniform(0.01, 0.99, n)) * 1e-5
+    cap = 12 * n  # the split windows are sized by the candidate counts (thousands per large cell)
+    opv, opia = oracle_state(oracle, rows, n_cells, capacity=cap)
+    oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+    pv, pia = mirror_to_device(mb, ctx, opv, opia, capacity=cap)
+    it, oit = mb.make_interaction(AR, AR, 4.11e-10, 0.81, 273.0), oracle.interaction("Ar", "Ar")
+    s0 = mb.estimate_sigma_g_w_max(it, AR, AR, 300.0, 300.0, Fnum)
+    cf, ocf = mb.CollisionFactors(n_cells, s0, ctx), oracle.CF(n_cells, s0)
+    g = mb.Grid1DUniform(L, n_cells)
+    dt, V = 2.59e-9 * 0.3, L / n_cells
+    total = 0
+    for t in range(1, 4):
+        mb.ntc(mb.PhiloxRng(t), cf, None, it, pv, pia, (1, n_cells), 1, dt, V, equal_weight=not vw)
+        oracle.ntc(oracle.Rng.philox(1234, t), ocf, oit, opv, opia, 1, n_cells, 1, dt, V, equal_weight=not vw)
+        d = cf.download()
+        np.testing.assert_array_equal(d["n_coll"], ocf.n_coll)
+        np.testing.assert_array_equal(d["n_coll_performed"], ocf.n_coll_performed)
+        np.testing.assert_array_equal(d["n_eq_w_coll_performed"], ocf.n_eq_w_coll_performed)
+        np.testing.assert_allclose(d["sigma_g_w_max"], ocf.sigma_g_w_max, rtol=1e-13)
+        assert_same_pia(opia, pia)
+        nt = int(opia.n_total[0])
+        a, b = pv.logical(1, nt), opv.logical(1, nt)
+        assert_rows_close(a, b, 1e-12, "ntc large cells")
+        np.testing.assert_array_equal(a[:, 0], b[:, 0])
+        total += int(ocf.n_coll.sum())
+        # fold the split particles back into their cells (general sort path) so that the next step may split again
+        mb.sort_particles(None, g, pv, pia, 1)
+        oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+        assert_same_pia(opia, pia)
+    assert total > 200 * len([x for x in sizes if x >= 2048])  # the large cells really ran long candidate loops
+    if vw:
+        assert int(opia.n_total[0]) > n
+
+
 def test_ntc_capacity_error(mb, oracle, ctx):
     """the reference would resize!; the device reports MB_ERR_CAPACITY and leaves the state untouched."""
     n_cells, ppc, dt = 4, 300, 2.59e-9 * 60
