@@ -61,7 +61,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--particles", type=float, default=1e8)
     ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--only", default="", help="c2: only the BKW variable-weight 0-D ensemble section")
+    ap.add_argument("--only", default="", help="c2: only the BKW variable-weight 0-D ensemble section; c4: only the variable-weight Couette loop")
     args = ap.parse_args()
     peak = 6533.8
     try:
@@ -83,7 +83,7 @@ def main():
                           "algorithmic_bytes_per_particle": bytes_per_particle, "achieved_GBps": gbs, "frac_of_measured_hbm_peak": gbs / peak, "note": note}),
               flush=True)
 
-    if args.only != "c2":
+    if args.only == "":
         # ---- C5: fp_linear!, 1e6 cells x 100
         ppc = 100
         nc = int(args.particles // ppc)
@@ -167,6 +167,53 @@ def main():
         pv.close()
         pia.close()
         del a
+
+    if args.only in ("", "c4"):
+        # ---- C4: 1-D Couette, variable weight, octree merging (couette_varweight_octree.jl:30-135; 500 sampled per cell, merged to
+        #      100 at t = 0, threshold 130): per step ntc! -> merge_octree_N2_based! where n_local > 130 -> convect_particles! ->
+        #      sort_particles! (squashes first) -> compute_props_sorted!.  Sampled on the device.
+        nx = max(int(args.particles // 100), 64)
+        ppc_s, thr, tgt = 500, 130, 100
+        grid4 = mb.Grid1DUniform(nx * DX, nx, wall_offset=1e-6)
+        Fnum = DX * NDENS / ppc_s
+        pv, pia = mb.ParticleVector(int(nx * ppc_s * 1.01) + 1024, ctx), mb.ParticleIndexerArray(nx, 1, ctx)
+        t_s = one(lambda: mb.sample_particles_equal_weight(mb.PhiloxRng(0), grid4, pv, pia, 1, AR, float(NDENS), 300.0, Fnum))
+        n0 = int(pia.n_total[0])
+        report("sample_particles_equal_weight! (grid, number density)", "C4: %d cells x ~%d" % (nx, ppc_s), n0, t_s, 60, "write 56 B + cell id per particle")
+        oc4 = mb.OctreeN2Merge(mb.OctreeN2Merge.OctreeBinMidSplit, mb.OctreeN2Merge.OctreeInitBinMinMaxVel, max_Nbins=6000)
+        t_m = one(lambda: mb.merge_octree_N2_based(mb.PhiloxRng(0), oc4, pv, pia, (1, nx), 1, tgt, grid4, threshold=thr))
+        report("merge_octree_N2_based (t = 0: 500 -> 100)", "C4: %d cells" % nx, n0, t_m, 56 * 600 / 500.0, "CTA kernel (cells above 256 particles)")
+        mb.squash_pia(pv, pia, 1)
+        walls4 = mb.MaxwellWalls1D(300.0, 300.0, -500.0, 500.0, 1.0, 1.0)
+        cf4 = mb.CollisionFactors(nx, mb.estimate_sigma_g_w_max(it, AR, AR, 300.0, 300.0, DX * NDENS / tgt), ctx)
+        pp4 = mb.PhysProps(nx, 1, ctx=ctx)
+        acc, nsteps, n_hist = {}, 40, []
+        for t in range(1, nsteps + 1):
+            r = mb.PhiloxRng(t)
+            tt = {"ntc": one(lambda: mb.ntc(r, cf4, None, it, pv, pia, (1, nx), 1, DT, DX)),
+                  "merge": one(lambda: mb.merge_octree_N2_based(r, oc4, pv, pia, (1, nx), 1, tgt, grid4, threshold=thr)),
+                  "convect": one(lambda: mb.convect_particles(r, grid4, walls4, pv, pia, 1, AR, DT)),
+                  "sort": one(lambda: mb.sort_particles(None, grid4, pv, pia, 1)),
+                  "props": one(lambda: mb.compute_props_sorted([pv], pia, [AR], pp4))}
+            if t > nsteps // 2:
+                n_hist.append(int(pia.n_total[0]))
+                for k, v in tt.items():
+                    acc.setdefault(k, []).append(v)
+        n_mean = sum(n_hist) / len(n_hist)
+        tot = 0.0
+        for k, bpp in (("ntc", 64), ("merge", 112), ("convect", 44), ("sort", 128 + 112), ("props", 32)):
+            v = acc[k]
+            tot += sum(v) / len(v)
+            report("C4 step: " + k, "%d cells, ~%.3g particles, mean of steps %d-%d" % (nx, n_mean, nsteps // 2 + 1, nsteps), int(n_mean), sum(v) / len(v), bpp,
+                   "max %.2f ms" % max(v))
+        d = pp4.download()
+        print(json.dumps({"op": "C4 step total", "ms": tot, "particle_steps_per_s": n_mean / (tot * 1e-3), "mean_T_K": float(d["T"].mean()),
+                          "mean_np_per_cell": float(d["np"].mean())}), flush=True)
+        pv.close()
+        pia.close()
+    if args.only == "c4":
+        ctx.close()
+        return
 
     # ---- C2: 0-D BKW variable-weight relaxation with octree N:2 merging (bkw_varweight_octree.jl / test_bkw_varweight_octree.jl:43-47):
     #      an ensemble of independent cells, each the nv = 40 grid sample (~33.5k particles) merged to 8000 at t = 0, then per step

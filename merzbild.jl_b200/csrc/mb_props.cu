@@ -21,6 +21,9 @@ struct PropsArgs {
     double moment_factor, moment_vref;  // physical_props.jl:176-177
     double n_scale;        // 1 or inv_V (ndens variant :425)
     const int* run_if_flag;  // nullable: run only if *run_if_flag != 0 (the sort's cached moments are not valid)
+    double* lpa;           // nullable: phys_props.lpa[species] = length(particles[species]) (:151), written by the kernel (no host sync)
+    double lpa_val;
+    int64_t n_lo;          // k_props<32>: cells with more than n_lo particles (the smaller ones are taken by k_props_reg)
 };
 
 template <int G>
@@ -49,12 +52,14 @@ __global__ void __launch_bounds__(256) k_props(PropsArgs a) {
     const double* __restrict__ VX = a.pv.a[F_VX];
     const double* __restrict__ VY = a.pv.a[F_VY];
     const double* __restrict__ VZ = a.pv.a[F_VZ];
+    if (a.lpa != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *a.lpa = a.lpa_val;
     for (int64_t r = grp0; r < nr; r += ngrp) {
         const int64_t c = a.cell_lo - 1 + r;
         const Indexer q = a.ix[c];
         const int64_t lo1 = q.start1 - 1, n1 = q.end1 >= q.start1 ? q.end1 - q.start1 + 1 : 0;
         const int64_t lo2 = q.start2 - 1, n2 = (!a.sorted && q.n_group2 > 0) ? q.end2 - q.start2 + 1 : 0;
         const int64_t nn = n1 + n2;
+        if (G == 32 && nn <= a.n_lo && nn > 0) continue;  // group-uniform; k_props_reg
         double n = 0, sx = 0, sy = 0, sz = 0;
         for (int64_t j = tid; j < nn; j += G) {
             const int64_t i = j < n1 ? lo1 + j : lo2 + (j - n1);
@@ -106,6 +111,73 @@ __global__ void __launch_bounds__(256) k_props(PropsArgs a) {
             a.n[c] = n * a.n_scale;
             a.T[c] = T;
             a.v[3 * c + 0] = vx; a.v[3 * c + 1] = vy; a.v[3 * c + 2] = vz;
+        }
+    }
+}
+
+// Cells of 1 .. 32 K particles (both groups together): warp per cell with the cell in registers -- read once from HBM, both passes
+// of the reference's two-pass formulation from registers.  Same per-lane accumulation order and butterfly as k_props<32>, so the
+// results are bit-identical.  A warp takes 32 consecutive cells at a time (one read of their sizes).
+template <int K>
+__global__ void __launch_bounds__(128) k_props_reg(PropsArgs a, int n_lo) {
+    if (a.run_if_flag != nullptr && *a.run_if_flag == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t nr = a.cell_hi - a.cell_lo + 1;
+    const double* __restrict__ W = a.pv.a[F_W];
+    const double* __restrict__ VX = a.pv.a[F_VX];
+    const double* __restrict__ VY = a.pv.a[F_VY];
+    const double* __restrict__ VZ = a.pv.a[F_VZ];
+    for (int64_t r0 = gw * 32; r0 < nr; r0 += nwarps * 32) {
+        const int64_t myr = r0 + lane;
+        int64_t my_nn = 0;
+        if (myr < nr) {
+            const Indexer q = a.ix[a.cell_lo - 1 + myr];
+            my_nn = (q.end1 >= q.start1 ? q.end1 - q.start1 + 1 : 0) + ((!a.sorted && q.n_group2 > 0) ? q.end2 - q.start2 + 1 : 0);
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, my_nn > n_lo && my_nn <= 32 * K);
+        while (todo) {
+            const int64_t c = a.cell_lo - 1 + r0 + (__ffs(todo) - 1);
+            todo &= todo - 1;
+            const Indexer q = a.ix[c];
+            const int64_t lo1 = q.start1 - 1, n1 = q.end1 >= q.start1 ? q.end1 - q.start1 + 1 : 0;
+            const int64_t lo2 = q.start2 - 1, n2 = (!a.sorted && q.n_group2 > 0) ? q.end2 - q.start2 + 1 : 0;
+            const int nn = (int)(n1 + n2);
+            double w[K], vx[K], vy[K], vz[K];
+            double n = 0, sx = 0, sy = 0, sz = 0;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const int j = lane + 32 * k;
+                w[k] = 0.0; vx[k] = 0.0; vy[k] = 0.0; vz[k] = 0.0;
+                if (j < nn) {
+                    const int64_t i = j < n1 ? lo1 + j : lo2 + (j - n1);
+                    w[k] = W[i]; vx[k] = VX[i]; vy[k] = VY[i]; vz[k] = VZ[i];
+                    n += w[k];
+                    sx += vx[k] * w[k]; sy += vy[k] * w[k]; sz += vz[k] * w[k];
+                }
+            }
+            n = group_sum<32>(n, nullptr);
+            sx = group_sum<32>(sx, nullptr); sy = group_sum<32>(sy, nullptr); sz = group_sum<32>(sz, nullptr);
+            double mx = 0, my = 0, mz = 0, T = 0;
+            if (n > 0.0) {
+                mx = sx / n; my = sy / n; mz = sz / n;
+                double E = 0;
+#pragma unroll
+                for (int k = 0; k < K; k++)
+                    if (lane + 32 * k < nn) {
+                        const double cx = vx[k] - mx, cy = vy[k] - my, cz = vz[k] - mz;
+                        E += w[k] * (cx * cx + cy * cy + cz * cz);
+                    }
+                E = group_sum<32>(E, nullptr);
+                E *= 0.5 * a.mass / (n * k_B);
+                T = (2.0 / 3.0) * E;
+            }
+            if (lane == 0) {
+                a.np[c] = (double)nn;
+                a.n[c] = n * a.n_scale;
+                a.T[c] = T;
+                a.v[3 * c + 0] = mx; a.v[3 * c + 1] = my; a.v[3 * c + 2] = mz;
+            }
         }
     }
 }
@@ -163,14 +235,22 @@ static int props_launch(mb_ctx* ctx, mb_pv* const* pvs, mb_pia* pia, const doubl
             a.run_if_flag = ctx->d_flags + 2;  // the regular kernel below only runs if the sort fell back to the general path
         }
         const int64_t avg = (pia->n_bound[s] > 0 ? pia->n_bound[s] : pvs[s]->cap) / (nc > 0 ? nc : 1);
-        if (avg > 4096) k_props<256><<<(int)(nr < N_SM * 8 ? nr : N_SM * 8), 256, 0, ctx->stream>>>(a);
-        else k_props<32><<<grid_for(nr * 32, 256, 8), 256, 0, ctx->stream>>>(a);
-        MB_LAUNCH_CHECK(ctx);
-        if (!sorted) {
-            const double lpa = (double)pvs[s]->cap;  // phys_props.lpa[species] = length(particles[species]) :151
-            MB_CUDA(cudaMemcpyAsync(P->lpa + s, &lpa, 8, cudaMemcpyHostToDevice, ctx->stream));
-            MB_CUDA(cudaStreamSynchronize(ctx->stream));
+        a.lpa = sorted ? nullptr : P->lpa + s;  // phys_props.lpa[species] = length(particles[species]) :151
+        a.lpa_val = (double)pvs[s]->cap;
+        a.n_lo = 0;
+        if (avg > 4096) {
+            k_props<256><<<(int)(nr < N_SM * 8 ? nr : N_SM * 8), 256, 0, ctx->stream>>>(a);
+        } else {
+            if (!a.with_moments) {  // small cells from registers; the streaming kernel takes the rest
+                a.n_lo = 256;
+                k_props_reg<4><<<grid_for(nr, 128, 12), 128, 0, ctx->stream>>>(a, 0);
+                MB_LAUNCH_CHECK(ctx);
+                k_props_reg<8><<<grid_for(nr, 128, 8), 128, 0, ctx->stream>>>(a, 128);
+                MB_LAUNCH_CHECK(ctx);
+            }
+            k_props<32><<<grid_for(nr * 32, 256, 8), 256, 0, ctx->stream>>>(a);
         }
+        MB_LAUNCH_CHECK(ctx);
     }
     return MB_OK;
 }

@@ -21,6 +21,7 @@
 #include <cstdlib>
 
 #include "mb_convect.cuh"
+#include "mb_scan.cuh"
 
 namespace mb {
 
@@ -536,9 +537,12 @@ __global__ void k_clear_cls_flags(int* flags) { flags[F_OUTSIDE] = 0; flags[F_CL
 __global__ void k_flag_from_cls(int* flags, int drop) { flags[2] = (flags[F_CLS_BAD] != 0 || (!drop && flags[F_OUTSIDE] != 0)) ? 1 : 0; }
 
 // ------------------------------------------------------------------------------------------------ general path
+// src (nullable): physical position of logical (squashed) position i -- the squash of a non-contiguous species is folded into the
+// sort instead of moving the payload twice (see k_build_src)
 __global__ void __launch_bounds__(256) k_gen_classify(const double* __restrict__ X, const int32_t* cell_in, int32_t* cell_out,
                                                       int32_t* __restrict__ key, const int64_t* n_total_p, int64_t n_cells, double inv_dx,
-                                                      int64_t cell_offset, int use_x, int drop, int32_t* __restrict__ hist, int* flags) {
+                                                      int64_t cell_offset, int use_x, int drop, int32_t* __restrict__ hist, int* flags,
+                                                      const int32_t* __restrict__ src) {
     // drop != 0 (after a slab exchange): a particle whose cell is outside [0, n_cells) left the slab and is dropped
     if (flags[2] == 0) return;
     const int64_t n_total = *n_total_p;
@@ -552,8 +556,9 @@ __global__ void __launch_bounds__(256) k_gen_classify(const double* __restrict__
         int nc = -1;
         bool counted = false;
         if (valid) {
-            if (use_x) { nc = cell_of(X[i], inv_dx, cell_offset); cell_out[i] = nc + 1; }
-            else nc = cell_in[i] - 1;
+            const int64_t ph = src ? (int64_t)src[i] : i;
+            if (use_x) { nc = cell_of(X[ph], inv_dx, cell_offset); cell_out[i] = nc + 1; }
+            else nc = cell_in[ph] - 1;
             if (nc < 0 || nc >= n_cells) {
                 if (drop) nc = -1;
                 else { atomicOr(&flags[0], DEVERR_BAD_CELL); nc = nc < 0 ? 0 : (int)(n_cells - 1); }
@@ -713,13 +718,61 @@ __global__ void __launch_bounds__(256) k_gen_sort_segments(int32_t* __restrict__
     }
 }
 
-__global__ void __launch_bounds__(256) k_gen_gather(SoA in, SoA out, const int32_t* __restrict__ perm, const int64_t* n_total_p, const int* flags) {
+// cell_out (nullable; the variant that sorts by stored cell ids, grid_sorting.jl:128): the ids are permuted along with the particles,
+// so that an ensemble of 0-D cells can be re-sorted step after step (device-side extension: the reference leaves particles.cell stale)
+__global__ void __launch_bounds__(256) k_gen_gather(SoA in, SoA out, const int32_t* __restrict__ perm, const int64_t* n_total_p, const int* flags,
+                                                    const int32_t* __restrict__ src, const int32_t* __restrict__ key, int32_t* __restrict__ cell_out) {
     if (flags[2] == 0) return;
     const int64_t n_total = *n_total_p;
     for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n_total; j += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = perm[j];
+        const int64_t ph = src ? (int64_t)src[i] : i;
 #pragma unroll
-        for (int f = 0; f < 7; f++) out.a[f][j] = in.a[f][i];
+        for (int f = 0; f < 7; f++) out.a[f][j] = in.a[f][ph];
+        if (cell_out) cell_out[j] = key[i] + 1;
+    }
+}
+
+// squash_pia! folded into the sort (grid_sorting.jl:69-71 squashes first): instead of moving the payload to close the holes and then
+// moving it again in the sort, only the map logical (squashed) position -> physical position is built (4 B per particle).  The
+// squashed order walks group 1 of all cells, then group 2 of all cells (particles.jl:622-682); newlo = exclusive scan of the segment
+// sizes.  One warp per tile of output positions, bisection over the segment starts.
+static __global__ void k_sq_counts(const Indexer* __restrict__ ix, int64_t nc, int32_t* __restrict__ cnt) {
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
+        const Indexer q = ix[c];
+        cnt[c] = (int32_t)q.n_group1;
+        cnt[nc + c] = (int32_t)q.n_group2;
+    }
+}
+constexpr int SRC_TILE = 2048;
+static __global__ void __launch_bounds__(256) k_build_src(const Indexer* __restrict__ ix, int64_t nc, const int64_t* __restrict__ newlo,
+                                                          int32_t* __restrict__ src, int* flags) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t nseg = 2 * nc, total = newlo[nseg];
+    for (int64_t d0 = warp0 * SRC_TILE; d0 < total; d0 += nwarps * SRC_TILE) {
+        const int64_t d1 = d0 + SRC_TILE < total ? d0 + SRC_TILE : total;
+        int64_t lo = 0, hi = nseg - 1;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi + 1) >> 1;
+            if (newlo[mid] <= d0) lo = mid; else hi = mid - 1;
+        }
+        int64_t sgm = lo, d = d0;
+        while (d < d1) {
+            const int64_t s_lo = newlo[sgm], s_hi = newlo[sgm + 1];
+            if (s_hi > d) {
+                const bool g2 = sgm >= nc;
+                const Indexer q = ix[g2 ? sgm - nc : sgm];
+                const int64_t olo = (g2 ? q.start2 : q.start1) - 1;
+                if (olo < s_lo && lane == 0) atomicOr(&flags[0], DEVERR_PRECONDITION);  // the reference only ever shifts left
+                const int64_t e = s_hi < d1 ? s_hi : d1;
+                const int64_t src0 = olo + (d - s_lo);
+                for (int64_t j = lane; j < e - d; j += 32) src[d + j] = (int32_t)(src0 + j);
+                d = e;
+            }
+            sgm++;
+        }
     }
 }
 
@@ -891,7 +944,10 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
     MB_ARG(pia->n_cells < (int64_t)INT_MAX && pv->cap < (int64_t)INT_MAX, "more than 2^31 cells or particles per GPU");
     MB_CUDA(cudaSetDevice(ctx->device));
     const int s = (int)species - 1;
-    if (!pia->contiguous[s]) {  // grid_sorting.jl:69-71
+    // grid_sorting.jl:69-71: squash first.  A non-contiguous species never has the sorted layout (a merge cleared it), so the sort
+    // takes the general path and the squash is folded into it (k_build_src); the separate payload pass is only the fallback.
+    const bool fuse_squash = !pia->contiguous[s] && !(ctx->band_w > 0 && pia->sorted_layout[s]) && pv->n_arrivals == 0 && !pv->drop_oob;
+    if (!pia->contiguous[s] && !fuse_squash) {
         int r = mb_squash_pia(ctx, pv, pia, species);
         if (r) return r;
     }
@@ -946,10 +1002,25 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
         ProfScope ps(ctx, PROF_SORT_GENERAL);
         S.perm = (int32_t*)ctx_scratch(ctx, 3, (size_t)cap * 4);
         if (!S.perm) return MB_ERR_CUDA;
+        const int64_t nb = pia->n_bound[s] > 0 ? pia->n_bound[s] : cap;
+        int32_t* src = nullptr;
+        if (fuse_squash) {
+            src = (int32_t*)ctx_scratch(ctx, 8, (size_t)cap * 4);
+            int32_t* cnt = (int32_t*)ctx_scratch(ctx, 4, (size_t)(2 * nc) * 4);
+            int64_t* p64 = (int64_t*)ctx_scratch(ctx, 5, ((size_t)(2 * nc + 1) + gs_partial_count(2 * nc)) * 8);
+            if (!src || !cnt || !p64) return MB_ERR_CUDA;
+            ProfScope ps2(ctx, PROF_SQUASH);
+            k_sq_counts<<<grid_for(nc, 256), 256, 0, st>>>(ix, nc, cnt);
+            MB_LAUNCH_CHECK(ctx);
+            r = device_exclusive_scan(ctx, cnt, 2 * nc, p64, p64 + (2 * nc + 1));
+            if (r) return r;
+            k_build_src<<<grid_for((nb + SRC_TILE - 1) / SRC_TILE * 32, 256, 8), 256, 0, st>>>(ix, nc, p64, src, ctx->d_flags);
+            MB_LAUNCH_CHECK(ctx);
+        }
         MB_CUDA(cudaMemsetAsync(S.hist, 0, (size_t)nc * 4, st));  // harmless for the band result: hist is not read again
-        const int pgrid = grid_for(pia->n_bound[s] > 0 ? pia->n_bound[s] : cap, 256, 16);
+        const int pgrid = grid_for(nb, 256, 16);
         k_gen_classify<<<pgrid, 256, 0, st>>>(pv->cur.a[F_X], pv->cell, pv->cell, S.key, B.n_old, nc, use_x ? grid->inv_dx : 0.0,
-                                             use_x ? grid->cell_offset : 0, use_x ? 1 : 0, drop ? 1 : 0, S.hist, S.flags);
+                                             use_x ? grid->cell_offset : 0, use_x ? 1 : 0, drop ? 1 : 0, S.hist, S.flags, src);
         MB_LAUNCH_CHECK(ctx);
         k_scan_reduce<3><<<nscan, SCAN_BLOCK, 0, st>>>(nullptr, nullptr, S.hist, nc, S.partial, S.flags, 1);
         MB_LAUNCH_CHECK(ctx);
@@ -963,7 +1034,7 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
         MB_LAUNCH_CHECK(ctx);
         k_gen_sort_segments<<<grid_for(nc * 256, 256, 8), 256, 0, st>>>(S.perm, S.start, nc, S.flags);
         MB_LAUNCH_CHECK(ctx);
-        k_gen_gather<<<pgrid, 256, 0, st>>>(pv->cur, pv->alt, S.perm, S.start + nc, S.flags);
+        k_gen_gather<<<pgrid, 256, 0, st>>>(pv->cur, pv->alt, S.perm, S.start + nc, S.flags, src, S.key, use_x ? nullptr : pv->cell);
         MB_LAUNCH_CHECK(ctx);
     }
     // ping-pong
