@@ -118,6 +118,62 @@ def main():
     if rank == 0:
         print("MULTIRANK_OK couette step conserves the global population over", world, "ranks", flush=True)
     ctx.sync()
+
+    # phase 3: the variable-weight Couette loop over slabs (C4: couette_multithreaded_varweight_octree.jl): ntc! with splits ->
+    # merge_octree_N2_based! above the threshold -> squash_pia! -> convect (specular walls) -> exchange -> sort.  Splits, merges,
+    # specular walls and the exchange all conserve weight and kinetic energy, so the GLOBAL sums must stay put
+    # (test_couette_varweight_octree_chunking.jl:137 asks 4 eps per step of the density; energy to 1e-11 here).
+    nx3, ppc3 = 64, 160
+    G3 = mb.Grid1DUniform(nx3 * 1e-5, nx3)
+    slab3 = G3.slab(rank, world)
+    pv3 = mb.ParticleVector(6 * slab3.n_cells * ppc3, ctx)
+    pia3 = mb.ParticleIndexerArray(slab3.n_cells, 1, ctx)
+    Fnum3 = 1e-5 * 5e22 / ppc3
+    ctx.set_seed(4321 + rank)
+    mb.sample_particles_equal_weight(mb.PhiloxRng(0), slab3, pv3, pia3, 1, AR, ppc3, 300.0, Fnum3)
+    oc = mb.OctreeN2Merge(mb.OctreeN2Merge.OctreeBinMidSplit, mb.OctreeN2Merge.OctreeInitBinMinMaxVel, max_Nbins=6000)
+    mb.merge_octree_N2_based(mb.PhiloxRng(0), oc, pv3, pia3, (1, slab3.n_cells), 1, 100, slab3, threshold=130)
+    mb.squash_pia(pv3, pia3, 1)
+    cf3 = mb.CollisionFactors(slab3.n_cells, mb.estimate_sigma_g_w_max(it, AR, AR, 300.0, 300.0, 1e-5 * 5e22 / 100), ctx)
+    walls3 = mb.MaxwellWalls1D(300.0, 300.0, 0.0, 0.0, 0.0, 0.0)
+
+    def totals():
+        nt = int(pia3.n_total[0])
+        a = pv3.logical(1, nt)
+        t = torch.tensor([a[:, 0].sum(), (a[:, 0] * (a[:, 1:4] ** 2).sum(1)).sum(), float(nt)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        return t.cpu().numpy()
+
+    t0 = totals()
+    merged_cells, sent3 = 0, 0
+    dt3 = 2.59e-9 * 8
+    for t in range(1, 31):
+        r = mb.PhiloxRng(t, rank)
+        mb.ntc(r, cf3, None, it, pv3, pia3, (1, slab3.n_cells), 1, dt3, slab3.dx)
+        merged_cells += int((pia3.indexer[0, :, 0] > 130).sum())
+        mb.merge_octree_N2_based(r, oc, pv3, pia3, (1, slab3.n_cells), 1, 100, slab3, threshold=130)
+        mb.squash_pia(pv3, pia3, 1)
+        mb.convect_particles(r, slab3, walls3, pv3, pia3, 1, AR, dt3)
+        sc, rc = mb.exchange_slab(ctx, slab3, pv3, pia3, 1, counts=True)
+        sent3 += int(sc.sum())
+        mb.sort_particles(None, slab3, pv3, pia3, 1)
+        ok, where = pia3.check(1)
+        assert ok, (rank, t, where)
+        if t % 10 == 0:
+            t1 = totals()
+            assert abs(t1[0] - t0[0]) <= 4e-16 * t * t0[0] * 8, (t, t1[0], t0[0])
+            assert abs(t1[1] - t0[1]) <= 1e-11 * t0[1], (t, t1[1], t0[1])
+    nt = int(pia3.n_total[0])
+    a = pv3.logical(1, nt)
+    lc = np.floor(a[:, 4] * G3.inv_dx).astype(np.int64) - slab3.cell_offset
+    assert lc.min() >= 0 and lc.max() < slab3.n_cells and np.all(np.diff(lc) >= 0)
+    stats = torch.tensor([float(merged_cells), float(sent3)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(stats)
+    assert stats[0].item() > 20 and stats[1].item() > 100, stats
+    if rank == 0:
+        print("MULTIRANK_OK variable-weight loop (ntc splits, octree merge, squash, exchange, sort) conserves global weight and energy;",
+              int(stats[0].item()), "cell merges,", int(stats[1].item()), "particles exchanged", flush=True)
+    ctx.sync()
     dist.destroy_process_group()
 
 

@@ -20,4 +20,4 @@ def test_slab_exchange_matches_single_domain(nproc, mode):
            str(29500 + nproc + (10 if mode == "edge" else 0)), os.path.join(ROOT, "tests", "multirank_worker.py"), mode]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert out.stdout.count("MULTIRANK_OK") == 2, out.stdout[-3000:]
+    assert out.stdout.count("MULTIRANK_OK") == 3, out.stdout[-3000:]
