@@ -4,6 +4,7 @@
 #pragma once
 #include "mb_common.cuh"
 #include "mb_scan.cuh"
+#include "mb_segcopy.cuh"
 
 namespace mb {
 
@@ -31,58 +32,49 @@ __device__ __forceinline__ void append_split(const SoA& s, Indexer& q, int64_t w
 }
 
 // pack the per-cell windows to the left (cell order) so the layout equals the reference's sequential appends
-// Load balance as in k_squash_move: one warp per tile of PK_TILE packed output positions, bisection over the packed offsets.
-constexpr int PK_TILE = 1024;
-static __global__ void __launch_bounds__(256) k_ntc_pack(SoA cur, SoA alt, Indexer* __restrict__ ix, int64_t cell_lo, int64_t nr,
-                                                         const int64_t* __restrict__ win, const int64_t* __restrict__ packed,
-                                                         const int32_t* __restrict__ nsplit, const int64_t* n_total, int phase,
-                                                         int32_t* __restrict__ cell_id) {
-    const int64_t nt = *n_total;
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int64_t total = packed[nr];
-    for (int64_t d0 = warp0 * PK_TILE; d0 < total; d0 += nwarps * PK_TILE) {
-        const int64_t d1 = d0 + PK_TILE < total ? d0 + PK_TILE : total;
-        int64_t lo = 0, hi = nr - 1;
-        while (lo < hi) {
-            const int64_t mid = (lo + hi + 1) >> 1;
-            if (packed[mid] <= d0) lo = mid; else hi = mid - 1;
-        }
-        int64_t r = lo, d = d0;
-        while (d < d1) {
-            const int64_t s_lo = packed[r], s_hi = packed[r + 1];
-            if (s_hi > d) {
-                const int64_t e = s_hi < d1 ? s_hi : d1;
-                const bool moved = win[r] != s_lo;
-                const int64_t src0 = nt + win[r] + (d - s_lo), dst0 = nt + d;
-                if (phase == 0) {
-                    if (moved)
-                        for (int64_t j = lane; j < e - d; j += 32)
-#pragma unroll
-                            for (int f = 0; f < 7; f++) alt.a[f][dst0 + j] = cur.a[f][src0 + j];
-                } else {
-                    for (int64_t j = lane; j < e - d; j += 32) {
-                        if (moved)
-#pragma unroll
-                            for (int f = 0; f < 7; f++) cur.a[f][dst0 + j] = alt.a[f][dst0 + j];
-                        // device-side extension: the new particles carry their cell id, so that an ensemble of 0-D cells can be re-sorted
-                        // by sort_particles!(gridsort, particles, pia, species) (grid_sorting.jl:128) without a grid
-                        cell_id[dst0 + j] = (int32_t)(cell_lo + r);
-                    }
-                    if (lane == 0 && moved && d == s_lo) {  // the warp that holds the window's first particle rewrites its range
-                        Indexer q = ix[cell_lo - 1 + r];
-                        q.start2 = nt + s_lo + 1;
-                        q.end2 = nt + s_lo + (s_hi - s_lo);
-                        ix[cell_lo - 1 + r] = q;
-                    }
-                }
-                d = e;
-            }
-            r++;
+// the split windows: window r holds nsplit[r] particles at n_total + win[r] and moves to n_total + packed[r]
+struct PackDesc {
+    const int64_t* win;
+    const int64_t* packed;
+    const int32_t* nsplit;
+    const int64_t* n_total;
+    __device__ __forceinline__ void get(int64_t r, int64_t& n, int64_t& src, int64_t& dst) const {
+        const int64_t nt = *n_total;
+        n = nsplit[r];
+        src = nt + win[r];
+        dst = nt + packed[r];
+    }
+};
+// phase 0: moved windows -> alt (in place would overwrite unread sources); phase 1: back into cur at the packed position, the
+// window's group-2 range rewritten, and -- device-side extension -- the cell id of every new particle, so that an ensemble of 0-D
+// cells can be re-sorted by sort_particles!(gridsort, particles, pia, species) (grid_sorting.jl:128) without a grid
+struct PackAct {
+    SoA cur, alt;
+    Indexer* ix;
+    int64_t cell_lo;
+    int32_t* cell_id;
+    int phase;
+    __device__ __forceinline__ void seg(int64_t r, int64_t n, int64_t src, int64_t dst) const {
+        if (phase == 1 && src != dst) {
+            Indexer q = ix[cell_lo - 1 + r];
+            q.start2 = dst + 1;
+            q.end2 = dst + n;
+            ix[cell_lo - 1 + r] = q;
         }
     }
-}
+    __device__ __forceinline__ void elem(int64_t r, int64_t src, int64_t dst) const {
+        if (phase == 0) {
+            if (src != dst)
+#pragma unroll
+                for (int f = 0; f < 7; f++) alt.a[f][dst] = cur.a[f][src];
+        } else {
+            if (src != dst)
+#pragma unroll
+                for (int f = 0; f < 7; f++) cur.a[f][dst] = alt.a[f][dst];
+            cell_id[dst] = (int32_t)(cell_lo + r);
+        }
+    }
+};
 static __global__ void k_add_total(int64_t* n_total, const int64_t* packed, int64_t nr) {
     *n_total += packed[nr];
 }
@@ -93,14 +85,15 @@ static inline int pack_windows(mb_ctx* ctx, mb_pv* pv, Indexer* ix, int64_t cell
                                int64_t* packed, int64_t* partial, int64_t* n_total) {
     int r = device_exclusive_scan(ctx, nsplit, nr, packed, partial);
     if (r) return r;
-    const int64_t nb = pv->cap;  // upper bound on the appended particles; the kernels read the exact total from the scan
-    const int gw = grid_for((nb + PK_TILE - 1) / PK_TILE * 32, 256, 4);
+    PackDesc D{win, packed, nsplit, n_total};
     if (nr > 1) {
-        k_ntc_pack<<<gw, 256, 0, ctx->stream>>>(pv->cur, pv->alt, ix, cell_lo, nr, win, packed, nsplit, n_total, 0, pv->cell);
-        MB_LAUNCH_CHECK(ctx);
+        PackAct A0{pv->cur, pv->alt, ix, cell_lo, pv->cell, 0};
+        r = seg_copy(ctx, 7, pv->cap, nr, D, A0);
+        if (r) return r;
     }
-    k_ntc_pack<<<gw, 256, 0, ctx->stream>>>(pv->cur, pv->alt, ix, cell_lo, nr, win, packed, nsplit, n_total, 1, pv->cell);
-    MB_LAUNCH_CHECK(ctx);
+    PackAct A1{pv->cur, pv->alt, ix, cell_lo, pv->cell, 1};
+    r = seg_copy(ctx, 7, pv->cap, nr, D, A1);
+    if (r) return r;
     k_add_total<<<1, 1, 0, ctx->stream>>>(n_total, packed, nr);
     MB_LAUNCH_CHECK(ctx);
     return MB_OK;

@@ -22,6 +22,7 @@
 
 #include "mb_convect.cuh"
 #include "mb_scan.cuh"
+#include "mb_segcopy.cuh"
 
 namespace mb {
 
@@ -736,7 +737,7 @@ __global__ void __launch_bounds__(256) k_gen_gather(SoA in, SoA out, const int32
 // squash_pia! folded into the sort (grid_sorting.jl:69-71 squashes first): instead of moving the payload to close the holes and then
 // moving it again in the sort, only the map logical (squashed) position -> physical position is built (4 B per particle).  The
 // squashed order walks group 1 of all cells, then group 2 of all cells (particles.jl:622-682); newlo = exclusive scan of the segment
-// sizes.  One warp per tile of output positions, bisection over the segment starts.
+// sizes.  Load balance over segment sizes: mb_segcopy.cuh.
 static __global__ void k_sq_counts(const Indexer* __restrict__ ix, int64_t nc, int32_t* __restrict__ cnt) {
     for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
         const Indexer q = ix[c];
@@ -744,37 +745,11 @@ static __global__ void k_sq_counts(const Indexer* __restrict__ ix, int64_t nc, i
         cnt[nc + c] = (int32_t)q.n_group2;
     }
 }
-constexpr int SRC_TILE = 2048;
-static __global__ void __launch_bounds__(256) k_build_src(const Indexer* __restrict__ ix, int64_t nc, const int64_t* __restrict__ newlo,
-                                                          int32_t* __restrict__ src, int* flags) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int64_t nseg = 2 * nc, total = newlo[nseg];
-    for (int64_t d0 = warp0 * SRC_TILE; d0 < total; d0 += nwarps * SRC_TILE) {
-        const int64_t d1 = d0 + SRC_TILE < total ? d0 + SRC_TILE : total;
-        int64_t lo = 0, hi = nseg - 1;
-        while (lo < hi) {
-            const int64_t mid = (lo + hi + 1) >> 1;
-            if (newlo[mid] <= d0) lo = mid; else hi = mid - 1;
-        }
-        int64_t sgm = lo, d = d0;
-        while (d < d1) {
-            const int64_t s_lo = newlo[sgm], s_hi = newlo[sgm + 1];
-            if (s_hi > d) {
-                const bool g2 = sgm >= nc;
-                const Indexer q = ix[g2 ? sgm - nc : sgm];
-                const int64_t olo = (g2 ? q.start2 : q.start1) - 1;
-                if (olo < s_lo && lane == 0) atomicOr(&flags[0], DEVERR_PRECONDITION);  // the reference only ever shifts left
-                const int64_t e = s_hi < d1 ? s_hi : d1;
-                const int64_t src0 = olo + (d - s_lo);
-                for (int64_t j = lane; j < e - d; j += 32) src[d + j] = (int32_t)(src0 + j);
-                d = e;
-            }
-            sgm++;
-        }
-    }
-}
+struct SrcMapAct {
+    int32_t* srcmap;
+    __device__ __forceinline__ void seg(int64_t, int64_t, int64_t, int64_t) const {}
+    __device__ __forceinline__ void elem(int64_t, int64_t src, int64_t dst) const { srcmap[dst] = (int32_t)src; }
+};
 
 __global__ void k_set_flag(int* flags, int idx, int v) { flags[idx] = v; }
 
@@ -1014,8 +989,10 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
             MB_LAUNCH_CHECK(ctx);
             r = device_exclusive_scan(ctx, cnt, 2 * nc, p64, p64 + (2 * nc + 1));
             if (r) return r;
-            k_build_src<<<grid_for((nb + SRC_TILE - 1) / SRC_TILE * 32, 256, 8), 256, 0, st>>>(ix, nc, p64, src, ctx->d_flags);
-            MB_LAUNCH_CHECK(ctx);
+            SquashDesc D{ix, nc, p64, ctx->d_flags};
+            SrcMapAct A{src};
+            r = seg_copy(ctx, 7, cap, 2 * nc, D, A);
+            if (r) return r;
         }
         MB_CUDA(cudaMemsetAsync(S.hist, 0, (size_t)nc * 4, st));  // harmless for the band result: hist is not read again
         const int pgrid = grid_for(nb, 256, 16);

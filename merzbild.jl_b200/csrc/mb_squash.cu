@@ -5,6 +5,7 @@
 // sort's ping-pong buffer at their new positions and the buffers are swapped.
 #include "mb_common.cuh"
 #include "mb_scan.cuh"
+#include "mb_segcopy.cuh"
 
 namespace mb {
 
@@ -18,49 +19,18 @@ static __global__ void k_squash_counts(const Indexer* __restrict__ ix, int64_t n
 
 // every live particle is copied once into the sort's ping-pong buffer at its new position (56 B read + 56 B written per particle,
 // moved or not); the buffers are then swapped on the host side, so no second payload pass is needed.  The cell ids go through a
-// staging array and are copied back by k_squash_cell_back.
-// Load balance: the OUTPUT range [0, n_total) is cut into tiles of SQ_TILE positions, one warp per tile; the warp finds the segment
-// that holds the tile's first position by bisection over the new starts and walks on from there, so a 0-D cell of 1e4 particles and a
-// Couette cell of 1e2 cost the same per particle.
-constexpr int SQ_TILE = 2048;
-static __global__ void __launch_bounds__(256) k_squash_move(SoA cur, SoA alt, const int32_t* __restrict__ cell, int32_t* __restrict__ cell_stage,
-                                                            const Indexer* __restrict__ ix, int64_t nc, const int64_t* __restrict__ newlo, int* flags) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int64_t nseg = 2 * nc, total = newlo[nseg];
-    for (int64_t d0 = warp0 * SQ_TILE; d0 < total; d0 += nwarps * SQ_TILE) {
-        const int64_t d1 = d0 + SQ_TILE < total ? d0 + SQ_TILE : total;
-        // last segment whose new start is <= d0 (empty segments share their successor's start, so this one is not empty)
-        int64_t lo = 0, hi = nseg - 1;
-        while (lo < hi) {
-            const int64_t mid = (lo + hi + 1) >> 1;
-            if (newlo[mid] <= d0) lo = mid; else hi = mid - 1;
-        }
-        int64_t sgm = lo, d = d0;
-        while (d < d1) {
-            const int64_t s_lo = newlo[sgm], s_hi = newlo[sgm + 1];
-            if (s_hi > d) {
-                const bool g2 = sgm >= nc;
-                const Indexer q = ix[g2 ? sgm - nc : sgm];
-                const int64_t olo = (g2 ? q.start2 : q.start1) - 1;
-                if (olo < s_lo) {  // the reference only ever shifts left (particles.jl:641,659,672: `if offset > 0`)
-                    if (lane == 0) atomicOr(&flags[0], DEVERR_PRECONDITION);
-                } else {
-                    const int64_t e = s_hi < d1 ? s_hi : d1;
-                    const int64_t src0 = olo + (d - s_lo);
-                    for (int64_t j = lane; j < e - d; j += 32) {
+// staging array and are copied back by k_squash_cell_back.  Load balance over segment sizes: mb_segcopy.cuh.
+struct SquashMoveAct {
+    SoA cur, alt;
+    const int32_t* cell;
+    int32_t* cell_stage;
+    __device__ __forceinline__ void seg(int64_t, int64_t, int64_t, int64_t) const {}
+    __device__ __forceinline__ void elem(int64_t, int64_t src, int64_t dst) const {
 #pragma unroll
-                        for (int f = 0; f < 7; f++) alt.a[f][d + j] = cur.a[f][src0 + j];
-                        cell_stage[d + j] = cell[src0 + j];
-                    }
-                }
-                d = s_hi < d1 ? s_hi : d1;
-            }
-            sgm++;
-        }
+        for (int f = 0; f < 7; f++) alt.a[f][dst] = cur.a[f][src];
+        cell_stage[dst] = cell[src];
     }
-}
+};
 static __global__ void k_squash_cell_back(int32_t* __restrict__ cell, const int32_t* __restrict__ cell_stage, const int64_t* __restrict__ n_total_p) {
     const int64_t n = *n_total_p;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) cell[i] = cell_stage[i];
@@ -100,10 +70,12 @@ extern "C" int mb_squash_pia(mb_ctx* ctx, mb_pv* pv, mb_pia* pia, int64_t specie
     MB_LAUNCH_CHECK(ctx);
     r = device_exclusive_scan(ctx, cnt, 2 * nc, newlo, partial);
     if (r) return r;
-    const int64_t nb = pia->n_bound[s] > 0 ? pia->n_bound[s] : pv->cap;
-    const int g = grid_for((nb + SQ_TILE - 1) / SQ_TILE * 32, 256, 8);
-    k_squash_move<<<g, 256, 0, st>>>(pv->cur, pv->alt, pv->cell, cell_stage, ix, nc, newlo, ctx->d_flags);
-    MB_LAUNCH_CHECK(ctx);
+    {
+        SquashDesc D{ix, nc, newlo, ctx->d_flags};
+        SquashMoveAct A{pv->cur, pv->alt, pv->cell, cell_stage};
+        r = seg_copy(ctx, 7, pv->cap, 2 * nc, D, A);
+        if (r) return r;
+    }
     k_squash_cell_back<<<grid_for(pia->n_bound[s] > 0 ? pia->n_bound[s] : pv->cap, 256, 8), 256, 0, st>>>(pv->cell, cell_stage, pia->d_n_total + s);
     MB_LAUNCH_CHECK(ctx);
     {   // ping-pong: the squashed particles live in the other buffer now
