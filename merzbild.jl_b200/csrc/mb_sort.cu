@@ -583,20 +583,27 @@ __global__ void __launch_bounds__(256) k_gen_scatter_idx(const int32_t* __restri
     const int64_t n_total = *n_total_p;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t nround = (n_total + stride - 1) / stride;
-    for (int64_t r = 0; r < nround; r++) {
-        const int64_t i = r * stride + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-        const int nc = i < n_total ? key[i] : -1;
-        const bool valid = nc >= 0;
-        const unsigned act = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-            const unsigned peers = __match_any_sync(act, nc);
-            const int leader = __ffs(peers) - 1;
-            int base = 0;
-            if (lane == leader) base = atomicAdd(&cursor[nc], __popc(peers));
-            base = __shfl_sync(peers, base, leader);
-            perm[start[nc] + base + __popc(peers & lt)] = (int32_t)i;
+    // every warp walks a CONTIGUOUS chunk of 32 x SC_ROUNDS positions in ascending order, so that the indices of a cell whose
+    // particles are contiguous in the input (the usual case: a nearly sorted layout) are appended by one warp in ascending order
+    // and k_gen_sort_segments* finds most cells already sorted (it stays the safety net: correctness never depends on the order
+    // in which the atomics land)
+    constexpr int SC_ROUNDS = 32;
+    const int64_t warp_g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t base0 = warp_g * 32 * SC_ROUNDS; base0 < n_total; base0 += nwarps * 32 * SC_ROUNDS) {
+        for (int k = 0; k < SC_ROUNDS; k++) {
+            const int64_t i = base0 + k * 32 + lane;
+            const int nc = i < n_total ? key[i] : -1;
+            const bool valid = nc >= 0;
+            const unsigned act = __ballot_sync(0xffffffffu, valid);
+            if (act == 0) continue;
+            if (valid) {
+                const unsigned peers = __match_any_sync(act, nc);
+                const int leader = __ffs(peers) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(&cursor[nc], __popc(peers));
+                base = __shfl_sync(peers, base, leader);
+                perm[start[nc] + base + __popc(peers & lt)] = (int32_t)i;
+            }
         }
     }
 }
@@ -692,14 +699,27 @@ __global__ void __launch_bounds__(256) k_gen_sort_segments_warp(int32_t* __restr
 }
 // larger segments: one CTA per cell
 __global__ void __launch_bounds__(256) k_gen_sort_segments(int32_t* __restrict__ perm, const int64_t* __restrict__ start, int64_t n_cells,
-                                                           const int* flags) {
+                                                           const int* flags, int cpb) {
     if (flags[2] == 0) return;
     __shared__ int32_t sh[SEG_SMEM];
     __shared__ int unsorted;
-    for (int64_t c = blockIdx.x; c < n_cells; c += gridDim.x) {
+    __shared__ int s_list[256], s_nlist;
+    // the CTA looks at cpb (<= 256) cells at a time (one coalesced read of their bounds) and sorts the large ones among them one by one
+    for (int64_t cbase = (int64_t)blockIdx.x * cpb; cbase < n_cells; cbase += (int64_t)gridDim.x * cpb) {
+      __syncthreads();
+      if (threadIdx.x == 0) s_nlist = 0;
+      __syncthreads();
+      {
+          const int64_t cc = cbase + threadIdx.x;
+          if ((int)threadIdx.x < cpb && cc < n_cells && start[cc + 1] - start[cc] > WSEG) s_list[atomicAdd(&s_nlist, 1)] = threadIdx.x;
+      }
+      __syncthreads();
+      const int nlist = s_nlist;
+      for (int li = 0; li < nlist; li++) {
+        // the order of the list does not matter: every listed cell is sorted independently
+        const int64_t c = cbase + s_list[li];
         const int64_t lo = start[c];
         const int64_t n = start[c + 1] - lo;
-        if (n <= WSEG) continue;  // block-uniform; small segments: k_gen_sort_segments_warp
         int32_t* seg = perm + lo;
         __syncthreads();
         if (threadIdx.x == 0) unsorted = 0;
@@ -716,6 +736,7 @@ __global__ void __launch_bounds__(256) k_gen_sort_segments(int32_t* __restrict__
         } else {
             bitonic_ascending(seg, n);  // large cell: network directly in global memory (L2-resident)
         }
+      }
     }
 }
 
@@ -1009,7 +1030,12 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
         MB_LAUNCH_CHECK(ctx);
         k_gen_sort_segments_warp<<<grid_for(nc * 8, 256, 6), 256, 0, st>>>(S.perm, S.start, nc, S.flags);
         MB_LAUNCH_CHECK(ctx);
-        k_gen_sort_segments<<<grid_for(nc * 256, 256, 8), 256, 0, st>>>(S.perm, S.start, nc, S.flags);
+        {
+            const int gseg = grid_for(nc * 256, 256, 8);
+            int cpb = 256;  // cells a CTA looks at per round: 256 on long grids, fewer when there are few (large) cells
+            while (cpb > 1 && nc < (int64_t)gseg * cpb) cpb >>= 1;
+            k_gen_sort_segments<<<gseg, 256, 0, st>>>(S.perm, S.start, nc, S.flags, cpb);
+        }
         MB_LAUNCH_CHECK(ctx);
         k_gen_gather<<<pgrid, 256, 0, st>>>(pv->cur, pv->alt, S.perm, S.start + nc, S.flags, src, S.key, use_x ? nullptr : pv->cell);
         MB_LAUNCH_CHECK(ctx);
