@@ -43,6 +43,7 @@ struct MergeArgs {
     int* flags;
     int* noncontig;
     int small_max;  // cells with n_local <= small_max are merged by k_merge_warp
+    int cpb;        // k_merge: cells a CTA looks at per round
 };
 
 static __global__ void k_merge_counts(const Indexer* __restrict__ ix, int64_t cell_lo, int64_t nr, int64_t threshold, int32_t* __restrict__ cnt) {
@@ -147,11 +148,24 @@ __global__ void __launch_bounds__(MT) k_merge(MergeArgs a) {
     double* outbuf = a.outbuf + (int64_t)blockIdx.x * 2 * B * 7;
     const double* __restrict__ PW = a.pv.a[F_W];
 
-    for (int64_t r = blockIdx.x; r < nr; r += gridDim.x) {
+    // the CTA looks at cpb (<= blockDim.x) cells at a time (one coalesced read of their sizes) and merges, one after the other, the
+    // ones that need it and are too large for k_merge_warp
+    __shared__ int s_list[MT], s_nlist;
+    for (int64_t rbase = (int64_t)blockIdx.x * a.cpb; rbase < nr; rbase += (int64_t)gridDim.x * a.cpb) {
+      __syncthreads();
+      if (tid == 0) s_nlist = 0;
+      __syncthreads();
+      if (tid < a.cpb && rbase + tid < nr) {
+          const int64_t n_l = a.ix[a.cell_lo - 1 + rbase + tid].n_local;
+          if (n_l > 0 && (a.threshold < 0 || n_l > a.threshold) && n_l > a.small_max) s_list[atomicAdd(&s_nlist, 1)] = tid;
+      }
+      __syncthreads();
+      const int nlist = s_nlist;
+      for (int li = 0; li < nlist; li++) {
+        const int64_t r = rbase + s_list[li];  // the order of the list does not matter: cells are independent
         const int64_t cell = a.cell_lo + r;
         const Indexer q = a.ix[cell - 1];
         const int N = (int)q.n_local;
-        if (N <= 0 || !(a.threshold < 0 || N > a.threshold) || N <= a.small_max) continue;  // block-uniform; small cells: k_merge_warp
         int32_t* idx = a.idx + a.slice[r];
         int32_t* tmp = a.tmp + a.slice[r];
         uint8_t* oct = a.oct + a.slice[r];
@@ -633,6 +647,7 @@ __global__ void __launch_bounds__(MT) k_merge(MergeArgs a) {
             if (!(cell == a.n_cells_total) || n_del > q.n_group2) *a.noncontig = 1;  // :806-808
         }
         __syncthreads();
+      }
     }
 }
 
@@ -1120,6 +1135,8 @@ extern "C" int mb_merge_octree_N2(mb_ctx* ctx, const mb_octree_params* oc, mb_pv
             MB_CUDA(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
             attr_gsm = gsm;
         }
+        a.cpb = threads;  // chunks of cells per CTA round: only as large as still leaves >= 8 chunks per CTA (load balance)
+        while (a.cpb > 1 && nr < 8 * nCTA * a.cpb) a.cpb >>= 1;
         k_merge<<<(int)nCTA, threads, gsm, st>>>(a);
     }
     MB_LAUNCH_CHECK(ctx);

@@ -1033,7 +1033,7 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
         {
             const int gseg = grid_for(nc * 256, 256, 8);
             int cpb = 256;  // cells a CTA looks at per round: 256 on long grids, fewer when there are few (large) cells
-            while (cpb > 1 && nc < (int64_t)gseg * cpb) cpb >>= 1;
+            while (cpb > 1 && nc < (int64_t)8 * gseg * cpb) cpb >>= 1;
             k_gen_sort_segments<<<gseg, 256, 0, st>>>(S.perm, S.start, nc, S.flags, cpb);
         }
         MB_LAUNCH_CHECK(ctx);

@@ -16,7 +16,7 @@ WANT = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__regis
 
 
 def main(rep, out):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--print-units", "base"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     stalls = [h for h in hdr if "issue_stalled" in h and "per_issue_active" in h]
