@@ -161,6 +161,16 @@ def main():
             if rep > 0:
                 for k, v in (("merge", t_merge), ("squash", t_squash), ("sort", t_sort), ("ntc", t_ntc), ("props", t_props)):
                     res.setdefault(k, []).append(v)
+        # velocity-grid merging of the same cells (merge_grid_based!, 3 x 3 x 3 + 8 velocity cells, extents from the cell's PhysProps)
+        mgp = mb.GridN2Merge(3, 3, 3, 3.0)
+        tg = []
+        for rep in range(max(args.reps, 2)):
+            reset()
+            mb.compute_props([pv], pia, [AR], pp2)
+            tg.append(one(lambda: mb.merge_grid_based(mb.PhiloxRng(1), mgp, pv, pia, (1, nc), 1, AR, pp2, grid=grid, threshold=130)))
+        ng = int(pia.n_total[0])
+        report("merge_grid_based (3x3x3 + 8 velocity cells)", "C4: %d cells x %d -> %d particles" % (nc, ppc, ng), n, sorted(tg[1:])[len(tg[1:]) // 2],
+               56 * (n + ng) / n, "CTA per cell, one thread per velocity cell")
         med = {k: sorted(v)[len(v) // 2] for k, v in res.items()}
         report("merge_octree_N2_based (150 -> 100)", "C4: %d cells x %d" % (nc, ppc), n, med["merge"], 56 * (150 + 100) / 150.0,
                "56 (N + N_target) / N bytes per particle of a merged cell")

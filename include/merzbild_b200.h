@@ -202,6 +202,21 @@ int mb_compute_props_sorted(mb_ctx* ctx, mb_pv* const* pvs, mb_pia* pia, const d
 int mb_merge_octree_N2(mb_ctx* ctx, const mb_octree_params* oc, mb_pv* pv, mb_pia* pia, int64_t cell_lo, int64_t cell_hi, int64_t species,
                        int64_t threshold, int64_t target_np, const mb_grid1d* grid, uint32_t timestep, uint32_t substream);
 
+/* GridN2Merge(Nx, Ny, Nz, extent_multiplier) merging/merging_grid.jl:72-116 */
+typedef struct {
+    int32_t Nx, Ny, Nz;
+    double extent_multiplier[3];
+} mb_gridmerge_params;
+/* ---- merge_grid_based!(rng, merging_grid, particles, pia, cell, species, species_data, phys_props | vx_extent, vy_extent, vz_extent
+ *      [, grid::Grid1DUniform]) merging_grid.jl:597-703 for every cell of [cell_lo, cell_hi] with n_local > threshold (< 0: all).
+ *      Exactly one of `props` (the velocity grid follows T and v of the cell as last computed by compute_props*, :190-197) and
+ *      `extents6` (HOST: vx_lo, vx_hi, vy_lo, vy_hi, vz_lo, vz_hi, :210-221) is non-NULL.  grid != NULL: the 1-D variant, x of every
+ *      np >= 2 output clamped into [min_x, max_x] (:528-549).  A velocity exactly on an upper grid bound (the reference would index
+ *      past its grid) is reported as MB_ERR_PRECONDITION.  Leaves the species non-contiguous like the octree merge. ---- */
+int mb_merge_grid_based(mb_ctx* ctx, const mb_gridmerge_params* mg, mb_pv* pv, mb_pia* pia, int64_t cell_lo, int64_t cell_hi, int64_t species,
+                        double mass, mb_props* props, const double* extents6, int64_t threshold, const mb_grid1d* grid, uint32_t timestep,
+                        uint32_t substream);
+
 /* ---- initial conditions on the device: 1e8-1e9 particles are not sampled on the host and copied ----
  * sample_particles_equal_weight!(rng, particles, pia, cell, species, nparticles, m, T, Fnum, xlo, xhi, ylo, yhi, zlo, zhi;
  *     distribution, vx0, vy0, vz0)                                        distributions_and_sampling.jl:477-509   (grid == NULL, box6 given)

@@ -31,7 +31,7 @@ enum : int { DEVERR_CAPACITY = 1, DEVERR_PRECONDITION = 2, DEVERR_BAND_OVERFLOW 
 // draw d = the (d & 1)-th double of block d >> 1) is shared with the CPU oracle so that the sequential-per-entity
 // kernels replay the oracle draw for draw.
 // ---------------------------------------------------------------------------------------------------------------
-enum : uint32_t { OP_NTC = 1, OP_CONVECT = 2, OP_MERGE = 3, OP_SWPM = 4, OP_FP = 5, OP_SAMPLE = 6, OP_USER = 7 };
+enum : uint32_t { OP_NTC = 1, OP_CONVECT = 2, OP_MERGE = 3, OP_SWPM = 4, OP_FP = 5, OP_SAMPLE = 6, OP_USER = 7, OP_MERGE_GRID = 8 };
 
 MB_HD void philox_round(uint32_t c[4], const uint32_t k0, const uint32_t k1) {
 #ifdef __CUDA_ARCH__

@@ -25,7 +25,7 @@ export Context, PhiloxRng, DeviceParticleVector, DeviceParticleIndexerArray, Dev
        DeviceGrid1D, slab, sort_particles!, squash_pia!, restore_particle_ordering!, ntc!, ntc_equal_weight!, swpm!, fp_linear!,
        convect_particles!, convect_particles_and_compute_cell!, compute_props!, compute_props_sorted!,
        compute_props_with_total_moments!, avg_props!, clear_props!, merge_octree_N2_based!, exchange_particles!,
-       sample_particles_equal_weight!, sample_on_grid!,
+       sample_particles_equal_weight!, sample_on_grid!, merge_grid_based!,
        comm_unique_id, comm_init!, upload!, download, download_indexer, n_total, synchronize, kernel_launches
 
 const libmb = get(ENV, "MERZBILD_B200_LIB", joinpath(@__DIR__, "..", "merzbild_b200", "libmerzbild_b200.so"))
@@ -513,6 +513,44 @@ function merge_octree_N2_based!(rng::PhiloxRng, octree, pv::DeviceParticleVector
     check(ccall((:mb_merge_octree_N2, libmb), Cint,
                 (Ptr{Cvoid}, Ptr{COctreeParams}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int64, Ptr{CGrid1D}, UInt32, UInt32),
                 pv.ctx.h, Ref(oc), pv.h, pia.h, lo, hi, species, threshold, target_np, g, rng.timestep, rng.substream))
+end
+
+"GridN2Merge parameters (merging_grid.jl:72-116) as the C ABI takes them"
+struct CGridMergeParams
+    Nx::Int32
+    Ny::Int32
+    Nz::Int32
+    extent_multiplier::NTuple{3,Float64}
+end
+CGridMergeParams(mg) = CGridMergeParams(mg.Nx, mg.Ny, mg.Nz, (mg.extent_multiplier[1], mg.extent_multiplier[2], mg.extent_multiplier[3]))
+"""
+    merge_grid_based!(rng, merging_grid, pv, pia, cell, species, species_data, phys_props::DevicePhysProps[, grid]; threshold=-1)
+    merge_grid_based!(rng, merging_grid, pv, pia, cell, species, species_data, vx_extent, vy_extent, vz_extent[, grid]; threshold=-1)
+                                                                                                     merging_grid.jl:597-703
+`cell` may be a range; only cells with `n_local > threshold` are merged (threshold < 0: all).
+"""
+function merge_grid_based!(rng::PhiloxRng, merging_grid, pv::DeviceParticleVector, pia::DeviceParticleIndexerArray, cell, species::Integer,
+                           species_data, phys_props::DevicePhysProps, grid=nothing; threshold::Integer=-1)
+    lo, hi = cellrange(cell)
+    g = grid === nothing ? Ptr{CGrid1D}(C_NULL) : gridref(grid)
+    mg = merging_grid isa CGridMergeParams ? merging_grid : CGridMergeParams(merging_grid)
+    check(ccall((:mb_merge_grid_based, libmb), Cint,
+                (Ptr{Cvoid}, Ptr{CGridMergeParams}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Float64, Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{CGrid1D},
+                 UInt32, UInt32),
+                pv.ctx.h, Ref(mg), pv.h, pia.h, lo, hi, species, species_data[species].mass, phys_props.h, Ptr{Float64}(C_NULL), threshold, g,
+                rng.timestep, rng.substream))
+end
+function merge_grid_based!(rng::PhiloxRng, merging_grid, pv::DeviceParticleVector, pia::DeviceParticleIndexerArray, cell, species::Integer,
+                           species_data, vx_extent, vy_extent, vz_extent, grid=nothing; threshold::Integer=-1)
+    lo, hi = cellrange(cell)
+    g = grid === nothing ? Ptr{CGrid1D}(C_NULL) : gridref(grid)
+    mg = merging_grid isa CGridMergeParams ? merging_grid : CGridMergeParams(merging_grid)
+    ext = Float64[vx_extent[1], vx_extent[2], vy_extent[1], vy_extent[2], vz_extent[1], vz_extent[2]]
+    check(ccall((:mb_merge_grid_based, libmb), Cint,
+                (Ptr{Cvoid}, Ptr{CGridMergeParams}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Float64, Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{CGrid1D},
+                 UInt32, UInt32),
+                pv.ctx.h, Ref(mg), pv.h, pia.h, lo, hi, species, species_data[species].mass, Ptr{Cvoid}(C_NULL), ext, threshold, g,
+                rng.timestep, rng.substream))
 end
 
 # ------------------------------------------------------------------------------------------ initial conditions

@@ -54,6 +54,10 @@ class Interaction(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("m_r", "mu1", "mu2", "vhs_d", "vhs_o", "vhs_Tref", "vhs_muref", "vhs_factor")]
 
 
+class GridMergeParams(C.Structure):
+    _fields_ = [("Nx", C.c_int32), ("Ny", C.c_int32), ("Nz", C.c_int32), ("extent_multiplier", C.c_double * 3)]
+
+
 class OctreeParams(C.Structure):
     _fields_ = [("split", C.c_int32), ("init_bin_bounds", C.c_int32), ("bin_bounds_compute", C.c_int32), ("max_depth", C.c_int32),
                 ("max_Nbins", C.c_int64)]
@@ -121,6 +125,7 @@ SIGNATURES = {
     "mb_compute_props": (_int, [_vp, C.POINTER(_vp), _vp, _vp, _vp, _i32]),
     "mb_compute_props_sorted": (_int, [_vp, C.POINTER(_vp), _vp, _vp, _vp, C.POINTER(Grid1D), _i64, _i64]),
     "mb_merge_octree_N2": (_int, [_vp, C.POINTER(OctreeParams), _vp, _vp, _i64, _i64, _i64, _i64, _i64, C.POINTER(Grid1D), _u32, _u32]),
+    "mb_merge_grid_based": (_int, [_vp, C.POINTER(GridMergeParams), _vp, _vp, _i64, _i64, _i64, _f64, _vp, _vp, _i64, C.POINTER(Grid1D), _u32, _u32]),
     "mb_sample_particles_equal_weight": (_int, [_vp, C.POINTER(Grid1D), _vp, _vp, _i64, _i64, _i64, _i64, _f64, _f64, _f64, _f64, _vp, _i32, _vp, _u32, _u32]),
     "mb_sample_on_grid": (_int, [_vp, _i32, _vp, _vp, _i64, _i64, _i64, _i64, _f64, _f64, _f64, _vp, _f64, _f64, _f64, _vp, _u32, _u32, C.POINTER(_i64)]),
     "mb_comm_unique_id": (_int, [_vp]),
@@ -580,6 +585,28 @@ def merge_octree_N2_based(rng, octree, pv, pia, cell, species, target_np, grid=N
     lo, hi = _range(cell)
     _ck(lib().mb_merge_octree_N2(pv.ctx.h, C.byref(octree.c), pv.h, pia.h, lo, hi, int(species), int(threshold), int(target_np),
                                  grid.ref if grid is not None else None, rng.timestep, rng.substream))
+
+
+class GridN2Merge:
+    """GridN2Merge(Nx, Ny, Nz, extent_multiplier) (merging_grid.jl:72-116); extent_multiplier a scalar or 3 values."""
+
+    def __init__(self, Nx, Ny=None, Nz=None, extent_multiplier=3.5):
+        Ny = Nx if Ny is None else Ny
+        Nz = Nx if Nz is None else Nz
+        m = np.broadcast_to(np.asarray(extent_multiplier, dtype=np.float64), (3,))
+        self.c = GridMergeParams(int(Nx), int(Ny), int(Nz), (C.c_double * 3)(*m))
+
+
+def merge_grid_based(rng, merging_grid, pv, pia, cell, species, mass, phys_props_or_vx_extent, vy_extent=None, vz_extent=None, grid=None, threshold=-1):
+    """merge_grid_based!(rng, merging_grid, particles, pia, cell, species, species_data, phys_props[, grid]) or
+    merge_grid_based!(..., species_data, vx_extent, vy_extent, vz_extent[, grid]) (merging_grid.jl:597-703); ``cell`` may be a range."""
+    lo, hi = _range(cell)
+    if isinstance(phys_props_or_vx_extent, PhysProps):
+        props, ext = phys_props_or_vx_extent.h, None
+    else:
+        props, ext = None, _f64arr([*phys_props_or_vx_extent, *vy_extent, *vz_extent])
+    _ck(lib().mb_merge_grid_based(pv.ctx.h, C.byref(merging_grid.c), pv.h, pia.h, lo, hi, int(species), float(mass), props, _p(ext), int(threshold),
+                                  grid.ref if grid is not None else None, rng.timestep, rng.substream))
 
 
 def sample_particles_equal_weight(rng, *args, distribution="Maxwellian", vx0=0.0, vy0=0.0, vz0=0.0, cell_chunk=None):

@@ -4,6 +4,7 @@
 
 #include "mb_oracle.hpp"
 #include "mb_oracle_octree.hpp"
+#include "mb_oracle_gridmerge.hpp"
 #include "mb_oracle_parallel.hpp"
 
 using namespace mbo;
@@ -327,6 +328,49 @@ int64_t mbo_sample_on_grid_cells(const mbo_rng_spec* rs, int vdf_kind, void* pv_
         for (int64_t i = 1; i <= n; i++) pv.cell[off + i - 1] = cell;
     }
     return n;
+}
+
+// ---- velocity-grid merging ----
+void* mbo_gridmerge_create(int64_t nx, int64_t ny, int64_t nz, const double* mult3) { return new GridN2Merge(nx, ny, nz, mult3); }
+void mbo_gridmerge_free(void* g) { delete (GridN2Merge*)g; }
+int64_t mbo_gridmerge_index(void* g, const double* ext6, const double* v) {
+    GridN2Merge& mg = *(GridN2Merge*)g;
+    compute_velocity_extent_given(mg, ext6);
+    return compute_grid_index(mg, v);
+}
+// cell i (1-based): out = {np, w, v_mean[3], v_std_sq[3], x_mean[3], x_std_sq[3]} (14 doubles)
+void mbo_gridmerge_cell(void* g, int64_t i, double* out) {
+    const GridCell& c = ((GridN2Merge*)g)->cells[i - 1];
+    out[0] = (double)c.np; out[1] = c.w;
+    for (int d = 0; d < 3; d++) { out[2 + d] = c.v_mean[d]; out[5 + d] = c.v_std_sq[d]; out[8 + d] = c.x_mean[d]; out[11 + d] = c.x_std_sq[d]; }
+}
+// merge_grid_based! for the cells of [cell_lo, cell_hi] with n_local > threshold (threshold < 0: all).  Tv: per cell (T, vx, vy, vz) of the
+// species as PhysProps holds them (4 doubles per cell of the range), or NULL with ext6 = explicit extents.  Signs: Philox block (grid index - 1)
+// of the (OP_MERGE_GRID, timestep, cell) stream, or sequential draws.  Returns the number of cells whose particles fell off the grid index range.
+int64_t mbo_merge_grid_based(const mbo_rng_spec* rs, void* g, void* pv_, void* pia_, int64_t cell_lo, int64_t cell_hi, int64_t species, double mass,
+                             int64_t threshold, const double* Tv, const double* ext6, double L, int64_t nx) {
+    GridN2Merge& mg = *(GridN2Merge*)g;
+    ParticleVector& pv = *(ParticleVector*)pv_;
+    ParticleIndexerArray& pia = *(ParticleIndexerArray*)pia_;
+    Grid1DUniform grid(L > 0 ? L : 1.0, nx > 0 ? nx : 1);
+    const Grid1DUniform* gp = nx > 0 ? &grid : nullptr;
+    int64_t bad = 0;
+    for (int64_t cell = cell_lo; cell <= cell_hi; cell++) {
+        if (!(threshold < 0 || pia.at(cell, species).n_local > threshold)) continue;
+        if (pia.at(cell, species).n_local <= 0) continue;
+        const double* tv = Tv ? Tv + 4 * (cell - cell_lo) : nullptr;
+        const double zero[3] = {0, 0, 0};
+        bool ok;
+        if (rs->kind == 0) {
+            SeqSigns<Xoshiro256pp> s{*(Xoshiro256pp*)rs->seq};
+            ok = merge_grid_based(s, mg, pv, pia, cell, species, mass, tv ? tv[0] : 0.0, tv ? tv + 1 : zero, ext6, gp);
+        } else {
+            PhiloxSigns s{PhiloxStream(rs->seed, OP_MERGE_GRID, rs->substream, rs->timestep, (uint32_t)cell)};
+            ok = merge_grid_based(s, mg, pv, pia, cell, species, mass, tv ? tv[0] : 0.0, tv ? tv + 1 : zero, ext6, gp);
+        }
+        if (!ok) bad++;
+    }
+    return bad;
 }
 
 // ---- octree ----

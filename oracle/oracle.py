@@ -107,6 +107,11 @@ def lib():
     sig("mbo_sample_equal_weight_cell", None, vp, vp, vp, i64, i64, i64, f64, f64, f64, vp, C.c_int, vp)
     sig("mbo_sample_on_grid", i64, vp, C.c_int, vp, i64, f64, f64, f64, vp, f64, f64, f64, vp)
     sig("mbo_sample_equal_weight_cells", None, vp, vp, vp, vp, i64, i64, i64, i64, f64, f64, f64, f64, vp, C.c_int, vp)
+    sig("mbo_gridmerge_create", vp, i64, i64, i64, vp)
+    sig("mbo_gridmerge_free", None, vp)
+    sig("mbo_gridmerge_index", i64, vp, vp, vp)
+    sig("mbo_gridmerge_cell", None, vp, i64, vp)
+    sig("mbo_merge_grid_based", i64, vp, vp, vp, vp, i64, i64, i64, f64, i64, vp, vp, f64, i64)
     sig("mbo_sample_on_grid_cells", i64, vp, C.c_int, vp, vp, i64, i64, i64, i64, f64, f64, f64, vp, f64, f64, f64, vp)
     sig("mbo_octree_create", vp, C.c_int, C.c_int, C.c_int, i64, i64)
     sig("mbo_octree_free", None, vp)
@@ -514,6 +519,41 @@ def merge_octree_N2(rng, oc, pv, pia, cell_lo, cell_hi, species, target_np, thre
     """merge_octree_N2_based! (merging_octree_N2.jl:1060,1088) over the cells with n_local > threshold."""
     L, nx = grid if grid is not None else (0.0, 0)
     lib().mbo_merge_octree_N2(rng.ref, oc.h, pv.h, pia.h, cell_lo, cell_hi, species, threshold, target_np, L, nx, int(squash_after_each))
+
+
+class GridMerge:
+    """GridN2Merge(Nx, Ny, Nz, extent_multiplier) (merging_grid.jl:72-116)."""
+
+    def __init__(self, Nx, Ny=None, Nz=None, extent_multiplier=3.5):
+        Ny = Nx if Ny is None else Ny
+        Nz = Nx if Nz is None else Nz
+        m = _f64(np.broadcast_to(np.asarray(extent_multiplier, dtype=np.float64), (3,)))
+        self.Nx, self.Ny, self.Nz, self.Ntotal = Nx, Ny, Nz, Nx * Ny * Nz + 8
+        self.h = lib().mbo_gridmerge_create(Nx, Ny, Nz, _p(m))
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.mbo_gridmerge_free(self.h)
+            self.h = None
+
+    def index(self, extents, v):
+        """compute_grid_index (merging_grid.jl:235) for explicit extents ((vx_lo, vx_hi), (vy_lo, vy_hi), (vz_lo, vz_hi))."""
+        e, v = _f64(np.asarray(extents).reshape(6)), _f64(v)
+        return lib().mbo_gridmerge_index(self.h, _p(e), _p(v))
+
+    def cell(self, i):
+        out = np.zeros(14)
+        lib().mbo_gridmerge_cell(self.h, i, _p(out))
+        return dict(np=int(out[0]), w=out[1], v_mean=out[2:5], v_std_sq=out[5:8], x_mean=out[8:11], x_std_sq=out[11:14])
+
+
+def merge_grid_based(rng, mg, pv, pia, cell_lo, cell_hi, species, mass, T_v=None, extents=None, threshold=-1, grid=None):
+    """merge_grid_based! (merging_grid.jl:597-703) over cells cell_lo..cell_hi: T_v = array [n_range, 4] of (T, vx, vy, vz) per cell (the
+    PhysProps variant) or extents = ((vx_lo, vx_hi), (vy_lo, vy_hi), (vz_lo, vz_hi)); grid = (L, nx) for the 1-D variant."""
+    tv = None if T_v is None else _f64(np.asarray(T_v).reshape(-1, 4))
+    e = None if extents is None else _f64(np.asarray(extents).reshape(6))
+    L, nx = grid if grid is not None else (0.0, 0)
+    return lib().mbo_merge_grid_based(rng.ref, mg.h, pv.h, pia.h, cell_lo, cell_hi, species, mass, threshold, _p(tv), _p(e), L, nx)
 
 
 class Exchanger:

@@ -36,7 +36,7 @@ struct Philox4x32 {
 
 // operator ids (the "stream" word of the counter); must match merzbild.jl_b200/csrc/mb_philox.cuh
 enum : uint32_t {
-    OP_NTC = 1, OP_CONVECT = 2, OP_MERGE = 3, OP_SWPM = 4, OP_FP = 5, OP_SAMPLE = 6, OP_USER = 7
+    OP_NTC = 1, OP_CONVECT = 2, OP_MERGE = 3, OP_SWPM = 4, OP_FP = 5, OP_SAMPLE = 6, OP_USER = 7, OP_MERGE_GRID = 8
 };
 
 // One stream: key = 64-bit seed; counter = (block, entity, timestep, op | substream << 8).
