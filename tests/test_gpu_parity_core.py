@@ -489,6 +489,79 @@ def test_ntc_two_species_parity(mb, oracle, ctx):
     np.testing.assert_allclose(d["T"], o.T, rtol=1e-11)
 
 
+def test_ntc_three_species_all_pairs_parity(mb, oracle, ctx):
+    """More than two species: the reference's drivers loop ntc! over every species pair of a cell
+    (collision_factors[s1, s2, cell], collision_ntc.jl:46-155); here 3 species in 6 cells, variable weight, the six pair calls of a
+    step -- (1,1) (2,2) (3,3) one-ParticleVector, (2,1) (3,1) (3,2) two-ParticleVector -- over 4 steps with a sort per species in
+    between, device vs oracle draw for draw."""
+    rng = np.random.default_rng(33)
+    n_cells, L = 6, 6e-5
+    g, og = mb.Grid1DUniform(L, n_cells), (L, n_cells)
+    masses = [AR, HE, 2.0 * HE]
+    temps = [900.0, 360.0, 500.0]
+    counts = [300 * n_cells, 800 * n_cells, 500 * n_cells]
+    Fnum = 3e14
+    opvs, pvs = [], []
+    opia = oracle.OPIA(n_cells, 3)
+    for s, (m, T, n) in enumerate(zip(masses, temps, counts)):
+        rows = maxwellian_rows(rng, n, L, T=T, m=m, w=Fnum, vw=True)
+        opv = oracle.OPV(10 * n)  # the split windows are sized by the candidate counts
+        if n <= 2000:
+            opv.fill_identity(rows)
+        else:
+            opv.particles[:n] = rows
+            opv.index[:n] = np.arange(1, n + 1)
+            opv.nbuffer = len(opv) - n
+        opia.indexer[s, 0] = (n, 1, n, n, 0, -1, 0)
+        opia.n_total[s] = n
+        opvs.append(opv)
+    for s in range(3):
+        oracle.sort_particles(opvs[s], opia, s + 1, grid=og)
+    pia = mb.ParticleIndexerArray(n_cells, 3, ctx)
+    for s in range(3):
+        pv = mb.ParticleVector(len(opvs[s]), ctx)
+        pv.set_logical(1, opvs[s].logical(1, counts[s]))
+        pvs.append(pv)
+    pia.upload(opia.indexer.copy(), opia.n_total.copy(), opia.contiguous.copy())
+    pairs = [(1, 1), (2, 2), (3, 3), (2, 1), (3, 1), (3, 2)]
+    its, oits, cfs, ocfs = {}, {}, {}, {}
+    for a, b in pairs:
+        d, o, Tref = 3.5e-10 + 0.2e-10 * (a + b), 0.75 + 0.02 * a, 273.0
+        its[a, b] = mb.make_interaction(masses[a - 1], masses[b - 1], d, o, Tref)
+        oits[a, b] = oracle.make_interaction(masses[a - 1], masses[b - 1], d, o, Tref)
+        s0 = mb.estimate_sigma_g_w_max(its[a, b], masses[a - 1], masses[b - 1], temps[a - 1], temps[b - 1], 2 * Fnum)
+        cfs[a, b], ocfs[a, b] = mb.CollisionFactors(n_cells, s0, ctx), oracle.CF(n_cells, s0)
+    dt, V = 2.59e-9, L / n_cells
+    for t in range(1, 5):
+        for k, (a, b) in enumerate(pairs):
+            if a == b:
+                mb.ntc(mb.PhiloxRng(t, k), cfs[a, b], None, its[a, b], pvs[a - 1], pia, (1, n_cells), a, dt, V)
+                oracle.ntc(oracle.Rng.philox(1234, t, k), ocfs[a, b], oits[a, b], opvs[a - 1], opia, 1, n_cells, a, dt, V)
+            else:
+                mb.ntc2(mb.PhiloxRng(t, k), cfs[a, b], None, its[a, b], pvs[a - 1], pvs[b - 1], pia, (1, n_cells), a, b, dt, V)
+                oracle.ntc2(oracle.Rng.philox(1234, t, k), ocfs[a, b], oits[a, b], opvs[a - 1], opvs[b - 1], opia, 1, n_cells, a, b, dt, V)
+            d = cfs[a, b].download()
+            np.testing.assert_array_equal(d["n_coll"], ocfs[a, b].n_coll)
+            np.testing.assert_array_equal(d["n_coll_performed"], ocfs[a, b].n_coll_performed)
+            # the split particles of this pair call go to group 2: fold them back before the next call of the same species
+            for sp in {a, b}:
+                mb.sort_particles(None, g, pvs[sp - 1], pia, sp)
+                oracle.sort_particles(opvs[sp - 1], opia, sp, grid=og)
+        assert_same_pia(opia, pia)
+    assert sum(int(o.n_coll_performed.sum()) for o in ocfs.values()) > 100
+    for s in range(3):
+        nt = int(opia.n_total[s])
+        assert nt > counts[s]  # splits happened
+        a_, b_ = pvs[s].logical(1, nt), opvs[s].logical(1, nt)
+        np.testing.assert_array_equal(a_[:, 0], b_[:, 0])
+        assert_rows_close(a_, b_, 1e-11, "species %d" % (s + 1))
+    pp = mb.PhysProps(n_cells, 3, ctx=ctx)
+    mb.compute_props(pvs, pia, masses, pp)
+    d, o = pp.download(), oracle.compute_props(opvs, opia, masses)
+    np.testing.assert_allclose(d["T"], o.T, rtol=1e-10)
+    np.testing.assert_array_equal(d["np"], o.np)
+
+
 # ------------------------------------------------------------------------------------------------------------ time loop
 def test_couette_loop_parity(mb, oracle, ctx):
     """simulations/1D/couette_benchmarking.jl:58-85 order (collide all cells -> convect -> sort -> props), 25 steps on a small
