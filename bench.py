@@ -100,6 +100,12 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_name(particles_per_gpu):
+    n = max(int(round(particles_per_gpu / PPC)), 1) * PPC
+    return ("couette_ar_vhs_equal_weight (BENCHMARKS.md vs-SPARTA case: ppc=1000, dx=1e-5 m, dt=2.59e-9 s, n=5e22) scaled to "
+            "%.3g particles/GPU, slab partition" % n)
+
+
 def reference_arm(args, rank):
     if rank != 0:
         return
@@ -111,7 +117,10 @@ def reference_arm(args, rank):
         "impl": "reference", "metric": "particle-timesteps/s, 1D Couette Ar VHS", "value": v, "unit": "particle-timesteps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "couette_ar_vhs_equal_weight ppc=1000 dx=1e-5 (sample of nx=%d cells)" % nx, "particles": nx * PPC},
+        "config": {"workload": workload_name(args.particles_per_gpu), "particles": int(round(args.particles_per_gpu / PPC)) * PPC * max(args.gpus, 1),
+                   "cells": int(round(args.particles_per_gpu / PPC)) * max(args.gpus, 1), "ppc": PPC,
+                   "step": "ntc_equal_weight+convect+exchange(chunks)+sort+props_sorted",
+                   "sample": "each step runs on a bounded sample of this workload: %d cells x %d ppc = %.1e particles, all host threads" % (nx, PPC, nx * PPC)},
         "cpu_baseline": {"value": v, "unit": "particle-timesteps/s", "cores": threads, "kind": "port",
                          "sample": "C++ restatement of the reference's multithreaded Couette loop (Julia is not installed): %d cells x %d ppc, %d steps; "
                                    "collide+convect+sort %.2fs, exchange %.2fs, resort+props %.2fs" %
@@ -310,8 +319,7 @@ def main():
         "metric": "particle-timesteps/s, 1D Couette Ar VHS", "value": value, "unit": "particle-timesteps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "couette_ar_vhs_equal_weight (BENCHMARKS.md vs-SPARTA case: ppc=1000, dx=1e-5 m, dt=2.59e-9 s, n=5e22) scaled to "
-                               "%.3g particles/GPU, slab partition" % n, "particles": int(particles_all), "cells": nx * world, "ppc": PPC,
+        "config": {"workload": workload_name(args.particles_per_gpu), "particles": int(particles_all), "cells": nx * world, "ppc": PPC,
                    "step": "ntc_equal_weight+convect+%ssort+props_sorted" % ("exchange+" if world > 1 else ""), "sort_path": "band" if sort_path == 1 else "general",
                    "l2": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (56 * n / 1e9), "mean_T_K": T_mean},
         "roofline": roofline,
