@@ -64,8 +64,12 @@ __global__ void __launch_bounds__(128) k_ntc_prepass(NtcArgs a) {
     }
 }
 
-template <bool TWO>
-__global__ void __launch_bounds__(128) k_ntc(NtcArgs a) {
+// MINB: resident CTAs per SM the register allocation must allow.  Measured on the Couette bench (1.25e8 particles): 4 CTAs/SM
+// (118 registers) 1.04 ms, 6 CTAs (80 registers) 1.16 ms, 8 CTAs (64 registers, all cells resident in one wave) 1.21 ms -- the
+// kernel is bound by the DRAM random-access rate (one 64 B atom per picked field), not by latency, so more resident cells only
+// add spills.  MB_NTC_MINB selects the variant for experiments.
+template <bool TWO, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_ntc(NtcArgs a) {
     const int64_t nr = a.cell_hi - a.cell_lo + 1;
     const bool vw = !a.equal_weight;
     int64_t nt1 = 0, nt2 = 0;
@@ -363,9 +367,19 @@ static int ntc_impl(mb_ctx* ctx, mb_cf* cf, const mb_interaction* it, mb_pv* pv1
     int ch = 32;
     while (ch > 1 && nr < (int64_t)N_SM * 8 * 4 * ch) ch >>= 1;
     const int gwarp = grid_for((nr + ch - 1) / ch * 32, 128, 8);
+    static int minb = -1;
+    if (minb < 0) {
+        const char* e = getenv("MB_NTC_MINB");
+        minb = e ? atoi(e) : 4;
+    }
+    auto launch_one = [&]() {
+        if (minb >= 8) k_ntc<false, 8><<<g, 128, 0, st>>>(a);
+        else if (minb >= 6) k_ntc<false, 6><<<g, 128, 0, st>>>(a);
+        else k_ntc<false, 4><<<g, 128, 0, st>>>(a);
+    };
     if (equal_weight) {
-        if (two) k_ntc<true><<<g, 128, 0, st>>>(a);
-        else k_ntc<false><<<g, 128, 0, st>>>(a);
+        if (two) k_ntc<true, 4><<<g, 128, 0, st>>>(a);
+        else launch_one();
         MB_LAUNCH_CHECK(ctx);
         if (!two) {
             k_ntc_warp<<<gwarp, 128, 0, st>>>(a, ch);
@@ -391,8 +405,8 @@ static int ntc_impl(mb_ctx* ctx, mb_cf* cf, const mb_interaction* it, mb_pv* pv1
     r = device_exclusive_scan(ctx, a.ncoll32, nr, a.win, partial);
     if (r) return r;
     MB_CUDA(cudaMemsetAsync(a.nsplit1, 0, (size_t)(2 * nr) * 4, st));
-    if (two) k_ntc<true><<<g, 128, 0, st>>>(a);
-    else k_ntc<false><<<g, 128, 0, st>>>(a);
+    if (two) k_ntc<true, 4><<<g, 128, 0, st>>>(a);
+    else launch_one();
     MB_LAUNCH_CHECK(ctx);
     if (!two) {
         k_ntc_warp<<<gwarp, 128, 0, st>>>(a, ch);
