@@ -176,7 +176,10 @@ def main():
     indexer = np.zeros((1, nx, 7), dtype=np.int64)
     n_total = np.array([n], dtype=np.int64)
     contiguous = np.array([1], dtype=np.uint8)
-    pin = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(7)]
+    try:
+        pin = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(7)]
+    except RuntimeError:  # the box refuses to pin 7 GB per rank: pageable host buffers (the e2e leg is then slower, still valid)
+        pin = [torch.empty(n, dtype=torch.float64) for _ in range(7)]
     host = [p.numpy() for p in pin]
 
     pv = mb.ParticleVector(cap, ctx)

@@ -4,6 +4,8 @@
 #include <cstring>
 #include <mutex>
 
+#include <cstdlib>
+
 #include "mb_common.cuh"
 
 namespace mb {
@@ -104,6 +106,16 @@ int mb_ctx_create(int device, uint64_t seed, mb_ctx** out) {
     c->seed = seed;
     c->band_w = 2;
     c->state_gen = 1;
+    {   // L2 fetch granularity (experiment knob): the NTC gathers use 8 bytes of every sector they touch
+        const char* e = getenv("MB_L2_FETCH");
+        if (e) {
+            cudaError_t le = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
+            size_t got = 0;
+            cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+            fprintf(stderr, "[mb] cudaLimitMaxL2FetchGranularity <- %s: %s, now %zu\n", e, cudaGetErrorString(le), got);
+            cudaGetLastError();
+        }
+    }
     MB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     MB_CUDA(cudaMalloc(&c->d_flags, 16 * sizeof(int)));
     MB_CUDA(cudaMemset(c->d_flags, 0, 16 * sizeof(int)));
