@@ -128,10 +128,28 @@ def reference_arm(args, rank):
         "e2e": {"value": v, "unit": "particle-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract goes to the real stdout; everything libraries print (NCCL's version banner, torchrun
+    notices) was redirected to stderr at start-up."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -340,7 +358,7 @@ def main():
         line["cpu_baseline"] = {"value": r["particle_steps_per_s"], "unit": "particle-timesteps/s", "cores": threads, "kind": "port",
                                 "sample": "C++ restatement of the reference's multithreaded Couette loop (couette_multithreaded.jl:97-173): %d cells x %d ppc "
                                           "(%.0e particles), %d steps, %d OpenMP threads, %.1f s" % (nx_cpu, PPC, nx_cpu * PPC, k_cpu, threads, r["seconds"])}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
