@@ -547,10 +547,11 @@ extern "C" int mb_merge_grid_based(mb_ctx* ctx, const mb_gridmerge_params* mg, m
     a.cpb = threads;
     while (a.cpb > 1 && nr < 8 * nCTA * a.cpb) a.cpb >>= 1;
     const size_t smem = ((size_t)3 * NB + 2) * 4;
-    static size_t attr_smem = 0;
-    if (smem > 40 * 1024 && smem > attr_smem) {
+    static size_t attr_smem[64] = {0};  // function attributes are per device
+    size_t& as = attr_smem[ctx->device & 63];
+    if (smem > 40 * 1024 && smem > as) {
         MB_CUDA(cudaFuncSetAttribute(k_merge_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
+        as = smem;
     }
     a.small_max = 0;
     if (NB <= GW_NB) {  // small cells: one warp per cell

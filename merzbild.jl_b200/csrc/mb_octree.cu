@@ -1101,8 +1101,8 @@ extern "C" int mb_merge_octree_N2(mb_ctx* ctx, const mb_octree_params* oc, mb_pv
         const size_t smem = (ns == 160 ? merge_warp_smem<160>(BCs) : merge_warp_smem<NS_MAX>(BCs)) * MW_WARPS;
         a.small_max = smem <= 200 * 1024 ? ns : 0;
         if (a.small_max) {
-            static size_t attr_smem[2] = {0, 0};
-            size_t& as = attr_smem[ns == 160 ? 0 : 1];
+            static size_t attr_smem[64][2] = {{0}};  // function attributes are per device
+            size_t& as = attr_smem[ctx->device & 63][ns == 160 ? 0 : 1];
             if (smem > as) {
                 if (ns == 160) MB_CUDA(cudaFuncSetAttribute(k_merge_warp<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 else MB_CUDA(cudaFuncSetAttribute(k_merge_warp<NS_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1130,10 +1130,11 @@ extern "C" int mb_merge_octree_N2(mb_ctx* ctx, const mb_octree_params* oc, mb_pv
             set_error("merge_octree_N2_based!: max_Nbins / target_np too large for the arg-max group table");
             return MB_ERR_UNSUPPORTED;
         }
-        static size_t attr_gsm = 0;
-        if (gsm > 40 * 1024 && gsm > attr_gsm) {
+        static size_t attr_gsm[64] = {0};  // function attributes are per device
+        size_t& ag = attr_gsm[ctx->device & 63];
+        if (gsm > 40 * 1024 && gsm > ag) {
             MB_CUDA(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
-            attr_gsm = gsm;
+            ag = gsm;
         }
         a.cpb = threads;  // chunks of cells per CTA round: only as large as still leaves >= 8 chunks per CTA (load balance)
         while (a.cpb > 1 && nr < 8 * nCTA * a.cpb) a.cpb >>= 1;

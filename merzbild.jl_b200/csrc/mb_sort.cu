@@ -842,7 +842,8 @@ int convect_band_launch(mb_ctx* ctx, const ConvectArgs& a, const mb_grid1d* grid
     k_clear_cls_flags<<<1, 1, 0, st>>>(ctx->d_flags);
     MB_LAUNCH_CHECK(ctx);
     const int g = grid_for(nc * 32, 256, MB_CB_MINB);
-    static bool attr_set = false;
+    static bool attr_done[64] = {false};  // function attributes are per device
+    bool& attr_set = attr_done[ctx->device & 63];
     if (!attr_set) {
         MB_CUDA(cudaFuncSetAttribute(k_convect_band<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CB_SMEM));
         MB_CUDA(cudaFuncSetAttribute(k_convect_band<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, CB_SMEM));
