@@ -3,10 +3,13 @@
 // in the reference (its group-2 branch uses an undefined variable, collision_fp.jl:57); cells with n_local < 7 are skipped.
 //
 // One warp per cell; the cell is streamed from HBM once (w, v: 32 B/particle) and written once (v: 24 B); the intermediate
-// passes hit L1/L2.  The standard normals are counter-based: particle j of the cell uses Philox blocks 2j and 2j+1 of the
-// (OP_FP, substream, timestep, cell) stream through Box-Muller -- regenerated in each pass that needs them instead of being
-// stored -- and are standardised exactly (mean 0, variance 1 over the cell) like scale_norm_rands!.
+// passes hit L1/L2.  The standard normals are counter-based: particle j of the cell uses Philox block j of the
+// (OP_FP, substream, timestep, cell) stream through two fp32 Box-Muller transforms (mb_normals.h: explicitly rounded fp32
+// operations, bit-identical in the CPU oracle) -- regenerated in each pass that needs them instead of being stored in the streaming
+// kernel, generated once in the register kernels -- and are standardised exactly (mean 0, variance 1 over the cell) like
+// scale_norm_rands!.
 #include "mb_common.cuh"
+#include "mb_normals.h"
 
 namespace mb {
 
@@ -23,18 +26,13 @@ struct FpArgs {
 __device__ __forceinline__ void fp_normals(const FpArgs& a, uint32_t cell, int64_t j, double o[3]) {
     const uint32_t c3 = (OP_FP & 0xFFu) | (a.substream << 8);
     uint32_t r[4];
-    philox4x32_10((uint32_t)(2 * j), cell, a.timestep, c3, (uint32_t)a.seed, (uint32_t)(a.seed >> 32), r);
-    double u1 = u64_to_unit_double(r[0], r[1]), u2 = u64_to_unit_double(r[2], r[3]);
-    double rad = sqrt(-2.0 * log(fmax(1e-300, u1)));
-    double sn, cs;
-    sincos(twopi * u2, &sn, &cs);
-    o[0] = rad * cs;
-    o[1] = rad * sn;
-    philox4x32_10((uint32_t)(2 * j + 1), cell, a.timestep, c3, (uint32_t)a.seed, (uint32_t)(a.seed >> 32), r);
-    u1 = u64_to_unit_double(r[0], r[1]);
-    u2 = u64_to_unit_double(r[2], r[3]);
-    rad = sqrt(-2.0 * log(fmax(1e-300, u1)));
-    o[2] = rad * cos(twopi * u2);
+    philox4x32_10((uint32_t)j, cell, a.timestep, c3, (uint32_t)a.seed, (uint32_t)(a.seed >> 32), r);
+    float n0, n1, n2, n3;
+    mbn_box_muller(r[0], r[1], &n0, &n1);  // fp32, explicitly rounded operations: bit-identical in the CPU oracle (mb_normals.h)
+    mbn_box_muller(r[2], r[3], &n2, &n3);
+    o[0] = (double)n0;
+    o[1] = (double)n1;
+    o[2] = (double)n2;
 }
 __device__ __forceinline__ double wsum(double x) {
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
@@ -124,7 +122,7 @@ static __global__ void __launch_bounds__(256) k_fp_linear(FpArgs a, int n_lo) {
 // read once and written once.  The arithmetic (per-lane accumulation in ascending j, then the xor butterfly) is the same as in
 // k_fp_linear, so both kernels give bit-identical results.  Handles the cells with n_lo < n_local <= 32 K; the others are skipped.
 template <int K>
-static __global__ void __launch_bounds__(128) k_fp_linear_reg(FpArgs a, int n_lo) {
+static __global__ void __launch_bounds__(128, K == 4 ? 4 : 2) k_fp_linear_reg(FpArgs a, int n_lo) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;

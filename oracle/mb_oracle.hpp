@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "philox.hpp"
+#include "../merzbild.jl_b200/csrc/mb_normals.h"  // fp32 Box-Muller shared with the CUDA kernel (bit-identical normals)
 
 namespace mbo {
 
@@ -622,20 +623,18 @@ inline double compute_relaxation_time(const Interaction& it, double mass, double
     const double mu = it.vhs_muref * std::pow(T / it.vhs_Tref, it.vhs_o);
     return 2.0 * mu / p;
 }
-// Box-Muller normals for local particle j of a cell stream: Philox blocks 2j and 2j+1 of `base`.
+// Normals for local particle j of a cell stream: Philox block j of `base`, two fp32 Box-Muller transforms with explicitly rounded
+// operations (the header is shared with the CUDA kernel so that both sides produce the same bits; see mb_normals.h).
 inline void fp_normals_philox(const PhiloxStream& base, int64_t j, double out[3]) {
-    uint32_t c[4] = {(uint32_t)(2 * j), base.ctr[1], base.ctr[2], base.ctr[3]};
+    uint32_t c[4] = {(uint32_t)j, base.ctr[1], base.ctr[2], base.ctr[3]};
     uint32_t o[4];
     Philox4x32::block(c, base.key, o);
-    double u1 = PhiloxStream::to_double(o[0], o[1]), u2 = PhiloxStream::to_double(o[2], o[3]);
-    double r = std::sqrt(-2.0 * std::log(std::max(1e-300, u1)));
-    out[0] = r * std::cos(twopi * u2);
-    out[1] = r * std::sin(twopi * u2);
-    c[0] = (uint32_t)(2 * j + 1);
-    Philox4x32::block(c, base.key, o);
-    u1 = PhiloxStream::to_double(o[0], o[1]); u2 = PhiloxStream::to_double(o[2], o[3]);
-    r = std::sqrt(-2.0 * std::log(std::max(1e-300, u1)));
-    out[2] = r * std::cos(twopi * u2);
+    float n0, n1, n2, n3;
+    mbn_box_muller(o[0], o[1], &n0, &n1);
+    mbn_box_muller(o[2], o[3], &n2, &n3);
+    out[0] = (double)n0;
+    out[1] = (double)n1;
+    out[2] = (double)n2;
 }
 // collision_fp.jl:24-125; NormalSrc: void operator()(int64_t j, double out[3])
 template <class NormalSrc>
