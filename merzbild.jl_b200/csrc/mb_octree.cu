@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(MT) k_merge(MergeArgs a) {
     unsigned long long* s_gkey = (unsigned long long*)mg_dyn;
     int* s_gid = (int*)(s_gkey + ((a.Bmax + 31) >> 5) + 1);
     __shared__ int32_t s_p[SMALL_NP], s_q[SMALL_NP];
+    __shared__ double s_pw[SMALL_NP], s_qw[SMALL_NP];  // weights of the slice, gathered together with the velocities
     __shared__ uint8_t s_oct[SMALL_NP];
     __shared__ int s_mode, s_prevN;
     __shared__ double sh[MT / 32];
@@ -266,7 +267,9 @@ __global__ void __launch_bounds__(MT) k_merge(MergeArgs a) {
                         if (j < n) {
                             const int32_t pj = idx[bs + j];
                             s_p[j] = pj;
-                            o = (a.pv.a[F_VX][pj] > mid[0] ? 1 : 0) + (a.pv.a[F_VY][pj] > mid[1] ? 2 : 0) + (a.pv.a[F_VZ][pj] > mid[2] ? 4 : 0);
+                            const double pvx = a.pv.a[F_VX][pj], pvy = a.pv.a[F_VY][pj], pvz = a.pv.a[F_VZ][pj];
+                            s_pw[j] = PW[pj];  // same round trip as the velocities: the child weights below need no second gather
+                            o = (pvx > mid[0] ? 1 : 0) + (pvy > mid[1] ? 2 : 0) + (pvz > mid[2] ? 4 : 0);
                             s_oct[j] = (uint8_t)o;
                         }
 #pragma unroll
@@ -317,7 +320,7 @@ __global__ void __launch_bounds__(MT) k_merge(MergeArgs a) {
                             if (o == k) dest = basek[k] + (cnt[k] - 1 - (runk[k] + __popc(bal & lt)));
                             runk[k] += __popc(bal);
                         }
-                        if (dest >= 0) s_q[dest] = s_p[j];
+                        if (dest >= 0) { s_q[dest] = s_p[j]; s_qw[dest] = s_pw[j]; }
                     }
                     __syncwarp();
                     for (int j = lane; j < n; j += 32) idx[bs + j] = s_q[j];
@@ -328,7 +331,7 @@ __global__ void __launch_bounds__(MT) k_merge(MergeArgs a) {
                             const int hi_j = w_base + w_cnt - 1 - part * chunk;
                             int lo_j = hi_j - chunk + 1;
                             if (lo_j < w_base) lo_j = w_base;
-                            for (int j = hi_j; j >= lo_j; j--) w += PW[s_q[j]];
+                            for (int j = hi_j; j >= lo_j; j--) w += s_qw[j];
                         }
                         w += __shfl_xor_sync(0xffffffffu, w, 1);
                         w += __shfl_xor_sync(0xffffffffu, w, 2);
@@ -338,9 +341,30 @@ __global__ void __launch_bounds__(MT) k_merge(MergeArgs a) {
                     Nbins += n_ne - 1;
                     total_post = tp;
                     __syncwarp();
-                    merge_group_update(bin >> 5, Nbins, b_w, b_np, b_depth, a.oc.max_depth, s_gkey, s_gid);
-                    for (int g = Nb0 >> 5; g <= (Nbins - 1) >> 5; g++)
-                        if (g != (bin >> 5)) merge_group_update(g, Nbins, b_w, b_np, b_depth, a.oc.max_depth, s_gkey, s_gid);
+                    {   // the (at most three) groups the split touched: loads of all of them in flight together, then the reductions
+                        const int g0 = bin >> 5, g1 = Nb0 >> 5, g2 = (Nbins - 1) >> 5;
+                        const int gs[3] = {g0, g1, g2};
+                        unsigned long long key[3];
+#pragma unroll
+                        for (int t = 0; t < 3; t++) {
+                            const int b = 32 * gs[t] + lane;
+                            key[t] = 0ull;
+                            if (b < Nbins && b_np[b] > 2 && b_depth[b] < a.oc.max_depth) key[t] = (unsigned long long)__double_as_longlong(b_w[b]) + 1ull;
+                        }
+#pragma unroll
+                        for (int t = 0; t < 3; t++) {
+                            if ((t == 1 && g1 == g0) || (t == 2 && (g2 == g0 || g2 == g1))) continue;  // warp-uniform
+                            const unsigned hi = (unsigned)(key[t] >> 32), lo = (unsigned)key[t];
+                            const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+                            const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+                            const bool win = key[t] != 0ull && hi == mhi && lo == mlo;
+                            const unsigned bmin = __reduce_min_sync(0xffffffffu, win ? (unsigned)(32 * gs[t] + lane) : 0xffffffffu);
+                            if (lane == 0) {
+                                s_gkey[gs[t]] = ((unsigned long long)mhi << 32) | mlo;
+                                s_gid[gs[t]] = bmin == 0xffffffffu ? -1 : (int)bmin;
+                            }
+                        }
+                    }
                     __syncwarp();
                     if (Nbins + 7 > a.oc.max_Nbins) break;
                 }
