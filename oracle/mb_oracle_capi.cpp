@@ -106,6 +106,34 @@ void mbo_compute_com_g(const double* it8, const double* p1_7, const double* p2_7
     for (int d = 0; d < 3; d++) vcom3[d] = cd.v_com[d];
     *g = cd.g;
 }
+// collide_2particles_vhs! (collision_ntc.jl:223-270) / collide_2particles_vhs_equal_weight! (:294-309) on particles i, k of one
+// species in `cell`, as test/test_collision_vhs.jl calls them (compute_g! first); cf4 = {sigma_g_w_max, n_coll_performed,
+// n_eq_w_coll_performed, unused}
+void mbo_collide_2particles_vhs(const mbo_rng_spec* rs, const double* it8, void* pv_, void* pia_, int64_t i, int64_t k, int64_t cell, int64_t species,
+                                double dw_tol, int equal_weight, double* cf4) {
+    ParticleVector& pv = *(ParticleVector*)pv_;
+    ParticleIndexerArray& pia = *(ParticleIndexerArray*)pia_;
+    const Interaction& it = *(const Interaction*)it8;
+    CollisionData cd;
+    CollisionFactors cf;
+    cf.sigma_g_w_max = cf4[0];
+    cf.n_coll_performed = (int64_t)cf4[1];
+    cf.n_eq_w_coll_performed = (int64_t)cf4[2];
+    compute_g(cd, pv[i], pv[k]);
+    auto run = [&](auto& rng) {
+        if (equal_weight) collide_2particles_vhs_equal_weight(rng, cd, cf, it, pv[i], pv[k]);
+        else collide_2particles_vhs(rng, cd, cf, it, i, k, pv, pv, pia, cell, species, species, dw_tol);
+    };
+    if (rs->kind == 0) run(*(Xoshiro256pp*)rs->seq);
+    else { PhiloxStream s(rs->seed, OP_USER, rs->substream, rs->timestep, 0); run(s); }
+    cf4[0] = cf.sigma_g_w_max; cf4[1] = (double)cf.n_coll_performed; cf4[2] = (double)cf.n_eq_w_coll_performed;
+}
+int mbo_compute_octant(const double* v3, const double* mid3) { return compute_octant(v3, mid3); }
+void mbo_octree_vel_middle(void* o, double* out3) { for (int d = 0; d < 3; d++) out3[d] = ((OctreeN2Merge*)o)->vel_middle[d]; }
+void mbo_octree_compute_v_mean(void* o, int64_t bs, int64_t be, void* pv) { compute_v_mean(*(OctreeN2Merge*)o, bs, be, *(ParticleVector*)pv); }
+void mbo_octree_bounds_recompute(void* o, int64_t bin_id, int64_t bs, int64_t be, void* pv) {
+    bin_bounds_recompute(*(OctreeN2Merge*)o, bin_id, bs, be, *(ParticleVector*)pv);
+}
 void mbo_scatter_vhs(const mbo_rng_spec* rs, const double* it8, double* p1_7, double* p2_7) {
     CollisionData cd;
     Particle& a = *(Particle*)p1_7;

@@ -94,6 +94,11 @@ def lib():
     sig("mbo_estimate_sigma_g_w_max", f64, vp, f64, f64, f64, f64, f64, f64)
     sig("mbo_compute_com_g", None, vp, vp, vp, vp, vp)
     sig("mbo_scatter_vhs", None, prs, vp, vp, vp)
+    sig("mbo_collide_2particles_vhs", None, prs, vp, vp, vp, i64, i64, i64, i64, f64, C.c_int, vp)
+    sig("mbo_compute_octant", C.c_int, vp, vp)
+    sig("mbo_octree_vel_middle", None, vp, vp)
+    sig("mbo_octree_compute_v_mean", None, vp, i64, i64, vp)
+    sig("mbo_octree_bounds_recompute", None, vp, i64, i64, i64, vp)
     sig("mbo_ntc", None, prs, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, f64, f64, f64, C.c_int)
     sig("mbo_ntc2", None, prs, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, f64, f64, f64, C.c_int)
     sig("mbo_swpm", None, prs, vp, vp, vp, vp, vp, vp, i64, i64, i64, f64, f64, f64)
@@ -513,6 +518,32 @@ class Octree:
 
     def compute(self, pv, target_np):
         lib().mbo_octree_compute(self.h, pv.h, target_np)
+
+    @property
+    def vel_middle(self):
+        o = np.empty(3)
+        lib().mbo_octree_vel_middle(self.h, _p(o))
+        return o
+
+    def compute_v_mean(self, bs, be, pv):
+        lib().mbo_octree_compute_v_mean(self.h, bs, be, pv.h)
+
+    def bin_bounds_recompute(self, bin_id, bs, be, pv):
+        lib().mbo_octree_bounds_recompute(self.h, bin_id, bs, be, pv.h)
+
+
+def compute_octant(v, mid):
+    """compute_octant (merging_octree_N2.jl:304-316)"""
+    v, mid = _f64(v), _f64(mid)
+    return lib().mbo_compute_octant(_p(v), _p(mid))
+
+
+def collide_2particles_vhs(rng, it, pv, pia, i, k, cell=1, species=1, dw_tol=1e-16, equal_weight=False, sigma_g_w_max=0.0):
+    """collide_2particles_vhs! (collision_ntc.jl:223-270) / ..._equal_weight! (:294-309) after compute_g!; returns
+    (sigma_g_w_max, n_coll_performed, n_eq_w_coll_performed)."""
+    cf = _f64([sigma_g_w_max, 0.0, 0.0, 0.0])
+    lib().mbo_collide_2particles_vhs(rng.ref, _p(it), pv.h, pia.h, i, k, cell, species, dw_tol, int(equal_weight), _p(cf))
+    return cf[0], int(cf[1]), int(cf[2])
 
 
 def merge_octree_N2(rng, oc, pv, pia, cell_lo, cell_hi, species, target_np, threshold=-1, grid=None, squash_after_each=False):

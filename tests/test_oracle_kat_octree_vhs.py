@@ -1,0 +1,194 @@
+"""CPU suite: more of the reference's known-answer tests restated on the oracle --
+test/test_octree_sorting.jl (octant numbering, the order-exact 8-way split with its end-filled ranges, two index groups, an empty
+octant, nested second split), test/test_octree_bounds_and_splitting.jl (initial bin bounds of the three OctreeInitBin modes, mean
+split, bounds recompute) and test/test_collision_vhs.jl / test_collision_vhs_equal_weight.jl (one VHS collision: energy conservation,
+the split particle carries the weight difference and the PRE-collision velocity and position)."""
+import numpy as np
+
+SIGNS = [(-1, -1, -1), (1, -1, -1), (-1, 1, -1), (1, 1, -1), (-1, -1, 1), (1, -1, 1), (-1, 1, 1), (1, 1, 1)]
+C_LIGHT = 299_792_458.0
+
+
+def _in_octant(octant, v_val, w=1.0, v0=(0.0, 0.0, 0.0)):
+    return [w, *(np.array(SIGNS[octant - 1], dtype=float) * v_val + np.array(v0)), 0.0, 0.0, 0.0]
+
+
+def _state(oracle, rows, indexer=None):
+    rows = np.array(rows, dtype=float)
+    n = rows.shape[0]
+    pv, pia = oracle.OPV(n), oracle.OPIA(1, 1)
+    for i, r in enumerate(rows):
+        pv.add_particle(i + 1, r[0], r[1:4], r[4:7])
+    if indexer is None:
+        pia.set_single_cell(1, 1, n)
+    else:
+        pia.indexer[0, 0] = indexer
+        pia.n_total[0] = n
+    return pv, pia
+
+
+def _nine(extra_octant, reverse):
+    rows = []
+    for octant in (range(8, 0, -1) if reverse else range(1, 9)):
+        rows.append(_in_octant(octant, 1.0, w=octant))
+        if octant == extra_octant:
+            rows.append(_in_octant(octant, 2.0, w=octant))
+    return rows
+
+
+def _fifteen_nested(w_inner=0.5):
+    """create_15particles_nested (test_octree_sorting.jl:26-57): 8 particles inside octant 3 around (-2, 2, -2), one in every other octant"""
+    mia = [12, 15, 2, 14, 13, 7, 8, 10, 5, 6, 1, 9, 4, 3, 11]
+    vp = [None] * 15
+    i = 0
+    for vx in (-1.0, -3.0):
+        for vy in (1.0, 3.0):
+            for vz in (-3.0, -1.0):
+                vp[mia[i] - 1] = [w_inner, vx, vy, vz, 0.0, 0.0, 0.0]
+                i += 1
+    for octant in range(8, 0, -1):
+        if octant != 3:
+            vp[mia[i] - 1] = _in_octant(octant, 1.0)
+            i += 1
+    return vp
+
+
+def test_compute_octant(oracle):
+    """test_octree_sorting.jl:114-140: octant = 1 + (vx > mx) + 2 (vy > my) + 4 (vz > mz)"""
+    mid = (-1.0, -1.0, -1.0)
+    for o, s in enumerate(SIGNS, start=1):
+        assert oracle.compute_octant(2.0 * np.array(s, dtype=float), mid) == o
+
+
+def test_split_bin_order_reference_kat(oracle):
+    """test_octree_sorting.jl:142-205"""
+    oc = oracle.Octree(oracle.MID_SPLIT, oracle.INIT_C)
+    pv, pia = _state(oracle, _nine(3, True))  # octants 8, 7, 6, 5, 4, 3, 3, 2, 1
+    oc.init(pv, pia, 1, 1)
+    assert sorted(oc.particle_indexes_sorted(9)) == list(range(1, 10))
+    oc.split_bin(1, pv)
+    assert oc.Nbins == 8 and oc.particle_indexes_sorted(9).tolist() == [9, 8, 7, 6, 5, 4, 3, 2, 1]
+    # particles 1..9 in octants 4, 5, 6, 7, 8, 3, 3, 2, 1
+    rows = _nine(3, False)[4:9] + _nine(3, True)[5:9]
+    for indexer in (None, (9, 1, 3, 3, 4, 9, 6)):  # one index group, then two groups (1..3, 4..9)
+        pv, pia = _state(oracle, rows, indexer)
+        oc.init(pv, pia, 1, 1)
+        oc.split_bin(1, pv)
+        assert oc.Nbins == 8 and oc.particle_indexes_sorted(9).tolist() == [9, 8, 7, 6, 1, 2, 3, 4, 5]
+        assert [oc.bin(i)["start"] for i in range(1, 9)] == [1, 2, 3, 5, 6, 7, 8, 9]
+        assert [oc.bin(i)["end"] for i in range(1, 9)] == [1, 2, 4, 5, 6, 7, 8, 9]
+    assert [oc.bin(i)["np"] for i in range(1, 9)] == [1, 1, 2, 1, 1, 1, 1, 1]
+    assert [oc.bin(i)["w"] for i in range(1, 9)] == [1, 2, 6, 4, 5, 6, 7, 8]
+    # one empty octant (5): 7 particles in octants 8, 7, 6, 4, 3, 2, 1
+    rows7 = [_in_octant(o, 1.0, w=o) for o in range(8, 0, -1) if o != 5]
+    pv, pia = _state(oracle, rows7)
+    oc.init(pv, pia, 1, 1)
+    oc.split_bin(1, pv)
+    assert oc.Nbins == 7 and oc.particle_indexes_sorted(7).tolist() == [7, 6, 5, 4, 3, 2, 1]
+    assert [oc.bin(i)["start"] for i in range(1, 8)] == [1, 2, 3, 4, 5, 6, 7] == [oc.bin(i)["end"] for i in range(1, 8)]
+    assert [oc.bin(i)["w"] for i in range(1, 8)] == [1, 2, 3, 4, 6, 7, 8]
+
+
+def test_nested_split_reference_kat(oracle):
+    """test_octree_sorting.jl:207-260: 15 particles, 8 of them in octant 3; the first split leaves bin 3 = positions 3..10, the
+    second split of bin 3 gives 8 more bins of one particle each"""
+    pv, pia = _state(oracle, _fifteen_nested())
+    oc = oracle.Octree(oracle.MID_SPLIT, oracle.INIT_MINMAX_SYM)
+    oc.init(pv, pia, 1, 1)
+    b = oc.bin(1)
+    assert (b["start"], b["end"]) == (1, 15)
+    np.testing.assert_allclose(b["v_max"], [3.0, 3.0, 3.0], atol=1e-12)
+    np.testing.assert_allclose(b["v_min"], [-3.0, -3.0, -3.0], atol=1e-12)
+    oc.split_bin(1, pv)
+    assert oc.Nbins == 8
+    s = oc.particle_indexes_sorted(15)
+    assert s[:2].tolist() == [11, 3] and s[10:].tolist() == [4, 9, 1, 6, 5]
+    assert (oc.bin(3)["start"], oc.bin(3)["end"]) == (3, 10)
+    assert sorted(s[2:10].tolist()) == sorted([12, 15, 2, 14, 13, 7, 8, 10])
+    oc.split_bin(3, pv)
+    assert oc.Nbins == 15
+    assert all(oc.bin(i)["np"] == 1 for i in range(1, 16))
+    assert sorted(oc.particle_indexes_sorted(15).tolist()) == list(range(1, 16))
+    assert oc.bin(3)["depth"] == 2 and oc.bin(9)["depth"] == 2 and oc.bin(1)["depth"] == 1
+
+
+def test_init_bounds_and_mean_split_reference_kat(oracle):
+    """test_octree_bounds_and_splitting.jl:76-135"""
+    rows8 = [_in_octant(o, 1.0, v0=(1.0, 1.0, 1.0)) for o in range(1, 9)]
+    pv, pia = _state(oracle, rows8)
+    oc = oracle.Octree(oracle.MID_SPLIT, oracle.INIT_C)
+    oc.init(pv, pia, 1, 1)
+    np.testing.assert_allclose(oc.bin(1)["v_min"], [-C_LIGHT] * 3, atol=1e-12)
+    np.testing.assert_allclose(oc.bin(1)["v_max"], [C_LIGHT] * 3, atol=1e-12)
+    oc.split_bin(1, pv)
+    assert np.max(np.abs(oc.vel_middle)) < 1e-12
+    rows15 = _fifteen_nested(w_inner=1.0)
+    pv, pia = _state(oracle, rows15)
+    oc2 = oracle.Octree(oracle.MID_SPLIT, oracle.INIT_MINMAX_SYM)
+    oc2.init(pv, pia, 1, 1)
+    assert np.max(np.abs(oc2.bin(1)["v_min"] + oc2.bin(1)["v_max"])) < 1e-12
+    np.testing.assert_allclose(oc2.bin(1)["v_max"], [3.0, 3.0, 3.0], atol=1e-12)
+    oc3 = oracle.Octree(oracle.MID_SPLIT, oracle.INIT_MINMAX)
+    oc3.init(pv, pia, 1, 1)
+    np.testing.assert_allclose(oc3.bin(1)["v_min"], [-3.0, -1.0, -3.0], atol=1e-11)
+    np.testing.assert_allclose(oc3.bin(1)["v_max"], [1.0, 3.0, 1.0], atol=1e-11)
+    oc4 = oracle.Octree(oracle.MEAN_SPLIT, oracle.INIT_MINMAX)
+    oc4.init(pv, pia, 1, 1)
+    oc4.compute_v_mean(1, 15, pv)
+    np.testing.assert_allclose(oc4.vel_middle, np.array(rows15)[:, 1:4].mean(0), atol=1e-11)
+    # a far outlier moves exactly the bounds it exceeds (bin_bounds_recompute!)
+    prev = oc4.bin(1)
+    far = [1.0, 120_000.0, -440_000.0, 920_000.0, 0.0, 0.0, 0.0]
+    pv.set_logical(15, np.array([far]))
+    oc4.bin_bounds_recompute(1, 1, 15, pv)
+    b = oc4.bin(1)
+    assert b["v_min"][0] == prev["v_min"][0] and b["v_max"][0] == far[1]
+    assert b["v_min"][1] == far[2] and b["v_max"][1] == prev["v_max"][1]
+    assert b["v_min"][2] == prev["v_min"][2] and b["v_max"][2] == far[3]
+
+
+def _two(oracle, w1, w2, cap=3):
+    pv, pia = oracle.OPV(cap), oracle.OPIA(1, 1)
+    pv.add_particle(1, w1, (1.0, 0.0, 0.0), (0.0, 0.0, 0.0))
+    pv.add_particle(2, w2, (-1.0, 0.0, 0.0), (0.5, 0.25, 0.125))
+    pia.set_single_cell(1, 1, 2)
+    return pv, pia
+
+
+def test_collide_2particles_vhs_reference_kat(oracle):
+    """test_collision_vhs.jl: sigma_g_w_max reset to 0 makes the collision certain (R < 1)."""
+    m = oracle.MASS["Ar"]
+    it = oracle.interaction("Ar", "Ar")
+    for t in range(1, 6):
+        rng = oracle.Rng.philox(1234, t)
+        # equal weights: no split, energy conserved
+        pv, pia = _two(oracle, 1.0, 1.0)
+        sg, n_perf, n_eq = oracle.collide_2particles_vhs(rng, it, pv, pia, 1, 2)
+        a = pv.logical(1, 2)
+        assert n_perf == 1 and n_eq == 1 and pia.n_total[0] == 2 and sg > 0
+        assert abs(0.5 * m * (a[:, 1:4] ** 2).sum() - 0.5 * m * 2.0) < 1e-14 * m
+        np.testing.assert_allclose(a[:, 1:4].sum(0), [0.0, 0.0, 0.0], atol=1e-15)  # momentum
+        # w1 > w2: particle 1 is split; the new particle keeps the pre-collision velocity and position
+        pv, pia = _two(oracle, 2.0, 1.0)
+        sg, n_perf, n_eq = oracle.collide_2particles_vhs(rng, it, pv, pia, 1, 2)
+        a = pv.logical(1, 3)
+        assert n_perf == 1 and n_eq == 0 and pia.n_total[0] == 3
+        assert a[2, 0] == 1.0 and a[2, 1:4].tolist() == [1.0, 0.0, 0.0] and a[2, 4:7].tolist() == [0.0, 0.0, 0.0] and a[0, 0] == 1.0
+        assert tuple(pia.indexer[0, 0]) == (3, 1, 2, 2, 3, 3, 1)
+        ke0 = 0.5 * m * (2.0 * 1.0 + 1.0 * 1.0)
+        assert abs(0.5 * m * (a[:, 0] * (a[:, 1:4] ** 2).sum(1)).sum() - ke0) < 1e-14 * m
+        # w1 < w2: particle 2 is split
+        pv, pia = _two(oracle, 1.0, 3.5)
+        sg, n_perf, n_eq = oracle.collide_2particles_vhs(rng, it, pv, pia, 1, 2)
+        a = pv.logical(1, 3)
+        assert pia.n_total[0] == 3 and a[2, 0] == 2.5 and a[2, 1:4].tolist() == [-1.0, 0.0, 0.0] and a[2, 4:7].tolist() == [0.5, 0.25, 0.125]
+        assert a[1, 0] == 1.0
+        assert abs(0.5 * m * (a[:, 0] * (a[:, 1:4] ** 2).sum(1)).sum() - 0.5 * m * 4.5) < 1e-14 * m
+        # the equal-weight routine never splits, whatever the weights (test_collision_vhs_equal_weight.jl)
+        pv, pia = _two(oracle, 2.0, 1.0)
+        sg, n_perf, n_eq = oracle.collide_2particles_vhs(rng, it, pv, pia, 1, 2, equal_weight=True)
+        assert n_perf == 1 and n_eq == 1 and pia.n_total[0] == 2 and pv.logical(1, 2)[:, 0].tolist() == [2.0, 1.0]
+    # a sigma_g_w_max far above sigma g w makes the collision (almost) impossible: nothing changes
+    pv, pia = _two(oracle, 1.0, 1.0)
+    sg, n_perf, n_eq = oracle.collide_2particles_vhs(oracle.Rng.philox(1234, 1), it, pv, pia, 1, 2, sigma_g_w_max=1e30)
+    assert n_perf == 0 and sg == 1e30 and pv.logical(1, 2)[:, 1].tolist() == [1.0, -1.0]
