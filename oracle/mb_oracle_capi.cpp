@@ -358,6 +358,28 @@ int64_t mbo_sample_on_grid_cells(const mbo_rng_spec* rs, int vdf_kind, void* pv_
     return n;
 }
 
+// ---- surface properties (KAT hook, test/test_surface_props_1D_uniform.jl) ----
+// ops: sequence of n_ops (kind, element, row) with kind 0 = update_surface_incident!, 1 = update_surface_reflected! applied to the
+// particle rows7[row]; then optionally surface_props_scale! with (mass, dt, inv_areas2).  out22 as mbo_convect_particles returns it.
+void mbo_surface_props_kat(const double* rows7, const int64_t* ops3, int64_t n_ops, int do_scale, double mass, double dt, const double* inv_areas2,
+                           double* out22) {
+    SurfProps sp(1);
+    for (int64_t o = 0; o < n_ops; o++) {
+        const Particle& p = *(const Particle*)(rows7 + 7 * ops3[3 * o + 2]);
+        update_surface(p, 1, sp, ops3[3 * o + 1], ops3[3 * o] == 0);
+    }
+    if (do_scale) {
+        sp.inv_areas[0] = inv_areas2[0]; sp.inv_areas[1] = inv_areas2[1];
+        surface_props_scale(1, sp, mass, dt);
+    }
+    for (int e = 0; e < 2; e++) {
+        double* q = out22 + 11 * e;
+        q[0] = sp.np[e]; q[1] = sp.flux_incident[e]; q[2] = sp.flux_reflected[e];
+        for (int d = 0; d < 3; d++) { q[3 + d] = sp.force[d + 3 * e]; q[7 + d] = sp.shear_pressure[d + 3 * e]; }
+        q[6] = sp.normal_pressure[e]; q[10] = sp.kinetic_energy_flux[e];
+    }
+}
+
 // ---- velocity-grid merging ----
 void* mbo_gridmerge_create(int64_t nx, int64_t ny, int64_t nz, const double* mult3) { return new GridN2Merge(nx, ny, nz, mult3); }
 void mbo_gridmerge_free(void* g) { delete (GridN2Merge*)g; }

@@ -112,6 +112,7 @@ def lib():
     sig("mbo_sample_equal_weight_cell", None, vp, vp, vp, i64, i64, i64, f64, f64, f64, vp, C.c_int, vp)
     sig("mbo_sample_on_grid", i64, vp, C.c_int, vp, i64, f64, f64, f64, vp, f64, f64, f64, vp)
     sig("mbo_sample_equal_weight_cells", None, vp, vp, vp, vp, i64, i64, i64, i64, f64, f64, f64, f64, vp, C.c_int, vp)
+    sig("mbo_surface_props_kat", None, vp, vp, i64, C.c_int, f64, f64, vp, vp)
     sig("mbo_gridmerge_create", vp, i64, i64, i64, vp)
     sig("mbo_gridmerge_free", None, vp)
     sig("mbo_gridmerge_index", i64, vp, vp, vp)
@@ -530,6 +531,19 @@ class Octree:
 
     def bin_bounds_recompute(self, bin_id, bs, be, pv):
         lib().mbo_octree_bounds_recompute(self.h, bin_id, bs, be, pv.h)
+
+
+def surface_props_kat(rows, ops, scale=None):
+    """update_surface_incident! / update_surface_reflected! (surface_props.jl:77-131) applied in the order of ``ops`` =
+    [(kind, element, row)], kind 0 incident / 1 reflected; scale = (mass, dt, inv_areas) applies surface_props_scale! (:144-160).
+    Returns the 2 x 11 rows (np, flux_incident, flux_reflected, force[3], normal_pressure, shear_pressure[3], kinetic_energy_flux)."""
+    rows = _f64(np.asarray(rows).reshape(-1, 7))
+    o = np.ascontiguousarray(np.asarray(ops, dtype=np.int64).reshape(-1, 3))
+    out = np.zeros((2, 11))
+    m, dt, ia = scale if scale is not None else (0.0, 1.0, (1.0, 1.0))
+    ia = _f64(ia)
+    lib().mbo_surface_props_kat(_p(rows), _p(o), o.shape[0], int(scale is not None), m, dt, _p(ia), _p(out))
+    return out
 
 
 def compute_octant(v, mid):

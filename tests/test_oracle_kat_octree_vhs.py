@@ -192,3 +192,38 @@ def test_collide_2particles_vhs_reference_kat(oracle):
     pv, pia = _two(oracle, 1.0, 1.0)
     sg, n_perf, n_eq = oracle.collide_2particles_vhs(oracle.Rng.philox(1234, 1), it, pv, pia, 1, 2, sigma_g_w_max=1e30)
     assert n_perf == 0 and sg == 1e30 and pv.logical(1, 2)[:, 1].tolist() == [1.0, -1.0]
+
+
+def test_surface_props_reference_kat(oracle):
+    """test/test_surface_props_1D_uniform.jl:33-182: one particle hits each wall (incident, then reflected with a new velocity / weight);
+    np, fluxes, force, normal / shear pressure and kinetic energy flux, then the m / (dt A) scaling."""
+    eps2 = 2 * np.finfo(float).eps
+    left_in, right_in = [3.5, -9.0, 9.0, 0.0, 0.25, 0, 0], [10.5, 10.0, 0.0, 3.0, 3.9, 0, 0]
+    left_out, right_out = [3.5, 9.0, 9.0, 0.0, 0.25, 0, 0], [10.0, -1.0, -2.0, -4.0, 3.9, 0, 0]
+    rows = [left_in, right_in, left_out, right_out]
+    s = oracle.surface_props_kat(rows, [(0, 1, 0), (0, 2, 1)])
+    assert s[:, 0].tolist() == [1.0, 1.0] and s[:, 1].tolist() == [3.5, 10.5] and s[:, 2].tolist() == [0.0, 0.0]
+    np.testing.assert_allclose(s[0, 3:6], [3.5 * -9, 3.5 * 9, 0.0], atol=eps2 * 40)
+    np.testing.assert_allclose(s[1, 3:6], [10.5 * 10, 0.0, 10.5 * 3], atol=eps2 * 110)
+    assert abs(s[0, 6] - 9 * 3.5) < eps2 * 40 and abs(s[1, 6] - 10 * 10.5) < eps2 * 110
+    np.testing.assert_allclose(s[0, 7:10], [0.0, 9 * 3.5, 0.0], atol=eps2 * 40)
+    np.testing.assert_allclose(s[1, 7:10], [0.0, 0.0, 3 * 10.5], atol=eps2 * 40)
+    assert abs(s[0, 10] - 0.5 * 3.5 * 162) < eps2 * 300 and abs(s[1, 10] - 0.5 * 10.5 * 109) < eps2 * 600
+    ops = [(0, 1, 0), (0, 2, 1), (1, 1, 2), (1, 2, 3)]
+    s = oracle.surface_props_kat(rows, ops)
+    assert s[:, 0].tolist() == [1.0, 1.0] and s[:, 1].tolist() == [3.5, 10.5] and s[:, 2].tolist() == [-3.5, -10.0]
+    np.testing.assert_allclose(s[0, 3:6], [3.5 * -9 - 3.5 * 9, 0.0, 0.0], atol=eps2 * 70)
+    np.testing.assert_allclose(s[1, 3:6], [10.5 * 10 + 10.0, 20.0, 10.5 * 3 + 40.0], atol=eps2 * 120)
+    assert abs(s[0, 6] - (9 * 3.5 + 9 * 3.5)) < eps2 * 70 and abs(s[1, 6] - (10 * 10.5 + 1 * 10.0)) < eps2 * 120
+    np.testing.assert_allclose(s[0, 7:10], [0.0, 0.0, 0.0], atol=eps2 * 40)
+    np.testing.assert_allclose(s[1, 7:10], [0.0, 2 * 10.0, 3 * 10.5 + 4 * 10.0], atol=eps2 * 80)
+    ke_r = 0.5 * 10.5 * 109 - 0.5 * 10.0 * 21
+    assert abs(s[0, 10]) < eps2 * 300 and abs(s[1, 10] - ke_r) < eps2 * 600
+    m, dt, ia = oracle.MASS["Ar"], 1e-20, (0.5, 0.25)
+    sc = oracle.surface_props_kat(rows, ops, scale=(m, dt, ia))
+    f = m * np.array(ia) / dt
+    np.testing.assert_allclose(sc[:, 1], f * [3.5, 10.5], rtol=4e-16)
+    np.testing.assert_allclose(sc[:, 2], -f * [3.5, 10.0], rtol=4e-16)
+    np.testing.assert_allclose(sc[:, 6], f * [63.0, 115.0], rtol=4e-16)
+    np.testing.assert_allclose(sc[1, 7:10], f[1] * np.array([0.0, 20.0, 71.5]), rtol=4e-16)
+    assert abs(sc[1, 10] - f[1] * ke_r) <= 4e-16 * abs(f[1] * ke_r) and sc[:, 0].tolist() == [1.0, 1.0]
