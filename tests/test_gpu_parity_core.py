@@ -144,6 +144,35 @@ def test_sort_large_cell_segments(mb, oracle, ctx):
 
 
 # ------------------------------------------------------------------------------------------------------------ props
+def test_compute_props_sorted_chunks_reference_kat(mb, ctx):
+    """test/test_chunking.jl:57-105 through the C ABI: a cell chunk only touches its own cells (the others keep their values), the
+    grid variant of a PhysProps(...; ndens_not_Np=true) divides by the cell volume."""
+    rows = np.array([[i, 0.0, 0.0, 0.0, x, 0.0, 1.0] for i, x in zip((1.0, 2.0, 3.0, 4.0), (3.0, 3.0, 3.0, 7.0))])
+    pv, pia = mb.ParticleVector(4, ctx), mb.ParticleIndexerArray(5, 1, ctx)
+    pv.set_logical(1, rows)
+    ix = np.tile(np.array([0, 0, -1, 0, 0, -1, 0], dtype=np.int64), (1, 5, 1))
+    ix[0, 1] = (3, 1, 3, 3, 0, -1, 0)
+    ix[0, 3] = (1, 4, 4, 1, 0, -1, 0)
+    pia.upload(ix, np.array([4]), np.array([1], dtype=np.uint8))
+    pp = mb.PhysProps(5, 1, ctx=ctx)
+    mb.compute_props_sorted([pv], pia, [AR], pp, cell_chunk=(1, 1))
+    assert pp.download()["np"][0].tolist() == [0.0] * 5
+    mb.compute_props_sorted([pv], pia, [AR], pp, cell_chunk=(1, 3))
+    d = pp.download()
+    assert d["np"][0].tolist() == [0.0, 3.0, 0.0, 0.0, 0.0] and d["n"][0, 1] == 6.0
+    mb.compute_props_sorted([pv], pia, [AR], pp, cell_chunk=(3, 4))
+    d = pp.download()
+    assert d["np"][0].tolist() == [0.0, 3.0, 0.0, 1.0, 0.0] and d["n"][0, 3] == 4.0 and d["n"][0, 1] == 6.0  # cell 2 is not reset
+    g = mb.Grid1DUniform(10.0, 5)
+    pn = mb.PhysProps(5, 1, ndens_not_Np=True, ctx=ctx)
+    mb.compute_props_sorted([pv], pia, [AR], pn, g, cell_chunk=(1, 3))
+    d = pn.download()
+    assert d["np"][0].tolist() == [0.0, 3.0, 0.0, 0.0, 0.0] and d["n"][0, 1] == 3.0
+    mb.compute_props_sorted([pv], pia, [AR], pn, g, cell_chunk=(4, 4))
+    d = pn.download()
+    assert d["np"][0].tolist() == [0.0, 3.0, 0.0, 1.0, 0.0] and d["n"][0, 1] == 3.0 and d["n"][0, 3] == 2.0
+
+
 def test_compute_props_reference_kat(mb, oracle, ctx):
     """test/test_computes.jl:6-67: 2000 identical particles -> n, v exact, T ~ 0."""
     n = 2000

@@ -227,3 +227,33 @@ def test_surface_props_reference_kat(oracle):
     np.testing.assert_allclose(sc[:, 6], f * [63.0, 115.0], rtol=4e-16)
     np.testing.assert_allclose(sc[1, 7:10], f[1] * np.array([0.0, 20.0, 71.5]), rtol=4e-16)
     assert abs(sc[1, 10] - f[1] * ke_r) <= 4e-16 * abs(f[1] * ke_r) and sc[:, 0].tolist() == [1.0, 1.0]
+
+
+def _chunk_state(oracle):
+    """test/test_chunking.jl:6-55: 4 particles of weights 1..4, three in cell 2 and one in cell 4 of a 5-cell grid of length 10"""
+    rows = np.array([[i, 0.0, 0.0, 0.0, x, 0.0, 1.0] for i, x in zip((1.0, 2.0, 3.0, 4.0), (3.0, 3.0, 3.0, 7.0))])
+    pv, pia = oracle.OPV(4), oracle.OPIA(5, 1)
+    pv.fill_identity(rows)
+    pia.indexer[0, 1] = (3, 1, 3, 3, 0, -1, 0)
+    pia.indexer[0, 3] = (1, 4, 4, 1, 0, -1, 0)
+    pia.n_total[0] = 4
+    return rows, pv, pia
+
+
+def test_compute_props_sorted_chunks_reference_kat(oracle):
+    """test/test_chunking.jl:57-105: compute_props_sorted! on a cell chunk fills the chunk's cells and leaves the others as they were
+    (not reset); the grid variant divides by the cell volume (2.0)."""
+    m = oracle.MASS["Ar"]
+    rows, pv, pia = _chunk_state(oracle)
+    out = oracle.Props(5, 1)
+    oracle.compute_props_sorted([pv], pia, [m], 1, 1, out=out)
+    assert out.np[0].tolist() == [0.0] * 5
+    oracle.compute_props_sorted([pv], pia, [m], 1, 3, out=out)
+    assert out.np[0].tolist() == [0.0, 3.0, 0.0, 0.0, 0.0] and out.n[0, 1] == 6.0
+    oracle.compute_props_sorted([pv], pia, [m], 3, 4, out=out)
+    assert out.np[0].tolist() == [0.0, 3.0, 0.0, 1.0, 0.0] and out.n[0, 3] == 4.0 and out.n[0, 1] == 6.0  # cell 2 is not reset
+    out = oracle.Props(5, 1)
+    oracle.compute_props_sorted([pv], pia, [m], 1, 3, grid=(10.0, 5), out=out)
+    assert out.np[0].tolist() == [0.0, 3.0, 0.0, 0.0, 0.0] and out.n[0, 1] == 3.0
+    oracle.compute_props_sorted([pv], pia, [m], 4, 4, grid=(10.0, 5), out=out)
+    assert out.np[0].tolist() == [0.0, 3.0, 0.0, 1.0, 0.0] and out.n[0, 1] == 3.0 and out.n[0, 3] == 2.0
