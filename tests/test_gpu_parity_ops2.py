@@ -224,3 +224,35 @@ def test_fp_linear_parity(mb, oracle, ctx):
         Tx0 += np.var(start[s:e, 1])
         Tx1 += np.var(a[s:e, 1])
     assert Tx1 < Tx0  # the hot component cools
+
+
+def test_octree_merging_buffer_sorting_reference_kat(mb, oracle, ctx):
+    """test_octree_merging_buffer_sorting.jl:43-200 through the C ABI: a cell whose particles sit in two index groups around another
+    cell's particles; post-merge counts (target 6 -> 2 particles, target 16 -> 12), the pia with its hole after the merge
+    (contiguous == false), and after sort_particles! (squashes first): contiguous again, cell 2 directly behind cell 1."""
+    from test_oracle_kat_octree_vhs import _buffer_sorting_state
+
+    for n_gr1, target, expect_after, expect_c2 in ((50, 6, (2, 1, 2, 2), (10, 51, 60, 10)), (5, 16, (12, 1, 5, 5, 16, 22, 7), (10, 6, 15, 10))):
+        rows, opv, opia = _buffer_sorting_state(oracle, n_gr1)
+        pv, pia = mirror_to_device(mb, ctx, opv, opia)
+        pp = mb.PhysProps(2, 1, ctx=ctx)
+        mb.compute_props([pv], pia, [AR], pp)
+        d = pp.download()
+        assert d["np"][0].tolist() == [90.0, 10.0] and d["n"][0].tolist() == [90.0, 10000.0]
+        oc = oracle.Octree(oracle.MID_SPLIT, oracle.INIT_MINMAX)
+        oracle.merge_octree_N2(oracle.Rng.philox(1234, 1), oc, opv, opia, 1, 1, 1, target)
+        moc = mb.OctreeN2Merge(mb.OctreeN2Merge.OctreeBinMidSplit, mb.OctreeN2Merge.OctreeInitBinMinMaxVel)
+        mb.merge_octree_N2_based(mb.PhiloxRng(1), moc, pv, pia, 1, 1, target)
+        ix, nt, ct = pia.download()
+        assert tuple(ix[0, 0][:len(expect_after)]) == expect_after and tuple(ix[0, 1][:4]) == expect_c2 and ct[0] == 0
+        assert_same_pia(opia, pia)
+        mb.compute_props([pv], pia, [AR], pp)
+        d = pp.download()
+        assert d["np"][0].tolist() == [float(expect_after[0]), 10.0] and abs(d["n"][0, 0] - 90.0) < 1e-12 and d["n"][0, 1] == 10000.0
+        g = mb.Grid1DUniform(8.0, 2)
+        mb.sort_particles(None, g, pv, pia, 1)
+        oracle.sort_particles(opv, opia, 1, grid=(8.0, 2))
+        ix, nt, ct = pia.download()
+        k = expect_after[0]
+        assert tuple(ix[0, 0]) == (k, 1, k, k, 0, -1, 0) and tuple(ix[0, 1]) == (10, k + 1, k + 10, 10, 0, -1, 0) and ct[0] == 1 and nt[0] == k + 10
+        assert_rows_close(pv.logical(1, k + 10), opv.logical(1, k + 10), 1e-13, "after merge + sort")

@@ -257,3 +257,49 @@ def test_compute_props_sorted_chunks_reference_kat(oracle):
     assert out.np[0].tolist() == [0.0, 3.0, 0.0, 0.0, 0.0] and out.n[0, 1] == 3.0
     oracle.compute_props_sorted([pv], pia, [m], 4, 4, grid=(10.0, 5), out=out)
     assert out.np[0].tolist() == [0.0, 3.0, 0.0, 1.0, 0.0] and out.n[0, 1] == 3.0 and out.n[0, 3] == 2.0
+
+
+def _buffer_sorting_state(oracle, n_gr1):
+    """create_particles_and_pia (test_octree_merging_buffer_sorting.jl:4-41): 90 particles of cell 1 in two index groups
+    [1, n_gr1] and [n_gr1 + 11, 100], 10 heavy particles of cell 2 in between"""
+    rows = []
+    for i in range(1, 101):
+        heavy = n_gr1 + 1 <= i <= n_gr1 + 10
+        rows.append([1000.0 if heavy else 1.0, i - 1.0, i ** 2 + 3.0, np.sqrt(i + 5.0) ** (2 * (i % 2) - 1.0), 5.0 if heavy else 1.0, 0.0, 0.0])
+    rows = np.array(rows)
+    pv, pia = oracle.OPV(100), oracle.OPIA(2, 1)
+    pv.fill_identity(rows)
+    pia.indexer[0, 0] = (90, 1, n_gr1, n_gr1, n_gr1 + 11, 100, 90 - n_gr1)
+    pia.indexer[0, 1] = (10, n_gr1 + 1, n_gr1 + 10, 10, 0, -1, 0)
+    pia.n_total[0] = 100
+    return rows, pv, pia
+
+
+def test_octree_merging_buffer_sorting_reference_kat(oracle):
+    """test_octree_merging_buffer_sorting.jl:43-200: post-merge counts (target 6 -> 2 particles, target 16 -> 12), the LIFO buffer of
+    freed slots, pia after the merge (hole between the cells, contiguous == false) and after the sort (contiguous again)."""
+    m = oracle.MASS["Ar"]
+    rows, pv, pia = _buffer_sorting_state(oracle, 50)
+    p = oracle.compute_props([pv], pia, [m])
+    assert p.np[0].tolist() == [90.0, 10.0] and p.n[0].tolist() == [90.0, 10000.0] and pv.nbuffer == 0 and pia.contiguous[0] == 1
+    oc = oracle.Octree(oracle.MID_SPLIT, oracle.INIT_MINMAX)
+    oracle.merge_octree_N2(oracle.Rng.philox(1234, 1), oc, pv, pia, 1, 1, 1, 6)
+    p = oracle.compute_props([pv], pia, [m])
+    assert pia.contiguous[0] == 0 and p.np[0].tolist() == [2.0, 10.0]
+    assert abs(p.n[0, 0] - 90.0) < 1e-12 and p.n[0, 1] == 10000.0 and pv.nbuffer == 88
+    assert pv.buffer[:40].tolist() == [100 - i for i in range(40)]      # group 2 (61..100) freed from the end first
+    assert pv.buffer[40:88].tolist() == [50 - i for i in range(48)]     # then group 1 from 50 down to 3
+    assert tuple(pia.indexer[0, 0][:4]) == (2, 1, 2, 2) and pia.indexer[0, 0][6] <= 0 and pia.indexer[0, 0][4] <= 0
+    assert tuple(pia.indexer[0, 1][:4]) == (10, 51, 60, 10)
+    oracle.sort_particles(pv, pia, 1, grid=(8.0, 2))
+    p = oracle.compute_props([pv], pia, [m])
+    assert pia.contiguous[0] == 1 and p.np[0].tolist() == [2.0, 10.0] and abs(p.n[0, 0] - 90.0) < 1e-12
+    assert tuple(pia.indexer[0, 0]) == (2, 1, 2, 2, 0, -1, 0) and tuple(pia.indexer[0, 1]) == (10, 3, 12, 10, 0, -1, 0)
+    # 5 particles in group 1, 85 in group 2: target 16 gives 12 post-merge particles, all deletions fit into group 2
+    rows, pv, pia = _buffer_sorting_state(oracle, 5)
+    oc = oracle.Octree(oracle.MID_SPLIT, oracle.INIT_MINMAX)
+    oracle.merge_octree_N2(oracle.Rng.philox(1234, 2), oc, pv, pia, 1, 1, 1, 16)
+    p = oracle.compute_props([pv], pia, [m])
+    assert pia.contiguous[0] == 0 and p.np[0].tolist() == [12.0, 10.0] and abs(p.n[0, 0] - 90.0) < 1e-12 and pv.nbuffer == 78
+    assert pv.buffer[:78].tolist() == [100 - i for i in range(78)]
+    assert tuple(pia.indexer[0, 0]) == (12, 1, 5, 5, 16, 22, 7) and tuple(pia.indexer[0, 1][:4]) == (10, 6, 15, 10)
