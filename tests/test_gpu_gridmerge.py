@@ -156,3 +156,26 @@ def test_grid_merge_argument_errors(mb, ctx):
     pv, pia = mb.ParticleVector(16, ctx), mb.ParticleIndexerArray(1, 1, ctx)
     with pytest.raises(mb.MerzbildError):
         mb.merge_grid_based(mb.PhiloxRng(1), mb.GridN2Merge(32, 32, 32, 3.5), pv, pia, 1, 1, AR, (-1.0, 1.0), (-1.0, 1.0), (-1.0, 1.0))
+
+
+def test_grid_merging_buffer_sorting_reference_kat(mb, oracle, ctx):
+    """test_merging_grid_buffer_sorting.jl:44-204 through the C ABI: the reference's post-merge counts and indexers (2 particles with one
+    velocity cell at 10 thermal speeds; 10 with the inner cell + outer octants at 1 thermal speed; the second case keeps every
+    deletion inside group 2), and the sort that closes the hole between the cells."""
+    from test_oracle_kat_octree_vhs import _buffer_sorting_state
+
+    for n_gr1, mult, expect, expect_c2 in ((50, 10.0, (2, 1, 2, 2), (10, 51, 60, 10)), (5, 1.0, (10, 1, 5, 5, 16, 20, 5), (10, 6, 15, 10))):
+        rows, opv, opia = _buffer_sorting_state(oracle, n_gr1)
+        pv, pia = mirror_to_device(mb, ctx, opv, opia)
+        pp = mb.PhysProps(2, 1, ctx=ctx)
+        mb.compute_props([pv], pia, [AR], pp)
+        mb.merge_grid_based(mb.PhiloxRng(1), mb.GridN2Merge(1, 1, 1, mult), pv, pia, 1, 1, AR, pp)
+        ix, nt, ct = pia.download()
+        assert tuple(ix[0, 0][:len(expect)]) == expect and tuple(ix[0, 1][:4]) == expect_c2 and ct[0] == 0 and nt[0] == expect[0] + 10
+        mb.compute_props([pv], pia, [AR], pp)
+        d = pp.download()
+        assert d["np"][0].tolist() == [float(expect[0]), 10.0] and abs(d["n"][0, 0] - 90.0) < 1e-12 and d["n"][0, 1] == 10000.0
+        mb.sort_particles(None, mb.Grid1DUniform(8.0, 2), pv, pia, 1)
+        ix, nt, ct = pia.download()
+        k = expect[0]
+        assert tuple(ix[0, 0]) == (k, 1, k, k, 0, -1, 0) and tuple(ix[0, 1]) == (10, k + 1, k + 10, 10, 0, -1, 0) and ct[0] == 1

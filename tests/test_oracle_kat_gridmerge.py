@@ -111,3 +111,30 @@ def test_grid_merge_1d_clamps_x(oracle):
         assert tuple(pia.indexer[0, 0][:4]) == (2, 1, 2, 2) and tuple(pia.indexer[0, 1][:4]) == (2, 5, 6, 2) and pia.contiguous[0] == 0
     assert any(v for (g, t), v in outside.items() if not g)      # unclamped: some draw leaves the domain
     assert not any(v for (g, t), v in outside.items() if g)      # clamped: never
+
+
+def test_grid_merging_buffer_sorting_reference_kat(oracle):
+    """test_merging_grid_buffer_sorting.jl:44-204: one velocity cell at 10 thermal speeds merges 90 particles of two index groups to 2;
+    at 1 thermal speed (inner cell + outer octants) to 10; freed slots, pia with a hole, and the sort that closes it."""
+    from test_oracle_kat_octree_vhs import _buffer_sorting_state
+
+    m = AR
+    rows, pv, pia = _buffer_sorting_state(oracle, 50)
+    p = oracle.compute_props([pv], pia, [m])
+    Tv = np.column_stack([p.T[0], p.v[0]])
+    assert oracle.merge_grid_based(oracle.Rng.philox(1234, 1), oracle.GridMerge(1, 1, 1, 10.0), pv, pia, 1, 1, 1, m, T_v=Tv[:1]) == 0
+    p = oracle.compute_props([pv], pia, [m])
+    assert pia.contiguous[0] == 0 and p.np[0].tolist() == [2.0, 10.0] and abs(p.n[0, 0] - 90.0) < 1e-12 and pv.nbuffer == 88
+    assert pv.buffer[:40].tolist() == [100 - i for i in range(40)] and pv.buffer[40:88].tolist() == [50 - i for i in range(48)]
+    assert tuple(pia.indexer[0, 0][:4]) == (2, 1, 2, 2) and pia.indexer[0, 0][6] <= 0 and tuple(pia.indexer[0, 1][:4]) == (10, 51, 60, 10)
+    oracle.sort_particles(pv, pia, 1, grid=(8.0, 2))
+    assert pia.contiguous[0] == 1
+    assert tuple(pia.indexer[0, 0]) == (2, 1, 2, 2, 0, -1, 0) and tuple(pia.indexer[0, 1]) == (10, 3, 12, 10, 0, -1, 0)
+    rows, pv, pia = _buffer_sorting_state(oracle, 5)
+    p = oracle.compute_props([pv], pia, [m])
+    Tv = np.column_stack([p.T[0], p.v[0]])
+    assert oracle.merge_grid_based(oracle.Rng.philox(1234, 2), oracle.GridMerge(1, 1, 1, 1.0), pv, pia, 1, 1, 1, m, T_v=Tv[:1]) == 0
+    p = oracle.compute_props([pv], pia, [m])
+    assert pia.contiguous[0] == 0 and p.np[0].tolist() == [10.0, 10.0] and abs(p.n[0, 0] - 90.0) < 1e-12 and pv.nbuffer == 80
+    assert pv.buffer[:80].tolist() == [100 - i for i in range(80)]
+    assert tuple(pia.indexer[0, 0]) == (10, 1, 5, 5, 16, 20, 5) and tuple(pia.indexer[0, 1][:4]) == (10, 6, 15, 10)
