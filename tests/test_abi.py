@@ -87,3 +87,47 @@ def test_julia_shim_binds_the_header(mb):
     assert sorted(calls) == _declared()
     for name, arities in calls.items():
         assert arities == {len(mb.SIGNATURES[name][1])}, (name, arities, len(mb.SIGNATURES[name][1]))
+
+
+def _julia_ccall_types():
+    """(symbol -> list of argument-type tuples) for every ccall of the Julia shim."""
+    src = open(os.path.join(ROOT, "merzbild.jl_b200", "julia", "MerzbildB200.jl")).read()
+    src = re.sub(r"#[^\n]*", "", src)
+    out = {}
+    for m in re.finditer(r"ccall\(\(:(mb_[A-Za-z0-9_]+),\s*libmb\),\s*([A-Za-z0-9_{}]+),\s*\(", src):
+        i, depth = m.end(), 1
+        while depth:
+            depth += {"(": 1, ")": -1}.get(src[i], 0)
+            i += 1
+        body = src[m.end():i - 1]
+        flat, d = "", 0
+        for ch in body:
+            d += {"{": 1, "}": -1}.get(ch, 0)
+            flat += ch if not (ch == "," and d) else ";"
+        types = tuple(t.strip() for t in flat.split(",") if t.strip())
+        out.setdefault(m.group(1), []).append((m.group(2), types))
+    return out
+
+
+def test_julia_shim_argument_types_match_the_ctypes_mirror(mb):
+    """Position by position, every ccall of the Julia shim passes the same KIND of argument (pointer, Int64, Int32, UInt32, UInt64,
+    Float64, Cint) as the ctypes signature the GPU tests exercise, and declares the same return kind."""
+    def kind_py(t):
+        if t in (C.c_void_p, C.c_char_p) or (isinstance(t, type) and issubclass(t, C._Pointer)):
+            return "ptr"
+        return {C.c_int64: "i64", C.c_int32: "i32", C.c_uint32: "u32", C.c_uint64: "u64", C.c_double: "f64", C.c_int: "i32"}[t]
+
+    def kind_jl(t):
+        if t.startswith("Ptr{") or t.startswith("Ref{") or t in ("Cstring",):
+            return "ptr"
+        return {"Int64": "i64", "Int32": "i32", "Cint": "i32", "UInt32": "u32", "UInt64": "u64", "Float64": "f64", "Cdouble": "f64"}[t]
+
+    calls = _julia_ccall_types()
+    assert sorted(calls) == _declared()
+    for name, variants in calls.items():
+        res, args = mb.SIGNATURES[name]
+        want = [kind_py(t) for t in args]
+        for ret, types in variants:
+            got = [kind_jl(t) for t in types]
+            assert got == want, (name, got, want)
+            assert kind_jl(ret) == kind_py(res), (name, ret, res)
