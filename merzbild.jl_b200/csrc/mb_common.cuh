@@ -115,6 +115,7 @@ struct mb_ctx {
     void* pc_pv;
     void* pc_pia;
     int pc_species;
+    int pc_general;         // the general sort path filled the moment cache too (k_gen_gather_cells): valid whichever path ran
     // band classification cached by the fused convect kernel (valid while state_gen == cls_gen)
     uint64_t cls_gen;
     void* cls_pv;

@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(128) k_props_reg(PropsArgs a, int n_lo) {
 
 // compute_props_sorted! right after a band sort: the gather pass already holds np, n, vbar and sum w |v - vbar|^2 per cell
 static __global__ void k_props_cached(PropsArgs a, const double* __restrict__ pcache, const int* flags) {
-    if (flags[2] != 0) return;  // the general sort path ran: no cache
+    if (flags != nullptr && flags[2] != 0) return;  // the general sort path ran without filling the cache
     const int64_t nr = a.cell_hi - a.cell_lo + 1;
     for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nr; r += (int64_t)gridDim.x * blockDim.x) {
         const int64_t c = a.cell_lo - 1 + r;
@@ -230,8 +230,9 @@ static int props_launch(mb_ctx* ctx, mb_pv* const* pvs, mb_pia* pia, const doubl
         const int64_t nr = cell_hi - cell_lo + 1;
         if (sorted && ctx->pc_gen == ctx->state_gen && ctx->pc_pv == (void*)pvs[s] && ctx->pc_pia == (void*)pia && ctx->pc_species == (int)s + 1 &&
             ctx->scratch[10] != nullptr) {
-            k_props_cached<<<grid_for(nr, 256), 256, 0, ctx->stream>>>(a, (const double*)ctx->scratch[10], ctx->d_flags);
+            k_props_cached<<<grid_for(nr, 256), 256, 0, ctx->stream>>>(a, (const double*)ctx->scratch[10], ctx->pc_general ? nullptr : ctx->d_flags);
             MB_LAUNCH_CHECK(ctx);
+            if (ctx->pc_general) continue;     // both sort paths fill the cache: nothing left to compute
             a.run_if_flag = ctx->d_flags + 2;  // the regular kernel below only runs if the sort fell back to the general path
         }
         const int64_t avg = (pia->n_bound[s] > 0 ? pia->n_bound[s] : pvs[s]->cap) / (nc > 0 ? nc : 1);

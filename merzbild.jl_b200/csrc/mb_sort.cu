@@ -755,6 +755,62 @@ __global__ void __launch_bounds__(256) k_gen_gather(SoA in, SoA out, const int32
     }
 }
 
+// The gather by destination cell: a warp per cell reads the cell's slice of the permutation, gathers the payload, writes the cell as one
+// coalesced run and accumulates the cell's moments on the way (shifted by the velocity of the cell's first particle, exactly like
+// pass B of the band path), so that compute_props_sorted! right after a general-path sort costs no particle traffic either.
+// Used when the cells are small (the Couette shapes); 0-D cells of thousands of particles take k_gen_gather.
+__global__ void __launch_bounds__(256) k_gen_gather_cells(SoA in, SoA out, const int32_t* __restrict__ perm, const int64_t* __restrict__ start,
+                                                          int64_t n_cells, const int* flags, const int32_t* __restrict__ src,
+                                                          const int32_t* __restrict__ key, int32_t* __restrict__ cell_out, double* __restrict__ pcache) {
+    if (flags[2] == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t c = warp0; c < n_cells; c += nwarps) {
+        const int64_t lo = start[c];
+        const int n = (int)(start[c + 1] - lo);
+        double K1 = 0, K2 = 0, K3 = 0;
+        double an = 0, ax = 0, ay = 0, az = 0, aq = 0;
+        for (int j0 = 0; j0 < n; j0 += 32) {
+            const int j = j0 + lane;
+            double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+            if (j < n) {
+                const int64_t i = perm[lo + j];
+                const int64_t ph = src ? (int64_t)src[i] : i;
+                a0 = in.a[0][ph]; a1 = in.a[1][ph]; a2 = in.a[2][ph]; a3 = in.a[3][ph];
+                const double a4 = in.a[4][ph], a5 = in.a[5][ph], a6 = in.a[6][ph];
+                out.a[0][lo + j] = a0; out.a[1][lo + j] = a1; out.a[2][lo + j] = a2; out.a[3][lo + j] = a3;
+                out.a[4][lo + j] = a4; out.a[5][lo + j] = a5; out.a[6][lo + j] = a6;
+                if (cell_out) cell_out[lo + j] = key[i] + 1;
+            }
+            if (j0 == 0) {  // shift = velocity of the cell's first particle
+                K1 = __shfl_sync(0xffffffffu, a1, 0); K2 = __shfl_sync(0xffffffffu, a2, 0); K3 = __shfl_sync(0xffffffffu, a3, 0);
+            }
+            if (j < n) {
+                const double cx = a1 - K1, cy = a2 - K2, cz = a3 - K3;
+                an += a0; ax += a0 * cx; ay += a0 * cy; az += a0 * cz;
+                aq += a0 * (cx * cx + cy * cy + cz * cz);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            an += __shfl_xor_sync(0xffffffffu, an, o); ax += __shfl_xor_sync(0xffffffffu, ax, o);
+            ay += __shfl_xor_sync(0xffffffffu, ay, o); az += __shfl_xor_sync(0xffffffffu, az, o);
+            aq += __shfl_xor_sync(0xffffffffu, aq, o);
+        }
+        if (lane == 0) {
+            double* pc = pcache + 6 * c;
+            pc[0] = (double)n;
+            if (an > 0.0) {
+                const double mx = ax / an, my = ay / an, mz = az / an;  // mean of (v - K)
+                pc[1] = an; pc[2] = K1 + mx; pc[3] = K2 + my; pc[4] = K3 + mz;
+                pc[5] = aq - an * (mx * mx + my * my + mz * mz);        // sum w |v - vbar|^2
+            } else {
+                pc[1] = 0; pc[2] = 0; pc[3] = 0; pc[4] = 0; pc[5] = 0;
+            }
+        }
+    }
+}
+
 // squash_pia! folded into the sort (grid_sorting.jl:69-71 squashes first): instead of moving the payload to close the holes and then
 // moving it again in the sort, only the map logical (squashed) position -> physical position is built (4 B per particle).  The
 // squashed order walks group 1 of all cells, then group 2 of all cells (particles.jl:622-682); newlo = exclusive scan of the segment
@@ -995,6 +1051,7 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
         if (r) return r;
     }
     // general path (every kernel returns immediately unless flags[2] != 0)
+    bool gather_cells = false;
     {
         ProfScope ps(ctx, PROF_SORT_GENERAL);
         S.perm = (int32_t*)ctx_scratch(ctx, 3, (size_t)cap * 4);
@@ -1038,7 +1095,12 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
             k_gen_sort_segments<<<gseg, 256, 0, st>>>(S.perm, S.start, nc, S.flags, cpb);
         }
         MB_LAUNCH_CHECK(ctx);
-        k_gen_gather<<<pgrid, 256, 0, st>>>(pv->cur, pv->alt, S.perm, S.start + nc, S.flags, src, S.key, use_x ? nullptr : pv->cell);
+        gather_cells = nb / (nc > 0 ? nc : 1) <= 2048;  // small cells: gather by cell and cache the cell moments
+        if (gather_cells)
+            k_gen_gather_cells<<<grid_for(nc * 32, 256, 8), 256, 0, st>>>(pv->cur, pv->alt, S.perm, S.start, nc, S.flags, src, S.key,
+                                                                        use_x ? nullptr : pv->cell, B.pcache);
+        else
+            k_gen_gather<<<pgrid, 256, 0, st>>>(pv->cur, pv->alt, S.perm, S.start + nc, S.flags, src, S.key, use_x ? nullptr : pv->cell);
         MB_LAUNCH_CHECK(ctx);
     }
     // ping-pong
@@ -1054,7 +1116,8 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
     // the cached moments are valid only if the band path ran (device flag 2 == 0): the props kernel checks the flag itself
     ctx->state_gen++;
     ctx->cls_gen = 0;
-    ctx->pc_gen = try_band ? ctx->state_gen : 0;
+    ctx->pc_gen = (try_band || gather_cells) ? ctx->state_gen : 0;
+    ctx->pc_general = gather_cells ? 1 : 0;
     ctx->pc_pv = pv; ctx->pc_pia = pia; ctx->pc_species = (int)species;
     pia->contiguous[s] = 1;      // grid_sorting.jl:112
     pia->contig_pending[s] = 0;

@@ -144,6 +144,41 @@ def test_sort_large_cell_segments(mb, oracle, ctx):
 
 
 # ------------------------------------------------------------------------------------------------------------ props
+@pytest.mark.parametrize("n,n_cells", [(20000, 37), (3000, 64), (50000, 5)])
+def test_props_after_general_sort_use_the_cached_moments(mb, oracle, ctx, n, n_cells):
+    """compute_props_sorted! right after a general-path sort of small cells reads the moments the gather-by-cell pass cached (no particle
+    traffic); they must match the oracle's two-pass values like the band path's do (1e-10 on T, 1e-12 on n and v)."""
+    rng = np.random.default_rng(n + n_cells)
+    L = 2.0
+    rows = maxwellian_rows(rng, n, L, vw=True)
+    rows[:, 1:4] += np.array([400.0, -300.0, 150.0])  # a drift: the shifted one-pass sums must not lose digits
+    opv, opia = oracle_state(oracle, rows, n_cells, capacity=n)
+    pv, pia = mirror_to_device(mb, ctx, opv, opia)
+    g = mb.Grid1DUniform(L, n_cells)
+    mb.sort_particles(None, g, pv, pia, 1)
+    oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+    assert ctx.sort_last_path == 2
+    pp = mb.PhysProps(n_cells, 1, ctx=ctx)
+    l0 = ctx.kernel_launches
+    mb.compute_props_sorted([pv], pia, [AR], pp)
+    if n // n_cells <= 2048:
+        assert ctx.kernel_launches - l0 == 1  # the cached kernel only
+    d, o = pp.download(), oracle.compute_props_sorted([opv], opia, [AR])
+    np.testing.assert_array_equal(d["np"], o.np)
+    np.testing.assert_allclose(d["n"], o.n, rtol=1e-13)
+    np.testing.assert_allclose(d["v"], o.v, rtol=1e-12, atol=1e-12 * 500)
+    np.testing.assert_allclose(d["T"], o.T, rtol=1e-10)
+    # touching the particles in between voids the cache: the regular kernels run and give the same numbers
+    pv.set_logical(1, pv.logical(1, 1))
+    l0 = ctx.kernel_launches
+    mb.compute_props_sorted([pv], pia, [AR], pp)
+    if n // n_cells <= 2048:
+        assert ctx.kernel_launches - l0 > 1
+    d2 = pp.download()
+    np.testing.assert_allclose(d2["T"], o.T, rtol=1e-12)
+    np.testing.assert_allclose(d2["v"], o.v, rtol=1e-12, atol=1e-12 * 500)
+
+
 def test_compute_props_sorted_chunks_reference_kat(mb, ctx):
     """test/test_chunking.jl:57-105 through the C ABI: a cell chunk only touches its own cells (the others keep their values), the
     grid variant of a PhysProps(...; ndens_not_Np=true) divides by the cell volume."""
