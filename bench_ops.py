@@ -222,7 +222,8 @@ def main():
         tot = 0.0
         # ntc! gathers only the picked pairs and the merge only touches cells above the threshold: no per-particle byte count for them;
         # the sort is the general path with the squash folded in (key 4 + map 4 + perm 4 + record 56 read + 56 written)
-        for k, bpp in (("ntc", None), ("merge", None), ("convect", 44), ("sort", 124), ("props", 32)):
+        # props: the general path's gather by cell has cached the moments, so compute_props_sorted! moves no particle data
+        for k, bpp in (("ntc", None), ("merge", None), ("convect", 44), ("sort", 124), ("props", None)):
             v = acc[k]
             tot += sum(v) / len(v)
             report("C4 step: " + k, "%d cells, ~%.3g particles, mean of steps %d-%d" % (nx, n_mean, nsteps // 2 + 1, nsteps), int(n_mean), sum(v) / len(v), bpp,
