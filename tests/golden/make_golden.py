@@ -6,6 +6,11 @@ The fixtures are DATA the reference's own tests hold for the hot path (no refere
                               (50 cells, steps 14 001-50 000 of in.Couette) the reference validates its 1-D Couette runs against.
   * reference_vectors.json -- known-answer vectors quoted from the reference's test files (file:line given per entry) and
                               physical constants from data/*.toml, used to pin the CPU oracle.
+  * reference_histories.json -- time histories OUTPUT BY THE REFERENCE ITSELF: its committed golden runs test/data/*.nc (netCDF-4 files
+                              its regression tests compare against to 1e-13), read with the small HDF5 reader hdf5_min.py: 0-D temperature /
+                              moment histories (2 species, BKW with every collision + merging variant) and the 1-D Couette snapshots
+                              (cell profiles and wall properties every 1000 steps).  The oracle is held to them at distribution level
+                              (different generator, same physics): tests/test_oracle_reference_runs.py.
 Run:  python tests/golden/make_golden.py   (idempotent; commit the JSON it writes)
 """
 import json
@@ -80,8 +85,53 @@ def vectors():
     }
 
 
+def histories():
+    import sys
+
+    sys.path.insert(0, HERE)
+    from hdf5_min import H5File
+
+    data = os.path.join(REF, "test", "data")
+
+    def rd(name):
+        return H5File(os.path.join(data, name + ".nc"))
+
+    def lst(a):
+        return [float(x) for x in a.ravel()] if a.ndim == 1 else [lst(r) for r in a]
+
+    out = {"note": "arrays are in netCDF (C) order of the reference files: [timestep][species][cell](component)"}
+    # 0-D, two species (test/test_2species.jl, test/test_2species_varweight_octree.jl): every 25th of 801 records
+    for key, name in (("two_species", "2species_seed1234"), ("two_species_varweight_octree", "2species_varweight_octree_seed1234")):
+        f = rd(name)
+        sl = slice(0, 801, 25)
+        out[key] = {"source": f"test/data/{name}.nc", "timestep": lst(f.read("timestep")[sl]), "T": lst(f.read("T")[sl, :, 0]),
+                    "np": lst(f.read("np")[sl, :, 0]), "ndens": lst(f.read("ndens")[sl, :, 0])}
+    # 0-D BKW (test/test_bkw.jl, test_bkw_varweight_octree.jl, test_bkw_varweight_grid.jl, test_bkw_varweight_octree_swpm.jl): every 10th of 501
+    for key, name in (("bkw_20k", "bkw_20k_seed1234"), ("bkw_vw_octree", "bkw_vw_octree_seed1234"), ("bkw_vw_grid", "bkw_vw_grid_seed1234"),
+                      ("bkw_vw_octree_swpm", "bkw_vw_octree_swpm_seed1234")):
+        f = rd(name)
+        sl = slice(0, 501, 10)
+        out[key] = {"source": f"test/data/{name}.nc", "timestep": lst(f.read("timestep")[sl]), "moment_powers": [int(x) for x in f.read("moment_powers")],
+                    "moments": lst(f.read("moments")[sl, 0, 0, :]), "np": lst(f.read("np")[sl, 0, 0]), "T": lst(f.read("T")[sl, 0, 0]),
+                    "ndens": lst(f.read("ndens")[sl, 0, 0])}
+    # 1-D Couette, 50 cells (test/test_1D_couette*.jl): snapshots every 1000 steps, cell profiles and wall properties
+    pre = "couette_0.0005_50_500.0_300.0_"
+    for key, name in (("couette", "1000"), ("couette_vw200to150", "1000_vw200to150"), ("couette_vw200to150_swpm", "1000_vw200to150_swpm"),
+                      ("couette_fp_linear", "100_fp_linear"), ("couette_vw150to100_resort", "500_vw150to100_resort")):
+        f = rd(pre + name)
+        out[key] = {"source": f"test/data/{pre}{name}.nc", "timestep": lst(f.read("timestep")), "np": lst(f.read("np")[:, 0, :]),
+                    "ndens": lst(f.read("ndens")[:, 0, :]), "T": lst(f.read("T")[:, 0, :]), "v": lst(f.read("v")[:, 0, :, :])}
+        sname = pre + name + "_surf"
+        if os.path.exists(os.path.join(data, sname + ".nc")):
+            g = rd(sname)
+            out[key]["surf"] = {"source": f"test/data/{sname}.nc", "timestep": lst(g.read("timestep")),
+                                **{k: lst(g.read(k)[:, 0]) for k in ("np", "flux_incident", "flux_reflected", "force", "normal_pressure",
+                                                                     "shear_pressure", "kinetic_energy_flux")}}
+    return out
+
+
 if __name__ == "__main__":
-    for name, obj in (("sparta_couette.json", sparta()), ("reference_vectors.json", vectors())):
+    for name, obj in (("sparta_couette.json", sparta()), ("reference_vectors.json", vectors()), ("reference_histories.json", histories())):
         with open(os.path.join(HERE, name), "w") as f:
             json.dump(obj, f, indent=1)
         print("wrote", name)
