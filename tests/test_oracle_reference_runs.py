@@ -155,3 +155,92 @@ def test_bkw_moment_history_is_a_draw_of_the_oracle_ensemble(oracle, ref, key, t
     span = off_k.max(0) - off_k.min(0)
     off = rel(M_ref).mean(0)
     assert np.all(off < off_k.max(0) + span) and np.all(off > off_k.min(0) - span), (off, off_k.min(0), off_k.max(0))
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# 1-D Couette flow, 50 cells: snapshots every 1000 steps
+# ---------------------------------------------------------------------------------------------------------------------------------
+def _couette_run(oracle, seed, variant, n_steps, ppc, every=1000):
+    """The time loops of test/test_1D_couette.jl:64-95 ("ntc"), test_1D_couette_varweight.jl:62-105 ("vw": octree merge 200 -> 150 per
+    cell), test_1D_couette_varweight_swpm.jl:66-100 ("swpm": G = 1.5, same merge), test_1D_couette_varweight_index_resort.jl:62-114
+    ("resort": merge 150 -> 100, sigma_g_w_max estimated at the merged weight, restore_particle_ordering! every 500 steps) and
+    test_1D_couette_fp.jl:56-76 ("fp").  Returns snapshots [record][quantity][cell] of (np, n, T, vy)."""
+    m = oracle.MASS["Ar"]
+    it = oracle.interaction("Ar", "Ar")
+    T_wall, v_wall, L, ndens, nx, dt = 300.0, 500.0, 5e-4, 5e22, 50, 2.59e-9
+    V = L / nx
+    Fnum = V * ndens / ppc
+    thr, tgt = {"vw": (200, 150), "swpm": (200, 150), "resort": (150, 100)}.get(variant, (0, 0))
+    grid, walls = (L, nx), (T_wall, T_wall, -v_wall, v_wall, 1.0, 1.0)
+    pv, pia = oracle.OPV(ppc * nx), oracle.OPIA(nx, 1)
+    oracle.sample_equal_weight_grid(oracle.Rng.seq(3000 + seed), grid, pv, pia, 1, m, ndens, T_wall, Fnum)
+    F_cf = {"swpm": 1.0, "resort": Fnum * ppc / 100}.get(variant, Fnum)
+    cf = oracle.CF(nx, oracle.estimate_sigma_g_w_max(it, m, m, T_wall, T_wall, F_cf))
+    oc = oracle.Octree(oracle.MID_SPLIT, oracle.INIT_MINMAX, oracle.BOUNDS_INHERIT, 6000, 10)
+    rng = oracle.Rng.seq(seed)
+    if thr:
+        oracle.merge_octree_N2(rng, oc, pv, pia, 1, nx, 1, tgt, threshold=thr, grid=grid)
+        oracle.squash_pia(pv, pia, 1)
+
+    def snap():
+        p = oracle.compute_props([pv], pia, [m])
+        return np.stack([p.np[0], p.n[0], p.T[0], p.v[0, :, 1]])
+
+    out = [snap()]
+    for t in range(1, n_steps + 1):
+        if variant == "fp":
+            oracle.fp_linear(rng, it, m, pv, pia, 1, nx, 1, dt, V)
+        elif variant == "swpm":
+            oracle.swpm(rng, cf, it, pv, pia, 1, nx, 1, 1.5, dt, V)
+        else:
+            oracle.ntc(rng, cf, it, pv, pia, 1, nx, 1, dt, V)
+        if thr:
+            oracle.merge_octree_N2(rng, oc, pv, pia, 1, nx, 1, tgt, threshold=thr, grid=grid, squash_after_each=True)
+        oracle.convect_particles(rng, grid, walls, pv, pia, 1, [m], dt)
+        oracle.sort_particles(pv, pia, 1, grid=grid)
+        if variant == "resort" and t % 500 == 0:
+            oracle.restore_particle_ordering(pv)
+            assert oracle.check_unique_index(pv, pia, 1) == (True, 0)
+        if t % every == 0:
+            out.append(snap())
+    if thr:
+        assert pia.check(1) == (True, 0) and oracle.check_unique_index(pv, pia, 1) == (True, 0)
+    return np.array(out)
+
+
+@pytest.mark.parametrize("key,variant,ppc,n_steps,K", [("couette", "ntc", 1000, 3000, 4), ("couette_vw200to150", "vw", 1000, 6000, 6),
+                                                       ("couette_vw200to150_swpm", "swpm", 1000, 4000, 6),
+                                                       ("couette_vw150to100_resort", "resort", 500, 3000, 6),
+                                                       ("couette_fp_linear", "fp", 200, 3000, 4)])
+def test_couette_snapshots_agree_within_the_cell_noise(oracle, ref, key, variant, ppc, n_steps, K):
+    """The reference's golden Couette runs (NTC; NTC + octree merging; SWPM + merging; merging + index re-sorting; Fokker-Planck)
+    record np, n, T, v per cell every 1000 steps.  K oracle runs of the same loop give the mean profile and the per-cell spread of a
+    single run (pooled over cells: relative for n and T, absolute for v_y); the reference snapshot must differ from the mean profile
+    like one more run does: chi^2 / 50 cells < 2.2 per record and quantity (expected 1 +- 0.2), < 1.4 averaged over the records."""
+    r = ref[key]
+    n_rec = n_steps // 1000 + 1
+    assert r["timestep"][:n_rec] == [1000.0 * i for i in range(n_rec)]
+    R = np.stack([np.array(r["np"])[:n_rec], np.array(r["ndens"])[:n_rec], np.array(r["T"])[:n_rec], np.array(r["v"])[:n_rec, :, 1]], 1)
+    ens = np.array([_couette_run(oracle, 10 + s, variant, n_steps, ppc) for s in range(K)])  # [run][record][quantity][cell]
+    merging = variant in ("vw", "swpm", "resort")
+    # exact facts first: particle count at t = 0, total number density at every record
+    if not merging:
+        assert np.all(R[:, 0].sum(1) == 50 * ppc) and np.all(ens[:, :, 0].sum(2) == 50 * ppc)
+        assert np.all(R[0, 0] == ppc) and np.all(ens[:, 0, 0] == ppc)
+    n_tot = 50 * 5e22 * 1e-5
+    assert np.all(np.abs(R[:, 1].sum(1) / n_tot - 1) < 1e-12) and np.all(np.abs(ens[:, :, 1].sum(2) / n_tot - 1) < 1e-12)
+    mean = ens.mean(0)
+    chi = np.zeros((n_rec - 1, 3))
+    for rec in range(1, n_rec):
+        for q, relative in ((1, True), (2, True), (3, False)):
+            scale = mean[rec, q] if relative else 1.0
+            resid = (ens[:, rec, q] - mean[rec, q]) / scale
+            var = (resid ** 2).sum() / ((K - 1) * 50)  # pooled single-run variance
+            d = (R[rec, q] - mean[rec, q]) / scale
+            chi[rec - 1, q - 1] = (d ** 2).mean() / (var * (1.0 + 1.0 / K))
+    assert np.all(chi < 2.2), chi
+    assert np.all(chi.mean(0) < 1.4), chi.mean(0)
+    if merging:  # the per-cell counts stay between the target and the threshold + one step of splits, with the reference's mean
+        assert np.all(R[1:, 0] <= 1.3 * mean[1:, 0].max()) and abs(R[1:, 0].mean() / ens[:, 1:, 0].mean() - 1) < 0.03, (R[1:, 0].mean(), ens[:, 1:, 0].mean())
+    if merging:  # the merged initial state: counts per cell are deterministic up to the sampled velocities -- compare their means
+        assert abs(R[0, 0].mean() / ens[:, 0, 0].mean() - 1) < 0.02, (R[0, 0].mean(), ens[:, 0, 0].mean())
