@@ -3,13 +3,16 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may
 // import, link or execute anything under oracle/.  The product path (libmerzbild_b200.so) never does.
 //
-// Parity pin: the deterministic functions are pinned by the known-answer vectors the reference's own
-// tests hold (tests/test_oracle_kat_*.py restate test/test_grid_sorting.jl, test_convection_1D.jl,
-// test_computes.jl, test_octree_*.jl, test_collision_utils.jl, test_collision_fp.jl, test_pia_contiguous.jl,
-// test_particle_index_sorting.jl, test_indexing*.jl).  The stochastic functions are pinned in distribution
-// (BKW analytic moments test/test_bkw.jl:25-29, T_eq test/test_2species.jl:25, SPARTA Couette profile
-// test/data/external/) because the reference's seeded golden .nc files depend on Julia's StableRNGs bit
-// stream and an HDF5 reader, neither of which exists here: BIT-LEVEL STOCHASTIC PARITY IS UNPINNED.
+// Parity pin: (1) the deterministic functions are pinned by the known-answer vectors the reference's own tests hold
+// (tests/test_oracle_kat_*.py restate test/test_grid_sorting.jl, test_convection_1D.jl, test_computes.jl, test_octree_*.jl,
+// test_collision_utils.jl, test_collision_fp.jl, test_pia_contiguous.jl, test_particle_index_sorting.jl, test_indexing*.jl ...);
+// (2) the stochastic pipeline is pinned BIT-LEVEL by the reference's own seeded golden runs (test/data/*.nc, extracted into
+// tests/golden/reference_histories.json): with the StableRNGs.jl generator restated in philox.hpp the oracle reproduces the 0-D
+// two-species / BKW grid-merging histories and the 1-D Couette runs (NTC, SWPM, octree merging, surface properties, index
+// re-sorting) to round-off at every recorded step (tests/test_oracle_reference_bitlevel.py); (3) what cannot be replayed
+// (octree BKW: tie-breaking on a symmetric lattice; Chi-sampled BKW; Fokker-Planck: Julia's randn tables) is pinned in distribution
+// (tests/test_oracle_reference_runs.py, tests/test_oracle_stat.py: golden histories as draws of the oracle ensemble, BKW analytic
+// moments test/test_bkw.jl:25-29, T_eq test/test_2species.jl:25, SPARTA Couette profile test/data/external/).
 //
 // Every function cites the reference file:line (relative to /root/reference/src) it follows.
 // Indices stored in the containers are 1-based and inclusive exactly as in the reference, so a dump of

@@ -26,6 +26,7 @@ void mbo_philox_stream_doubles(uint64_t seed, uint32_t op, uint32_t substream, u
     for (int64_t i = 0; i < n; i++) out[i] = s.rand();
 }
 void* mbo_rng_create(uint64_t seed) { return new Xoshiro256pp(seed); }
+void* mbo_rng_create_stable(uint64_t seed) { return new Xoshiro256pp(Xoshiro256pp::stable_rng(seed)); }  // StableRNGs.jl StableRNG(seed)
 void mbo_rng_free(void* r) { delete (Xoshiro256pp*)r; }
 double mbo_rng_rand(void* r) { return ((Xoshiro256pp*)r)->rand(); }
 

@@ -312,8 +312,8 @@ template <class R>
 struct SeqSigns {  // sequential draws like the reference: 3 for v then 3 for x
     R& rng;
     void operator()(int64_t, double sv[3], double sx[3]) {
-        for (int d = 0; d < 3; d++) sv[d] = rng.rand() < 0.5 ? -1.0 : 1.0;
-        for (int d = 0; d < 3; d++) sx[d] = rng.rand() < 0.5 ? -1.0 : 1.0;
+        for (int d = 0; d < 3; d++) sv[d] = rng.sign();
+        for (int d = 0; d < 3; d++) sx[d] = rng.sign();
     }
 };
 

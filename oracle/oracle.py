@@ -57,6 +57,7 @@ def lib():
     sig("mbo_philox4x32_10", None, vp, vp, vp)
     sig("mbo_philox_stream_doubles", None, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, i64, vp)
     sig("mbo_rng_create", vp, C.c_uint64)
+    sig("mbo_rng_create_stable", vp, C.c_uint64)
     sig("mbo_rng_free", None, vp)
     sig("mbo_rng_rand", f64, vp)
     sig("mbo_pv_create", vp, i64)
@@ -169,6 +170,12 @@ class Rng:
     @staticmethod
     def seq(seed=1234):
         h = lib().mbo_rng_create(seed)
+        return Rng(RngSpec(0, h, 0, 0, 0), h)
+
+    @staticmethod
+    def stable(seed=1234):
+        """StableRNGs.jl ``StableRNG(seed)``: the generator of the reference's test suite (oracle/philox.hpp)."""
+        h = lib().mbo_rng_create_stable(seed)
         return Rng(RngSpec(0, h, 0, 0, 0), h)
 
     @staticmethod

@@ -78,11 +78,19 @@ struct PhiloxStream {
     }
 };
 
-// xoshiro256++ seeded with splitmix64: a plain sequential generator for the "one rng object passed
-// around" mode of the reference (used by the CPU baseline driver and the statistical tests; the
-// reference's own Xoshiro/StableRNG bit streams are not reproducible here -- see DESIGN.md).
+// The "one rng object passed around" mode of the reference: a plain sequential generator with two engines.
+//   engine 0: xoshiro256++ seeded with splitmix64 (CPU baseline driver, statistical tests);
+//   engine 1: the LehmerRNG of StableRNGs.jl (the generator of the reference's test suite, `StableRNG(seed)`): state =
+//             (seed << 1) | 1 as UInt128, each draw multiplies the state by 0x45a31efc5a35d971261fd0407a968add and returns its high
+//             64 bits; rand(Float64) = reinterpret(Float64, 0x3ff0000000000000 | (u & 0x000fffffffffffff)) - 1.0 (Julia's generic
+//             CloseOpen12 path for an rng whose native 52-bit type is UInt64); rand(rng, [-1.0, 1.0]) indexes the 2-element array with
+//             the low bit of one draw (SamplerRangeFast, mask 1).  Pinned by the reference's golden runs: with this engine the oracle
+//             reproduces test/data/*.nc of the reference to round-off (tests/test_oracle_reference_bitlevel.py).
+// (The struct keeps its historical name: every operator template of the oracle takes it by reference.)
 struct Xoshiro256pp {
     uint64_t s[4];
+    int engine = 0;
+    unsigned __int128 lehmer = 1;
     explicit Xoshiro256pp(uint64_t seed = 1234) {
         uint64_t z = seed;
         for (int i = 0; i < 4; i++) {
@@ -93,8 +101,18 @@ struct Xoshiro256pp {
             s[i] = x ^ (x >> 31);
         }
     }
+    static Xoshiro256pp stable_rng(uint64_t seed) {
+        Xoshiro256pp r(seed);
+        r.engine = 1;
+        r.lehmer = ((unsigned __int128)seed << 1) | 1;
+        return r;
+    }
     static inline uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
     inline uint64_t next() {
+        if (engine == 1) {
+            lehmer *= ((unsigned __int128)0x45a31efc5a35d971ull << 64) | 0x261fd0407a968addull;
+            return (uint64_t)(lehmer >> 64);
+        }
         const uint64_t result = rotl(s[0] + s[3], 23) + s[0];
         const uint64_t t = s[1] << 17;
         s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3];
@@ -102,7 +120,20 @@ struct Xoshiro256pp {
         s[3] = rotl(s[3], 45);
         return result;
     }
-    inline double rand() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+    inline double rand() {
+        const uint64_t u = next();
+        if (engine == 1) {
+            const uint64_t bits = 0x3ff0000000000000ull | (u & 0x000fffffffffffffull);
+            double d;
+            __builtin_memcpy(&d, &bits, 8);
+            return d - 1.0;
+        }
+        return (double)(u >> 11) * (1.0 / 9007199254740992.0);
+    }
+    inline double sign() {  // one element of direction_signs = [-1.0, 1.0] (constants.jl:39)
+        if (engine == 1) return (next() & 1) ? 1.0 : -1.0;  // SamplerRangeFast over 1:2: index = 1 + (u & 1)
+        return rand() < 0.5 ? -1.0 : 1.0;
+    }
 };
 
 }  // namespace mbo

@@ -105,7 +105,7 @@ def histories():
         f = rd(name)
         sl = slice(0, 801, 25)
         out[key] = {"source": f"test/data/{name}.nc", "timestep": lst(f.read("timestep")[sl]), "T": lst(f.read("T")[sl, :, 0]),
-                    "np": lst(f.read("np")[sl, :, 0]), "ndens": lst(f.read("ndens")[sl, :, 0])}
+                    "np": lst(f.read("np")[sl, :, 0]), "ndens": lst(f.read("ndens")[sl, :, 0]), "v": lst(f.read("v")[sl, :, 0, :])}
     # 0-D BKW (test/test_bkw.jl, test_bkw_varweight_octree.jl, test_bkw_varweight_grid.jl, test_bkw_varweight_octree_swpm.jl): every 10th of 501
     for key, name in (("bkw_20k", "bkw_20k_seed1234"), ("bkw_vw_octree", "bkw_vw_octree_seed1234"), ("bkw_vw_grid", "bkw_vw_grid_seed1234"),
                       ("bkw_vw_octree_swpm", "bkw_vw_octree_swpm_seed1234")):
@@ -113,7 +113,9 @@ def histories():
         sl = slice(0, 501, 10)
         out[key] = {"source": f"test/data/{name}.nc", "timestep": lst(f.read("timestep")[sl]), "moment_powers": [int(x) for x in f.read("moment_powers")],
                     "moments": lst(f.read("moments")[sl, 0, 0, :]), "np": lst(f.read("np")[sl, 0, 0]), "T": lst(f.read("T")[sl, 0, 0]),
-                    "ndens": lst(f.read("ndens")[sl, 0, 0])}
+                    "ndens": lst(f.read("ndens")[sl, 0, 0]), "v": lst(f.read("v")[sl, 0, 0, :]),
+                    "first_step": {"np": int(f.read("np")[1, 0, 0]), "T": float(f.read("T")[1, 0, 0]), "ndens": float(f.read("ndens")[1, 0, 0]),
+                                   "moments": lst(f.read("moments")[1, 0, 0, :])}}
     # 1-D Couette, 50 cells (test/test_1D_couette*.jl): snapshots every 1000 steps, cell profiles and wall properties
     pre = "couette_0.0005_50_500.0_300.0_"
     for key, name in (("couette", "1000"), ("couette_vw200to150", "1000_vw200to150"), ("couette_vw200to150_swpm", "1000_vw200to150_swpm"),
