@@ -8,9 +8,9 @@
 // test_collision_utils.jl, test_collision_fp.jl, test_pia_contiguous.jl, test_particle_index_sorting.jl, test_indexing*.jl ...);
 // (2) the stochastic pipeline is pinned BIT-LEVEL by the reference's own seeded golden runs (test/data/*.nc, extracted into
 // tests/golden/reference_histories.json): with the StableRNGs.jl generator restated in philox.hpp the oracle reproduces the 0-D
-// two-species / BKW grid-merging histories and the 1-D Couette runs (NTC, SWPM, octree merging, surface properties, index
-// re-sorting) to round-off at every recorded step (tests/test_oracle_reference_bitlevel.py); (3) what cannot be replayed
-// (octree BKW: tie-breaking on a symmetric lattice; Chi-sampled BKW; Fokker-Planck: Julia's randn tables) is pinned in distribution
+// two-species / BKW grid-merging histories and the 1-D Couette runs (NTC, SWPM, Fokker-Planck, octree merging, surface properties,
+// index re-sorting) to round-off at every recorded step (tests/test_oracle_reference_bitlevel.py); (3) what cannot be replayed
+// (octree BKW: tie-breaking on a symmetric lattice; Chi-sampled BKW) is pinned in distribution
 // (tests/test_oracle_reference_runs.py, tests/test_oracle_stat.py: golden histories as draws of the oracle ensemble, BKW analytic
 // moments test/test_bkw.jl:25-29, T_eq test/test_2species.jl:25, SPARTA Couette profile test/data/external/).
 //

@@ -212,6 +212,7 @@ void mbo_fp_linear(const mbo_rng_spec* rs, const double* it8, double mass, void*
         if (rs->kind == 0) {
             Xoshiro256pp& r = *(Xoshiro256pp*)rs->seq;
             auto src = [&](int64_t, double o[3]) {  // three sequential normals per particle like randn(rng) x3 (collision_fp.jl:164-170)
+                if (r.engine == 1) { o[0] = r.randn(); o[1] = r.randn(); o[2] = r.randn(); return; }  // StableRNG: Julia's ziggurat
                 for (int d = 0; d < 3; d += 2) {
                     const double u1 = std::max(1e-300, r.rand()), u2 = r.rand();
                     const double rr = std::sqrt(-2.0 * std::log(u1));

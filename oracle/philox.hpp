@@ -8,6 +8,7 @@
 // one sequential stream, so both the oracle and the CUDA path key an independent stream per
 // (seed, operator, substream, timestep, entity) -- see DESIGN.md "RNG convention".
 #pragma once
+#include <cmath>
 #include <cstdint>
 
 namespace mbo {
@@ -129,6 +130,54 @@ struct Xoshiro256pp {
             return d - 1.0;
         }
         return (double)(u >> 11) * (1.0 / 9007199254740992.0);
+    }
+    // randn(rng) of Julia's Random (stdlib normal.jl) for engine 1: 256-strip ziggurat of Marsaglia & Tsang as tabulated by Octave's
+    // randmtzig (r = 3.6541528853610088, 51-bit magnitude + sign bit from one 52-bit draw).  The tables are regenerated here from the
+    // construction (Julia hard-codes the resulting literals).  With the strip area at full precision (0.004928673233974655; randmtzig's
+    // source quotes it to 12 digits, 0.00492867323399, which shifts every sample by 3e-12 relative) the reference's golden Fokker-Planck
+    // run is reproduced to ~1e-14 relative with every cell count exact over 3000 steps; a residual last-bit difference in a table entry
+    // moves a sample by an ulp and a decision with probability ~2^-51.
+    struct Ziggurat {
+        uint64_t ki[256];
+        double wi[256], fi[256];
+        Ziggurat() {
+            const double R = 3.6541528853610088, NM = 2251799813685248.0;  // 2^51
+            const double AREA = 0.004928673233974655;  // r f(r) + int_r^inf f: the strip area to full precision (see above)
+            double x1 = R;
+            wi[255] = x1 / NM;
+            fi[255] = std::exp(-0.5 * x1 * x1);
+            ki[0] = (uint64_t)(x1 * fi[255] / AREA * NM);
+            wi[0] = AREA / fi[255] / NM;
+            fi[0] = 1.0;
+            for (int i = 254; i > 0; i--) {
+                const double x = std::sqrt(-2.0 * std::log(AREA / x1 + fi[i + 1]));
+                ki[i + 1] = (uint64_t)(x / x1 * NM);
+                wi[i] = x / NM;
+                fi[i] = std::exp(-0.5 * x * x);
+                x1 = x;
+            }
+            ki[1] = 0;
+        }
+    };
+    inline double randn() {
+        static const Ziggurat z;
+        const double R = 3.6541528853610087963519472518, INV_R = 1.0 / R;
+        while (true) {
+            const uint64_t r = next() & 0x000fffffffffffffull;
+            const int64_t rabs = (int64_t)(r >> 1);
+            const int idx = (int)(rabs & 0xFF);
+            const double x = (double)((r & 1) ? -rabs : rabs) * z.wi[idx];
+            if ((uint64_t)rabs < z.ki[idx]) return x;
+            if (idx == 0) {
+                while (true) {
+                    const double xx = -INV_R * std::log(rand());
+                    const double yy = -std::log(rand());
+                    if (yy + yy > xx * xx) return ((rabs >> 8) & 1) ? -R - xx : R + xx;
+                }
+            } else if ((z.fi[idx - 1] - z.fi[idx]) * rand() + z.fi[idx] < std::exp(-0.5 * x * x)) {
+                return x;
+            }
+        }
     }
     inline double sign() {  // one element of direction_signs = [-1.0, 1.0] (constants.jl:39)
         if (engine == 1) return (next() & 1) ? 1.0 : -1.0;  // SamplerRangeFast over 1:2: index = 1 + (u & 1)
