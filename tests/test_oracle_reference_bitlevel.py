@@ -4,7 +4,7 @@ oracle/philox.hpp (LehmerRNG: 128-bit multiplicative congruential state, high 64
 for rand(Float64), low bit for rand(rng, [-1.0, 1.0])) the oracle, driven through the same call sequence as the reference's test
 scripts, lands on the golden files' values to round-off -- every recorded step, every cell:
 
-  0-D  test_2species.jl                           sampling + ntc! (1 and 2 species, equal weights), 800 steps
+  0-D  test_2species.jl, test_2species_equal_weight.jl   sampling + ntc! / ntc_equal_weight! (1 and 2 species), 800 steps
   0-D  test_2species_varweight_octree.jl          variable-weight ntc! (splits) + merge_octree_N2_based!, 800 steps, ~130 merges
   0-D  test_bkw_varweight_grid.jl                 sample_on_grid!(bkw) + ntc! + merge_grid_based!, total moments M4..M10, 500 steps
   1-D  test_1D_couette.jl                         sample on grid + ntc! + convect_particles! (diffuse walls) + sort_particles!
@@ -50,8 +50,9 @@ def test_stable_rng_stream(oracle):
         assert rng.rand() == expect
 
 
-def _two_species(oracle, variable_weight):
-    """test/test_2species.jl:27-71, test/test_2species_varweight_octree.jl:14-83"""
+def _two_species(oracle, variable_weight, equal_weight_api=False):
+    """test/test_2species.jl:27-71, test/test_2species_varweight_octree.jl:14-83; equal_weight_api: ntc_equal_weight! instead of ntc!
+    (test/test_2species_equal_weight.jl:52-66, same golden file)"""
     mA, mH = oracle.MASS["Ar"], oracle.MASS["He"]
     TA, TH, dt, V = 3000.0, 360.0, 2.5e-3, 1.0
     nA, nH, FA, FH = (4000, 4000, 5e11, 5e12) if variable_weight else (400, 4000, 5e12, 5e12)
@@ -69,9 +70,9 @@ def _two_species(oracle, variable_weight):
     out = [oracle.compute_props([pvA, pvH], pia, [mA, mH])]
     n_merges = 0
     for ts in range(1, 801):
-        oracle.ntc(rng, cfAA, itAA, pvA, pia, 1, 1, 1, dt, V)
-        oracle.ntc2(rng, cfHA, itHA, pvH, pvA, pia, 1, 1, 2, 1, dt, V)
-        oracle.ntc(rng, cfHH, itHH, pvH, pia, 1, 1, 2, dt, V)
+        oracle.ntc(rng, cfAA, itAA, pvA, pia, 1, 1, 1, dt, V, equal_weight=equal_weight_api)
+        oracle.ntc2(rng, cfHA, itHA, pvH, pvA, pia, 1, 1, 2, 1, dt, V, equal_weight=equal_weight_api)
+        oracle.ntc(rng, cfHH, itHH, pvH, pia, 1, 1, 2, dt, V, equal_weight=equal_weight_api)
         if variable_weight:
             for s, (pv, n0) in enumerate(((pvA, nA), (pvH, nH))):
                 if pia.indexer[s, 0, 0] > round(1.2 * n0):
@@ -82,12 +83,13 @@ def _two_species(oracle, variable_weight):
     return out, n_merges
 
 
-@pytest.mark.parametrize("key,variable_weight", [("two_species", False), ("two_species_varweight_octree", True)])
-def test_two_species_runs_reproduce_the_golden_files(oracle, ref, key, variable_weight):
+@pytest.mark.parametrize("key,variable_weight,eq_api", [("two_species", False, False), ("two_species", False, True),
+                                                        ("two_species_varweight_octree", True, False)])
+def test_two_species_runs_reproduce_the_golden_files(oracle, ref, key, variable_weight, eq_api):
     """T to 9.3e-13 K (the reference's own tolerance, test_2species_varweight_octree.jl:93-95), v to 1e-12 m/s, n to 6e-15 relative,
     particle counts exactly -- at every 25th of the 800 steps, through ~130 octree merges in the variable-weight run."""
     r = ref[key]
-    out, n_merges = _two_species(oracle, variable_weight)
+    out, n_merges = _two_species(oracle, variable_weight, eq_api)
     assert len(out) == 33 and (n_merges > 100) == variable_weight
     for rec, p in enumerate(out):
         assert np.array_equal(p.np[:, 0], r["np"][rec])
