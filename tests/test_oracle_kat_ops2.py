@@ -268,3 +268,53 @@ def test_chunk_exchange_moves_particles_to_their_owner(oracle):
         got.append(rows)
     ids = np.sort(np.concatenate(got)[:, 0])
     np.testing.assert_array_equal(ids, np.sort(np.concatenate(allrows)[:, 0]))
+
+
+def test_chunked_varweight_couette_loses_no_particles(oracle):
+    """test/test_couette_varweight_octree_chunking.jl:5-139 restated: 50 cells in 4 chunks, each with its own particle vector, indexer,
+    octree and StableRNG(1234 + chunk); 400 particles per cell merged to 150 at t = 0; 50 steps of ntc! + merge (180 -> 150, squash after
+    every merged cell) + convect + sort per chunk, then exchange_particles! and sort_particles_after_exchange!.  At every step the
+    indexers are consistent, no index is used twice, and the total number density is conserved to 4 eps (:137)."""
+    m, it = oracle.MASS["Ar"], oracle.interaction("Ar", "Ar")
+    T_wall, v_wall, L, ndens, nx, ppc, dt = 300.0, 500.0, 5e-4, 5e22, 50, 400, 2.59e-9
+    n_chunks, thr, tgt = 4, 180, 150
+    V = L / nx
+    Fnum = V * ndens / ppc
+    grid, walls = (L, nx), (T_wall, T_wall, -v_wall, v_wall, 1.0, 1.0)
+    chunks = oracle.chunks(nx, n_chunks)
+    assert chunks == [(1, 13), (14, 26), (27, 38), (39, 50)]  # ChunkSplitters: the first nx mod n chunks are one longer
+    rngs = [oracle.Rng.stable(1234 + i) for i in range(n_chunks)]
+    pvs = [oracle.OPV(int(ppc * (hi - lo + 1) * 1.5)) for lo, hi in chunks]
+    pias = [oracle.OPIA(nx, 1) for _ in chunks]
+    ocs = [oracle.Octree(oracle.MID_SPLIT, oracle.INIT_MINMAX, oracle.BOUNDS_INHERIT, 6000, 10) for _ in chunks]
+    cfs = [oracle.CF(nx, oracle.estimate_sigma_g_w_max(it, m, m, T_wall, T_wall, Fnum)) for _ in chunks]
+    ex = oracle.Exchanger(chunks, nx)
+    for c, (lo, hi) in enumerate(chunks):
+        oracle.sample_equal_weight_grid(rngs[c], grid, pvs[c], pias[c], 1, m, ndens, T_wall, Fnum, lo, hi)
+        oracle.merge_octree_N2(rngs[c], ocs[c], pvs[c], pias[c], lo, hi, 1, tgt, grid=grid)
+        oracle.squash_pia(pvs[c], pias[c], 1)
+        assert np.all(pias[c].indexer[0, lo - 1:hi, 0] <= tgt) and pias[c].n_total[0] == pias[c].indexer[0, :, 0].sum()
+    props = oracle.Props(nx, 1)
+    moved = 0
+    for t in range(50):
+        for c, (lo, hi) in enumerate(chunks):
+            assert pias[c].check(1) == (True, 0)
+            assert oracle.check_unique_index(pvs[c], pias[c], 1) == (True, 0)
+        for c, (lo, hi) in enumerate(chunks):
+            for cell in range(lo, hi + 1):
+                oracle.ntc(rngs[c], cfs[c], it, pvs[c], pias[c], cell, cell, 1, dt, V)
+                if pias[c].indexer[0, cell - 1, 0] > thr:
+                    oracle.merge_octree_N2(rngs[c], ocs[c], pvs[c], pias[c], cell, cell, 1, tgt, grid=grid)
+                    oracle.squash_pia(pvs[c], pias[c], 1)
+            oracle.convect_particles(rngs[c], grid, walls, pvs[c], pias[c], 1, [m], dt)
+            ex.reset(c + 1)
+            oracle.sort_particles(pvs[c], pias[c], 1, grid=grid)
+            own = pias[c].indexer[0, lo - 1:hi, 0].sum()
+            moved += int(pias[c].n_total[0] - own)  # particles now sitting in cells of other chunks
+        ex.exchange(pvs, pias, 1)
+        for c, (lo, hi) in enumerate(chunks):
+            ex.sort_after_exchange(pvs[c], pias[c], c + 1, 1)
+            assert pias[c].n_total[0] == pias[c].indexer[0, lo - 1:hi, 0].sum()  # only own cells are populated afterwards
+            oracle.compute_props_sorted([pvs[c]], pias[c], [m], lo, hi, out=props)
+        assert abs(props.n.sum() - ndens * L) / (ndens * L) < 4 * np.finfo(float).eps, t
+    assert moved > 50  # the exchange did carry particles across chunk borders
