@@ -318,3 +318,127 @@ def test_chunked_varweight_couette_loses_no_particles(oracle):
             oracle.compute_props_sorted([pvs[c]], pias[c], [m], lo, hi, out=props)
         assert abs(props.n.sum() - ndens * L) / (ndens * L) < 4 * np.finfo(float).eps, t
     assert moved > 50  # the exchange did carry particles across chunk borders
+
+
+def test_particle_vector_index_indirection_and_buffer(oracle):
+    """test/test_indexing_particlevector.jl:8-83: pv[i] is particles[index[i]]; a fresh vector has the identity index, zeroed particles
+    and cell ids, and a descending buffer of free slots; resize!(+3) grows every array and pushes the new slots on top of the buffer
+    (buffer == [13, 12, ..., 1]); add_particle! pops one slot per particle."""
+    pv = oracle.OPV(10)
+    assert list(pv.index) == list(range(1, 11)) and len(pv) == 10 and np.all(pv.cell == 0)
+    rows = np.zeros((10, 7))
+    rows[:, 0] = np.arange(1, 11)
+    rows[:, 4] = 10.0 - np.arange(1, 11)
+    rows[:, 6] = 1.0
+    pv.particles[:] = rows
+    got = pv.logical(1, 10)
+    assert np.array_equal(got[:, 0], np.arange(1, 11)) and np.array_equal(got[:, 4], 10.0 - np.arange(1, 11))
+    pv.index[:] = np.arange(10, 0, -1)
+    got = pv.logical(1, 10)
+    assert np.array_equal(got[:, 0], 11.0 - np.arange(1, 11)) and np.array_equal(got[:, 4], np.arange(1, 11) - 1.0)
+    assert np.array_equal(pv.particles[:, 0], np.arange(1, 11))  # the storage itself did not move
+    old_nbuffer = pv.nbuffer
+    pv.resize(13)
+    assert len(pv) == 13 and len(pv.index) == 13 and len(pv.cell) == 13 and len(pv.buffer) == 13 and pv.particles.shape[0] == 13
+    assert pv.nbuffer == old_nbuffer + 3
+    assert list(pv.buffer) == list(range(13, 0, -1))
+
+    pv = oracle.OPV(3)
+    assert np.all(pv.logical(1, 3) == 0.0) and pv.nbuffer == 3
+    pv.add_particle(1, 20.0, [2.0, 2.0, 3.0], [11.0, 12.0, 14.0])
+    got = pv.logical(1, 3)
+    assert list(got[0]) == [20.0, 2.0, 2.0, 3.0, 11.0, 12.0, 14.0] and np.all(got[1:] == 0.0)
+    pv.add_particle(2, 40.0, [2.0, 2.0, 3.0], [11.0, 12.0, 14.0])
+    got = pv.logical(1, 3)
+    assert got[0, 0] == 20.0 and got[1, 0] == 40.0 and np.all(got[2] == 0.0) and pv.nbuffer == 1
+
+
+def test_particle_buffer_lifo_reference_kat(oracle):
+    """test/test_indexing_particlebuffer.jl:15-185: the free-slot buffer after sampling, resize!, and deletions from the end of either
+    group -- exact buffer contents and lengths, number density after each deletion, the emptied indexer (0, -1)."""
+    L = oracle.lib()
+    m = oracle.MASS["Ar"]
+    pv, pia = oracle.OPV(10), oracle.OPIA(1, 1)
+    assert list(pv.buffer) == list(range(10, 0, -1)) and pv.nbuffer == 10
+    rng = oracle.Rng.stable(1234)
+    oracle.sample_equal_weight_cell(rng, pv, pia, 1, 1, 6, m, 237.0, 1e10)
+    assert np.all(pv.logical(1, 6)[:, 0] == 1e10)
+    assert pv.nbuffer == 4 and list(pv.buffer) == list(range(10, 0, -1))
+    pv.resize(14)
+    assert list(pv.index) == list(range(1, 15)) and pv.nbuffer == 8
+    assert list(pv.buffer) == list(range(14, 0, -1))  # new slots go on top: older slots are used up first
+    oracle.sample_equal_weight_cell(rng, pv, pia, 1, 1, 3, 1.0, 237.0, 1e6)
+    lenbuf = pv.nbuffer
+    assert lenbuf == 5
+    rows = pv.logical(1, 9)
+    assert np.all(rows[:6, 0] == 1e10) and np.all(rows[6:, 0] == 1e6)
+    pia.indexer[0, 0] = (9, 1, 6, 6, 7, 9, 3)
+    pia.n_total[0] = 9
+
+    def dens():
+        p = oracle.compute_props([pv], pia, [m], Tref=1.0)
+        return p.np[0, 0], p.n[0, 0]
+
+    assert dens()[0] == 9.0 and abs(dens()[1] / (6e10 + 3e6) - 1) < 1e-15
+    L.mbo_delete_particle_end_group1(pv.h, pia.h, 1, 1)
+    assert tuple(pia.indexer[0, 0][1:3]) == (1, 5) and pv.nbuffer == lenbuf + 1
+    assert list(pv.buffer) == [14, 13, 12, 11, 10, 6, 8, 7, 6, 5, 4, 3, 2, 1]
+    assert list(pv.index) == list(range(1, 15))
+    assert dens()[0] == 8.0 and abs(dens()[1] / (5e10 + 3e6) - 1) < 1e-15
+    L.mbo_delete_particle_end_group2(pv.h, pia.h, 1, 1)
+    assert pv.nbuffer == lenbuf + 2 and list(pv.buffer) == [14, 13, 12, 11, 10, 6, 9, 7, 6, 5, 4, 3, 2, 1]
+    assert dens()[0] == 7.0 and abs(dens()[1] / (5e10 + 2e6) - 1) < 1e-15
+    L.mbo_delete_particle_end_group2(pv.h, pia.h, 1, 1)
+    L.mbo_delete_particle_end_group2(pv.h, pia.h, 1, 1)
+    assert list(pv.buffer) == [14, 13, 12, 11, 10, 6, 9, 8, 7, 5, 4, 3, 2, 1] and pv.nbuffer == lenbuf + 4
+    assert dens() == (5.0, 5e10) and pia.indexer[0, 0][4] == 0 and pia.indexer[0, 0][6] == 0
+    L.mbo_delete_particle_end_group2(pv.h, pia.h, 1, 1)  # nothing left in group 2: no change
+    assert list(pv.buffer) == [14, 13, 12, 11, 10, 6, 9, 8, 7, 5, 4, 3, 2, 1] and pv.nbuffer == lenbuf + 4
+    for _ in range(4):
+        L.mbo_delete_particle_end_group1(pv.h, pia.h, 1, 1)
+    assert list(pv.buffer) == [14, 13, 12, 11, 10, 6, 9, 8, 7, 5, 4, 3, 2, 1] and pv.nbuffer == lenbuf + 8
+    assert dens() == (1.0, 1e10) and tuple(pia.indexer[0, 0]) == (1, 1, 1, 1, 0, -1, 0)
+    L.mbo_delete_particle_end_group1(pv.h, pia.h, 1, 1)
+    assert pv.nbuffer == 14 and dens() == (0.0, 0.0) and tuple(pia.indexer[0, 0]) == (0, 0, -1, 0, 0, -1, 0)
+    L.mbo_delete_particle_end_group1(pv.h, pia.h, 1, 1)  # empty cell: no change
+    assert pv.nbuffer == 14 and tuple(pia.indexer[0, 0]) == (0, 0, -1, 0, 0, -1, 0)
+    assert list(pv.buffer) == [14, 13, 12, 11, 10, 6, 9, 8, 7, 5, 4, 3, 2, 1]
+
+
+def test_particle_deletion_with_unsorted_index_reference_kat(oracle):
+    """test/test_indexing_particlebuffer.jl:190-310: delete_particle_end_group1! / _group2! / delete_particle_end! / delete_particle!
+    on a scrambled index array -- the exact index and buffer arrays after every call (delete_particle! swaps the victim with the last
+    particle of its group first), and the density bookkeeping (weights = storage index)."""
+    L = oracle.lib()
+    m = oracle.MASS["Ar"]
+    pv, pia = oracle.OPV(14), oracle.OPIA(1, 1)
+    pia.indexer[0, 0] = (7, 1, 3, 3, 7, 10, 4)
+    pia.n_total[0] = 7
+    index0 = [10, 7, 9, 12, 1, 5, 11, 2, 13, 3, 4, 6, 14, 8]
+    pv.index[:] = index0
+    pv.buffer[:] = [12, 1, 5, 4, 6, 14, 8, 10, 7, 9, 11, 2, 13, 3]
+    pv.nbuffer = 7
+    for ind in index0:
+        pv.particles[ind - 1] = [float(ind), 0, 0, 0, 0, 0, 0]
+
+    def state():
+        p = oracle.compute_props([pv], pia, [m], Tref=1.0)
+        return list(pv.index), list(pv.buffer), pv.nbuffer, p.np[0, 0], p.n[0, 0]
+
+    assert state()[3:] == (7.0, 55.0)
+    L.mbo_delete_particle_end_group1(pv.h, pia.h, 1, 1)  # storage index 9 leaves
+    assert state() == (index0, [12, 1, 5, 4, 6, 14, 8, 9, 7, 9, 11, 2, 13, 3], 8, 6.0, 46.0)
+    L.mbo_delete_particle_end_group2(pv.h, pia.h, 1, 1)  # 3 leaves
+    assert state() == (index0, [12, 1, 5, 4, 6, 14, 8, 9, 3, 9, 11, 2, 13, 3], 9, 5.0, 43.0)
+    L.mbo_delete_particle_end(pv.h, pia.h, 1, 1)  # end of group 2: 13 leaves
+    assert state() == (index0, [12, 1, 5, 4, 6, 14, 8, 9, 3, 13, 11, 2, 13, 3], 10, 4.0, 30.0)
+    L.mbo_delete_particle(pv.h, pia.h, 1, 1, 1)  # logical 1 (storage 10): swapped with the last of group 1, then dropped
+    index1 = [7, 10, 9, 12, 1, 5, 11, 2, 13, 3, 4, 6, 14, 8]
+    assert state() == (index1, [12, 1, 5, 4, 6, 14, 8, 9, 3, 13, 10, 2, 13, 3], 11, 3.0, 20.0)
+    L.mbo_delete_particle(pv.h, pia.h, 1, 1, 7)  # logical 7 (storage 11)
+    index2 = [7, 10, 9, 12, 1, 5, 2, 11, 13, 3, 4, 6, 14, 8]
+    assert state() == (index2, [12, 1, 5, 4, 6, 14, 8, 9, 3, 13, 10, 11, 13, 3], 12, 2.0, 9.0)
+    L.mbo_delete_particle(pv.h, pia.h, 1, 1, 7)  # logical 7 again (storage 2)
+    assert state() == (index2, [12, 1, 5, 4, 6, 14, 8, 9, 3, 13, 10, 11, 2, 3], 13, 1.0, 7.0)
+    L.mbo_delete_particle_end(pv.h, pia.h, 1, 1)  # group 2 is empty: end of group 1 (storage 7)
+    assert state() == (index2, [12, 1, 5, 4, 6, 14, 8, 9, 3, 13, 10, 11, 2, 7], 14, 0.0, 0.0)
