@@ -8,9 +8,9 @@
 // test_collision_utils.jl, test_collision_fp.jl, test_pia_contiguous.jl, test_particle_index_sorting.jl, test_indexing*.jl ...);
 // (2) the stochastic pipeline is pinned BIT-LEVEL by the reference's own seeded golden runs (test/data/*.nc, extracted into
 // tests/golden/reference_histories.json): with the StableRNGs.jl generator restated in philox.hpp the oracle reproduces the 0-D
-// two-species / BKW grid-merging histories and the 1-D Couette runs (NTC, SWPM, Fokker-Planck, octree merging, surface properties,
+// two-species / BKW (equal weight, grid merging) histories and the 1-D Couette runs (NTC, SWPM, Fokker-Planck, octree merging, surface properties,
 // index re-sorting) to round-off at every recorded step (tests/test_oracle_reference_bitlevel.py); (3) what cannot be replayed
-// (octree BKW: tie-breaking on a symmetric lattice; Chi-sampled BKW) is pinned in distribution
+// (octree BKW: tie-breaking on a symmetric lattice) is pinned in distribution
 // (tests/test_oracle_reference_runs.py, tests/test_oracle_stat.py: golden histories as draws of the oracle ensemble, BKW analytic
 // moments test/test_bkw.jl:25-29, T_eq test/test_2species.jl:25, SPARTA Couette profile test/data/external/).
 //
@@ -22,6 +22,7 @@
 #include <cmath>
 #include <cstdint>
 #include <limits>
+#include <type_traits>
 #include <vector>
 
 #include "philox.hpp"
@@ -984,7 +985,27 @@ template <class R>
 inline void sample_bkw(R& rng, ParticleVector& pv, int64_t nparticles, int64_t offset, double m, double T, const double v0[3]) {  // :195-213
     const double vscale = std::sqrt(2 * k_B * T / m) * std::sqrt(0.3);
     std::vector<double> v_abs(nparticles), Th(nparticles), ph(nparticles);
-    for (int64_t i = 0; i < nparticles; i++) {
+    bool julia_chi = false;
+    if constexpr (std::is_same_v<R, Xoshiro256pp>) julia_chi = rng.engine == 1;
+    if (julia_chi) {
+        // StableRNG replay: rand(rng, Chi(5), n) of Distributions.jl = sqrt of Gamma(5/2, 2) drawn with the Marsaglia-Tsang sampler
+        // (samplers/gamma.jl GammaMTSampler: d = shape - 1/3, c = 1 / (3 sqrt(d)), squeeze constant 0.0331, randn + rand per trial)
+        if constexpr (std::is_same_v<R, Xoshiro256pp>) {
+            const double d = 2.5 - 1.0 / 3.0, c = 1.0 / (3.0 * std::sqrt(d)), kappa = d * 2.0, r = 331.0 / 10000.0;
+            for (int64_t i = 0; i < nparticles; i++) {
+                while (true) {
+                    double x = rng.randn();
+                    double cbrt_v = 1.0 + c * x;
+                    while (cbrt_v <= 0.0) { x = rng.randn(); cbrt_v = 1.0 + c * x; }
+                    const double v = cbrt_v * cbrt_v * cbrt_v;
+                    const double u = rng.rand();
+                    const double xsq = x * x;
+                    if (u < 1.0 - r * (xsq * xsq) || std::log(u) < xsq / 2.0 + d * (1.0 - v + std::log(v))) { v_abs[i] = std::sqrt(v * kappa); break; }
+                }
+            }
+        }
+    }
+    for (int64_t i = 0; i < nparticles && !julia_chi; i++) {
         double s = 0.0;
         for (int q = 0; q < 3; q++) {  // 3 Box-Muller pairs -> 6 normals, use 5
             const double u1 = std::max(1e-300, rng.rand()), u2 = rng.rand();

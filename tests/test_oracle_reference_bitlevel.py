@@ -6,6 +6,8 @@ scripts, lands on the golden files' values to round-off -- every recorded step, 
 
   0-D  test_2species.jl, test_2species_equal_weight.jl   sampling + ntc! / ntc_equal_weight! (1 and 2 species), 800 steps
   0-D  test_2species_varweight_octree.jl          variable-weight ntc! (splits) + merge_octree_N2_based!, 800 steps, ~130 merges
+  0-D  test_bkw.jl                                sample_bkw! (Chi(5) of Distributions.jl: Marsaglia-Tsang gamma sampler on Julia's
+                                                  ziggurat randn) + ntc!, 20 000 particles, total moments M4..M10, 500 steps
   0-D  test_bkw_varweight_grid.jl                 sample_on_grid!(bkw) + ntc! + merge_grid_based!, total moments M4..M10, 500 steps
   1-D  test_1D_couette.jl                         sample on grid + ntc! + convect_particles! (diffuse walls) + sort_particles!
   1-D  test_1D_couette_varweight.jl               + per-cell octree merging with position clamping + squash_pia! + SurfProps
@@ -19,8 +21,8 @@ libm, the oracle is compiled with -ffp-contract=off against glibc, so the last b
 
 Not reproducible at this level, and why: test_bkw_varweight_octree.jl / _octree_swpm.jl (the first merge acts on the symmetric
 velocity lattice of sample_on_grid!: mirror-image octree bins have weights that are equal up to the last bits of exp(), and the
-strict `w > max_w` choice of the bin to refine is decided by them; count, density and temperature still match -- checked below),
-and test_bkw.jl (Chi(5) sampler of Distributions.jl): those are held at distribution level in tests/test_oracle_reference_runs.py."""
+strict `w > max_w` choice of the bin to refine is decided by them; count, density and temperature still match -- checked below):
+those are held at distribution level in tests/test_oracle_reference_runs.py."""
 import json
 import os
 
@@ -96,6 +98,29 @@ def test_two_species_runs_reproduce_the_golden_files(oracle, ref, key, variable_
         assert np.max(np.abs(p.T[:, 0] - r["T"][rec])) < 9.3e-13
         assert np.max(np.abs(p.v[:, 0] - np.array(r["v"][rec]))) < 1e-12
         assert np.max(np.abs(p.n[:, 0] / np.array(r["ndens"][rec]) - 1.0)) < 6e-15
+
+
+def test_bkw_equal_weight_run_reproduces_the_golden_file(oracle, ref):
+    """test/test_bkw.jl:56-95: 20 000 equal-weight particles sampled from BKW(t = 0) -- |v| = sqrt(0.3) v_th chi_5 with chi_5 from
+    Distributions.jl's Chi(5) (sqrt of a Marsaglia-Tsang Gamma(5/2, 2) variate: randn + rand per trial), angles from two uniform arrays --
+    then 500 steps of ntc!: T, v and M4..M10 of the golden file at every 10th step to round-off."""
+    r = ref["bkw_20k"]
+    m, it, T0, n_dens, tref, magic = _bkw_setup(oracle)
+    n_p = 20000
+    Fnum = n_dens / n_p
+    pv, pia = oracle.OPV(n_p), oracle.OPIA(1, 1)
+    rng = oracle.Rng.stable(1234)
+    oracle.sample_equal_weight_cell(rng, pv, pia, 1, 1, n_p, m, T0, Fnum, distribution="BKW")
+    cf = oracle.CF(1, oracle.estimate_sigma_g_w_max(it, m, m, T0, T0, Fnum))
+    for ts in range(0, 501):
+        if ts:
+            oracle.ntc(rng, cf, it, pv, pia, 1, 1, 1, 0.025 * tref, 1.0)
+        if ts % 10 == 0:
+            rec = ts // 10
+            p = oracle.compute_props([pv], pia, [m], [4, 6, 8, 10], Tref=T0, with_moments=True)
+            assert p.np[0, 0] == n_p == r["np"][rec]
+            np.testing.assert_allclose(p.moments[0, 0], r["moments"][rec], rtol=1e-13)
+            assert abs(p.T[0, 0] - r["T"][rec]) < 1e-12 and np.max(np.abs(p.v[0, 0] - np.array(r["v"][rec]))) < 1e-12
 
 
 def test_bkw_grid_merging_run_reproduces_the_golden_file(oracle, ref):
