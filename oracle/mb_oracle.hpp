@@ -1072,7 +1072,9 @@ inline void sample_particles_equal_weight_grid(R& rng, const Grid1DUniform& grid
 inline double bkw_vdf(double vx, double vy, double vz, double m, double T, double scaled_time) {  // :168-177
     const double xk = 1.0 - 0.4 * std::exp(-scaled_time / 6.0);
     const double Csq = vx * vx + vy * vy + vz * vz;
-    return (5 * xk - 3 + 2 * (1.0 - xk) * Csq * m / (2 * k_B * xk * T)) * std::exp(-Csq * m / (2 * k_B * xk * T));
+    // `5 * xk - 3` is a fused multiply-add in the reference (@muladd): with xk = 0.6 it gives -1.1e-16 instead of 0, which moves the last
+    // bit of many weights -- and the octree merge's choice between mirror-image bins of this symmetric lattice hangs on those bits
+    return (std::fma(5.0, xk, -3.0) + 2 * (1.0 - xk) * Csq * m / (2 * k_B * xk * T)) * std::exp(-Csq * m / (2 * k_B * xk * T));
 }
 inline double maxwellian_vdf(double vx, double vy, double vz, double m, double T) {  // :150-152
     return std::pow(m / (2.0 * M_PI * k_B * T), 1.5) * std::exp(-m * (vx * vx + vy * vy + vz * vz) / (2.0 * k_B * T));
