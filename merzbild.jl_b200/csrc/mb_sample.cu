@@ -14,6 +14,7 @@
 // the stream is counter based every thread computes the draws of its own particle directly.
 #include "mb_common.cuh"
 #include "mb_scan.cuh"
+#include "mb_jlexp.h"
 
 namespace mb {
 
@@ -302,8 +303,8 @@ int mb_sample_on_grid(mb_ctx* ctx, int32_t vdf_kind, mb_pv* pv, mb_pia* pia, int
                 const double Csq = vg[i] * vg[i] + vg[j] * vg[j] + vg[k] * vg[k];
                 if (sqrt(Csq) <= cutoff_v) {
                     double f;
-                    if (vdf_kind == 0) f = pow(mass / (2.0 * PI * k_B * T), 1.5) * exp(-mass * Csq / (2.0 * k_B * T));  // maxwellian :150-152
-                    else f = (std::fma(5.0, 0.6, -3.0) + 2 * (1.0 - 0.6) * Csq * mass / (2 * k_B * 0.6 * T)) * exp(-Csq * mass / (2 * k_B * 0.6 * T));  // bkw :168-177, xk(0) = 0.6; `5 xk - 3` is fused in the reference (@muladd): -1.1e-16, not 0
+                    if (vdf_kind == 0) f = pow(mass / (2.0 * PI * k_B * T), 1.5) * mbjl::exp(-mass * Csq / (2.0 * k_B * T));  // maxwellian :150-152
+                    else f = (std::fma(5.0, 0.6, -3.0) + 2 * (1.0 - 0.6) * Csq * mass / (2 * k_B * 0.6 * T)) * mbjl::exp(-Csq * mass / (2 * k_B * 0.6 * T));  // bkw :168-177, xk(0) = 0.6; `5 xk - 3` is fused in the reference (@muladd): -1.1e-16, not 0
                     wsum += f;
                     if (f > 0.0) { w.push_back(f); ijk.push_back((int32_t)(i | (j << 10) | (k << 20))); }
                 }

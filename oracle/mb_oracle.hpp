@@ -7,12 +7,12 @@
 // (tests/test_oracle_kat_*.py restate test/test_grid_sorting.jl, test_convection_1D.jl, test_computes.jl, test_octree_*.jl,
 // test_collision_utils.jl, test_collision_fp.jl, test_pia_contiguous.jl, test_particle_index_sorting.jl, test_indexing*.jl ...);
 // (2) the stochastic pipeline is pinned BIT-LEVEL by the reference's own seeded golden runs (test/data/*.nc, extracted into
-// tests/golden/reference_histories.json): with the StableRNGs.jl generator restated in philox.hpp the oracle reproduces the 0-D
-// two-species / BKW (equal weight, grid merging) histories and the 1-D Couette runs (NTC, SWPM, Fokker-Planck, octree merging, surface properties,
-// index re-sorting) to round-off at every recorded step (tests/test_oracle_reference_bitlevel.py); (3) what cannot be replayed
-// (octree BKW: tie-breaking on a symmetric lattice) is pinned in distribution
-// (tests/test_oracle_reference_runs.py, tests/test_oracle_stat.py: golden histories as draws of the oracle ensemble, BKW analytic
-// moments test/test_bkw.jl:25-29, T_eq test/test_2species.jl:25, SPARTA Couette profile test/data/external/).
+// tests/golden/reference_histories.json): with the StableRNGs.jl generator, Julia's randn and exp restated (philox.hpp, mb_jlexp.h)
+// the oracle reproduces every golden run of this path -- 0-D two-species and BKW histories (equal weight, octree / grid merging,
+// SWPM), 1-D Couette (NTC, SWPM, Fokker-Planck, octree merging, surface properties, index re-sorting) -- to round-off at every
+// recorded step (tests/test_oracle_reference_bitlevel.py); (3) generator-independent pins on top (tests/test_oracle_reference_runs.py,
+// tests/test_oracle_stat.py: golden histories as draws of the oracle ensemble, BKW analytic moments test/test_bkw.jl:25-29, T_eq
+// test/test_2species.jl:25, SPARTA Couette profile test/data/external/).
 //
 // Every function cites the reference file:line (relative to /root/reference/src) it follows.
 // Indices stored in the containers are 1-based and inclusive exactly as in the reference, so a dump of
@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "philox.hpp"
+#include "../merzbild.jl_b200/csrc/mb_jlexp.h"    // exp() as Julia computes it: grid-sampled weights identical to the reference's, shared with the device library
 #include "../merzbild.jl_b200/csrc/mb_normals.h"  // fp32 Box-Muller shared with the CUDA kernel (bit-identical normals)
 
 namespace mbo {
@@ -1074,10 +1075,11 @@ inline double bkw_vdf(double vx, double vy, double vz, double m, double T, doubl
     const double Csq = vx * vx + vy * vy + vz * vz;
     // `5 * xk - 3` is a fused multiply-add in the reference (@muladd): with xk = 0.6 it gives -1.1e-16 instead of 0, which moves the last
     // bit of many weights -- and the octree merge's choice between mirror-image bins of this symmetric lattice hangs on those bits
-    return (std::fma(5.0, xk, -3.0) + 2 * (1.0 - xk) * Csq * m / (2 * k_B * xk * T)) * std::exp(-Csq * m / (2 * k_B * xk * T));
+    // exp as Julia evaluates it (mb_jlexp.h): its last bit differs from glibc's for ~1 % of the arguments, same consequence
+    return (std::fma(5.0, xk, -3.0) + 2 * (1.0 - xk) * Csq * m / (2 * k_B * xk * T)) * mbjl::exp(-Csq * m / (2 * k_B * xk * T));
 }
 inline double maxwellian_vdf(double vx, double vy, double vz, double m, double T) {  // :150-152
-    return std::pow(m / (2.0 * M_PI * k_B * T), 1.5) * std::exp(-m * (vx * vx + vy * vy + vz * vz) / (2.0 * k_B * T));
+    return std::pow(m / (2.0 * M_PI * k_B * T), 1.5) * mbjl::exp(-m * (vx * vx + vy * vy + vz * vz) / (2.0 * k_B * T));
 }
 // sample_on_grid! :312-346 with evaluate_distribution_on_grid! :253-268 ; vdf: 0 Maxwellian, 1 BKW(t=0)
 template <class R>

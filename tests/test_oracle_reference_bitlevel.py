@@ -8,6 +8,8 @@ scripts, lands on the golden files' values to round-off -- every recorded step, 
   0-D  test_2species_varweight_octree.jl          variable-weight ntc! (splits) + merge_octree_N2_based!, 800 steps, ~130 merges
   0-D  test_bkw.jl                                sample_bkw! (Chi(5) of Distributions.jl: Marsaglia-Tsang gamma sampler on Julia's
                                                   ziggurat randn) + ntc!, 20 000 particles, total moments M4..M10, 500 steps
+  0-D  test_bkw_varweight_octree.jl, test_bkw_varweight_octree_swpm.jl   sample_on_grid!(bkw) + ntc! / swpm! + octree merge
+                                                  10 000 -> 8 000 of a cell that starts on a mirror-symmetric velocity lattice, 500 steps
   0-D  test_bkw_varweight_grid.jl                 sample_on_grid!(bkw) + ntc! + merge_grid_based!, total moments M4..M10, 500 steps
   1-D  test_1D_couette.jl                         sample on grid + ntc! + convect_particles! (diffuse walls) + sort_particles!
   1-D  test_1D_couette_varweight.jl               + per-cell octree merging with position clamping + squash_pia! + SurfProps
@@ -19,10 +21,12 @@ scripts, lands on the golden files' values to round-off -- every recorded step, 
 those of the reference's own comparisons, or a few ulp of the quantity: the Julia build fuses multiply-adds (@muladd) and uses its own
 libm, the oracle is compiled with -ffp-contract=off against glibc, so the last bits differ while every random decision is the same.
 
-Not reproducible at this level, and why: test_bkw_varweight_octree.jl / _octree_swpm.jl (the first merge acts on the symmetric
-velocity lattice of sample_on_grid!: mirror-image octree bins have weights that are equal up to the last bits of exp(), and the
-strict `w > max_w` choice of the bin to refine is decided by them; count, density and temperature still match -- checked below):
-those are held at distribution level in tests/test_oracle_reference_runs.py."""
+The octree BKW runs are the delicate ones: the first merge acts on the mirror-symmetric lattice of sample_on_grid!, mirror-image
+octree bins carry weights that are equal up to the last bits, and the strict `w > max_w` choice of the bin to refine is decided by
+those bits.  They only come out right because the oracle evaluates the distribution exactly like the reference does: the `5 xk - 3`
+of bkw() as a fused multiply-add (@muladd) and exp() with Julia's own algorithm (merzbild.jl_b200/csrc/mb_jlexp.h; glibc's exp differs
+from it in the last bit for ~1 % of the arguments) -- see the two tests at the end of this file.  tests/test_oracle_reference_runs.py
+adds the generator-independent view (golden histories as draws of the oracle ensemble)."""
 import json
 import os
 
@@ -152,9 +156,9 @@ def test_bkw_grid_merging_run_reproduces_the_golden_file(oracle, ref):
 
 
 @pytest.mark.parametrize("key,swpm", [("bkw_vw_octree", False), ("bkw_vw_octree_swpm", True)])
-def test_bkw_octree_runs_first_merge_count(oracle, ref, key, swpm):
-    """The octree BKW runs are not bit-reproducible (module docstring: tie-breaking between mirror-image bins of the symmetric lattice),
-    but the first step's collisions are, and with them the particle count after the first merge (7995 / what the file holds), n and T."""
+def test_bkw_octree_runs_reproduce_the_golden_files(oracle, ref, key, swpm):
+    """test/test_bkw_varweight_octree.jl:62-100, test_bkw_varweight_octree_swpm.jl:66-100: counts exactly (7995 after the first merge,
+    a merge every ~9 steps), M4..M10 to 1e-13 relative, T to 5e-12 K, at every 10th of the 500 steps."""
     r = ref[key]
     m, it, T0, n_dens, tref, magic = _bkw_setup(oracle)
     pv, pia = oracle.OPV(40 ** 3), oracle.OPIA(1, 1)
@@ -162,22 +166,28 @@ def test_bkw_octree_runs_first_merge_count(oracle, ref, key, swpm):
     n_s = int(oracle.sample_on_grid(rng, "bkw", pv, 40, m, T0, n_dens))
     pia.set_single_cell(1, 1, n_s)
     oc = oracle.Octree(oracle.MID_SPLIT, oracle.INIT_MINMAX, oracle.BOUNDS_INHERIT, 6000, 10)
-    if swpm:
-        cf = oracle.CF(1, oracle.estimate_sigma_g_w_max(it, m, m, T0, T0, 1.0))
-        oracle.swpm(rng, cf, it, pv, pia, 1, 1, 1, 1.0, 0.025 * tref, 1.0)
-    else:
-        cf = oracle.CF(1, oracle.estimate_sigma_g_w_max(it, m, m, T0, T0, n_dens / n_s))
-        oracle.ntc(rng, cf, it, pv, pia, 1, 1, 1, 0.025 * tref, 1.0)
-    oracle.merge_octree_N2(rng, oc, pv, pia, 1, 1, 1, 8000)
+    cf = oracle.CF(1, oracle.estimate_sigma_g_w_max(it, m, m, T0, T0, 1.0 if swpm else n_dens / n_s))
     p = oracle.compute_props([pv], pia, [m], [4, 6, 8, 10], Tref=T0, with_moments=True)
-    f = H5_first_record(r)
-    assert int(p.np[0, 0]) == f["np"]
-    assert abs(p.T[0, 0] - f["T"]) < 2e-12 and abs(p.n[0, 0] / f["ndens"] - 1.0) < 1e-13
-    np.testing.assert_allclose(p.moments[0, 0], f["moments"], rtol=2e-3)  # a handful of the ~4000 bins differ
-
-
-def H5_first_record(r):  # the record after step 1 (full resolution; the other fixtures hold every 10th)
-    return r["first_step"]
+    n_merges = 0
+    for ts in range(1, 501):
+        if swpm:
+            oracle.swpm(rng, cf, it, pv, pia, 1, 1, 1, 1.0, 0.025 * tref, 1.0)
+        else:
+            oracle.ntc(rng, cf, it, pv, pia, 1, 1, 1, 0.025 * tref, 1.0)
+        if p.np[0, 0] > 10000:
+            oracle.merge_octree_N2(rng, oc, pv, pia, 1, 1, 1, 8000)
+            n_merges += 1
+        p = oracle.compute_props([pv], pia, [m], [4, 6, 8, 10], Tref=T0, with_moments=True)
+        if ts == 1:
+            f = r["first_step"]
+            assert int(p.np[0, 0]) == f["np"]
+            np.testing.assert_allclose(p.moments[0, 0], f["moments"], rtol=1e-13)
+        if ts % 10 == 0:
+            rec = ts // 10
+            assert int(p.np[0, 0]) == int(r["np"][rec]), (ts, p.np[0, 0], r["np"][rec])
+            np.testing.assert_allclose(p.moments[0, 0], r["moments"][rec], rtol=1e-13)
+            assert abs(p.T[0, 0] - r["T"][rec]) < 5e-12 and abs(p.n[0, 0] / r["ndens"][rec] - 1.0) < 1e-13
+    assert n_merges >= 20
 
 
 # ---------------------------------------------------------------------------------------------------------------------------------
@@ -255,9 +265,9 @@ def test_couette_runs_reproduce_the_golden_files(oracle, ref, key, variant, ppc,
 
 
 def test_bkw_octree_first_merge_depends_on_the_last_bits_of_the_weights(oracle, ref):
-    """Why the octree BKW runs cannot be replayed bit for bit: moving every sampled weight by +-1 ulp leaves the post-merge count (7995)
-    and the number of bins unchanged but shifts the merged moments by 1e-5 ... 1e-3 -- the size of the oracle's distance to the golden
-    file after step 1 (5e-5), i.e. that distance is tie-breaking between mirror-image bins, not a difference in the algorithm."""
+    """Why the octree BKW replay needs the reference's exact arithmetic for the sampled weights: moving every weight by +-1 ulp leaves the
+    post-merge count (7995) and the number of bins unchanged but shifts the merged moments by 1e-5 ... 1e-3 (tie-breaking between
+    mirror-image bins) -- whereas the unperturbed oracle sits on the golden file to round-off."""
     m, it, T0, n_dens, tref, magic = _bkw_setup(oracle)
 
     def first_step(perturb_seed):
@@ -279,10 +289,27 @@ def test_bkw_octree_first_merge_depends_on_the_last_bits_of_the_weights(oracle, 
 
     base = first_step(0)
     golden = np.array(ref["bkw_vw_octree"]["first_step"]["moments"])
-    to_golden = np.max(np.abs(base[2] - golden))
-    shifts = []
+    assert np.max(np.abs(base[2] - golden)) < 1e-14
     for s in (1, 2, 3):
         n, nb, mom = first_step(s)
         assert n == base[0] == 7995 and nb == base[1]
-        shifts.append(np.max(np.abs(mom - base[2])))
-    assert 1e-6 < to_golden < 2e-3 and max(shifts) > 0.2 * to_golden and min(shifts) > 1e-7, (to_golden, shifts)
+        assert 1e-7 < np.max(np.abs(mom - golden)) < 2e-3
+
+
+def test_julia_exp_table_and_accuracy(oracle):
+    """mb_jlexp.h: the packed table equals its definition (tests/golden/make_jlexp_table.py, needs mpmath); the first entries are the
+    literals of Julia's base/special/exp.jl (0xaac00b1afa5abcbe, 0x9b60163da9fb3335, ...)."""
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "merzbild.jl_b200", "csrc", "mb_jlexp.h")).read()
+    body = src[src.index("J_TABLE[256] = {"):src.index("};")]
+    got = [int(x, 16) for x in re.findall(r"0x([0-9a-f]{16})ull", body)]
+    assert len(got) == 256 and got[:5] == [0x0, 0xAAC00B1AFA5ABCBE, 0x9B60163DA9FB3335, 0xAB502168143B0280, 0xADC02C9A3E778060]
+    pytest.importorskip("mpmath")
+    import sys
+
+    sys.path.insert(0, GOLDEN)
+    from make_jlexp_table import table
+
+    assert got == table()

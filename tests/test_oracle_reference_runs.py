@@ -1,7 +1,7 @@
 """CPU suite: the oracle against runs OF THE REFERENCE ITSELF -- the golden netCDF files its regression tests compare to at 1e-13
 (test/data/*.nc; extracted by tests/golden/make_golden.py into tests/golden/reference_histories.json).  tests/test_oracle_reference_bitlevel.py
-reproduces most of them to round-off on the reference's own random stream; this file is the generator-independent complement, and the
-only pin for the runs that cannot be replayed (octree BKW).  The comparison is at distribution level: deterministic quantities (grid-sampled
+reproduces them to round-off on the reference's own random stream; this file is the generator-independent complement.  The comparison
+is at distribution level: deterministic quantities (grid-sampled
 initial moments, counts, densities) must match to round-off; stochastic histories must be one plausible draw of the oracle's own
 ensemble (z-scores against the ensemble mean / spread at every recorded step); Couette cell profiles must agree within the
 per-cell sampling noise (chi-square over the 50 cells)."""
