@@ -87,12 +87,11 @@ struct PhiloxStream {
 //             CloseOpen12 path for an rng whose native 52-bit type is UInt64); rand(rng, [-1.0, 1.0]) indexes the 2-element array with
 //             the low bit of one draw (SamplerRangeFast, mask 1).  Pinned by the reference's golden runs: with this engine the oracle
 //             reproduces test/data/*.nc of the reference to round-off (tests/test_oracle_reference_bitlevel.py).
-// (The struct keeps its historical name: every operator template of the oracle takes it by reference.)
-struct Xoshiro256pp {
+struct SeqRng {
     uint64_t s[4];
     int engine = 0;
     unsigned __int128 lehmer = 1;
-    explicit Xoshiro256pp(uint64_t seed = 1234) {
+    explicit SeqRng(uint64_t seed = 1234) {
         uint64_t z = seed;
         for (int i = 0; i < 4; i++) {
             z += 0x9E3779B97F4A7C15ull;
@@ -102,8 +101,8 @@ struct Xoshiro256pp {
             s[i] = x ^ (x >> 31);
         }
     }
-    static Xoshiro256pp stable_rng(uint64_t seed) {
-        Xoshiro256pp r(seed);
+    static SeqRng stable_rng(uint64_t seed) {
+        SeqRng r(seed);
         r.engine = 1;
         r.lehmer = ((unsigned __int128)seed << 1) | 1;
         return r;
@@ -184,5 +183,6 @@ struct Xoshiro256pp {
         return rand() < 0.5 ? -1.0 : 1.0;
     }
 };
+using Xoshiro256pp = SeqRng;  // the name the operator templates and the C API were written against
 
 }  // namespace mbo
