@@ -442,3 +442,72 @@ def test_particle_deletion_with_unsorted_index_reference_kat(oracle):
     assert state() == (index2, [12, 1, 5, 4, 6, 14, 8, 9, 3, 13, 10, 11, 2, 3], 13, 1.0, 7.0)
     L.mbo_delete_particle_end(pv.h, pia.h, 1, 1)  # group 2 is empty: end of group 1 (storage 7)
     assert state() == (index2, [12, 1, 5, 4, 6, 14, 8, 9, 3, 13, 10, 11, 2, 7], 14, 0.0, 0.0)
+
+
+def _two_chunk_setup(oracle, positions, caps, ranges):
+    """Two chunks of a 2-cell grid (chunk i owns cell i); particle np of chunk c has w = c, v = (c^3 np, 1 - np, np), x = (pos, 0.5, 1 + c);
+    ranges[c] = [(n, start, end) for cell 1, cell 2]."""
+    pvs, pias = [], []
+    for c in (1, 2):
+        pv, pia = oracle.OPV(caps[c - 1]), oracle.OPIA(2, 1)
+        for k, x in enumerate(positions[c - 1], start=1):
+            pv.add_particle(k, float(c), [c ** 3 * k, -k + 1.0, k], [x, 0.5, 1.0 + c])
+        pia.n_total[0] = len(positions[c - 1])
+        for cell, (n, s, e) in enumerate(ranges[c - 1]):
+            pia.indexer[0, cell] = (n, s, e, n, 0, -1, 0) if n else (0, 0, -1, 0, 0, -1, 0)
+        pvs.append(pv)
+        pias.append(pia)
+    return pvs, pias
+
+
+def test_particle_exchange_reference_kat(oracle):
+    """test/test_particle_exchange.jl:46-330: reset!, and exchange_particles! between two chunks -- nothing to move; equal numbers of
+    strangers (pure swap: the exchanger's indexer points at the swapped-in slots); unequal numbers (swap, then push with a resize by
+    the shortfall + DELTA_PARTICLES = 256; the sender's freed slots go to its buffer)."""
+    ex = oracle.Exchanger([(1, 2), (3, 4)], 4)
+    assert ex.indexer.shape == (4, 2, 7)
+    ex.indexer[:] = 7
+    ex.reset(1)
+    ex.reset(2)
+    assert np.all(ex.indexer[:, :, 1:] == np.array([0, -1, 0, 0, -1, 0]))  # n_local is not used by the exchanger (:57-70)
+
+    ex = oracle.Exchanger([(1, 1), (2, 2)], 2)
+    # scenario 1: every particle already sits in its owner's cell
+    pvs, pias = _two_chunk_setup(oracle, [[3.0] * 4, [6.0] * 4], [4, 4], [[(4, 1, 4), (0, 0, -1)], [(0, 0, -1), (4, 1, 4)]])
+    ex.reset(1); ex.reset(2)
+    ex.exchange(pvs, pias, 1)
+    for c in (1, 2):
+        rows = pvs[c - 1].logical(1, 4)
+        assert len(pvs[c - 1]) == 4 and np.all(rows[:, 0] == c) and np.array_equal(rows[:, 1], c ** 3 * np.arange(1, 5)) and np.all(rows[:, 6] == 1.0 + c)
+    # scenario 2: 1,1,2,2 in both chunks -> pure swap
+    pvs, pias = _two_chunk_setup(oracle, [[0.0, 1.0, 3.0, 4.0], [-2.0, -1.0, 6.0, 5.0]], [4, 4], [[(2, 1, 2), (2, 3, 4)], [(2, 1, 2), (2, 3, 4)]])
+    ex.reset(1); ex.reset(2)
+    ex.exchange(pvs, pias, 1)
+    for c, (pos, w) in enumerate((([0.0, 1.0, -2.0, -1.0], [1, 1, 2, 2]), ([3.0, 4.0, 6.0, 5.0], [1, 1, 2, 2]))):
+        rows = pvs[c].logical(1, 4)
+        assert len(pvs[c]) == 4 and list(rows[:, 4]) == pos and list(rows[:, 0]) == w
+    I = ex.indexer  # [cell, chunk]: (n_local, start1, end1, n_group1, start2, end2, n_group2)
+    assert tuple(I[0, 1, 1:4]) == (3, 4, 2) and tuple(I[0, 0, 1:3]) == (0, -1)  # cell 1 received two particles from chunk 2, in slots 3..4
+    assert tuple(I[1, 0, 1:4]) == (1, 2, 2) and tuple(I[1, 1, 1:3]) == (0, -1)
+    assert np.all(I[:, :, 4:] == np.array([0, -1, 0]))
+    assert tuple(pias[0].indexer[0, 0]) == (2, 1, 2, 2, 0, -1, 0) and tuple(pias[0].indexer[0, 1][:4]) == (0, 0, -1, 0)
+    assert tuple(pias[1].indexer[0, 0][:4]) == (0, 0, -1, 0) and tuple(pias[1].indexer[0, 1]) == (2, 3, 4, 2, 0, -1, 0)
+    # scenario 3: 1,1,2 and 1,1,1,2 -> one swap, two pushes into chunk 1 (resized), chunk 2 keeps two freed slots
+    pvs, pias = _two_chunk_setup(oracle, [[0.0, 1.0, 4.0], [-2.0, -1.0, 1.5, 6.0]], [3, 4], [[(2, 1, 2), (1, 3, 3)], [(3, 1, 3), (1, 4, 4)]])
+    assert pvs[0].nbuffer == 0 and pvs[1].nbuffer == 0
+    ex.reset(1); ex.reset(2)
+    ex.exchange(pvs, pias, 1)
+    assert len(pvs[0]) == 5 + 256 and len(pvs[1]) == 4
+    r0, r1 = pvs[0].logical(1, 5), pvs[1].logical(1, 4)
+    assert list(r0[:, 4]) == [0.0, 1.0, -2.0, -1.0, 1.5] and list(r0[:, 0]) == [1, 1, 2, 2, 2]
+    assert list(r1[:, 4]) == [4.0, -1.0, 1.5, 6.0] and list(r1[:, 0]) == [1, 2, 2, 2]  # the sent particles are not erased, only freed
+    assert pvs[0].nbuffer == 256 and np.all(pvs[0].buffer[:256] > 5)
+    assert pvs[1].nbuffer == 2 and list(pvs[1].buffer[:2]) == [2, 3]
+    assert pias[0].n_total[0] == 5 and pias[1].n_total[0] == 4
+    assert tuple(pias[0].indexer[0, 0][:4]) == (2, 1, 2, 2) and tuple(pias[0].indexer[0, 1][:4]) == (0, 0, -1, 0)
+    assert tuple(pias[1].indexer[0, 0][:4]) == (0, 0, -1, 0) and tuple(pias[1].indexer[0, 1][:4]) == (1, 4, 4, 1)
+    I = ex.indexer
+    assert tuple(I[0, 1, 1:]) == (3, 3, 1, 4, 5, 2)  # from chunk 2 into cell 1: one swapped (slot 3), two pushed (slots 4..5)
+    assert tuple(I[1, 0, 1:]) == (1, 1, 1, 0, -1, 0)  # from chunk 1 into cell 2: one swapped, none pushed
+    for i in (0, 1):
+        assert tuple(I[i, i, 1:]) == (0, -1, 0, 0, -1, 0)
