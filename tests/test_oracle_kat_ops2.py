@@ -511,3 +511,65 @@ def test_particle_exchange_reference_kat(oracle):
     assert tuple(I[1, 0, 1:]) == (1, 1, 1, 0, -1, 0)  # from chunk 1 into cell 2: one swapped, none pushed
     for i in (0, 1):
         assert tuple(I[i, i, 1:]) == (0, -1, 0, 0, -1, 0)
+
+
+def test_particle_exchange_three_chunks_reference_kat(oracle):
+    """test/test_particle_exchange.jl:540-735: 4 cells in 3 chunks ([1], [2, 3], [4]); chunk contents by cell [1,1,2,3,4,4], [1,3,4],
+    [1,2,3,3].  exchange_particles! visits the pairs in 1-factorisation order (1-2, 1-3, 2-3), swapping strangers pairwise and pushing
+    the rest: exact particle order, lengths, freed-slot buffers, the senders' indexers and the exchanger's (chunk, cell) ranges."""
+    chunks, n_cells = [(1, 1), (2, 3), (4, 4)], 4
+    positions = [[0.0, 0.5, 2.0, 3.0, 4.5, 5.0], [1.5, 3.5, 5.5], [-1.0, 2.5, 4.0, 4.5]]
+    cells = [[1, 1, 2, 3, 4, 4], [1, 3, 4], [1, 2, 3, 3]]
+    np_in_cells = [[2, 1, 1, 2], [1, 0, 1, 1], [1, 1, 2, 0]]
+    offsets = [[1, 3, 4, 5], [1, 1, 2, 3], [1, 2, 3, 3]]
+    pvs, pias = [oracle.OPV(8), oracle.OPV(4), oracle.OPV(5)], [oracle.OPIA(n_cells, 1) for _ in range(3)]
+    for c in range(3):
+        for k, (x, cell) in enumerate(zip(positions[c], cells[c]), start=1):
+            pvs[c].add_particle(k, float(cell), [c + 1.0, -(c + 1.0), c + 1.0], [x, 0.5, 0.0])
+        pias[c].n_total[0] = len(positions[c])
+        for cell in range(n_cells):
+            n = np_in_cells[c][cell]
+            pias[c].indexer[0, cell] = (n, offsets[c][cell], offsets[c][cell] + n - 1, n, 0, -1, 0) if n else (0, 0, -1, 0, 0, -1, 0)
+    ex = oracle.Exchanger(chunks, n_cells)
+    for c in (1, 2, 3):
+        ex.reset(c)
+    ex.exchange(pvs, pias, 1)
+    assert [int(p.n_total[0]) for p in pias] == [6, 6, 5]  # includes particles that were pushed away
+    assert [len(p) for p in pvs] == [8, 6 + 256, 5]
+    assert pvs[0].nbuffer == 4 and list(pvs[0].buffer[:4]) == [8, 7, 4, 6]
+    assert pvs[1].nbuffer == 256
+    assert pvs[2].nbuffer == 2 and list(pvs[2].buffer[:2]) == [3, 4]
+    new_positions = [[0.0, 0.5, 1.5, 3.0, -1.0, 5.0], [2.0, 3.5, 2.5, 3.0, 4.0, 4.5], [4.5, 5.5, 4.0, 4.5, 5.0]]
+    new_weights = [[1.0, 1.0, 1.0, 3.0, 1.0, 4.0], [2.0, 3.0, 2.0, 3.0, 3.0, 3.0], [4.0, 4.0, 3.0, 3.0, 4.0]]
+    new_vx = [[1.0, 1.0, 2.0, 1.0, 3.0, 1.0], [1.0, 2.0, 3.0, 1.0, 3.0, 3.0], [1.0, 2.0, 3.0, 3.0, 1.0]]
+    for c in range(3):
+        rows = pvs[c].logical(1, len(new_positions[c]))
+        assert list(rows[:, 4]) == new_positions[c] and list(rows[:, 0]) == new_weights[c] and list(rows[:, 1]) == new_vx[c]
+    kept = [[2, 0, 0, 0], [0, 0, 1, 0], [0, 0, 0, 0]]
+    for c in range(3):
+        for cell in range(n_cells):
+            ix = tuple(pias[c].indexer[0, cell])
+            n = kept[c][cell]
+            assert ix[0] == n and ix[3] == n and ix[4:] == (0, -1, 0)
+            if n:
+                assert ix[1:3] == (offsets[c][cell], offsets[c][cell] + n - 1)
+    I = ex.indexer  # [cell, chunk, (n_local, start1, end1, n_group1, start2, end2, n_group2)]
+    E = (0, -1, 0)
+    want = {  # (cell, from chunk): (start1, end1, n_group1, start2, end2, n_group2)
+        (1, 1): E + E, (1, 2): (3, 3, 1) + E, (1, 3): (5, 5, 1) + E,
+        (2, 1): (1, 1, 1) + E, (2, 2): E + E, (2, 3): (3, 3, 1) + E,
+        (3, 1): E + (4, 4, 1), (3, 2): E + E, (3, 3): E + (5, 6, 2),
+        (4, 1): (1, 1, 1) + (5, 5, 1), (4, 2): (2, 2, 1) + E, (4, 3): E + E,
+    }
+    for (cell, chunk), w in want.items():
+        assert tuple(I[cell - 1, chunk - 1, 1:]) == w, (cell, chunk, tuple(I[cell - 1, chunk - 1, 1:]))
+    # every cell's particles (own range + what the exchanger points at) are all there: counts 4, 2, 4, 3 with weight = cell id
+    owner = [1, 2, 2, 3]
+    for cell in range(1, 5):
+        c = owner[cell - 1] - 1
+        ix = pias[c].indexer[0, cell - 1]
+        got = [pvs[c].logical(i, i)[0, 0] for i in range(ix[1], ix[2] + 1)]
+        for ch in range(3):
+            s1, e1, _, s2, e2, _ = I[cell - 1, ch, 1:]
+            got += [pvs[c].logical(i, i)[0, 0] for i in range(s1, e1 + 1)] + [pvs[c].logical(i, i)[0, 0] for i in range(s2, e2 + 1)]
+        assert got == [float(cell)] * [4, 2, 4, 3][cell - 1], (cell, got)
