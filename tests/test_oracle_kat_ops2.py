@@ -573,3 +573,41 @@ def test_particle_exchange_three_chunks_reference_kat(oracle):
             s1, e1, _, s2, e2, _ = I[cell - 1, ch, 1:]
             got += [pvs[c].logical(i, i)[0, 0] for i in range(s1, e1 + 1)] + [pvs[c].logical(i, i)[0, 0] for i in range(s2, e2 + 1)]
         assert got == [float(cell)] * [4, 2, 4, 3][cell - 1], (cell, got)
+
+
+def test_sort_particles_after_exchange_reference_kat(oracle):
+    """test/test_particle_resort_after_exchange.jl:3-135 (case 1): the three-chunk exchange above followed by
+    sort_particles_after_exchange!: every chunk ends with exactly its own cells populated (n_total 4 / 6 / 3), group 2 empty, cell ranges
+    (1..4), (1..2, 3..6), (1..3), weights equal to the cell id, no index used twice."""
+    chunks, n_cells = [(1, 1), (2, 3), (4, 4)], 4
+    positions = [[0.0, 0.5, 2.0, 3.0, 4.5, 5.0], [1.5, 3.5, 5.5], [-1.0, 2.5, 4.0, 4.5]]
+    cells = [[1, 1, 2, 3, 4, 4], [1, 3, 4], [1, 2, 3, 3]]
+    np_in_cells = [[2, 1, 1, 2], [1, 0, 1, 1], [1, 1, 2, 0]]
+    offsets = [[1, 3, 4, 5], [1, 1, 2, 3], [1, 2, 3, 3]]
+    pvs, pias = [oracle.OPV(8), oracle.OPV(4), oracle.OPV(5)], [oracle.OPIA(n_cells, 1) for _ in range(3)]
+    for c in range(3):
+        for k, (x, cell) in enumerate(zip(positions[c], cells[c]), start=1):
+            pvs[c].add_particle(k, float(cell), [c + 1.0, -(c + 1.0), c + 1.0], [x, 0.5, 0.0])
+        pias[c].n_total[0] = len(positions[c])
+        for cell in range(n_cells):
+            n = np_in_cells[c][cell]
+            pias[c].indexer[0, cell] = (n, offsets[c][cell], offsets[c][cell] + n - 1, n, 0, -1, 0) if n else (0, 0, -1, 0, 0, -1, 0)
+    ex = oracle.Exchanger(chunks, n_cells)
+    for c in (1, 2, 3):
+        ex.reset(c)
+    ex.exchange(pvs, pias, 1)
+    for c in (1, 2, 3):
+        ex.sort_after_exchange(pvs[c - 1], pias[c - 1], c, 1)
+    assert [int(p.n_total[0]) for p in pias] == [4, 6, 3]
+    want = [{1: (4, 1, 4)}, {2: (2, 1, 2), 3: (4, 3, 6)}, {4: (3, 1, 3)}]
+    for c in range(3):
+        assert oracle.check_unique_index(pvs[c], pias[c], 1) == (True, 0)
+        for cell in range(1, n_cells + 1):
+            ix = tuple(pias[c].indexer[0, cell - 1])
+            assert ix[4:] == (0, -1, 0)
+            if cell in want[c]:
+                n, s, e = want[c][cell]
+                assert ix[:4] == (n, s, e, n)
+                assert np.all(pvs[c].logical(s, e)[:, 0] == float(cell))
+            else:
+                assert ix[:4] == (0, 0, -1, 0)
