@@ -128,3 +128,27 @@ def test_sample_slab_uses_global_cells(mb, ctx):
     a = pv.logical(1, 25 * 8)
     gc = np.floor(a[:, 4] * G.inv_dx).astype(int)
     assert np.array_equal(gc, np.repeat(np.arange(50, 75), 8))
+
+
+def test_device_bkw_lattice_equals_the_reference_golden_initial_record(mb, ctx):
+    """Device against an OUTPUT OF THE REFERENCE, no oracle in between: sample_on_grid!(bkw) on the 40^3 velocity lattice is deterministic
+    in weights and velocities, and record 0 of the reference's golden files bkw_vw_octree / _grid / _octree_swpm_seed1234.nc holds its
+    count, n, T and total moments M4..M10 (tests/golden/reference_histories.json).  The device's weight table is evaluated with the
+    reference's arithmetic (fused 5 xk - 3, Julia's exp: mb_jlexp.h), so count and n are exact and T / moments agree to the rounding of
+    the device's reduction order."""
+    import json
+    import os
+
+    ref = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_histories.json")))
+    T0, n_dens = 273.0, 1e23
+    pv, pia = mb.ParticleVector(40 ** 3, ctx), mb.ParticleIndexerArray(1, 1, ctx)
+    n = mb.sample_on_grid(mb.PhiloxRng(0), "bkw", pv, pia, (1, 1), 1, 40, AR, T0, n_dens)
+    pp = mb.PhysProps(1, 1, [4, 6, 8, 10], Tref=T0, ctx=ctx)
+    mb.compute_props_with_total_moments([pv], pia, [AR], pp)
+    d = pp.download()
+    for key in ("bkw_vw_octree", "bkw_vw_grid", "bkw_vw_octree_swpm"):
+        r = ref[key]
+        assert n == int(r["np"][0]) == 30976 and d["np"][0, 0] == n
+        assert abs(d["n"][0, 0] / r["ndens"][0] - 1.0) < 1e-14
+        assert abs(d["T"][0, 0] - r["T"][0]) < 1e-10
+        np.testing.assert_allclose(d["moments"][0, 0], r["moments"][0], rtol=1e-12)
