@@ -27,4 +27,8 @@ def mb():
     """The product: ctypes mirror of the reference API over libmerzbild_b200.so (CUDA, sm_100a)."""
     import merzbild_b200 as m
 
+    if not os.path.exists(m.LIB_PATH):  # fresh checkout: build the library from source like __graft_entry__.build() does (nvcc, sm_100a)
+        import subprocess
+
+        subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(ROOT, "merzbild.jl_b200", "csrc"), "all"])
     return m
