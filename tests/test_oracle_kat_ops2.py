@@ -611,3 +611,48 @@ def test_sort_particles_after_exchange_reference_kat(oracle):
                 assert np.all(pvs[c].logical(s, e)[:, 0] == float(cell))
             else:
                 assert ix[:4] == (0, 0, -1, 0)
+
+
+def test_particle_exchange_push_only_reference_kats(oracle):
+    """test/test_particle_exchange.jl:332-538: (a) every particle of chunk 2 belongs to chunk 1's cell -- four pushes into a resized chunk 1,
+    chunk 2 keeps all four slots in its buffer in order [1, 2, 3, 4]; (b) 3 cells in 2 chunks, chunk 2 empty but pre-allocated: the two
+    cell-3 particles of chunk 1 are pushed into slots 1..2 of chunk 2 without a resize, chunk 1 frees slots [4, 5]."""
+    E = (0, -1, 0)
+    # (a)
+    ex = oracle.Exchanger([(1, 1), (2, 2)], 2)
+    pvs, pias = _two_chunk_setup(oracle, [[0.0, 1.0], [-2.0, -1.0, 1.5, 0.5]], [2, 4], [[(2, 1, 2), (0, 0, -1)], [(4, 1, 4), (0, 0, -1)]])
+    ex.reset(1); ex.reset(2)
+    ex.exchange(pvs, pias, 1)
+    assert [int(p.n_total[0]) for p in pias] == [6, 4] and [len(p) for p in pvs] == [6 + 256, 4]
+    assert pvs[0].nbuffer == 256 and pvs[1].nbuffer == 4 and list(pvs[1].buffer[:4]) == [1, 2, 3, 4]
+    r0 = pvs[0].logical(1, 6)
+    assert list(r0[:, 4]) == [0.0, 1.0, -2.0, -1.0, 1.5, 0.5] and list(r0[:, 0]) == [1, 1, 2, 2, 2, 2]
+    assert tuple(pias[0].indexer[0, 0]) == (2, 1, 2, 2, 0, -1, 0) and tuple(pias[1].indexer[0, 0]) == (0, 0, -1, 0, 0, -1, 0)
+    for c in (0, 1):
+        assert tuple(pias[c].indexer[0, 1]) == (0, 0, -1, 0, 0, -1, 0)
+    I = ex.indexer
+    assert tuple(I[0, 1, 1:]) == E + (3, 6, 4)  # cell 1 from chunk 2: nothing swapped, four pushed into slots 3..6
+    assert tuple(I[1, 0, 1:]) == E + E and tuple(I[0, 0, 1:]) == E + E and tuple(I[1, 1, 1:]) == E + E
+    # (b)
+    chunks, n_cells = [(1, 2), (3, 3)], 3
+    pvs, pias = [oracle.OPV(5), oracle.OPV(4)], [oracle.OPIA(n_cells, 1), oracle.OPIA(n_cells, 1)]
+    for k, (x, cell) in enumerate(zip([0.0, 1.0, 2.0, 6.0, 6.5], [1, 1, 2, 3, 3]), start=1):
+        pvs[0].add_particle(k, float(cell), [1.0, -1.0, 1.0], [x, 0.5, 0.0])
+    pias[0].n_total[0] = 5
+    for cell, (n, off) in enumerate(zip([2, 1, 2], [1, 3, 4])):
+        pias[0].indexer[0, cell] = (n, off, off + n - 1, n, 0, -1, 0)
+    ex = oracle.Exchanger(chunks, n_cells)
+    ex.reset(1); ex.reset(2)
+    ex.exchange(pvs, pias, 1)
+    assert [int(p.n_total[0]) for p in pias] == [5, 2] and [len(p) for p in pvs] == [5, 4]
+    assert pvs[0].nbuffer == 2 and list(pvs[0].buffer[:2]) == [4, 5] and pvs[1].nbuffer == 2
+    r0, r1 = pvs[0].logical(1, 5), pvs[1].logical(1, 2)
+    assert list(r0[:, 4]) == [0.0, 1.0, 2.0, 6.0, 6.5] and list(r0[:, 0]) == [1, 1, 2, 3, 3]
+    assert list(r1[:, 4]) == [6.0, 6.5] and list(r1[:, 0]) == [3, 3] and list(r1[:, 1]) == [1.0, 1.0]
+    assert [tuple(pias[0].indexer[0, c][:4]) for c in range(3)] == [(2, 1, 2, 2), (1, 3, 3, 1), (0, 0, -1, 0)]
+    assert all(tuple(pias[1].indexer[0, c]) == (0, 0, -1, 0, 0, -1, 0) for c in range(3))
+    I = ex.indexer
+    for cell in (0, 1):
+        for ch in (0, 1):
+            assert tuple(I[cell, ch, 1:]) == E + E
+    assert tuple(I[2, 1, 1:]) == E + E and tuple(I[2, 0, 1:]) == E + (1, 2, 2)
