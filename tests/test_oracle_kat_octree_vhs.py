@@ -303,3 +303,23 @@ def test_octree_merging_buffer_sorting_reference_kat(oracle):
     assert pia.contiguous[0] == 0 and p.np[0].tolist() == [12.0, 10.0] and abs(p.n[0, 0] - 90.0) < 1e-12 and pv.nbuffer == 78
     assert pv.buffer[:78].tolist() == [100 - i for i in range(78)]
     assert tuple(pia.indexer[0, 0]) == (12, 1, 5, 5, 16, 22, 7) and tuple(pia.indexer[0, 1][:4]) == (10, 6, 15, 10)
+
+
+def test_swpm_collision_factor_estimate_is_the_ntc_estimate_at_unit_weight(oracle):
+    """test/test_collision_utils_swpm.jl:53-85: create_collision_factors_swpm_array(pia, interactions, species, T; mult_factor) fills
+    sigma_g_max with estimate_sigma_g_w_max at Fnum = 1 -- for one temperature and for a temperature per species (Ar 300 K, He 600 K),
+    all four species pairs; the estimate is linear in Fnum and in mult_factor."""
+    mA, mH = oracle.MASS["Ar"], oracle.MASS["He"]
+    its = {("Ar", "Ar"): (oracle.interaction("Ar", "Ar"), mA, mA), ("He", "He"): (oracle.interaction("He", "He"), mH, mH),
+           ("Ar", "He"): (oracle.make_interaction(mA, mH, *oracle.VHS[("Ar", "He")]), mA, mH),
+           ("He", "Ar"): (oracle.make_interaction(mH, mA, *oracle.VHS[("Ar", "He")]), mH, mA)}
+    for Ts in ({"Ar": 300.0, "He": 300.0}, {"Ar": 300.0, "He": 600.0}):
+        for (a, b), (it, m1, m2) in its.items():
+            swpm = oracle.estimate_sigma_g_w_max(it, m1, m2, Ts[a], Ts[b], 1.0, 2.0)
+            ntc = oracle.estimate_sigma_g_w_max(it, m1, m2, Ts[a], Ts[b], 1.0, 1.0)
+            assert swpm > 0 and abs(swpm - 2.0 * ntc) <= 2 * np.finfo(float).eps * swpm
+            assert abs(oracle.estimate_sigma_g_w_max(it, m1, m2, Ts[a], Ts[b], 5e12, 2.0) / (5e12 * swpm) - 1.0) < 4e-16
+    # symmetric in the pair
+    a = oracle.estimate_sigma_g_w_max(its[("Ar", "He")][0], mA, mH, 300.0, 600.0, 1.0)
+    b = oracle.estimate_sigma_g_w_max(its[("He", "Ar")][0], mH, mA, 600.0, 300.0, 1.0)
+    assert abs(a / b - 1.0) < 1e-15
