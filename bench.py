@@ -122,7 +122,8 @@ def reference_arm(args, rank):
                    "step": "ntc_equal_weight+convect+exchange(chunks)+sort+props_sorted",
                    "sample": "each step runs on a bounded sample of this workload: %d cells x %d ppc = %.1e particles, all host threads" % (nx, PPC, nx * PPC)},
         "cpu_baseline": {"value": v, "unit": "particle-timesteps/s", "cores": threads, "kind": "port",
-                         "sample": "C++ restatement of the reference's multithreaded Couette loop (Julia is not installed): %d cells x %d ppc, %d steps; "
+                         "sample": "C++ restatement of the reference's multithreaded Couette loop (Julia is not installed; the same operator code replays the "
+                                   "reference's golden runs to round-off, tests/test_oracle_reference_bitlevel.py): %d cells x %d ppc, %d steps; "
                                    "collide+convect+sort %.2fs, exchange %.2fs, resort+props %.2fs" %
                                    (nx, PPC, args.steps, r["collide_convect_sort_s"], r["exchange_s"], r["resort_props_s"])},
         "e2e": {"value": v, "unit": "particle-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -356,7 +357,8 @@ def main():
         k_cpu = int(min(max(15.0 * cal["particle_steps_per_s"] / (nx_cpu * PPC), 20), 2000))
         r = run_cpu_port(nx_cpu, PPC, k_cpu, 3, threads)
         line["cpu_baseline"] = {"value": r["particle_steps_per_s"], "unit": "particle-timesteps/s", "cores": threads, "kind": "port",
-                                "sample": "C++ restatement of the reference's multithreaded Couette loop (couette_multithreaded.jl:97-173): %d cells x %d ppc "
+                                "sample": "C++ restatement of the reference's multithreaded Couette loop (couette_multithreaded.jl:97-173; the same operator code "
+                                          "replays the reference's golden runs to round-off): %d cells x %d ppc "
                                           "(%.0e particles), %d steps, %d OpenMP threads, %.1f s" % (nx_cpu, PPC, nx_cpu * PPC, k_cpu, threads, r["seconds"])}
     emit(line)
     if world > 1:
