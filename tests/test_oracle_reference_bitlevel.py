@@ -199,7 +199,7 @@ def _surf_columns(s, rec):
                            c("shear_pressure"), c("kinetic_energy_flux")[:, None]], 1)
 
 
-@pytest.mark.parametrize("key,variant,ppc,n_steps,thr,tgt", [("couette", "ntc", 1000, 3000, 0, 0),
+@pytest.mark.parametrize("key,variant,ppc,n_steps,thr,tgt", [("couette", "ntc", 1000, 6000, 0, 0),
                                                              ("couette_vw200to150", "vw", 1000, 6000, 200, 150),
                                                              ("couette_vw200to150_swpm", "swpm", 1000, 4000, 200, 150),
                                                              ("couette_vw150to100_resort", "resort", 500, 3000, 150, 100),
