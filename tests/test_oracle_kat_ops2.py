@@ -656,3 +656,44 @@ def test_particle_exchange_push_only_reference_kats(oracle):
         for ch in (0, 1):
             assert tuple(I[cell, ch, 1:]) == E + E
     assert tuple(I[2, 1, 1:]) == E + E and tuple(I[2, 0, 1:]) == E + (1, 2, 2)
+
+
+def test_sort_particles_after_exchange_full_swap_reference_kat(oracle):
+    """test/test_particle_resort_after_exchange.jl:159-296 (case 2): chunks [1] and [2, 3, 4] hold exactly each other's particles
+    ([2, 3, 4] and [1, 1, 1, 1]); after exchange + re-sort chunk 1 has four particles in cell 1 (resized by the push), chunk 2 one per
+    cell in slots 1, 2, 3; writing through the logical view afterwards touches every particle exactly once."""
+    chunks, n_cells = [(1, 1), (2, 4)], 4
+    positions, cells = [[2.0, 3.0, 4.0], [-1.0, -0.5, 0.5, 1.0]], [[2, 3, 4], [1, 1, 1, 1]]
+    np_in_cells, offsets = [[0, 1, 1, 1], [4, 0, 0, 0]], [[0, 1, 2, 3], [1, 0, 0, 0]]
+    pvs, pias = [oracle.OPV(3), oracle.OPV(4)], [oracle.OPIA(n_cells, 1), oracle.OPIA(n_cells, 1)]
+    for c in range(2):
+        for k, (x, cell) in enumerate(zip(positions[c], cells[c]), start=1):
+            pvs[c].add_particle(k, float(cell), [c + 1.0, -(c + 1.0), c + 1.0], [x, 0.5, 0.0])
+        pias[c].n_total[0] = len(positions[c])
+        for cell in range(n_cells):
+            n = np_in_cells[c][cell]
+            pias[c].indexer[0, cell] = (n, offsets[c][cell], offsets[c][cell] + n - 1, n, 0, -1, 0) if n else (0, 0, -1, 0, 0, -1, 0)
+    ex = oracle.Exchanger(chunks, n_cells)
+    ex.reset(1); ex.reset(2)
+    ex.exchange(pvs, pias, 1)
+    for c in (1, 2):
+        ex.sort_after_exchange(pvs[c - 1], pias[c - 1], c, 1)
+    assert [len(p) for p in pvs] == [4 + 256, 4] and [int(p.n_total[0]) for p in pias] == [4, 3]
+    want = [{1: (4, 1, 4)}, {2: (1, 1, 1), 3: (1, 2, 2), 4: (1, 3, 3)}]
+    for c in range(2):
+        assert oracle.check_unique_index(pvs[c], pias[c], 1) == (True, 0)
+        for cell in range(1, n_cells + 1):
+            ix = tuple(pias[c].indexer[0, cell - 1])
+            assert ix[4:] == (0, -1, 0)
+            if cell in want[c]:
+                n, s, e = want[c][cell]
+                assert ix[:4] == (n, s, e, n) and np.all(pvs[c].logical(s, e)[:, 0] == float(cell))
+            else:
+                assert ix[:4] == (0, 0, -1, 0)
+    # no storage slot is shared between logical positions: rewrite the weights through the logical view and read them back
+    for c in range(2):
+        nt = int(pias[c].n_total[0])
+        rows = pvs[c].logical(1, nt).copy()
+        rows[:, 0] = 100.0 * (c + 1) + np.arange(nt)
+        pvs[c].set_logical(1, rows)
+        assert np.array_equal(pvs[c].logical(1, nt)[:, 0], 100.0 * (c + 1) + np.arange(nt))
