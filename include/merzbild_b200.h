@@ -93,7 +93,7 @@ int mb_timer_start(mb_ctx* ctx);
 int mb_timer_stop(mb_ctx* ctx, double* elapsed_ms);   /* synchronises */
 int mb_flush_l2(mb_ctx* ctx);                  /* writes a 256 MiB scratch buffer (> 126 MB L2) */
 /* per-kernel CUDA-event profiling (off by default).  Sections: 0 sort.classify, 1 sort.scan, 2 sort.scatter, 3 sort.general,
- * 4 ntc, 5 convect, 6 props, 7 merge, 8 fp, 9 exchange, 10 squash.  mb_prof_read synchronises, returns the summed device
+ * 4 ntc, 5 convect, 6 props, 7 merge, 8 fp, 9 exchange, 10 squash, 11 sort.extras.  mb_prof_read synchronises, returns the summed device
  * time and the number of timed launches of a section since the last read, and resets it. */
 int mb_prof_enable(mb_ctx* ctx, int32_t on);
 int mb_prof_read(mb_ctx* ctx, int32_t section, double* total_ms, int64_t* launches);
@@ -138,8 +138,12 @@ int mb_check_pia(mb_pia* pia, int64_t species, int32_t* ok, int64_t* where);
 int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia, int64_t species);
 /* which algorithm the last mb_sort_particles used: 1 = band (nearly-sorted fast path), 2 = general */
 int mb_sort_last_path(mb_ctx* ctx);
-/* force the general path (tests) */
-int mb_sort_set_band_halfwidth(mb_ctx* ctx, int32_t w);  /* 0 disables the band path; default 2 */
+/* band half-width w of the fast path: 0 disables it (general path only), else 1, 2, 4, 8 or 15; default 2.  Choose w of the order of
+ * 3 sigma_v dt / dx: particles that move further than w cells in one step ("extras") are still sorted correctly by the band path
+ * (hybrid: they are ranked separately), only more slowly, so w need not bound the displacement. */
+int mb_sort_set_band_halfwidth(mb_ctx* ctx, int32_t w);
+/* number of extras (band outliers + slab-exchange arrivals) the last band-path sort placed; -1 if the general path ran.  Synchronises. */
+int64_t mb_sort_last_extras(mb_ctx* ctx);
 
 /* ---- squash_pia!(pv, pia, species) particles.jl:622-682; restore_particle_ordering! :1086-1137 (no-op on device) ---- */
 int mb_squash_pia(mb_ctx* ctx, mb_pv* pv, mb_pia* pia, int64_t species);

@@ -21,7 +21,7 @@ constexpr double EPS = 2.220446049250313e-16;     // Julia eps()
 constexpr int N_SM = 148;                         // B200
 
 // device-side error flag bits (ctx->d_flags[0])
-// other slots of ctx->d_flags: [2] the sort's general path must run, [4..11] per-species "a merge left holes",
+// other slots of ctx->d_flags: [2] the sort's general path must run, [3] extras of the last band sort, [4..11] per-species "a merge left holes",
 // [12..15] written by the fused convect + classify kernel (mb_sort.cu)
 enum { F_OUTSIDE = 12, F_CLS_BAD = 13, F_FAR = 14, F_CLS_REDO = 15 };
 enum : int { DEVERR_CAPACITY = 1, DEVERR_PRECONDITION = 2, DEVERR_BAND_OVERFLOW = 4, DEVERR_BAD_CELL = 8, DEVERR_OCTREE = 16 };
@@ -106,8 +106,8 @@ struct mb_ctx {
     void* l2_scratch;
     size_t l2_scratch_bytes;
     // generic scratch arena (grown on demand, stream-ordered reuse)
-    void* scratch[12];
-    size_t scratch_bytes[12];
+    void* scratch[16];
+    size_t scratch_bytes[16];
     int sort_last_path;
     int band_w;
     // moments cached by the band sort's gather pass (valid while state_gen == pc_gen)
@@ -115,7 +115,8 @@ struct mb_ctx {
     void* pc_pv;
     void* pc_pia;
     int pc_species;
-    int pc_general;         // the general sort path filled the moment cache too (k_gen_gather_cells): valid whichever path ran
+    int pc_general;         // the general sort path fills the moment cache (k_gen_gather_cells)
+    int pc_band;            // the band path fills it (k_band_scatter + k_band_combine; narrow bands only)
     // band classification cached by the fused convect kernel (valid while state_gen == cls_gen)
     uint64_t cls_gen;
     void* cls_pv;
@@ -210,7 +211,7 @@ int pv_ensure_alt(mb_pv* pv);
     } while (0)
 
 enum { PROF_SORT_CLASSIFY = 0, PROF_SORT_SCAN = 1, PROF_SORT_SCATTER = 2, PROF_SORT_GENERAL = 3, PROF_NTC = 4, PROF_CONVECT = 5, PROF_PROPS = 6,
-       PROF_MERGE = 7, PROF_FP = 8, PROF_EXCHANGE = 9, PROF_SQUASH = 10, PROF_NSEC = 11 };
+       PROF_MERGE = 7, PROF_FP = 8, PROF_EXCHANGE = 9, PROF_SQUASH = 10, PROF_SORT_EXTRAS = 11, PROF_NSEC = 12 };
 void prof_begin(mb_ctx* ctx, int section);
 void prof_end(mb_ctx* ctx);
 struct ProfScope {

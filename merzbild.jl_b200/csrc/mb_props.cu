@@ -20,7 +20,8 @@ struct PropsArgs {
     const int32_t* powers;
     double moment_factor, moment_vref;  // physical_props.jl:176-177
     double n_scale;        // 1 or inv_V (ndens variant :425)
-    const int* run_if_flag;  // nullable: run only if *run_if_flag != 0 (the sort's cached moments are not valid)
+    const int* run_if_flag;  // nullable: run only if (*run_if_flag != 0) == run_if_nonzero (the sort's cached moments are not valid)
+    int run_if_nonzero;
     double* lpa;           // nullable: phys_props.lpa[species] = length(particles[species]) (:151), written by the kernel (no host sync)
     double lpa_val;
     int64_t n_lo;          // k_props<32>: cells with more than n_lo particles (the smaller ones are taken by k_props_reg)
@@ -43,7 +44,7 @@ __device__ __forceinline__ double group_sum(double x, double* sh) {
 template <int G>
 __global__ void __launch_bounds__(256) k_props(PropsArgs a) {
     __shared__ double sh[8];
-    if (a.run_if_flag != nullptr && *a.run_if_flag == 0) return;
+    if (a.run_if_flag != nullptr && (*a.run_if_flag != 0) != (a.run_if_nonzero != 0)) return;
     const int tid = G == 32 ? (threadIdx.x & 31) : threadIdx.x;
     const int64_t grp0 = G == 32 ? ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5) : blockIdx.x;
     const int64_t ngrp = G == 32 ? (((int64_t)gridDim.x * blockDim.x) >> 5) : gridDim.x;
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(256) k_props(PropsArgs a) {
 // results are bit-identical.  A warp takes 32 consecutive cells at a time (one read of their sizes).
 template <int K>
 __global__ void __launch_bounds__(128) k_props_reg(PropsArgs a, int n_lo) {
-    if (a.run_if_flag != nullptr && *a.run_if_flag == 0) return;
+    if (a.run_if_flag != nullptr && (*a.run_if_flag != 0) != (a.run_if_nonzero != 0)) return;
     const int lane = threadIdx.x & 31;
     const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t nr = a.cell_hi - a.cell_lo + 1;
@@ -183,8 +184,9 @@ __global__ void __launch_bounds__(128) k_props_reg(PropsArgs a, int n_lo) {
 }
 
 // compute_props_sorted! right after a band sort: the gather pass already holds np, n, vbar and sum w |v - vbar|^2 per cell
-static __global__ void k_props_cached(PropsArgs a, const double* __restrict__ pcache, const int* flags) {
-    if (flags != nullptr && flags[2] != 0) return;  // the general sort path ran without filling the cache
+static __global__ void k_props_cached(PropsArgs a, const double* __restrict__ pcache, const int* flags, int valid_if_general) {
+    // flags != nullptr: only one of the two sort paths fills the cache; flags[2] != 0 tells that the general path ran
+    if (flags != nullptr && (flags[2] != 0) != (valid_if_general != 0)) return;
     const int64_t nr = a.cell_hi - a.cell_lo + 1;
     for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nr; r += (int64_t)gridDim.x * blockDim.x) {
         const int64_t c = a.cell_lo - 1 + r;
@@ -227,13 +229,17 @@ static int props_launch(mb_ctx* ctx, mb_pv* const* pvs, mb_pia* pia, const doubl
         a.moment_vref = std::pow(masses[s] / (2 * k_B * P->Tref), 0.5);                         // :177
         a.n_scale = n_scale;
         a.run_if_flag = nullptr;
+        a.run_if_nonzero = 1;
         const int64_t nr = cell_hi - cell_lo + 1;
         if (sorted && ctx->pc_gen == ctx->state_gen && ctx->pc_pv == (void*)pvs[s] && ctx->pc_pia == (void*)pia && ctx->pc_species == (int)s + 1 &&
             ctx->scratch[10] != nullptr) {
-            k_props_cached<<<grid_for(nr, 256), 256, 0, ctx->stream>>>(a, (const double*)ctx->scratch[10], ctx->pc_general ? nullptr : ctx->d_flags);
+            const bool both = ctx->pc_general && ctx->pc_band;
+            k_props_cached<<<grid_for(nr, 256), 256, 0, ctx->stream>>>(a, (const double*)ctx->scratch[10], both ? nullptr : ctx->d_flags,
+                                                                      ctx->pc_general ? 1 : 0);
             MB_LAUNCH_CHECK(ctx);
-            if (ctx->pc_general) continue;     // both sort paths fill the cache: nothing left to compute
-            a.run_if_flag = ctx->d_flags + 2;  // the regular kernel below only runs if the sort fell back to the general path
+            if (both) continue;                // both sort paths fill the cache: nothing left to compute
+            a.run_if_flag = ctx->d_flags + 2;  // the regular kernel below only runs if the sort took the path that does not fill the cache
+            a.run_if_nonzero = ctx->pc_band ? 1 : 0;
         }
         const int64_t avg = (pia->n_bound[s] > 0 ? pia->n_bound[s] : pvs[s]->cap) / (nc > 0 ? nc : 1);
         a.lpa = sorted ? nullptr : P->lpa + s;  // phys_props.lpa[species] = length(particles[species]) :151

@@ -14,7 +14,12 @@
 //      A scan over cells gives the new cell starts; pass B (a warp per old cell again) streams the cell once and stores
 //      every particle at start(c) + sum_{c'' < c'} M(c'', c) + rank.  HBM traffic: pass A 8 B (x) [+ 8 B vx and 8 B x
 //      written when fused with the convection] + 4 B (word); pass B 4 + 56 + 56 B = 116 B / particle.
-//  (2) GENERAL path (arbitrary input; taken when a particle leaves the band, or the layout is not sorted):
+//      HYBRID: a particle that leaves the band (|c - c'| > w) or arrives from a neighbouring slab is an "extra": it is appended
+//      to a short list (original position, destination cell) and counted per destination cell as BEFORE the band (it came from a
+//      source cell < c - w) or AFTER it (source > c + w, or a slab-exchange arrival).  The destination cell is laid out as
+//      [extras before | band groups by source cell | extras after]; the extras are ranked among themselves by their original
+//      position, so the result is still the reference's stable order, and the band work is never thrown away for a few outliers.
+//  (2) GENERAL path (arbitrary input; taken when the layout is not sorted, or the extras do not fit their list):
 //      histogram with warp-aggregated atomics, scan, unstable atomic scatter of particle indices into the cell
 //      buckets, per-cell ascending sort of the indices (== stable order), gather of the payload.
 #include <climits>
@@ -38,9 +43,42 @@ struct SortScratch {
     int32_t* M;        // [n_cells * W] band matrix
     int64_t* O;        // [n_cells * W] destination offsets
     int32_t* cursor;   // [n_cells] (general path)
-    int32_t* perm;     // [cap]     (general path)
+    int32_t* perm;     // [cap]     (general path); band path: slot[] = original positions of the extras, indexed by output position
     int* flags;        // ctx->d_flags
 };
+
+// the extras of the hybrid band path (see the header comment)
+struct ExBufs {
+    int32_t* n;        // number of extras appended (may exceed cap: overflow -> general path)
+    int32_t* idx;      // [cap] original logical position (0-based)
+    int32_t* cell;     // [cap] destination cell * 2 + class (0: before the band, 1: after it)
+    int32_t* cntB;     // [n_cells] extras before the band per destination cell
+    int32_t* cntA;     // [n_cells] extras after the band (incl. slab-exchange arrivals)
+    int32_t* curB;     // [n_cells] slot cursors
+    int32_t* curA;
+    int32_t cap;
+};
+constexpr int EX_REGION_MAX = 4096;  // extras per (cell, class) ranked by counting; beyond that the general path runs
+
+// All lanes of the warp call it; returns true if the list is full (the caller requests the general path).
+__device__ __forceinline__ bool extras_append(const ExBufs& E, bool is, int32_t i, int nc, int cls, int lane, unsigned lt) {
+    const unsigned m = __ballot_sync(0xffffffffu, is);
+    if (m == 0) return false;
+    int base = 0;
+    const int leader = __ffs(m) - 1;
+    if (lane == leader) base = atomicAdd(E.n, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    bool ovf = false;
+    if (is) {
+        const int e = base + __popc(m & lt);
+        if (e >= 0 && e < E.cap) {
+            E.idx[e] = i;
+            E.cell[e] = nc * 2 + cls;
+            atomicAdd((cls ? E.cntA : E.cntB) + nc, 1);
+        } else ovf = true;
+    }
+    return ovf;
+}
 
 // flags[2] = 1 -> the general path must run (band overflow or band not applicable)
 
@@ -77,7 +115,7 @@ template <int W>
 __global__ void __launch_bounds__(256) k_band_classify(const double* __restrict__ X, const int32_t* cell_in, int32_t* cell_out,
                                                        const Indexer* __restrict__ ix, int64_t n_cells, double inv_dx, int64_t cell_offset,
                                                        int use_x, int drop, int32_t* __restrict__ M, int64_t* __restrict__ seg_lo,
-                                                       int32_t* __restrict__ seg_n, uint32_t* __restrict__ dr, int* flags, const int* only_if) {
+                                                       int32_t* __restrict__ seg_n, uint32_t* __restrict__ dr, ExBufs E, int* flags, const int* only_if) {
     if (only_if != nullptr && *only_if == 0) return;  // the fused convect kernel already classified every cell
     constexpr int w = W / 2;
     __shared__ int s_cnt[8][32];
@@ -101,20 +139,23 @@ __global__ void __launch_bounds__(256) k_band_classify(const double* __restrict_
         for (int64_t b = 0; b < n; b += 32) {
             const int64_t i = lo + b + lane;
             const bool valid = b + lane < n;
-            int d = 255;
+            int d = 255, nc = 0, cls = 0;
+            bool ex = false;
             if (valid) {
-                int nc;
                 if (use_x) { nc = cell_of(X[i], inv_dx, cell_offset); cell_out[i] = nc + 1; }
                 else nc = cell_in[i] - 1;
                 const bool inside = nc >= 0 && nc < n_cells;
                 const int64_t dd = (int64_t)nc - c + w;
-                if (inside && dd >= 0 && dd < W) d = (int)dd;
-                else if (!(drop && !inside)) bad = true;
+                if (inside) {
+                    if (dd >= 0 && dd < W) d = (int)dd;
+                    else { ex = true; cls = dd < 0 ? 1 : 0; }  // moved further than w cells: an extra of the destination cell
+                } else if (!drop) bad = true;                   // outside the slab and no exchange: the general path reports it
                 // edge exchange: a leaver from a cell further than w from that slab face was never sent
                 if (!inside && drop == 2 && ((nc < 0 && c >= w) || (nc >= n_cells && c < n_cells - w)))
                     atomicOr(&flags[0], DEVERR_BAND_OVERFLOW);
             }
             classify_batch(d, valid, lt, cnt_s, dr + (valid ? i : 0));
+            if (extras_append(E, ex, (int32_t)i, nc, cls, lane, lt)) bad = true;
         }
         if (__any_sync(0xffffffffu, bad)) {
             if (lane == 0) atomicOr(&flags[2], 1);
@@ -124,17 +165,28 @@ __global__ void __launch_bounds__(256) k_band_classify(const double* __restrict_
     }
 }
 
-// arrivals of the slab exchange (appended after the old layout): key + per-cell arrival count
-static __global__ void k_band_arrivals(const double* __restrict__ X, const int64_t* n_total_p, const int64_t* n_arr_p, int64_t n_cells, double inv_dx,
-                                       int64_t cell_offset, int32_t* cell_out, int32_t* __restrict__ key_arr, int32_t* __restrict__ acnt, int* flags) {
+// arrivals of the slab exchange (appended after the old layout): extras of class "after" of their cells (their original positions
+// follow every particle of the old layout, in arrival order)
+static __global__ void __launch_bounds__(256) k_band_arrivals(const double* __restrict__ X, const int64_t* n_total_p, const int64_t* n_arr_p,
+                                                             int64_t n_cells, double inv_dx, int64_t cell_offset, int32_t* cell_out, ExBufs E,
+                                                             int* flags) {
     const int64_t n_arr = *n_arr_p;
     const int64_t base = *n_total_p - n_arr;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_arr; t += (int64_t)gridDim.x * blockDim.x) {
-        const int nc = cell_of(X[base + t], inv_dx, cell_offset);
-        cell_out[base + t] = nc + 1;
-        if (nc < 0 || nc >= n_cells) { atomicOr(&flags[2], 1); key_arr[t] = -1; continue; }  // the general path reports it
-        key_arr[t] = nc;
-        atomicAdd(&acnt[nc], 1);
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t nround = (n_arr + stride - 1) / stride;
+    for (int64_t r = 0; r < nround; r++) {  // warp-uniform trip count
+        const int64_t t = r * stride + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+        bool ex = false;
+        int nc = 0;
+        if (t < n_arr) {
+            nc = cell_of(X[base + t], inv_dx, cell_offset);
+            cell_out[base + t] = nc + 1;
+            if (nc < 0 || nc >= n_cells) atomicOr(&flags[2], 1);  // the general path reports it
+            else ex = true;
+        }
+        if (extras_append(E, ex, (int32_t)(base + t), nc, 1, lane, lt)) atomicOr(&flags[2], 1);
     }
 }
 
@@ -153,9 +205,9 @@ __device__ __forceinline__ int band_hist(const int32_t* __restrict__ M, int64_t 
 
 // scan step 1: per-block sums of the per-cell counts (band: derived from M and stored to hist; general: hist given)
 template <int W>
-__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_reduce(const int32_t* __restrict__ M, const int32_t* __restrict__ acnt,
-                                                           int32_t* __restrict__ hist, int64_t n_cells, int64_t* __restrict__ partial,
-                                                           const int* flags, int mode) {
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_reduce(const int32_t* __restrict__ M, const int32_t* __restrict__ cntB,
+                                                           const int32_t* __restrict__ cntA, int32_t* __restrict__ hist, int64_t n_cells,
+                                                           int64_t* __restrict__ partial, int* flags, int mode) {
     // mode 0: band (runs always; cheap), mode 1: general (runs only if flags[2])
     if (mode == 1 && flags[2] == 0) return;
     __shared__ int64_t red[SCAN_BLOCK / 32];
@@ -165,7 +217,12 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_reduce(const int32_t* __res
         const int64_t c = base + k * SCAN_BLOCK + threadIdx.x;
         if (c < n_cells) {
             int h;
-            if (mode == 0) { h = band_hist<W>(M, c, n_cells) + (acnt ? acnt[c] : 0); hist[c] = h; }
+            if (mode == 0) {
+                const int eb = cntB[c], ea = cntA[c];
+                if (eb > EX_REGION_MAX || ea > EX_REGION_MAX) atomicOr(&flags[2], 1);  // too many extras in one cell to rank by counting
+                h = band_hist<W>(M, c, n_cells) + eb + ea;
+                hist[c] = h;
+            }
             else h = hist[c];
             s += h;
         }
@@ -278,8 +335,8 @@ constexpr int SC_U = MB_SC_U;  // particles per lane in flight
 template <int W>
 __global__ void __launch_bounds__(256, MB_SC_MINB) k_band_scatter(SoA in_, SoA out_, const uint32_t* __restrict__ dr, const int32_t* __restrict__ M,
                                                       const int64_t* __restrict__ seg_lo, const int32_t* __restrict__ seg_n,
-                                                      const int64_t* __restrict__ start, int64_t n_cells, double* __restrict__ P,
-                                                      const int* flags) {
+                                                      const int64_t* __restrict__ start, const int32_t* __restrict__ cntB, int64_t n_cells,
+                                                      double* __restrict__ P, const int* flags) {
     if (flags[2] != 0) return;  // general path takes over
     constexpr int w = W / 2;
     __shared__ int64_t s_off[8][32];
@@ -295,11 +352,14 @@ __global__ void __launch_bounds__(256, MB_SC_MINB) k_band_scatter(SoA in_, SoA o
             const int64_t cd = c + lane - w;  // destination cell of group d = lane
             int64_t off = 0;
             if (cd >= 0 && cd < n_cells) {
-                off = start[cd];
-                for (int k = 1; lane + k < W; k++) {  // sources c - k < c that also feed cd
+                off = start[cd] + cntB[cd];  // the extras that came from further left sit in front of the band groups
+                int acc = 0;
+#pragma unroll
+                for (int k = 1; k < W; k++) {  // sources c - k < c that also feed cd (independent loads, all in flight together)
                     const int64_t cs = c - k;
-                    if (cs >= 0) off += M[cs * W + lane + k];
+                    if (lane + k < W && cs >= 0) acc += M[cs * W + lane + k];
                 }
+                off += acc;
             }
             s_off[wid][lane] = off;
         }
@@ -357,31 +417,46 @@ __global__ void __launch_bounds__(256, MB_SC_MINB) k_band_scatter(SoA in_, SoA o
     }
 }
 
-// slab-exchange arrivals (a few dozen per step): behind everything the band delivers to the cell, in arrival order
-static __global__ void __launch_bounds__(256) k_band_place_arrivals(SoA in_, SoA out_, const int32_t* __restrict__ key_arr, const int64_t* n_arr_p,
-                                                                   const int64_t* n_old_p, const int32_t* __restrict__ hist,
-                                                                   const int32_t* __restrict__ acnt, const int64_t* __restrict__ start,
-                                                                   const int* flags) {
+// The extras (band outliers and slab-exchange arrivals).  Step 1: every extra takes a slot of its (cell, class) region of the
+// OUTPUT layout and leaves its original position there (slot[] is indexed by output position; the order inside a region is
+// whatever the atomics produce).  Step 2: every extra ranks itself inside its region by counting the smaller original positions
+// (regions hold a handful of entries) and copies its record to region start + rank: ascending original position, the
+// reference's stable order.
+static __global__ void __launch_bounds__(256) k_extra_slots(ExBufs E, const int64_t* __restrict__ start, const int32_t* __restrict__ hist,
+                                                           int32_t* __restrict__ slot, const int* flags) {
     if (flags[2] != 0) return;
-    const int64_t n_arr = *n_arr_p, abase = *n_old_p - n_arr;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_arr; t += (int64_t)gridDim.x * blockDim.x) {
-        const int c = key_arr[t];
-        if (c < 0) continue;
+    const int n = min(*E.n, E.cap);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int cc = E.cell[e], c = cc >> 1, cls = cc & 1;
+        const int64_t rs = cls ? start[c] + hist[c] - E.cntA[c] : start[c];
+        const int k = atomicAdd((cls ? E.curA : E.curB) + c, 1);
+        slot[rs + k] = E.idx[e];
+    }
+}
+static __global__ void __launch_bounds__(256) k_extra_place(ExBufs E, const int64_t* __restrict__ start, const int32_t* __restrict__ hist,
+                                                           const int32_t* __restrict__ slot, SoA in_, SoA out_, const int* flags) {
+    if (flags[2] != 0) return;
+    const int n = min(*E.n, E.cap);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int cc = E.cell[e], c = cc >> 1, cls = cc & 1;
+        const int m = cls ? E.cntA[c] : E.cntB[c];
+        const int64_t rs = cls ? start[c] + hist[c] - m : start[c];
+        const int32_t i = E.idx[e];
         int rank = 0;
-        for (int64_t u = 0; u < t; u++) rank += key_arr[u] == c;
-        const int64_t pos = start[c] + (hist[c] - acnt[c]) + rank, ia = abase + t;  // hist = band + arrivals
+        for (int t = 0; t < m; t++) rank += slot[rs + t] < i;
+        const int64_t pos = rs + rank;
 #pragma unroll
-        for (int f = 0; f < 7; f++) out_.a[f][pos] = in_.a[f][ia];
+        for (int f = 0; f < 7; f++) out_.a[f][pos] = in_.a[f][i];
     }
 }
 
 // Moments of the freshly sorted cells: the staying group's sums from P, plus the movers and arrivals of the cell read back
 // from the output (they sit in known sub-ranges of the cell, ~5 % of it), in source order -- deterministic.
 template <int W>
-__global__ void __launch_bounds__(128) k_band_combine(const double* __restrict__ P, const int32_t* __restrict__ M, const int32_t* __restrict__ acnt,
-                                                      const int64_t* __restrict__ seg_lo, const int32_t* __restrict__ seg_n,
-                                                      const int64_t* __restrict__ start, SoA in_, SoA out_, int64_t n_cells,
-                                                      double* __restrict__ pcache, const int* flags) {
+__global__ void __launch_bounds__(128) k_band_combine(const double* __restrict__ P, const int32_t* __restrict__ M, const int32_t* __restrict__ cntB,
+                                                      const int32_t* __restrict__ cntA, const int64_t* __restrict__ seg_lo,
+                                                      const int32_t* __restrict__ seg_n, const int64_t* __restrict__ start, SoA in_, SoA out_,
+                                                      int64_t n_cells, double* __restrict__ pcache, const int* flags) {
     if (flags[2] != 0) return;
     constexpr int w = W / 2;
     const double* __restrict__ o0 = out_.a[0]; const double* __restrict__ o1 = out_.a[1]; const double* __restrict__ o2 = out_.a[2];
@@ -394,14 +469,15 @@ __global__ void __launch_bounds__(128) k_band_combine(const double* __restrict__
         int64_t pos = start[c];
         const int64_t pos0 = pos;
 #pragma unroll
-        for (int k = 0; k <= W; k++) {  // k == W: the arrivals
+        for (int k = -1; k <= W; k++) {  // k == -1: the extras before the band, k == W: the extras after it (incl. arrivals)
             int cnt;
-            if (k < W) {
+            if (k < 0) cnt = cntB[c];
+            else if (k < W) {
                 const int64_t cs = c - w + k;
                 if (cs < 0 || cs >= n_cells) continue;
                 cnt = M[cs * W + (W - 1 - k)];
             } else {
-                cnt = acnt != nullptr ? acnt[c] : 0;
+                cnt = cntA[c];
             }
             if (k != w) {
                 for (int t = 0; t < cnt; t++) {
@@ -441,7 +517,7 @@ constexpr int CB_SMEM = 8 * CB_SMEM_WARP;
 
 template <int W>
 __global__ void __launch_bounds__(256, MB_CB_MINB) k_convect_band(ConvectArgs a, int32_t* __restrict__ M, int64_t* __restrict__ seg_lo,
-                                                                  int32_t* __restrict__ seg_n, uint32_t* __restrict__ dr, int* flags) {
+                                                                  int32_t* __restrict__ seg_n, uint32_t* __restrict__ dr, ExBufs E, int* flags) {
     constexpr int w = W / 2;
     extern __shared__ __align__(16) unsigned char cb_smem[];  // CB_SMEM bytes: per warp rx | rv | cnt
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -475,7 +551,8 @@ __global__ void __launch_bounds__(256, MB_CB_MINB) k_convect_band(ConvectArgs a,
         cnt_s[lane] = 0;
         __syncwarp();
         bool bad = false, outside = false, far = false;
-        // one particle: returns d (255: not counted)
+        int xnc = 0;
+        // one particle: returns d (255: not counted, 254: an extra -- inside the slab but further than w cells away, cell in xnc)
         auto move = [&](int j, double x_old, double vx) -> int {
             double x_new = fma(vx, dt, x_old);  // @muladd x[1] + v[1] * dt
             if (x_new >= L || x_new <= 0.0) x_new = convect_wall(a, lo + j, x_old, vx, x_new);
@@ -487,8 +564,8 @@ __global__ void __launch_bounds__(256, MB_CB_MINB) k_convect_band(ConvectArgs a,
             const int d = nc - c + w;
             if (nc >= 0 && nc < n_cells) {
                 if (d >= 0 && d < W) return d;
-                bad = true;
-                return 255;
+                xnc = nc;
+                return 254;
             }
             outside = true;
             if ((nc < 0 && c >= w) || (nc >= n_cells && c < n_cells - w)) far = true;
@@ -517,7 +594,9 @@ __global__ void __launch_bounds__(256, MB_CB_MINB) k_convect_band(ConvectArgs a,
             issue(k + CB_PF);
             int d = 255;
             if (valid) d = move(j, x0, v0);
-            classify_batch(d, valid, lt, cnt_s, drc + (valid ? j : 0));
+            const bool ex = d == 254;
+            classify_batch(ex ? 255 : d, valid, lt, cnt_s, drc + (valid ? j : 0));
+            if (extras_append(E, ex, (int32_t)(lo + j), xnc, xnc < c ? 1 : 0, lane, lt)) bad = true;
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         bad = __any_sync(0xffffffffu, bad);
@@ -534,6 +613,8 @@ __global__ void __launch_bounds__(256, MB_CB_MINB) k_convect_band(ConvectArgs a,
 }
 
 __global__ void k_clear_cls_flags(int* flags) { flags[F_OUTSIDE] = 0; flags[F_CLS_BAD] = 0; flags[F_FAR] = 0; flags[F_CLS_REDO] = 0; }
+// number of extras of the last band sort (diagnostic: mb_sort_last_extras)
+__global__ void k_save_extras(const int32_t* n, int* flags) { flags[3] = *n; }
 // flags[2] (general path needed) from the cached classification: band overflow, or a particle outside the slab with no exchange
 __global__ void k_flag_from_cls(int* flags, int drop) { flags[2] = (flags[F_CLS_BAD] != 0 || (!drop && flags[F_OUTSIDE] != 0)) ? 1 : 0; }
 
@@ -834,8 +915,7 @@ struct BandBufs {
     int64_t* seg_lo;
     int32_t* seg_n;
     uint32_t* dr;      // [cap] d << 24 | rank inside the (source cell -> destination cell) group
-    int32_t* acnt;     // nullable (no arrivals)
-    int32_t* key_arr;
+    ExBufs E;          // band outliers and slab-exchange arrivals
     int64_t n_arr;     // host upper bound
     const int64_t* d_n_arr;  // device: exact
     int64_t* n_old;    // device copy of n_total before the sort
@@ -848,27 +928,37 @@ struct BandBufs {
 
 // The scratch layout of a sort is a pure function of (capacity, n_cells, W), so the fused convect + classify kernel (which runs
 // before the sort call) and the sort itself address the same buffers.
+constexpr int W_MAX = 31;  // widest band (w = 15): the group id lives in a lane
 static int sort_scratch_layout(mb_ctx* ctx, int64_t cap, int64_t nc, int W, SortScratch& S, BandBufs& B) {
     const int nscan = (int)((nc + SCAN_TILE - 1) / SCAN_TILE);
     S.flags = ctx->d_flags;
     S.key = (int32_t*)ctx_scratch(ctx, 0, (size_t)cap * 4);  // general: keys; band: dr
-    // slot 1: hist | cursor | seg_n | acnt | key_arr | M   (int32); sized for the widest band so that W may change between calls
-    const size_t n32 = (size_t)nc * (4 + 17) + 4096 + 64;
+    // slot 1 (int32): hist | cursor | seg_n | cntB | cntA | curB | curA | ex_n (64) | M; sized for the widest band so that W may change
+    const size_t n32 = (size_t)nc * (7 + W_MAX) + 128;
     int32_t* p32 = (int32_t*)ctx_scratch(ctx, 1, n32 * 4);
     // slot 2: start | partial | n_old | seg_lo   (int64)
     const size_t n64 = (size_t)(nc + 1) + (size_t)(nscan + 2) + 2 + (size_t)nc + 64;
     int64_t* p64 = (int64_t*)ctx_scratch(ctx, 2, n64 * 8);
-    if (!S.key || !p32 || !p64) return MB_ERR_CUDA;
+    // slot 12: the extras list (original position, destination cell)
+    const int64_t ex_cap = cap / 4 + 65536;
+    int32_t* pex = (int32_t*)ctx_scratch(ctx, 12, (size_t)ex_cap * 8);
+    if (!S.key || !p32 || !p64 || !pex) return MB_ERR_CUDA;
     S.hist = p32;
     S.cursor = p32 + nc;
-    S.M = p32 + 4 * nc + 4096;
+    S.M = p32 + 7 * nc + 64;
     S.start = p64;
     S.partial = p64 + (nc + 1);
     S.O = nullptr;
     S.perm = nullptr;
     B.seg_n = p32 + 2 * nc;
-    B.acnt = p32 + 3 * nc;
-    B.key_arr = p32 + 4 * nc;
+    B.E.cntB = p32 + 3 * nc;
+    B.E.cntA = p32 + 4 * nc;
+    B.E.curB = p32 + 5 * nc;
+    B.E.curA = p32 + 6 * nc;
+    B.E.n = p32 + 7 * nc;
+    B.E.idx = pex;
+    B.E.cell = pex + ex_cap;
+    B.E.cap = (int32_t)(ex_cap < INT_MAX / 2 ? ex_cap : INT_MAX / 2);
     B.n_old = S.partial + (nscan + 2);
     B.seg_lo = B.n_old + 2;
     B.dr = (uint32_t*)S.key;
@@ -879,6 +969,11 @@ static int sort_scratch_layout(mb_ctx* ctx, int64_t cap, int64_t nc, int W, Sort
     B.d_nt_write = nullptr;
     B.P = nullptr;
     (void)W;
+    return MB_OK;
+}
+// cntB | cntA | curB | curA | ex_n are cleared before every classification
+static int extras_clear(mb_ctx* ctx, const BandBufs& B, int64_t nc) {
+    MB_CUDA(cudaMemsetAsync(B.E.cntB, 0, ((size_t)4 * nc + 64) * 4, ctx->stream));
     return MB_OK;
 }
 
@@ -897,6 +992,7 @@ int convect_band_launch(mb_ctx* ctx, const ConvectArgs& a, const mb_grid1d* grid
     cudaStream_t st = ctx->stream;
     k_clear_cls_flags<<<1, 1, 0, st>>>(ctx->d_flags);
     MB_LAUNCH_CHECK(ctx);
+    if (extras_clear(ctx, B, nc)) return MB_ERR_CUDA;
     const int g = grid_for(nc * 32, 256, MB_CB_MINB);
     static bool attr_done[64] = {false};  // function attributes are per device
     bool& attr_set = attr_done[ctx->device & 63];
@@ -905,12 +1001,14 @@ int convect_band_launch(mb_ctx* ctx, const ConvectArgs& a, const mb_grid1d* grid
         MB_CUDA(cudaFuncSetAttribute(k_convect_band<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, CB_SMEM));
         MB_CUDA(cudaFuncSetAttribute(k_convect_band<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, CB_SMEM));
         MB_CUDA(cudaFuncSetAttribute(k_convect_band<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, CB_SMEM));
+        MB_CUDA(cudaFuncSetAttribute(k_convect_band<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, CB_SMEM));
         attr_set = true;
     }
-    if (w == 1) k_convect_band<3><<<g, 256, CB_SMEM, st>>>(a, S.M, B.seg_lo, B.seg_n, B.dr, ctx->d_flags);
-    else if (w == 2) k_convect_band<5><<<g, 256, CB_SMEM, st>>>(a, S.M, B.seg_lo, B.seg_n, B.dr, ctx->d_flags);
-    else if (w == 4) k_convect_band<9><<<g, 256, CB_SMEM, st>>>(a, S.M, B.seg_lo, B.seg_n, B.dr, ctx->d_flags);
-    else k_convect_band<17><<<g, 256, CB_SMEM, st>>>(a, S.M, B.seg_lo, B.seg_n, B.dr, ctx->d_flags);
+    if (w == 1) k_convect_band<3><<<g, 256, CB_SMEM, st>>>(a, S.M, B.seg_lo, B.seg_n, B.dr, B.E, ctx->d_flags);
+    else if (w == 2) k_convect_band<5><<<g, 256, CB_SMEM, st>>>(a, S.M, B.seg_lo, B.seg_n, B.dr, B.E, ctx->d_flags);
+    else if (w == 4) k_convect_band<9><<<g, 256, CB_SMEM, st>>>(a, S.M, B.seg_lo, B.seg_n, B.dr, B.E, ctx->d_flags);
+    else if (w == 8) k_convect_band<17><<<g, 256, CB_SMEM, st>>>(a, S.M, B.seg_lo, B.seg_n, B.dr, B.E, ctx->d_flags);
+    else k_convect_band<31><<<g, 256, CB_SMEM, st>>>(a, S.M, B.seg_lo, B.seg_n, B.dr, B.E, ctx->d_flags);
     MB_LAUNCH_CHECK(ctx);
     // the classification stays valid until something other than a slab exchange touches the particles
     ctx->cls_gen = ctx->state_gen;
@@ -929,23 +1027,24 @@ static int launch_band(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pi
     const int use_x = grid != nullptr;
     const int nscan = (int)((nc + SCAN_TILE - 1) / SCAN_TILE);
     const int wgrid = grid_for(nc * 32, 256, 8);
+    const int egrid = N_SM * 4;  // the number of extras is only known on the device: grid-stride over the list
     {
         ProfScope ps(ctx, PROF_SORT_CLASSIFY);
+        if (!cls_cached && extras_clear(ctx, B, nc)) return MB_ERR_CUDA;
         // with a cached classification this is a stub unless a cell was too big for the fused kernel's staging area
         k_band_classify<W><<<wgrid, 256, 0, st>>>(pv->cur.a[F_X], pv->cell, pv->cell, ix, nc, use_x ? grid->inv_dx : 0.0,
-                                                 use_x ? grid->cell_offset : 0, use_x, B.drop, S.M, B.seg_lo, B.seg_n, B.dr, S.flags,
+                                                 use_x ? grid->cell_offset : 0, use_x, B.drop, S.M, B.seg_lo, B.seg_n, B.dr, B.E, S.flags,
                                                  cls_cached ? S.flags + F_CLS_REDO : nullptr);
         MB_LAUNCH_CHECK(ctx);
         if (B.n_arr > 0) {
-            MB_CUDA(cudaMemsetAsync(B.acnt, 0, (size_t)nc * 4, st));
             k_band_arrivals<<<grid_for(B.n_arr, 256), 256, 0, st>>>(pv->cur.a[F_X], B.n_old, B.d_n_arr, nc, grid->inv_dx, grid->cell_offset, pv->cell,
-                                                                  B.key_arr, B.acnt, S.flags);
+                                                                  B.E, S.flags);
             MB_LAUNCH_CHECK(ctx);
         }
     }
     {
         ProfScope ps(ctx, PROF_SORT_SCAN);
-        k_scan_reduce<W><<<nscan, SCAN_BLOCK, 0, st>>>(S.M, B.n_arr > 0 ? B.acnt : nullptr, S.hist, nc, S.partial, S.flags, 0);
+        k_scan_reduce<W><<<nscan, SCAN_BLOCK, 0, st>>>(S.M, B.E.cntB, B.E.cntA, S.hist, nc, S.partial, S.flags, 0);
         MB_LAUNCH_CHECK(ctx);
         k_scan_partials<<<1, 1024, 0, st>>>(S.partial, nscan, S.flags, 0);
         MB_LAUNCH_CHECK(ctx);
@@ -954,18 +1053,23 @@ static int launch_band(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pi
     }
     {
         ProfScope ps(ctx, PROF_SORT_SCATTER);
-        k_band_scatter<W><<<grid_for(nc * 32, 256, MB_SC_GRID), 256, 0, st>>>(pv->cur, pv->alt, B.dr, S.M, B.seg_lo, B.seg_n, S.start, nc, B.P, S.flags);
+        k_band_scatter<W><<<grid_for(nc * 32, 256, MB_SC_GRID), 256, 0, st>>>(pv->cur, pv->alt, B.dr, S.M, B.seg_lo, B.seg_n, S.start, B.E.cntB, nc,
+                                                                              B.P, S.flags);
         MB_LAUNCH_CHECK(ctx);
-        if (B.n_arr > 0) {
-            k_band_place_arrivals<<<grid_for(B.n_arr, 256), 256, 0, st>>>(pv->cur, pv->alt, B.key_arr, B.d_n_arr, B.n_old, S.hist, B.acnt, S.start,
-                                                                        S.flags);
-            MB_LAUNCH_CHECK(ctx);
-        }
     }
     {
+        ProfScope ps(ctx, PROF_SORT_EXTRAS);
+        k_extra_slots<<<egrid, 256, 0, st>>>(B.E, S.start, S.hist, S.perm, S.flags);
+        MB_LAUNCH_CHECK(ctx);
+        k_extra_place<<<egrid, 256, 0, st>>>(B.E, S.start, S.hist, S.perm, pv->cur, pv->alt, S.flags);
+        MB_LAUNCH_CHECK(ctx);
+        k_save_extras<<<1, 1, 0, st>>>(B.E.n, S.flags);
+        MB_LAUNCH_CHECK(ctx);
+    }
+    if (B.P != nullptr) {
         ProfScope ps(ctx, PROF_SORT_SCAN);
-        k_band_combine<W><<<grid_for(nc, 128, 16), 128, 0, st>>>(B.P, S.M, B.n_arr > 0 ? B.acnt : nullptr, B.seg_lo, B.seg_n, S.start, pv->cur,
-                                                               pv->alt, nc, B.pcache, S.flags);
+        k_band_combine<W><<<grid_for(nc, 128, 16), 128, 0, st>>>(B.P, S.M, B.E.cntB, B.E.cntA, B.seg_lo, B.seg_n, S.start, pv->cur, pv->alt, nc,
+                                                               B.pcache, S.flags);
         MB_LAUNCH_CHECK(ctx);
     }
     return MB_OK;
@@ -980,7 +1084,7 @@ extern "C" {
 int mb_squash_pia(mb_ctx* ctx, mb_pv* pv, mb_pia* pia, int64_t species);
 
 int mb_sort_set_band_halfwidth(mb_ctx* ctx, int32_t w) {
-    MB_ARG(ctx && (w == 0 || w == 1 || w == 2 || w == 4 || w == 8), "band half-width must be 0, 1, 2, 4 or 8");
+    MB_ARG(ctx && (w == 0 || w == 1 || w == 2 || w == 4 || w == 8 || w == 15), "band half-width must be 0, 1, 2, 4, 8 or 15");
     ctx->band_w = w;
     return MB_OK;
 }
@@ -988,6 +1092,11 @@ int mb_sort_last_path(mb_ctx* ctx) {
     if (!ctx) return -1;
     if (mb_sync(ctx)) return -1;
     return ctx->sort_last_path == 1 && ctx->h_flags[2] == 0 ? 1 : 2;
+}
+int64_t mb_sort_last_extras(mb_ctx* ctx) {
+    if (!ctx) return -1;
+    if (mb_sync(ctx)) return -1;
+    return ctx->sort_last_path == 1 && ctx->h_flags[2] == 0 ? (int64_t)ctx->h_flags[3] : -1;
 }
 
 int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia, int64_t species) {
@@ -1012,8 +1121,8 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
     const int drop = pv->drop_oob;
     const int64_t n_arr = pv->n_arrivals;
     const bool use_x = grid != nullptr;
-    // band path: sorted layout; slab-exchange arrivals are merged in as long as they are few (each receiving cell scans the list)
-    const bool try_band = w > 0 && pia->sorted_layout[s] && n_arr <= 4096 && (n_arr == 0 || use_x);
+    // band path: sorted layout; band outliers and slab-exchange arrivals are merged in as "extras" as long as they fit their list
+    const bool try_band = w > 0 && pia->sorted_layout[s] && n_arr <= cap / 8 && (n_arr == 0 || use_x);
     const int nscan = (int)((nc + SCAN_TILE - 1) / SCAN_TILE);
 
     SortScratch S;
@@ -1030,10 +1139,14 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
     // moments of the sorted cells come for free in the gather pass (used by compute_props_sorted! if nothing changes in between)
     B.pcache = (double*)ctx_scratch(ctx, 10, (size_t)nc * 6 * 8);
     if (!B.pcache) return MB_ERR_CUDA;
-    if (try_band) {
+    // the band path caches the cell moments only for narrow bands (most of a cell stays: the few movers are re-read by k_band_combine)
+    const bool band_moments = try_band && w <= 2;
+    if (band_moments) {
         B.P = (double*)ctx_scratch(ctx, 11, (size_t)nc * 5 * 8);
         if (!B.P) return MB_ERR_CUDA;
     }
+    S.perm = (int32_t*)ctx_scratch(ctx, 3, (size_t)cap * 4);  // general path: permutation; band path: slots of the extras
+    if (!S.perm) return MB_ERR_CUDA;
 
     MB_CUDA(cudaMemcpyAsync(B.n_old, d_nt, 8, cudaMemcpyDeviceToDevice, st));  // n_total before the sort (the scan may rewrite it)
     // classification cached by the fused convect kernel?  (same particles, same grid, nothing but a slab exchange in between)
@@ -1047,15 +1160,14 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
         if (w == 1) r = launch_band<3>(ctx, grid, pv, pia, species, S, B, cls_cached);
         else if (w == 2) r = launch_band<5>(ctx, grid, pv, pia, species, S, B, cls_cached);
         else if (w == 4) r = launch_band<9>(ctx, grid, pv, pia, species, S, B, cls_cached);
-        else r = launch_band<17>(ctx, grid, pv, pia, species, S, B, cls_cached);
+        else if (w == 8) r = launch_band<17>(ctx, grid, pv, pia, species, S, B, cls_cached);
+        else r = launch_band<31>(ctx, grid, pv, pia, species, S, B, cls_cached);
         if (r) return r;
     }
     // general path (every kernel returns immediately unless flags[2] != 0)
     bool gather_cells = false;
     {
         ProfScope ps(ctx, PROF_SORT_GENERAL);
-        S.perm = (int32_t*)ctx_scratch(ctx, 3, (size_t)cap * 4);
-        if (!S.perm) return MB_ERR_CUDA;
         const int64_t nb = pia->n_bound[s] > 0 ? pia->n_bound[s] : cap;
         int32_t* src = nullptr;
         if (fuse_squash) {
@@ -1078,7 +1190,7 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
         k_gen_classify<<<pgrid, 256, 0, st>>>(pv->cur.a[F_X], pv->cell, pv->cell, S.key, B.n_old, nc, use_x ? grid->inv_dx : 0.0,
                                              use_x ? grid->cell_offset : 0, use_x ? 1 : 0, drop ? 1 : 0, S.hist, S.flags, src);
         MB_LAUNCH_CHECK(ctx);
-        k_scan_reduce<3><<<nscan, SCAN_BLOCK, 0, st>>>(nullptr, nullptr, S.hist, nc, S.partial, S.flags, 1);
+        k_scan_reduce<3><<<nscan, SCAN_BLOCK, 0, st>>>(nullptr, nullptr, nullptr, S.hist, nc, S.partial, S.flags, 1);
         MB_LAUNCH_CHECK(ctx);
         k_scan_partials<<<1, 1024, 0, st>>>(S.partial, nscan, S.flags, 1);
         MB_LAUNCH_CHECK(ctx);
@@ -1116,8 +1228,9 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
     // the cached moments are valid only if the band path ran (device flag 2 == 0): the props kernel checks the flag itself
     ctx->state_gen++;
     ctx->cls_gen = 0;
-    ctx->pc_gen = (try_band || gather_cells) ? ctx->state_gen : 0;
+    ctx->pc_gen = (band_moments || gather_cells) ? ctx->state_gen : 0;
     ctx->pc_general = gather_cells ? 1 : 0;
+    ctx->pc_band = band_moments ? 1 : 0;
     ctx->pc_pv = pv; ctx->pc_pia = pia; ctx->pc_species = (int)species;
     pia->contiguous[s] = 1;      // grid_sorting.jl:112
     pia->contig_pending[s] = 0;

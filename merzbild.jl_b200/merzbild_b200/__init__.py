@@ -103,6 +103,7 @@ SIGNATURES = {
     "mb_sort_particles": (_int, [_vp, C.POINTER(Grid1D), _vp, _vp, _i64]),
     "mb_sort_last_path": (_int, [_vp]),
     "mb_sort_set_band_halfwidth": (_int, [_vp, _i32]),
+    "mb_sort_last_extras": (_i64, [_vp]),
     "mb_squash_pia": (_int, [_vp, _vp, _vp, _i64]),
     "mb_restore_particle_ordering": (_int, [_vp, _vp]),
     "mb_make_interaction": (_int, [_f64, _f64, _f64, _f64, _f64, C.POINTER(Interaction)]),
@@ -216,7 +217,7 @@ class Context:
         _ck(lib().mb_flush_l2(self.h))
 
     PROF_SECTIONS = ("sort.classify", "sort.scan", "sort.scatter", "sort.general", "ntc", "convect", "props", "merge", "fp", "exchange",
-                     "squash")
+                     "squash", "sort.extras")
 
     def prof_enable(self, on=True):
         _ck(lib().mb_prof_enable(self.h, int(on)))
@@ -237,6 +238,11 @@ class Context:
     @property
     def sort_last_path(self):
         return lib().mb_sort_last_path(self.h)
+
+    @property
+    def sort_last_extras(self):
+        """band outliers + slab-exchange arrivals placed by the last band-path sort (-1: the general path ran)"""
+        return int(lib().mb_sort_last_extras(self.h))
 
 
 _default_ctx = None

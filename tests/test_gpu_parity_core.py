@@ -82,7 +82,7 @@ def test_sort_general_random(mb, oracle, ctx, n, n_cells):
         np.testing.assert_array_equal(pv.cell(1, n), opv.cell[:n])  # pv.cell is written by the grid variant and not permuted
 
 
-@pytest.mark.parametrize("w", [1, 2, 4, 8])
+@pytest.mark.parametrize("w", [1, 2, 4, 8, 15])
 def test_sort_band_path(mb, oracle, ctx, w):
     """the per-timestep case: sorted layout + small displacements -> band path; same bits as the oracle and as the general path."""
     rng = np.random.default_rng(7 + w)
@@ -114,16 +114,74 @@ def test_sort_band_path(mb, oracle, ctx, w):
             assert ctx.sort_last_path == 1, "band path expected"
             assert_same_pia(opia, pia)
             np.testing.assert_array_equal(pv.logical(1, n), opv.logical(1, n))
-        # a particle that leaves the band -> automatic fall back to the general path, same result
+            assert ctx.sort_last_extras == 0
+        # particles that leave the band are ranked separately (hybrid): still the band path, same result
         cur = opv.logical(1, n)
+        c_old = np.floor(cur[:, 4] * (1.0 / dx))
         cur[::997, 4] = rng.uniform(0, L, len(cur[::997]))
+        n_out = int(np.sum(np.abs(np.floor(cur[:, 4] * (1.0 / dx)) - c_old) > w))
         opv.set_logical(1, cur)
         pv.set_logical(1, cur)
         mb.sort_particles(None, g, pv, pia, 1)
         oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
-        assert ctx.sort_last_path == 2
+        assert ctx.sort_last_path == 1
+        assert ctx.sort_last_extras == n_out > 0
         assert_same_pia(opia, pia)
         np.testing.assert_array_equal(pv.logical(1, n), opv.logical(1, n))
+    finally:
+        ctx.set_band_halfwidth(2)
+
+
+@pytest.mark.parametrize("w", [1, 2, 15])
+@pytest.mark.parametrize("frac", [0.001, 0.01, 0.1, 0.6])
+def test_sort_band_with_outliers(mb, oracle, ctx, w, frac):
+    """Hybrid band sort (grid_sorting.jl:58-113 is the contract: stable counting sort): a fraction of the particles jumps anywhere in the
+    domain, far outside the band.  They are ranked among themselves by original position in front of / behind the band groups of their
+    destination cell; logical order and pia stay bit-identical to the oracle's, the band path is kept (no fall back), and for narrow
+    bands the cached cell moments (movers, extras included) still serve compute_props_sorted!."""
+    rng = np.random.default_rng(int(1000 * frac) + w)
+    n, n_cells, L = 70000, 350, 3.5
+    dx = L / n_cells
+    inv_dx = 1.0 / dx  # get_cell multiplies by inv_dx (grid_uniform1D.jl:97-99)
+    rows = maxwellian_rows(rng, n, L, vw=True)
+    rows[:, 1:4] += np.array([500.0, -200.0, 100.0])
+    opv, opia = oracle_state(oracle, rows, n_cells)
+    pv, pia = mirror_to_device(mb, ctx, opv, opia)
+    g = mb.Grid1DUniform(L, n_cells)
+    ctx.set_band_halfwidth(w)
+    try:
+        mb.sort_particles(None, g, pv, pia, 1)
+        oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+        pp = mb.PhysProps(n_cells, 1, ctx=ctx)
+        for step in range(3):
+            cur = opv.logical(1, n)
+            c_old = np.floor(cur[:, 4] * inv_dx)
+            cur[:, 4] = np.clip(cur[:, 4] + rng.uniform(-0.9 * w * dx, 0.9 * w * dx, n), 1e-9, L - 1e-9)
+            jump = rng.uniform(0, 1, n) < frac
+            if step == 2:  # a crowd lands in two cells: long extras regions in front of and behind the band
+                far = np.flatnonzero(jump)
+                cur[far[: len(far) // 2], 4] = rng.uniform(10 * dx, 11 * dx, len(far) // 2)
+                cur[far[len(far) // 2:], 4] = rng.uniform((n_cells - 20) * dx, (n_cells - 19) * dx, len(far) - len(far) // 2)
+            else:
+                cur[jump, 4] = rng.uniform(1e-9, L - 1e-9, int(jump.sum()))
+            n_out = int(np.sum(np.abs(np.floor(cur[:, 4] * inv_dx) - c_old) > w))
+            opv.set_logical(1, cur)
+            pv.set_logical(1, cur)
+            mb.sort_particles(None, g, pv, pia, 1)
+            oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+            crowd = step == 2 and n_out // 2 > 4096  # more extras in one cell than the ranking handles: general path, same result
+            assert ctx.sort_last_path == (2 if crowd else 1)
+            if not crowd:
+                assert ctx.sort_last_extras == n_out
+            assert_same_pia(opia, pia)
+            np.testing.assert_array_equal(pv.logical(1, n), opv.logical(1, n))
+            assert pia.check(1) == (True, 0)
+            mb.compute_props_sorted([pv], pia, [AR], pp)
+            d, o = pp.download(), oracle.compute_props_sorted([opv], opia, [AR])
+            np.testing.assert_array_equal(d["np"], o.np)
+            np.testing.assert_allclose(d["n"], o.n, rtol=1e-13)
+            np.testing.assert_allclose(d["v"], o.v, rtol=1e-12, atol=1e-12 * 500)
+            np.testing.assert_allclose(d["T"], o.T, rtol=1e-12)
     finally:
         ctx.set_band_halfwidth(2)
 
@@ -662,7 +720,7 @@ def test_couette_loop_parity(mb, oracle, ctx):
 
 # --------------------------------------------------------------------------------------- fused convect + band classification
 @pytest.mark.parametrize("n_cells,ppc,w,dt_mult,acc", [(40, 300, 2, 4, 1.0), (6, 3000, 1, 2, 0.5), (64, 50, 4, 12, 1.0), (3, 700, 8, 30, 0.0),
-                                                        (200, 7, 2, 4, 1.0)])
+                                                        (200, 7, 2, 4, 1.0), (64, 50, 1, 24, 1.0), (300, 40, 15, 100, 0.7)])
 def test_convect_then_sort_uses_cached_classification(mb, oracle, ctx, n_cells, ppc, w, dt_mult, acc):
     """convect_particles! on a sorted layout classifies while it moves the particles and the following sort_particles! starts at the
     scan: the result must be the bit-exact stable counting sort of the oracle (grid_sorting.jl:58-113), including cells bigger
@@ -685,9 +743,11 @@ def test_convect_then_sort_uses_cached_classification(mb, oracle, ctx, n_cells, 
             paths.append(ctx.sort_last_path)
             assert_same_pia(opia, pia)
             assert_rows_close(pv.logical(1, n), opv.logical(1, n), 1e-12, f"fused convect+sort step {t}")
-        if paths.count(1) == len(paths):
-            # clear + convect_band | flag, classify stub, 3 scan, scatter, combine, 8 general-path stubs
-            assert launches == 17, launches
+        assert paths.count(1) == len(paths), paths  # outliers (dt_mult 24 with w = 1: every fifth particle) no longer leave the band path
+        # clear + convect_band | flag, classify stub, 3 scan, scatter, 3 extras, combine (narrow bands), 8 general-path stubs
+        assert launches == (20 if w <= 2 else 19), launches
+        if (w, dt_mult) == (1, 24):
+            assert ctx.sort_last_extras > n // 20
     finally:
         ctx.set_band_halfwidth(2)
 
