@@ -251,12 +251,18 @@ int mb_comm_init(mb_ctx* ctx, const void* nccl_unique_id128, int rank, int nrank
  * just more keys).  x coordinates stay global; the slab grid (mb_grid1d_slab) carries the cell offset.
  * n_sent2/n_recv2 (nullable, host, 2 x int64: left, right) report the counts and synchronise. */
 /* mode 0 (default): when the species is in the sorted layout (it was sorted and only moved by convection since) the exchange
- * only looks at the w cells next to each slab face (w = the sort's band half-width) and swaps fixed-size messages of up to 2048
- * particles per direction without any host synchronisation; a leaver from any other cell, or more than 2048 per direction, is
+ * only looks at the w cells next to each slab face (w = the sort's band half-width) and swaps fixed-size messages of up to 8192
+ * particles per direction without any host synchronisation; a leaver from any other cell, or more than 8192 per direction, is
  * reported as an error by the next synchronising call.  Otherwise, and always with mode 1 or when the counts are requested,
  * every particle is examined and the message sizes are negotiated through the host.  All ranks must use the same mode. */
 int mb_exchange_set_mode(mb_ctx* ctx, int32_t mode);
 int mb_exchange_slab(mb_ctx* ctx, const mb_grid1d* slab, mb_pv* pv, mb_pia* pia, int64_t species, int64_t* n_sent2, int64_t* n_recv2);
+/* exchange_particles!(exchanger, pv_chunks, pia_chunks, cell_chunks, species) parallel.jl:443-450 with the chunks of ONE process (the
+ * reference's own use: logical chunks, test/test_couette_varweight_octree_chunking.jl:87-138): chunk i owns slab i of n_chunks
+ * (slabs[i] = mb_grid1d_slab(global, i, n_chunks)) in its own context (same or different devices).  Same pack / unpack kernels and
+ * the same two modes as mb_exchange_slab; the transport between neighbouring chunks is a device-to-device copy instead of
+ * ncclSend/ncclRecv, so no communicator is needed.  Synchronises the chunks' streams. */
+int mb_exchange_chunks(int32_t n_chunks, mb_ctx* const* ctxs, const mb_grid1d* slabs, mb_pv* const* pvs, mb_pia* const* pias, int64_t species);
 
 #ifdef __cplusplus
 }

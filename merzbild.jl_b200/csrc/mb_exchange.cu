@@ -12,6 +12,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "mb_common.cuh"
 #include "mb_scan.cuh"
@@ -138,8 +139,10 @@ static __global__ void __launch_bounds__(XB) k_xch_pack(SoA pv, const int64_t* n
     int64_t pl = offL[blockIdx.x] + sl[threadIdx.x] - l, pr = offR[blockIdx.x] + sr[threadIdx.x] - r;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const int64_t tl = offL[nblocks], tr = offR[nblocks];
-        counts[0] = tl;
-        counts[1] = tr;
+        counts[0] = tl < cap ? tl : cap;  // what the send buffer holds; layout [nL, cap, nR, cap]: one 2-word message per neighbour
+        counts[1] = cap;
+        counts[2] = tr < cap ? tr : cap;
+        counts[3] = cap;
         if (tl > cap || tr > cap) {
             atomicOr(&flags[0], DEVERR_CAPACITY);
             flags[1] = (int)(tl > tr ? tl : tr);
@@ -180,7 +183,7 @@ static __global__ void __launch_bounds__(256) k_xch_unpack(SoA pv, int64_t* n_to
 // pack the leavers (stable, logical order) behind a count header, and the neighbours swap FIXED-size messages -- no host
 // round trip, no scan over all particles.  A leaver from any other cell is a band overflow: the fused convect kernel (F_FAR)
 // or the sort's classify pass reports it as a device error instead of losing the particle silently.
-constexpr int XE_CAP = 2048;             // leavers per direction and step
+constexpr int XE_CAP = 8192;             // leavers per direction and step
 constexpr int XE_MSG = 8 + 7 * XE_CAP;   // doubles per message: [0] = count (int64 bits), payload from [8] (64-byte aligned)
 
 static __global__ void __launch_bounds__(256) k_xch_edge_pack(SoA pv, const Indexer* __restrict__ ix, int64_t n_cells, int w, double inv_dx,
@@ -257,6 +260,143 @@ static __global__ void k_xch_add_total(int64_t* n_total_p, int64_t cap, int64_t 
     if (*n_total_p + add <= cap) *n_total_p += add;
 }
 
+
+// ------------------------------------------------------------------------------------------------ host phases
+// mb_exchange_slab (one rank per process, NCCL transport) and mb_exchange_chunks (all chunks in one process, copy transport) share
+// these: xch_begin packs the leavers, the transport moves the staging buffers, xch_finish_* appends the arrivals.
+struct XchPlan {
+    bool edge, hasL, hasR;
+    int left, right, s;
+};
+struct XchCounts {
+    int64_t sL, sR, rL, rR;   // particles actually moved (clamped to the receiver's staging capacity)
+    bool clamped;
+};
+
+static int xch_begin(mb_ctx* ctx, const mb_grid1d* slab, mb_pv* pv, mb_pia* pia, int64_t species, int rank, int nranks, bool want_counts,
+                     XchPlan& P) {
+    MB_ARG(species >= 1 && species <= pia->n_species, "species out of range");
+    MB_ARG(pia->n_cells == slab->n_cells, "slab.n_cells != pia.n_cells");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    const int s = (int)species - 1;
+    if (!pia->contiguous[s]) {
+        set_error("mb_exchange_slab needs a contiguous species (sort or squash first)");
+        return MB_ERR_PRECONDITION;
+    }
+    {   // the own particles are not touched: a classification cached by the fused convect kernel stays valid
+        const bool keep = ctx->cls_gen == ctx->state_gen;
+        ctx->state_gen++;
+        if (keep) ctx->cls_gen = ctx->state_gen;
+    }
+    cudaStream_t st = ctx->stream;
+    // staging buffers: capacity / 8 particles per direction
+    const size_t want = (size_t)pv->cap / 8 + 65536;
+    if (ctx->xch_cap < want) {
+        MB_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < 2; i++) {
+            if (ctx->xch_send[i]) cudaFree(ctx->xch_send[i]);
+            if (ctx->xch_recv[i]) cudaFree(ctx->xch_recv[i]);
+            MB_CUDA(cudaMalloc(&ctx->xch_send[i], want * 56));
+            MB_CUDA(cudaMalloc(&ctx->xch_recv[i], want * 56));
+        }
+        ctx->xch_cap = want;
+    }
+    P.s = s;
+    P.left = rank - 1;
+    P.right = rank + 1;
+    P.hasL = nranks > 1 && P.left >= 0;
+    P.hasR = nranks > 1 && P.right < nranks;
+    // edge exchange: every rank takes the same decision (it only depends on the operator sequence)
+    P.edge = ctx->xch_mode == 0 && pia->sorted_layout[s] && ctx->band_w > 0 && pv->n_arrivals == 0 && !want_counts;
+    int64_t* d_nt = pia->d_n_total + s;
+    if (P.edge) {
+        k_xch_edge_pack<<<2, 256, 0, st>>>(pv->cur, pia->d_indexer + (int64_t)s * pia->n_cells, pia->n_cells, ctx->band_w, slab->inv_dx,
+                                         slab->cell_offset, (double*)ctx->xch_send[0], (double*)ctx->xch_send[1], P.hasL ? 1 : 0, P.hasR ? 1 : 0,
+                                         ctx->d_flags);
+        MB_LAUNCH_CHECK(ctx);
+        return MB_OK;
+    }
+    const int64_t nb_part = pia->n_bound[s] > 0 ? pia->n_bound[s] : pv->cap;
+    const int64_t nblocks = (nb_part + XT - 1) / XT;
+    int32_t* cnt = (int32_t*)ctx_scratch(ctx, 4, (size_t)(2 * nblocks) * 4);
+    int64_t* p64 = (int64_t*)ctx_scratch(ctx, 5, ((size_t)2 * (nblocks + 1) + gs_partial_count(nblocks)) * 8);
+    if (!cnt || !p64) return MB_ERR_CUDA;
+    int64_t* offL = p64;
+    int64_t* offR = p64 + (nblocks + 1);
+    int64_t* partial = p64 + 2 * (nblocks + 1);
+    k_xch_count<<<(int)nblocks, XB, 0, st>>>(pv->cur.a[F_X], d_nt, slab->inv_dx, slab->cell_offset, slab->n_cells, cnt, cnt + nblocks);
+    MB_LAUNCH_CHECK(ctx);
+    int r = device_exclusive_scan(ctx, cnt, nblocks, offL, partial);
+    if (r) return r;
+    r = device_exclusive_scan(ctx, cnt + nblocks, nblocks, offR, partial);
+    if (r) return r;
+    k_xch_pack<<<(int)nblocks, XB, 0, st>>>(pv->cur, d_nt, slab->inv_dx, slab->cell_offset, slab->n_cells, offL, offR, (double*)ctx->xch_send[0],
+                                            (double*)ctx->xch_send[1], (int64_t)ctx->xch_cap, nblocks, ctx->d_xch_counts, ctx->d_flags);
+    MB_LAUNCH_CHECK(ctx);
+    return MB_OK;
+}
+
+// h: [0] nL [1] my cap [2] nR [3] my cap [4] rL [5] capL [6] rR [7] capR.  Both sides of a face compute the same number.
+static XchCounts xch_negotiate(const int64_t* h, int64_t my_cap, const XchPlan& P) {
+    XchCounts K;
+    K.sL = P.hasL ? (h[0] < h[5] ? h[0] : h[5]) : 0;
+    K.sR = P.hasR ? (h[2] < h[7] ? h[2] : h[7]) : 0;
+    K.rL = P.hasL ? (h[4] < my_cap ? h[4] : my_cap) : 0;
+    K.rR = P.hasR ? (h[6] < my_cap ? h[6] : my_cap) : 0;
+    K.clamped = (P.hasL && (K.sL != h[0] || K.rL != h[4])) || (P.hasR && (K.sR != h[2] || K.rR != h[6]));
+    return K;
+}
+
+static int xch_finish_edge(mb_ctx* ctx, mb_pv* pv, mb_pia* pia, const XchPlan& P) {
+    cudaStream_t st = ctx->stream;
+    int64_t* d_nt = pia->d_n_total + P.s;
+    if (P.hasL || P.hasR) {
+        const double* rL = (const double*)ctx->xch_recv[0];
+        const double* rR = (const double*)ctx->xch_recv[1];
+        k_xch_edge_unpack<<<16, 256, 0, st>>>(pv->cur, d_nt, pv->cap, rL, rR, P.hasL ? 1 : 0, P.hasR ? 1 : 0, ctx->d_flags);
+        MB_LAUNCH_CHECK(ctx);
+        k_xch_edge_commit<<<1, 1, 0, st>>>(d_nt, pv->cap, rL, rR, P.hasL ? 1 : 0, P.hasR ? 1 : 0, pv->d_n_arr);
+        MB_LAUNCH_CHECK(ctx);
+        pv->n_arrivals += 2 * XE_CAP;  // upper bound; the exact number stays on the device
+    }
+    pv->drop_oob = 2;
+    pia->h_valid = false;
+    pia->n_bound[P.s] = pv->cap;
+    return MB_OK;
+}
+
+static int xch_finish_full(mb_ctx* ctx, mb_pv* pv, mb_pia* pia, const XchPlan& P, const XchCounts& K, int64_t* n_sent2, int64_t* n_recv2) {
+    cudaStream_t st = ctx->stream;
+    int64_t* d_nt = pia->d_n_total + P.s;
+    const int64_t* h = ctx->h_xch_counts;
+    if (K.rL + K.rR > 0) {
+        k_xch_unpack<<<grid_for(K.rL + K.rR, 256), 256, 0, st>>>(pv->cur, d_nt, pv->cap, (const double*)ctx->xch_recv[0], K.rL,
+                                                               (const double*)ctx->xch_recv[1], K.rR, ctx->d_flags);
+        MB_LAUNCH_CHECK(ctx);
+        k_xch_add_total<<<1, 1, 0, st>>>(d_nt, pv->cap, K.rL + K.rR);
+        MB_LAUNCH_CHECK(ctx);
+        k_add_i64<<<1, 1, 0, st>>>(pv->d_n_arr, K.rL + K.rR);
+        MB_LAUNCH_CHECK(ctx);
+    }
+    // the layout of the own particles is untouched: the next sort drops the leavers and merges the arrivals (band path if sorted)
+    if (h[0] + h[2] > 0 && pv->drop_oob == 0) pv->drop_oob = 1;
+    pv->n_arrivals += K.rL + K.rR;
+    pia->h_valid = false;
+    pia->n_bound[P.s] = pv->cap;
+    if (n_sent2) { n_sent2[0] = K.sL; n_sent2[1] = K.sR; }
+    if (n_recv2) { n_recv2[0] = K.rL; n_recv2[1] = K.rR; }
+    // errors are reported only now, after every neighbour got the messages it was waiting for
+    if ((!P.hasL && h[0] > 0) || (!P.hasR && h[2] > 0)) {
+        set_error("mb_exchange_slab: particles left the global domain (convect must clamp them to [min_x, max_x])");
+        return MB_ERR_PRECONDITION;
+    }
+    if (K.clamped) {
+        set_error("mb_exchange_slab: more leavers than the staging buffers hold (capacity / 8 + 65536 particles per direction): particles were lost");
+        return MB_ERR_CAPACITY;
+    }
+    return MB_OK;
+}
+
 }  // namespace mb
 
 using namespace mb;
@@ -296,143 +436,120 @@ int mb_exchange_set_mode(mb_ctx* ctx, int32_t mode) {
 
 int mb_exchange_slab(mb_ctx* ctx, const mb_grid1d* slab, mb_pv* pv, mb_pia* pia, int64_t species, int64_t* n_sent2, int64_t* n_recv2) {
     MB_ARG(ctx && slab && pv && pia, "NULL handle");
-    MB_ARG(species >= 1 && species <= pia->n_species, "species out of range");
-    MB_ARG(pia->n_cells == slab->n_cells, "slab.n_cells != pia.n_cells");
     if (ctx->nranks > 1 && !ctx->nccl_comm) {
         set_error("mb_exchange_slab: call mb_comm_init first");
         return MB_ERR_NCCL;
     }
-    MB_CUDA(cudaSetDevice(ctx->device));
-    const int s = (int)species - 1;
-    if (!pia->contiguous[s]) {
-        set_error("mb_exchange_slab needs a contiguous species (sort or squash first)");
-        return MB_ERR_PRECONDITION;
-    }
     ProfScope ps(ctx, PROF_EXCHANGE);
-    {   // the own particles are not touched: a classification cached by the fused convect kernel stays valid
-        const bool keep = ctx->cls_gen == ctx->state_gen;
-        ctx->state_gen++;
-        if (keep) ctx->cls_gen = ctx->state_gen;
-    }
+    XchPlan P;
+    int r = xch_begin(ctx, slab, pv, pia, species, ctx->rank, ctx->nranks, n_sent2 || n_recv2, P);
+    if (r) return r;
     cudaStream_t st = ctx->stream;
-    // staging buffers: capacity / 8 particles per direction
-    const size_t want = (size_t)pv->cap / 8 + 65536;
-    if (ctx->xch_cap < want) {
-        MB_CUDA(cudaStreamSynchronize(st));
-        for (int i = 0; i < 2; i++) {
-            if (ctx->xch_send[i]) cudaFree(ctx->xch_send[i]);
-            if (ctx->xch_recv[i]) cudaFree(ctx->xch_recv[i]);
-            MB_CUDA(cudaMalloc(&ctx->xch_send[i], want * 56));
-            MB_CUDA(cudaMalloc(&ctx->xch_recv[i], want * 56));
-        }
-        ctx->xch_cap = want;
-    }
-    const int left = ctx->rank - 1, right = ctx->rank + 1;
-    const bool hasL = ctx->nranks > 1 && left >= 0, hasR = ctx->nranks > 1 && right < ctx->nranks;
-    int64_t* d_nt = pia->d_n_total + s;
-    if (ctx->xch_mode == 0 && pia->sorted_layout[s] && ctx->band_w > 0 && pv->n_arrivals == 0 && !n_sent2 && !n_recv2) {
-        // edge exchange (every rank takes the same decision: it only depends on the operator sequence)
-        double* sL = (double*)ctx->xch_send[0];
-        double* sR = (double*)ctx->xch_send[1];
-        double* rL = (double*)ctx->xch_recv[0];
-        double* rR = (double*)ctx->xch_recv[1];
-        k_xch_edge_pack<<<2, 256, 0, st>>>(pv->cur, pia->d_indexer + (int64_t)s * pia->n_cells, pia->n_cells, ctx->band_w, slab->inv_dx,
-                                         slab->cell_offset, sL, sR, hasL ? 1 : 0, hasR ? 1 : 0, ctx->d_flags);
-        MB_LAUNCH_CHECK(ctx);
-        if (hasL || hasR) {
+    ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+    if (P.edge) {
+        if (P.hasL || P.hasR) {
             MB_NCCL(g_nccl.GroupStart());
-            if (hasL) {
-                MB_NCCL(g_nccl.Send(sL, XE_MSG, ncclFloat64, left, (ncclComm_t)ctx->nccl_comm, st));
-                MB_NCCL(g_nccl.Recv(rL, XE_MSG, ncclFloat64, left, (ncclComm_t)ctx->nccl_comm, st));
+            if (P.hasL) {
+                MB_NCCL(g_nccl.Send(ctx->xch_send[0], XE_MSG, ncclFloat64, P.left, comm, st));
+                MB_NCCL(g_nccl.Recv(ctx->xch_recv[0], XE_MSG, ncclFloat64, P.left, comm, st));
             }
-            if (hasR) {
-                MB_NCCL(g_nccl.Send(sR, XE_MSG, ncclFloat64, right, (ncclComm_t)ctx->nccl_comm, st));
-                MB_NCCL(g_nccl.Recv(rR, XE_MSG, ncclFloat64, right, (ncclComm_t)ctx->nccl_comm, st));
+            if (P.hasR) {
+                MB_NCCL(g_nccl.Send(ctx->xch_send[1], XE_MSG, ncclFloat64, P.right, comm, st));
+                MB_NCCL(g_nccl.Recv(ctx->xch_recv[1], XE_MSG, ncclFloat64, P.right, comm, st));
             }
             MB_NCCL(g_nccl.GroupEnd());
-            k_xch_edge_unpack<<<8, 256, 0, st>>>(pv->cur, d_nt, pv->cap, rL, rR, hasL ? 1 : 0, hasR ? 1 : 0, ctx->d_flags);
-            MB_LAUNCH_CHECK(ctx);
-            k_xch_edge_commit<<<1, 1, 0, st>>>(d_nt, pv->cap, rL, rR, hasL ? 1 : 0, hasR ? 1 : 0, pv->d_n_arr);
-            MB_LAUNCH_CHECK(ctx);
-            pv->n_arrivals += 2 * XE_CAP;  // upper bound; the exact number stays on the device
         }
-        pv->drop_oob = 2;
-        pia->h_valid = false;
-        pia->n_bound[s] = pv->cap;
-        return MB_OK;
+        return xch_finish_edge(ctx, pv, pia, P);
     }
-    const int64_t nb_part = pia->n_bound[s] > 0 ? pia->n_bound[s] : pv->cap;
-    const int64_t nblocks = (nb_part + XT - 1) / XT;
-    int32_t* cnt = (int32_t*)ctx_scratch(ctx, 4, (size_t)(2 * nblocks) * 4);
-    int64_t* p64 = (int64_t*)ctx_scratch(ctx, 5, ((size_t)2 * (nblocks + 1) + gs_partial_count(nblocks)) * 8);
-    if (!cnt || !p64) return MB_ERR_CUDA;
-    int64_t* offL = p64;
-    int64_t* offR = p64 + (nblocks + 1);
-    int64_t* partial = p64 + 2 * (nblocks + 1);
-    k_xch_count<<<(int)nblocks, XB, 0, st>>>(pv->cur.a[F_X], d_nt, slab->inv_dx, slab->cell_offset, slab->n_cells, cnt, cnt + nblocks);
-    MB_LAUNCH_CHECK(ctx);
-    int r = device_exclusive_scan(ctx, cnt, nblocks, offL, partial);
-    if (r) return r;
-    r = device_exclusive_scan(ctx, cnt + nblocks, nblocks, offR, partial);
-    if (r) return r;
-    k_xch_pack<<<(int)nblocks, XB, 0, st>>>(pv->cur, d_nt, slab->inv_dx, slab->cell_offset, slab->n_cells, offL, offR, (double*)ctx->xch_send[0],
-                                            (double*)ctx->xch_send[1], (int64_t)ctx->xch_cap, nblocks, ctx->d_xch_counts, ctx->d_flags);
-    MB_LAUNCH_CHECK(ctx);
-    // counts: send [nL, nR] to the neighbours, receive theirs
-    MB_CUDA(cudaMemsetAsync(ctx->d_xch_counts + 2, 0, 2 * 8, st));
-    if (hasL || hasR) {
+    // full exchange: the neighbours swap (count, receive capacity), then the payloads.  Between the two phases NOTHING returns early:
+    // a rank that bailed out here would leave its neighbours blocked in their payload receive.  Local errors are collected and
+    // reported after the payload phase; counts are clamped to what the receiver can take, identically on both sides.
+    int64_t* dc = ctx->d_xch_counts;  // [0] nL [1] cap [2] nR [3] cap | received: [4] rL [5] capL [6] rR [7] capR
+    MB_CUDA(cudaMemsetAsync(dc + 4, 0, 4 * 8, st));
+    if (P.hasL || P.hasR) {
         MB_NCCL(g_nccl.GroupStart());
-        if (hasL) {
-            MB_NCCL(g_nccl.Send(ctx->d_xch_counts + 0, 1, ncclInt64, left, (ncclComm_t)ctx->nccl_comm, st));
-            MB_NCCL(g_nccl.Recv(ctx->d_xch_counts + 2, 1, ncclInt64, left, (ncclComm_t)ctx->nccl_comm, st));
+        if (P.hasL) {
+            MB_NCCL(g_nccl.Send(dc + 0, 2, ncclInt64, P.left, comm, st));
+            MB_NCCL(g_nccl.Recv(dc + 4, 2, ncclInt64, P.left, comm, st));
         }
-        if (hasR) {
-            MB_NCCL(g_nccl.Send(ctx->d_xch_counts + 1, 1, ncclInt64, right, (ncclComm_t)ctx->nccl_comm, st));
-            MB_NCCL(g_nccl.Recv(ctx->d_xch_counts + 3, 1, ncclInt64, right, (ncclComm_t)ctx->nccl_comm, st));
+        if (P.hasR) {
+            MB_NCCL(g_nccl.Send(dc + 2, 2, ncclInt64, P.right, comm, st));
+            MB_NCCL(g_nccl.Recv(dc + 6, 2, ncclInt64, P.right, comm, st));
         }
         MB_NCCL(g_nccl.GroupEnd());
     }
-    MB_CUDA(cudaMemcpyAsync(ctx->h_xch_counts, ctx->d_xch_counts, 4 * 8, cudaMemcpyDeviceToHost, st));
-    r = mb_sync(ctx);  // the payload sizes must be known on the host to post the receives
-    if (r) return r;
-    const int64_t sL = ctx->h_xch_counts[0], sR = ctx->h_xch_counts[1], rL = ctx->h_xch_counts[2], rR = ctx->h_xch_counts[3];
-    if (rL > (int64_t)ctx->xch_cap || rR > (int64_t)ctx->xch_cap) {
-        set_error("mb_exchange_slab: arrivals exceed the staging capacity");
-        return MB_ERR_CAPACITY;
-    }
-    if ((!hasL && sL > 0) || (!hasR && sR > 0)) {
-        set_error("mb_exchange_slab: particles left the global domain (convect must clamp them to [min_x, max_x])");
-        return MB_ERR_PRECONDITION;
-    }
-    if (hasL || hasR) {
+    MB_CUDA(cudaMemcpyAsync(ctx->h_xch_counts, dc, 8 * 8, cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));  // the payload sizes must be known on the host to post the receives (no error flags consumed here)
+    XchCounts K = xch_negotiate(ctx->h_xch_counts, (int64_t)ctx->xch_cap, P);
+    if (P.hasL || P.hasR) {
         MB_NCCL(g_nccl.GroupStart());
-        if (hasL) {
-            if (sL > 0) MB_NCCL(g_nccl.Send(ctx->xch_send[0], (size_t)sL * 7, ncclFloat64, left, (ncclComm_t)ctx->nccl_comm, st));
-            if (rL > 0) MB_NCCL(g_nccl.Recv(ctx->xch_recv[0], (size_t)rL * 7, ncclFloat64, left, (ncclComm_t)ctx->nccl_comm, st));
+        if (P.hasL) {
+            if (K.sL > 0) MB_NCCL(g_nccl.Send(ctx->xch_send[0], (size_t)K.sL * 7, ncclFloat64, P.left, comm, st));
+            if (K.rL > 0) MB_NCCL(g_nccl.Recv(ctx->xch_recv[0], (size_t)K.rL * 7, ncclFloat64, P.left, comm, st));
         }
-        if (hasR) {
-            if (sR > 0) MB_NCCL(g_nccl.Send(ctx->xch_send[1], (size_t)sR * 7, ncclFloat64, right, (ncclComm_t)ctx->nccl_comm, st));
-            if (rR > 0) MB_NCCL(g_nccl.Recv(ctx->xch_recv[1], (size_t)rR * 7, ncclFloat64, right, (ncclComm_t)ctx->nccl_comm, st));
+        if (P.hasR) {
+            if (K.sR > 0) MB_NCCL(g_nccl.Send(ctx->xch_send[1], (size_t)K.sR * 7, ncclFloat64, P.right, comm, st));
+            if (K.rR > 0) MB_NCCL(g_nccl.Recv(ctx->xch_recv[1], (size_t)K.rR * 7, ncclFloat64, P.right, comm, st));
         }
         MB_NCCL(g_nccl.GroupEnd());
     }
-    if (rL + rR > 0) {
-        k_xch_unpack<<<grid_for(rL + rR, 256), 256, 0, st>>>(pv->cur, d_nt, pv->cap, (const double*)ctx->xch_recv[0], rL,
-                                                           (const double*)ctx->xch_recv[1], rR, ctx->d_flags);
-        MB_LAUNCH_CHECK(ctx);
-        k_xch_add_total<<<1, 1, 0, st>>>(d_nt, pv->cap, rL + rR);
-        MB_LAUNCH_CHECK(ctx);
-        k_add_i64<<<1, 1, 0, st>>>(pv->d_n_arr, rL + rR);
-        MB_LAUNCH_CHECK(ctx);
+    return xch_finish_full(ctx, pv, pia, P, K, n_sent2, n_recv2);
+}
+
+/* exchange_particles!(exchanger, pv_chunks, pia_chunks, cell_chunks, species) parallel.jl:443-450 for chunks that live in ONE process:
+ * the same pack / unpack kernels as mb_exchange_slab, the transport is a device-to-device copy between the chunks' staging buffers. */
+int mb_exchange_chunks(int32_t n_chunks, mb_ctx* const* ctxs, const mb_grid1d* slabs, mb_pv* const* pvs, mb_pia* const* pias, int64_t species) {
+    MB_ARG(n_chunks >= 1 && ctxs && slabs && pvs && pias, "NULL");
+    for (int i = 0; i < n_chunks; i++) MB_ARG(ctxs[i] && pvs[i] && pias[i] && pvs[i]->ctx == ctxs[i], "chunk handles");
+    for (int i = 0; i < n_chunks; i++)
+        for (int j = 0; j < i; j++) MB_ARG(ctxs[i] != ctxs[j], "every chunk needs its own context (its staging buffers live there)");
+    std::vector<XchPlan> P(n_chunks);
+    int first_err = MB_OK;
+    for (int i = 0; i < n_chunks; i++) {
+        ProfScope ps(ctxs[i], PROF_EXCHANGE);
+        int r = xch_begin(ctxs[i], slabs + i, pvs[i], pias[i], species, i, n_chunks, false, P[i]);
+        if (r) return r;  // nothing has been moved yet
+        MB_ARG(P[i].edge == P[0].edge, "the chunks disagree on the exchange mode (same operator sequence and mb_exchange_set_mode on every chunk)");
     }
-    // the layout of the own particles is untouched: the next sort drops the leavers and merges the arrivals (band path if sorted)
-    if (sL + sR > 0 && pv->drop_oob == 0) pv->drop_oob = 1;
-    pv->n_arrivals += rL + rR;
-    pia->h_valid = false;
-    pia->n_bound[s] = pv->cap;
-    if (n_sent2) { n_sent2[0] = sL; n_sent2[1] = sR; }
-    if (n_recv2) { n_recv2[0] = rL; n_recv2[1] = rR; }
-    return MB_OK;
+    std::vector<XchCounts> K(n_chunks);
+    if (!P[0].edge) {
+        for (int i = 0; i < n_chunks; i++) {
+            MB_CUDA(cudaSetDevice(ctxs[i]->device));
+            MB_CUDA(cudaMemcpyAsync(ctxs[i]->h_xch_counts, ctxs[i]->d_xch_counts, 4 * 8, cudaMemcpyDeviceToHost, ctxs[i]->stream));
+        }
+    }
+    for (int i = 0; i < n_chunks; i++) {  // every pack has finished before a neighbour reads the staging buffer
+        MB_CUDA(cudaSetDevice(ctxs[i]->device));
+        MB_CUDA(cudaStreamSynchronize(ctxs[i]->stream));
+    }
+    if (!P[0].edge) {
+        for (int i = 0; i < n_chunks; i++) {  // what NCCL's count exchange delivers
+            int64_t* h = ctxs[i]->h_xch_counts;
+            h[4] = h[5] = h[6] = h[7] = 0;
+            if (i > 0) { h[4] = ctxs[i - 1]->h_xch_counts[2]; h[5] = (int64_t)ctxs[i - 1]->xch_cap; }
+            if (i + 1 < n_chunks) { h[6] = ctxs[i + 1]->h_xch_counts[0]; h[7] = (int64_t)ctxs[i + 1]->xch_cap; }
+        }
+        for (int i = 0; i < n_chunks; i++) K[i] = xch_negotiate(ctxs[i]->h_xch_counts, (int64_t)ctxs[i]->xch_cap, P[i]);
+    }
+    for (int i = 0; i < n_chunks; i++) {
+        MB_CUDA(cudaSetDevice(ctxs[i]->device));
+        cudaStream_t st = ctxs[i]->stream;
+        if (P[0].edge) {
+            if (i > 0) MB_CUDA(cudaMemcpyAsync(ctxs[i]->xch_recv[0], ctxs[i - 1]->xch_send[1], (size_t)XE_MSG * 8, cudaMemcpyDefault, st));
+            if (i + 1 < n_chunks) MB_CUDA(cudaMemcpyAsync(ctxs[i]->xch_recv[1], ctxs[i + 1]->xch_send[0], (size_t)XE_MSG * 8, cudaMemcpyDefault, st));
+        } else {
+            if (K[i].rL > 0) MB_CUDA(cudaMemcpyAsync(ctxs[i]->xch_recv[0], ctxs[i - 1]->xch_send[1], (size_t)K[i].rL * 56, cudaMemcpyDefault, st));
+            if (K[i].rR > 0) MB_CUDA(cudaMemcpyAsync(ctxs[i]->xch_recv[1], ctxs[i + 1]->xch_send[0], (size_t)K[i].rR * 56, cudaMemcpyDefault, st));
+        }
+        ProfScope ps(ctxs[i], PROF_EXCHANGE);
+        int r = P[0].edge ? xch_finish_edge(ctxs[i], pvs[i], pias[i], P[i]) : xch_finish_full(ctxs[i], pvs[i], pias[i], P[i], K[i], nullptr, nullptr);
+        if (r && !first_err) first_err = r;
+    }
+    for (int i = 0; i < n_chunks; i++) {  // the staging buffers may be repacked by the next call
+        MB_CUDA(cudaSetDevice(ctxs[i]->device));
+        MB_CUDA(cudaStreamSynchronize(ctxs[i]->stream));
+    }
+    return first_err;
 }
 
 }  // extern "C"

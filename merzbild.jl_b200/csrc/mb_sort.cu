@@ -1122,7 +1122,7 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
     const int64_t n_arr = pv->n_arrivals;
     const bool use_x = grid != nullptr;
     // band path: sorted layout; band outliers and slab-exchange arrivals are merged in as "extras" as long as they fit their list
-    const bool try_band = w > 0 && pia->sorted_layout[s] && n_arr <= cap / 8 && (n_arr == 0 || use_x);
+    const bool try_band = w > 0 && pia->sorted_layout[s] && n_arr <= cap / 8 + 32768 && (n_arr == 0 || use_x);
     const int nscan = (int)((nc + SCAN_TILE - 1) / SCAN_TILE);
 
     SortScratch S;

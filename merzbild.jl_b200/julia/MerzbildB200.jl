@@ -617,6 +617,22 @@ function comm_unique_id()
 end
 comm_init!(ctx::Context, id::Vector{UInt8}, rank::Integer, nranks::Integer) =
     check(ccall((:mb_comm_init, libmb), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint), ctx.h, id, rank, nranks))
+"""
+    exchange_particles!(ctxs, slabs, pv_chunks, pia_chunks, species)
+
+`exchange_particles!(exchanger, pv_chunks, pia_chunks, cell_chunks, species)` (parallel.jl:443-450) for logical chunks of one process:
+chunk `i` owns `slabs[i] = slab(grid, i - 1, n_chunks)` in its own `Context`; `sort_particles!` of every chunk afterwards plays the
+role of `sort_particles_after_exchange!` (parallel.jl:467-532).
+"""
+function exchange_particles!(ctxs::Vector{Context}, slabs::Vector{DeviceGrid1D}, pv_chunks::Vector{DeviceParticleVector},
+                             pia_chunks::Vector{DeviceParticleIndexerArray}, species::Integer=1)
+    n = length(ctxs)
+    hc = Ptr{Cvoid}[c.h for c in ctxs]; hp = Ptr{Cvoid}[p.h for p in pv_chunks]; hi = Ptr{Cvoid}[p.h for p in pia_chunks]
+    gs = CGrid1D[s.c for s in slabs]
+    check(ccall((:mb_exchange_chunks, libmb), Cint, (Int32, Ptr{Ptr{Cvoid}}, Ptr{CGrid1D}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Int64),
+                n, hc, gs, hp, hi, species))
+    nothing
+end
 "0: edge exchange when the layout allows it (no host synchronisation), 1: always the full exchange; same on all ranks"
 exchange_set_mode!(ctx::Context, mode::Integer) = check(ccall((:mb_exchange_set_mode, libmb), Cint, (Ptr{Cvoid}, Int32), ctx.h, mode))
 """

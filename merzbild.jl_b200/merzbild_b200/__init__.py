@@ -133,6 +133,7 @@ SIGNATURES = {
     "mb_comm_init": (_int, [_vp, _vp, _int, _int]),
     "mb_exchange_set_mode": (_int, [_vp, _i32]),
     "mb_exchange_slab": (_int, [_vp, C.POINTER(Grid1D), _vp, _vp, _i64, _vp, _vp]),
+    "mb_exchange_chunks": (_int, [_i32, _vp, _vp, _vp, _vp, _i64]),
 }
 
 
@@ -669,6 +670,21 @@ def comm_init(ctx, unique_id, rank, nranks):
 def exchange_set_mode(ctx, mode):
     """0: edge exchange when the layout allows it (no host synchronisation), 1: always the full exchange."""
     _ck(lib().mb_exchange_set_mode(ctx.h, int(mode)))
+
+
+def exchange_particles(ctxs, slabs, pv_chunks, pia_chunks, species=1):
+    """exchange_particles!(exchanger, pv_chunks, pia_chunks, cell_chunks, species) (parallel.jl:443-450) for logical chunks that live in
+    this process, one context per chunk (slabs[i] = grid.slab(i, n_chunks)); sort_particles! of every chunk then plays the role of
+    sort_particles_after_exchange! (parallel.jl:467-532)."""
+    n = len(ctxs)
+    assert len(slabs) == len(pv_chunks) == len(pia_chunks) == n
+    hc = (C.c_void_p * n)(*[c.h for c in ctxs])
+    hp = (C.c_void_p * n)(*[p.h for p in pv_chunks])
+    hi = (C.c_void_p * n)(*[p.h for p in pia_chunks])
+    gs = (Grid1D * n)()
+    for i, g in enumerate(slabs):
+        C.memmove(C.byref(gs[i]), C.byref(g.c), C.sizeof(Grid1D))
+    _ck(lib().mb_exchange_chunks(n, hc, gs, hp, hi, int(species)))
 
 
 def exchange_slab(ctx, slab, pv, pia, species=1, counts=False):

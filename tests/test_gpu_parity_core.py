@@ -205,7 +205,7 @@ def test_sort_large_cell_segments(mb, oracle, ctx):
 @pytest.mark.parametrize("n,n_cells", [(20000, 37), (3000, 64), (50000, 5)])
 def test_props_after_general_sort_use_the_cached_moments(mb, oracle, ctx, n, n_cells):
     """compute_props_sorted! right after a general-path sort of small cells reads the moments the gather-by-cell pass cached (no particle
-    traffic); they must match the oracle's two-pass values like the band path's do (1e-10 on T, 1e-12 on n and v)."""
+    traffic); they must match the oracle's two-pass values like the band path's do (1e-12 on T and v, 1e-13 on n)."""
     rng = np.random.default_rng(n + n_cells)
     L = 2.0
     rows = maxwellian_rows(rng, n, L, vw=True)
@@ -225,7 +225,7 @@ def test_props_after_general_sort_use_the_cached_moments(mb, oracle, ctx, n, n_c
     np.testing.assert_array_equal(d["np"], o.np)
     np.testing.assert_allclose(d["n"], o.n, rtol=1e-13)
     np.testing.assert_allclose(d["v"], o.v, rtol=1e-12, atol=1e-12 * 500)
-    np.testing.assert_allclose(d["T"], o.T, rtol=1e-10)
+    np.testing.assert_allclose(d["T"], o.T, rtol=1e-12)
     # touching the particles in between voids the cache: the regular kernels run and give the same numbers
     pv.set_logical(1, pv.logical(1, 1))
     l0 = ctx.kernel_launches
@@ -714,8 +714,56 @@ def test_couette_loop_parity(mb, oracle, ctx):
     assert_rows_close(pv.logical(1, n), opv.logical(1, n), 1e-10, "couette loop")
     d, o = pp.download(), oracle.compute_props_sorted([opv], opia, [AR])
     np.testing.assert_array_equal(d["np"], o.np)
-    np.testing.assert_allclose(d["T"], o.T, rtol=1e-10)
+    np.testing.assert_allclose(d["T"], o.T, rtol=1e-10)  # 25 steps of libm-level differences in the particles themselves
     np.testing.assert_allclose(d["v"], o.v, rtol=1e-9, atol=1e-9 * 500)
+    # the moments the bench reads (cached by the band sort) against the two-pass oracle ON THE DEVICE'S OWN PARTICLES: 1e-12
+    opv2, opia2 = oracle_state(oracle, pv.logical(1, n), n_cells)
+    opia2.indexer[:] = pia.indexer
+    o2 = oracle.compute_props_sorted([opv2], opia2, [AR])
+    np.testing.assert_allclose(d["n"], o2.n, rtol=1e-13)
+    np.testing.assert_allclose(d["T"], o2.T, rtol=1e-12)
+    np.testing.assert_allclose(d["v"], o2.v, rtol=1e-12, atol=1e-12 * 500)
+
+
+@pytest.mark.parametrize("w", [1, 2])
+def test_cached_moments_meet_1e12(mb, oracle, ctx, w):
+    """compute_props_sorted! (physical_props.jl:317-454) from the moments the band sort accumulates on the fly -- the path bench.py
+    times -- at ppc = 1000 with a mean velocity of 500 m/s on top of a 250 m/s thermal spread: n to 1e-13, v and T to 1e-12 of the
+    two-pass oracle, step after step (stayers summed in the scatter pass, movers and extras added by the combine pass)."""
+    rng = np.random.default_rng(40 + w)
+    n_cells, ppc, L = 64, 1000, 64e-5
+    n = n_cells * ppc
+    dx = L / n_cells
+    rows = maxwellian_rows(rng, n, L, vw=True)
+    rows[:, 1:4] += np.array([500.0, -500.0, 500.0])
+    opv, opia = oracle_state(oracle, rows, n_cells)
+    pv, pia = mirror_to_device(mb, ctx, opv, opia)
+    g = mb.Grid1DUniform(L, n_cells)
+    pp = mb.PhysProps(n_cells, 1, ctx=ctx)
+    ctx.set_band_halfwidth(w)
+    try:
+        mb.sort_particles(None, g, pv, pia, 1)
+        oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+        for step in range(4):
+            cur = opv.logical(1, n)
+            cur[:, 4] = np.clip(cur[:, 4] + rng.normal(0, 0.3 * w * dx, n).clip(-0.95 * w * dx, 0.95 * w * dx), 1e-12, L - 1e-12)
+            if step == 3:
+                cur[::501, 4] = rng.uniform(1e-12, L - 1e-12, len(cur[::501]))  # a few extras
+            opv.set_logical(1, cur)
+            pv.set_logical(1, cur)
+            mb.sort_particles(None, g, pv, pia, 1)
+            oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+            assert ctx.sort_last_path == 1
+            l0 = ctx.kernel_launches
+            mb.compute_props_sorted([pv], pia, [AR], pp)
+            assert ctx.kernel_launches - l0 == 1  # the cached kernel only
+            d, o = pp.download(), oracle.compute_props_sorted([opv], opia, [AR])
+            np.testing.assert_array_equal(d["np"], o.np)
+            np.testing.assert_allclose(d["n"], o.n, rtol=1e-13)
+            np.testing.assert_allclose(d["v"], o.v, rtol=1e-12, atol=1e-12 * 500)
+            np.testing.assert_allclose(d["T"], o.T, rtol=1e-12)
+    finally:
+        ctx.set_band_halfwidth(2)
 
 
 # --------------------------------------------------------------------------------------- fused convect + band classification
