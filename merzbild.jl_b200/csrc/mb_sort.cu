@@ -58,7 +58,7 @@ struct ExBufs {
     int32_t* curA;
     int32_t cap;
 };
-constexpr int EX_REGION_MAX = 4096;  // extras per (cell, class) ranked by counting; beyond that the general path runs
+constexpr int EX_REGION_MAX = 1024;  // extras per (cell, class) a warp orders in shared memory; beyond that the general path runs
 
 // All lanes of the warp call it; returns true if the list is full (the caller requests the general path).
 __device__ __forceinline__ bool extras_append(const ExBufs& E, bool is, int32_t i, int nc, int cls, int lane, unsigned lt) {
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_reduce(const int32_t* __res
             int h;
             if (mode == 0) {
                 const int eb = cntB[c], ea = cntA[c];
-                if (eb > EX_REGION_MAX || ea > EX_REGION_MAX) atomicOr(&flags[2], 1);  // too many extras in one cell to rank by counting
+                if (eb > EX_REGION_MAX || ea > EX_REGION_MAX) atomicOr(&flags[2], 1);  // too many extras in one cell for the region sort
                 h = band_hist<W>(M, c, n_cells) + eb + ea;
                 hist[c] = h;
             }
@@ -419,9 +419,8 @@ __global__ void __launch_bounds__(256, MB_SC_MINB) k_band_scatter(SoA in_, SoA o
 
 // The extras (band outliers and slab-exchange arrivals).  Step 1: every extra takes a slot of its (cell, class) region of the
 // OUTPUT layout and leaves its original position there (slot[] is indexed by output position; the order inside a region is
-// whatever the atomics produce).  Step 2: every extra ranks itself inside its region by counting the smaller original positions
-// (regions hold a handful of entries) and copies its record to region start + rank: ascending original position, the
-// reference's stable order.
+// whatever the atomics produce).  Step 2 (k_extra_regions) puts every region into ascending original position -- the reference's
+// stable order -- and moves the records.
 static __global__ void __launch_bounds__(256) k_extra_slots(ExBufs E, const int64_t* __restrict__ start, const int32_t* __restrict__ hist,
                                                            int32_t* __restrict__ slot, const int* flags) {
     if (flags[2] != 0) return;
@@ -433,20 +432,71 @@ static __global__ void __launch_bounds__(256) k_extra_slots(ExBufs E, const int6
         slot[rs + k] = E.idx[e];
     }
 }
-static __global__ void __launch_bounds__(256) k_extra_place(ExBufs E, const int64_t* __restrict__ start, const int32_t* __restrict__ hist,
-                                                           const int32_t* __restrict__ slot, SoA in_, SoA out_, const int* flags) {
+// Step 2, a warp per region (32 consecutive cells per round, one coalesced read of their counters; almost all are empty): the
+// region's original positions are put into ascending order in shared memory (the warp-level bitonic network of the general path)
+// and the records are copied to their final places.
+static __global__ void __launch_bounds__(256) k_extra_regions(ExBufs E, const int64_t* __restrict__ start, const int32_t* __restrict__ hist,
+                                                             const int32_t* __restrict__ slot, int64_t n_cells, SoA in_, SoA out_,
+                                                             const int* flags) {
     if (flags[2] != 0) return;
-    const int n = min(*E.n, E.cap);
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-        const int cc = E.cell[e], c = cc >> 1, cls = cc & 1;
-        const int m = cls ? E.cntA[c] : E.cntB[c];
-        const int64_t rs = cls ? start[c] + hist[c] - m : start[c];
-        const int32_t i = E.idx[e];
-        int rank = 0;
-        for (int t = 0; t < m; t++) rank += slot[rs + t] < i;
-        const int64_t pos = rs + rank;
+    __shared__ int32_t shw[8][EX_REGION_MAX];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int32_t* sh = shw[wid];
+    const int64_t gw = (int64_t)blockIdx.x * 8 + wid, nwarps = (int64_t)gridDim.x * 8;
+    for (int64_t c0 = gw * 32; c0 < n_cells; c0 += nwarps * 32) {
+        const int64_t c = c0 + lane;
+        int mB = 0, mA = 0;
+        int64_t rB = 0, rA = 0;
+        if (c < n_cells) {
+            mB = E.cntB[c]; mA = E.cntA[c];
+            if (mB | mA) { rB = start[c]; rA = rB + hist[c] - mA; }
+        }
+        for (int cls = 0; cls < 2; cls++) {
+            unsigned todo = __ballot_sync(0xffffffffu, (cls ? mA : mB) > 0);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int64_t rs = __shfl_sync(0xffffffffu, cls ? rA : rB, src);
+                const int n = __shfl_sync(0xffffffffu, cls ? mA : mB, src);
+                __syncwarp();
+                for (int i = lane; i < n; i += 32) sh[i] = slot[rs + i];
+                __syncwarp();
+                bool uns = false;
+                for (int i = lane; i + 1 < n; i += 32) uns |= sh[i] > sh[i + 1];
+                if (__any_sync(0xffffffffu, uns)) {
+                    int m = 1;
+                    while (m < n) m <<= 1;
+                    for (int k = 2; k <= m; k <<= 1) {
+                        const int hk = k >> 1;
+                        for (int t = lane; t < (m >> 1); t += 32) {
+                            const int blk = t / hk, off = t - blk * hk;
+                            const int i = blk * k + off, p = blk * k + k - 1 - off;
+                            if (p < n) {
+                                const int32_t x = sh[i], y = sh[p];
+                                if (x > y) { sh[i] = y; sh[p] = x; }
+                            }
+                        }
+                        __syncwarp();
+                        for (int j = k >> 2; j > 0; j >>= 1) {
+                            for (int t = lane; t < (m >> 1); t += 32) {
+                                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                                const int p = i + j;
+                                if (p < n) {
+                                    const int32_t x = sh[i], y = sh[p];
+                                    if (x > y) { sh[i] = y; sh[p] = x; }
+                                }
+                            }
+                            __syncwarp();
+                        }
+                    }
+                }
+                for (int t = lane; t < n; t += 32) {
+                    const int64_t i = sh[t], pos = rs + t;
 #pragma unroll
-        for (int f = 0; f < 7; f++) out_.a[f][pos] = in_.a[f][i];
+                    for (int f = 0; f < 7; f++) out_.a[f][pos] = in_.a[f][i];
+                }
+            }
+        }
     }
 }
 
@@ -1061,7 +1111,7 @@ static int launch_band(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pi
         ProfScope ps(ctx, PROF_SORT_EXTRAS);
         k_extra_slots<<<egrid, 256, 0, st>>>(B.E, S.start, S.hist, S.perm, S.flags);
         MB_LAUNCH_CHECK(ctx);
-        k_extra_place<<<egrid, 256, 0, st>>>(B.E, S.start, S.hist, S.perm, pv->cur, pv->alt, S.flags);
+        k_extra_regions<<<grid_for(nc, 256, 4), 256, 0, st>>>(B.E, S.start, S.hist, S.perm, nc, pv->cur, pv->alt, S.flags);
         MB_LAUNCH_CHECK(ctx);
         k_save_extras<<<1, 1, 0, st>>>(B.E.n, S.flags);
         MB_LAUNCH_CHECK(ctx);
@@ -1230,7 +1280,7 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
     ctx->cls_gen = 0;
     ctx->pc_gen = (band_moments || gather_cells) ? ctx->state_gen : 0;
     ctx->pc_general = gather_cells ? 1 : 0;
-    ctx->pc_band = band_moments ? 1 : 0;
+    ctx->pc_band = (band_moments || !try_band) ? 1 : 0;  // no band attempt: the general path runs unconditionally, its cache is valid as is
     ctx->pc_pv = pv; ctx->pc_pia = pia; ctx->pc_species = (int)species;
     pia->contiguous[s] = 1;      // grid_sorting.jl:112
     pia->contig_pending[s] = 0;

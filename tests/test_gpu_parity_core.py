@@ -169,7 +169,7 @@ def test_sort_band_with_outliers(mb, oracle, ctx, w, frac):
             pv.set_logical(1, cur)
             mb.sort_particles(None, g, pv, pia, 1)
             oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
-            crowd = step == 2 and n_out // 2 > 4096  # more extras in one cell than the ranking handles: general path, same result
+            crowd = step == 2 and n_out // 2 > 1024  # more extras in one cell than the ranking handles: general path, same result
             assert ctx.sort_last_path == (2 if crowd else 1)
             if not crowd:
                 assert ctx.sort_last_extras == n_out
