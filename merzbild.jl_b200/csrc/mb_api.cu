@@ -40,6 +40,7 @@ void* ctx_scratch(mb_ctx* ctx, int slot, size_t bytes) {
     return p;
 }
 
+// sections may nest (the squash folded into the general sort path): every begin takes its own event pair, a stack pairs the ends
 void prof_begin(mb_ctx* c, int section) {
     if (c->prof_used == c->prof_sec->size()) {
         cudaEvent_t a, b;
@@ -49,12 +50,16 @@ void prof_begin(mb_ctx* c, int section) {
         c->prof_ev->push_back(b);
         c->prof_sec->push_back(section);
     }
-    (*c->prof_sec)[c->prof_used] = section;
-    cudaEventRecord((*c->prof_ev)[2 * c->prof_used], c->stream);
+    const size_t i = c->prof_used++;
+    (*c->prof_sec)[i] = section;
+    c->prof_stack->push_back(i);
+    cudaEventRecord((*c->prof_ev)[2 * i], c->stream);
 }
 void prof_end(mb_ctx* c) {
-    cudaEventRecord((*c->prof_ev)[2 * c->prof_used + 1], c->stream);
-    c->prof_used++;
+    if (c->prof_stack->empty()) return;
+    const size_t i = c->prof_stack->back();
+    c->prof_stack->pop_back();
+    cudaEventRecord((*c->prof_ev)[2 * i + 1], c->stream);
 }
 
 static int alloc_soa(SoA& s, int64_t cap) {
@@ -128,6 +133,7 @@ int mb_ctx_create(int device, uint64_t seed, mb_ctx** out) {
     c->nranks = 1;
     c->prof_ev = new std::vector<cudaEvent_t>();
     c->prof_sec = new std::vector<int>();
+    c->prof_stack = new std::vector<size_t>();
     *out = c;
     return MB_OK;
 }
@@ -152,6 +158,7 @@ int mb_ctx_destroy(mb_ctx* c) {
     for (auto e : *c->prof_ev) cudaEventDestroy(e);
     delete c->prof_ev;
     delete c->prof_sec;
+    delete c->prof_stack;
     cudaStreamDestroy(c->stream);
     delete c;
     return MB_OK;
@@ -204,6 +211,7 @@ int mb_prof_enable(mb_ctx* c, int32_t on) {
     MB_CUDA(cudaStreamSynchronize(c->stream));
     c->prof_on = on;
     c->prof_used = 0;
+    c->prof_stack->clear();
     return MB_OK;
 }
 int mb_prof_read(mb_ctx* c, int32_t section, double* total_ms, int64_t* launches) {

@@ -129,6 +129,7 @@ struct mb_ctx {
     std::vector<cudaEvent_t>* prof_ev;   // pairs (begin, end)
     std::vector<int>* prof_sec;          // section of pair i
     size_t prof_used;                    // pairs in use
+    std::vector<size_t>* prof_stack;     // open sections (they may nest)
     // NCCL (dlopen'ed lazily)
     void* nccl_comm;
     int rank, nranks;
@@ -219,6 +220,15 @@ struct ProfScope {
     ProfScope(mb_ctx* ctx, int section) : c(ctx) { if (c->prof_on) prof_begin(c, section); }
     ~ProfScope() { if (c->prof_on) prof_end(c); }
 };
+
+// Stream keys.  The rank of a slab-partitioned run and the species (pair) an operator works on are part of every Philox key, so a
+// caller who ports the reference's pattern -- one rng handed to ntc!(s1), ntc!(s2), ntc!(s1, s2) and to the convection of every
+// species in the same step, the same seed on every rank -- gets independent streams without managing substreams by hand.
+// Rank 0 / species 1 leave seed and substream unchanged.  The caller's substream has 12 bits.
+inline uint64_t stream_seed(const mb_ctx* c) { return c->seed ^ (0x9E3779B97F4A7C15ULL * (uint64_t)c->rank); }
+inline uint32_t stream_substream(uint32_t substream, int64_t s1, int64_t s2) {
+    return (substream & 0xFFFu) | ((uint32_t)((s1 - 1) & 0x3F) << 12) | ((uint32_t)((s2 - 1) & 0x3F) << 18);
+}
 
 inline int grid_for(int64_t n, int block, int per_sm = 8) {
     int64_t need = (n + block - 1) / block;

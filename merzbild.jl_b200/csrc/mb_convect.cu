@@ -52,7 +52,7 @@ extern "C" int mb_convect_particles(mb_ctx* ctx, const mb_grid1d* grid, const mb
         a.acc[wl] = walls->accommodation[wl];
     }
     a.dt = dt;
-    a.seed = ctx->seed; a.timestep = timestep; a.substream = substream;
+    a.seed = stream_seed(ctx); a.timestep = timestep; a.substream = stream_substream(substream, species, species);
     a.compute_cell = compute_cell;
     a.surf = nullptr;
     ctx->state_gen++;

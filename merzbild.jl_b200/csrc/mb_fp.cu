@@ -21,6 +21,7 @@ struct FpArgs {
     double mass, dt, V;
     uint64_t seed;
     uint32_t timestep, substream;
+    int* flags;
 };
 
 __device__ __forceinline__ void fp_normals(const FpArgs& a, uint32_t cell, int64_t j, double o[3]) {
@@ -59,6 +60,10 @@ static __global__ void __launch_bounds__(256) k_fp_linear(FpArgs a, int n_lo) {
         const int64_t cell = a.cell_lo + r;
         const Indexer q = a.ix[cell - 1];
         const int64_t n = q.n_local, lo = q.start1 - 1;
+        if (q.n_group2 != 0 || q.n_group1 != q.n_local) {  // only defined for sorted cells (the reference's group-2 branch throws, collision_fp.jl:57)
+            if (lane == 0) atomicOr(&a.flags[0], DEVERR_PRECONDITION);
+            continue;
+        }
         // scale_norm_rands!: exact standardisation over the n draws of each component
         double m[3] = {0, 0, 0}, s2[3] = {0, 0, 0};
         for (int64_t j = lane; j < n; j += 32) {
@@ -142,6 +147,10 @@ static __global__ void __launch_bounds__(128, K == 4 ? 4 : 2) k_fp_linear_reg(Fp
         const Indexer q = a.ix[cell - 1];
         const int n = (int)q.n_local;
         const int64_t lo = q.start1 - 1;
+        if (q.n_group2 != 0 || q.n_group1 != q.n_local) {  // see k_fp_linear
+            if (lane == 0) atomicOr(&a.flags[0], DEVERR_PRECONDITION);
+            continue;
+        }
         double w[K], vx[K], vy[K], vz[K], o0[K], o1[K], o2[K];
 #pragma unroll
         for (int k = 0; k < K; k++) {
@@ -236,7 +245,8 @@ extern "C" int mb_fp_linear(mb_ctx* ctx, const mb_interaction* it, double mass, 
     a.cell_lo = cell_lo; a.cell_hi = cell_hi;
     a.it = *it;
     a.mass = mass; a.dt = dt; a.V = V;
-    a.seed = ctx->seed; a.timestep = timestep; a.substream = substream;
+    a.seed = stream_seed(ctx); a.timestep = timestep; a.substream = stream_substream(substream, species, species);
+    a.flags = ctx->d_flags;
     ProfScope ps(ctx, PROF_FP);
     ctx->state_gen++;
     // three size classes, each kernel skips the cells of the others: n <= 128 and n <= 256 in registers, larger cells streamed

@@ -519,7 +519,7 @@ extern "C" int mb_merge_grid_based(mb_ctx* ctx, const mb_gridmerge_params* mg, m
     a.has_grid = grid != nullptr;
     a.min_x = grid ? grid->min_x : 0.0;
     a.max_x = grid ? grid->max_x : 0.0;
-    a.seed = ctx->seed; a.timestep = timestep; a.substream = substream;
+    a.seed = stream_seed(ctx); a.timestep = timestep; a.substream = stream_substream(substream, species, species);
     a.flags = ctx->d_flags;
     a.idx = (int32_t*)ctx_scratch(ctx, 0, (size_t)cap * 4);
     a.bin_of = (int32_t*)ctx_scratch(ctx, 3, (size_t)cap * 4);

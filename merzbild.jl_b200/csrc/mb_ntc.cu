@@ -353,7 +353,7 @@ static int ntc_impl(mb_ctx* ctx, mb_cf* cf, const mb_interaction* it, mb_pv* pv1
     a.it = *it;
     a.cell_lo = cell_lo; a.cell_hi = cell_hi;
     a.dt = dt; a.V = V; a.dw_tol = dw_tol;
-    a.seed = ctx->seed; a.timestep = timestep; a.substream = substream;
+    a.seed = stream_seed(ctx); a.timestep = timestep; a.substream = stream_substream(substream, s1, s2);
     a.equal_weight = equal_weight;
     a.flags = ctx->d_flags;
     a.single_cell_tail = (nr == 1);

@@ -1072,7 +1072,7 @@ extern "C" int mb_merge_octree_N2(mb_ctx* ctx, const mb_octree_params* oc, mb_pv
     a.has_grid = grid != nullptr;
     a.min_x = grid ? grid->min_x : 0.0;
     a.max_x = grid ? grid->max_x : 0.0;
-    a.seed = ctx->seed; a.timestep = timestep; a.substream = substream;
+    a.seed = stream_seed(ctx); a.timestep = timestep; a.substream = stream_substream(substream, species, species);
     a.flags = ctx->d_flags;
     // index slices
     a.idx = (int32_t*)ctx_scratch(ctx, 0, (size_t)cap * 4);

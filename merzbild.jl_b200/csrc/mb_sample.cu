@@ -210,10 +210,10 @@ static int sample_common(mb_ctx* ctx, mb_pv* pv, mb_pia* pia, int64_t cell_lo, i
     a.nr = nr;
     a.cap = pv->cap;
     a.flags = ctx->d_flags;
-    a.k0 = (uint32_t)ctx->seed;
-    a.k1 = (uint32_t)(ctx->seed >> 32);
+    a.k0 = (uint32_t)stream_seed(ctx);
+    a.k1 = (uint32_t)(stream_seed(ctx) >> 32);
     a.timestep = timestep;
-    a.opword = (OP_SAMPLE & 0xFFu) | (substream << 8);
+    a.opword = (OP_SAMPLE & 0xFFu) | (stream_substream(substream, species, species) << 8);
     a.cnt = (int32_t*)ctx_scratch(ctx, 4, (size_t)nr * 4);
     int64_t* p64 = (int64_t*)ctx_scratch(ctx, 5, ((size_t)(nr + 1) + gs_partial_count(nr)) * 8);
     if (!a.cnt || !p64) return MB_ERR_CUDA;

@@ -152,7 +152,7 @@ extern "C" int mb_swpm(mb_ctx* ctx, mb_cf* cf, const mb_interaction* it, mb_pv* 
     a.it = *it;
     a.cell_lo = cell_lo; a.cell_hi = cell_hi;
     a.G = G; a.dt = dt; a.V = V;
-    a.seed = ctx->seed; a.timestep = timestep; a.substream = substream;
+    a.seed = stream_seed(ctx); a.timestep = timestep; a.substream = stream_substream(substream, species, species);
     a.flags = ctx->d_flags;
     a.single_cell_tail = nr == 1;
     int32_t* p32 = (int32_t*)ctx_scratch(ctx, 4, (size_t)(2 * nr) * 4);

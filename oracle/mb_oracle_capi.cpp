@@ -19,6 +19,11 @@ struct mbo_rng_spec {
     uint32_t substream;  // Philox counter word 3, bits 8..31
 };
 
+// The device folds the species (pair) of an operator into the caller's 12-bit substream (merzbild.jl_b200/csrc/mb_common.cuh,
+// stream_substream): species 1 leaves it unchanged.  Restated here so that multi-species runs replay the device's streams.
+static inline uint32_t fold_substream(uint32_t substream, int64_t s1, int64_t s2) {
+    return (substream & 0xFFFu) | ((uint32_t)((s1 - 1) & 0x3F) << 12) | ((uint32_t)((s2 - 1) & 0x3F) << 18);
+}
 // ---- philox (KAT hook) ----
 void mbo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { Philox4x32::block(ctr, key, out); }
 void mbo_philox_stream_doubles(uint64_t seed, uint32_t op, uint32_t substream, uint32_t timestep, uint32_t entity, int64_t n, double* out) {
@@ -157,7 +162,7 @@ void mbo_ntc(const mbo_rng_spec* rs, double* sgwm, int64_t* n_coll, int64_t* n_p
         CollisionFactors cf;
         cf.sigma_g_w_max = sgwm[cell - 1];
         if (rs->kind == 0) ntc(*(Xoshiro256pp*)rs->seq, cf, cd, it, pv, pia, cell, species, dt, V, dw_tol, equal_weight != 0);
-        else { PhiloxStream s(rs->seed, OP_NTC, rs->substream, rs->timestep, (uint32_t)cell); ntc(s, cf, cd, it, pv, pia, cell, species, dt, V, dw_tol, equal_weight != 0); }
+        else { PhiloxStream s(rs->seed, OP_NTC, fold_substream(rs->substream, species, species), rs->timestep, (uint32_t)cell); ntc(s, cf, cd, it, pv, pia, cell, species, dt, V, dw_tol, equal_weight != 0); }
         sgwm[cell - 1] = cf.sigma_g_w_max;
         if (n_coll) n_coll[cell - 1] = cf.n_coll;
         if (n_perf) n_perf[cell - 1] = cf.n_coll_performed;
@@ -175,7 +180,7 @@ void mbo_ntc2(const mbo_rng_spec* rs, double* sgwm, int64_t* n_coll, int64_t* n_
         CollisionFactors cf;
         cf.sigma_g_w_max = sgwm[cell - 1];
         if (rs->kind == 0) ntc2(*(Xoshiro256pp*)rs->seq, cf, cd, it, p1, p2, pia, cell, s1, s2, dt, V, dw_tol, equal_weight != 0);
-        else { PhiloxStream s(rs->seed, OP_NTC, rs->substream, rs->timestep, (uint32_t)cell); ntc2(s, cf, cd, it, p1, p2, pia, cell, s1, s2, dt, V, dw_tol, equal_weight != 0); }
+        else { PhiloxStream s(rs->seed, OP_NTC, fold_substream(rs->substream, s1, s2), rs->timestep, (uint32_t)cell); ntc2(s, cf, cd, it, p1, p2, pia, cell, s1, s2, dt, V, dw_tol, equal_weight != 0); }
         sgwm[cell - 1] = cf.sigma_g_w_max;
         if (n_coll) n_coll[cell - 1] = cf.n_coll;
         if (n_perf) n_perf[cell - 1] = cf.n_coll_performed;
@@ -192,7 +197,7 @@ void mbo_swpm(const mbo_rng_spec* rs, double* sgm, int64_t* n_coll, int64_t* n_p
         CollisionFactorsSWPM cf;
         cf.sigma_g_max = sgm[cell - 1];
         if (rs->kind == 0) swpm(*(Xoshiro256pp*)rs->seq, cf, cd, it, pv, pia, cell, species, G, dt, V);
-        else { PhiloxStream s(rs->seed, OP_SWPM, rs->substream, rs->timestep, (uint32_t)cell); swpm(s, cf, cd, it, pv, pia, cell, species, G, dt, V); }
+        else { PhiloxStream s(rs->seed, OP_SWPM, fold_substream(rs->substream, species, species), rs->timestep, (uint32_t)cell); swpm(s, cf, cd, it, pv, pia, cell, species, G, dt, V); }
         sgm[cell - 1] = cf.sigma_g_max;
         if (n_coll) n_coll[cell - 1] = cf.n_coll;
         if (n_perf) n_perf[cell - 1] = cf.n_coll_performed;
@@ -222,7 +227,7 @@ void mbo_fp_linear(const mbo_rng_spec* rs, const double* it8, double mass, void*
             };
             fp_linear(src, it, mass, pv, pia, cell, species, dt, V);
         } else {
-            PhiloxStream base(rs->seed, OP_FP, rs->substream, rs->timestep, (uint32_t)cell);
+            PhiloxStream base(rs->seed, OP_FP, fold_substream(rs->substream, species, species), rs->timestep, (uint32_t)cell);
             auto src = [&](int64_t j, double o[3]) { fp_normals_philox(base, j, o); };
             fp_linear(src, it, mass, pv, pia, cell, species, dt, V);
         }
@@ -282,7 +287,7 @@ void mbo_convect_particles(const mbo_rng_spec* rs, double L, int64_t nx, const d
         convect_particles([&](int64_t) -> Xoshiro256pp& { return r; }, g, b, pv, pia, species, sd[species - 1].mass, spp, dt, compute_cell != 0);
     } else {
         PhiloxStream s;
-        convect_particles([&](int64_t i) -> PhiloxStream& { s.reset(rs->seed, OP_CONVECT, rs->substream, rs->timestep, (uint32_t)(i - 1)); return s; }, g, b,
+        convect_particles([&](int64_t i) -> PhiloxStream& { s.reset(rs->seed, OP_CONVECT, fold_substream(rs->substream, species, species), rs->timestep, (uint32_t)(i - 1)); return s; }, g, b,
                           pv, pia, species, sd[species - 1].mass, spp, dt, compute_cell != 0);
     }
     if (surf22) {
@@ -333,7 +338,7 @@ void mbo_sample_equal_weight_cells(const mbo_rng_spec* rs, const double* grid2, 
             sample_particles_equal_weight(rng, pv, pia, cell, species, nparticles, m, T, Fnum, b[0], b[1], b[2], b[3], b[4], b[5], distribution, v0, true);
         };
         if (rs->kind == 0) one(*(Xoshiro256pp*)rs->seq);
-        else { PhiloxStream s(rs->seed, OP_SAMPLE, rs->substream, rs->timestep, (uint32_t)cell); one(s); }
+        else { PhiloxStream s(rs->seed, OP_SAMPLE, fold_substream(rs->substream, species, species), rs->timestep, (uint32_t)cell); one(s); }
     }
 }
 // ensemble of 0-D cells, each the sample_on_grid! population appended at n_total + 1 with the cell's indexer set as
@@ -351,7 +356,7 @@ int64_t mbo_sample_on_grid_cells(const mbo_rng_spec* rs, int vdf_kind, void* pv_
                                v_offset, off);
         };
         if (rs->kind == 0) one(*(Xoshiro256pp*)rs->seq);
-        else { PhiloxStream s(rs->seed, OP_SAMPLE, rs->substream, rs->timestep, (uint32_t)cell); one(s); }
+        else { PhiloxStream s(rs->seed, OP_SAMPLE, fold_substream(rs->substream, species, species), rs->timestep, (uint32_t)cell); one(s); }
         ParticleIndexer& ix = pia.at(cell, species);
         ix.n_local = n; ix.start1 = off + 1; ix.end1 = off + n; ix.n_group1 = n; ix.start2 = 0; ix.end2 = -1; ix.n_group2 = 0;
         pia.n_total[species - 1] += n;
@@ -417,7 +422,7 @@ int64_t mbo_merge_grid_based(const mbo_rng_spec* rs, void* g, void* pv_, void* p
             SeqSigns<Xoshiro256pp> s{*(Xoshiro256pp*)rs->seq};
             ok = merge_grid_based(s, mg, pv, pia, cell, species, mass, tv ? tv[0] : 0.0, tv ? tv + 1 : zero, ext6, gp);
         } else {
-            PhiloxSigns s{PhiloxStream(rs->seed, OP_MERGE_GRID, rs->substream, rs->timestep, (uint32_t)cell)};
+            PhiloxSigns s{PhiloxStream(rs->seed, OP_MERGE_GRID, fold_substream(rs->substream, species, species), rs->timestep, (uint32_t)cell)};
             ok = merge_grid_based(s, mg, pv, pia, cell, species, mass, tv ? tv[0] : 0.0, tv ? tv + 1 : zero, ext6, gp);
         }
         if (!ok) bad++;
@@ -467,7 +472,7 @@ void mbo_merge_octree_N2(const mbo_rng_spec* rs, void* o, void* pv_, void* pia_,
     for (int64_t cell = cell_lo; cell <= cell_hi; cell++) {
         if (threshold >= 0 && !(pia.at(cell, species).n_local > threshold)) continue;
         if (rs->kind == 0) { SeqSigns<Xoshiro256pp> s{*(Xoshiro256pp*)rs->seq}; merge_octree_N2_based(s, oc, pv, pia, cell, species, target_np, gp); }
-        else { PhiloxSigns s{PhiloxStream(rs->seed, OP_MERGE, rs->substream, rs->timestep, (uint32_t)cell)}; merge_octree_N2_based(s, oc, pv, pia, cell, species, target_np, gp); }
+        else { PhiloxSigns s{PhiloxStream(rs->seed, OP_MERGE, fold_substream(rs->substream, species, species), rs->timestep, (uint32_t)cell)}; merge_octree_N2_based(s, oc, pv, pia, cell, species, target_np, gp); }
         if (squash_after_each) squash_pia(pv, pia, species);
     }
 }

@@ -263,3 +263,93 @@ def test_fp_linear_ensemble_conserves_and_isotropises(mb, oracle, ctx):
         np.testing.assert_allclose(e, e0, rtol=1e-12)
         ratio.append(var[0] / var[1])
     assert all(b < a for a, b in zip(ratio, ratio[1:])) and ratio[-1] < 0.6 * (ratio[0] - 1) + 1, ratio
+
+
+def test_fp_linear_relaxation_rate(mb, ctx):
+    """fp_linear! (collision_fp.jl:24-125) is an exact Ornstein-Uhlenbeck step on the centred velocities: v <- A v + C xi with
+    A = exp(-dt / tau), C^2 = (2/3) e_s (1 - A^2) and standardised xi, so the anisotropy of a cell's temperature, T_x - T, is multiplied
+    by A^2 = exp(-2 dt / tau) every step, tau = 2 mu / p from compute_relaxation_time (:143-151) with mu = mu_ref (T / T_ref)^omega.
+    Pinned here QUANTITATIVELY and independently of the oracle (tau is recomputed in numpy from the formulas of the reference):
+    the decay rate of the ensemble anisotropy over 10 steps of 0.05 tau agrees within 2 %."""
+    n_cells, ppc, V = 4096, 100, 1e-5
+    rng = np.random.default_rng(21)
+    n = n_cells * ppc
+    Fnum = V * 5e22 / ppc
+    sig = math.sqrt(K_B * 300.0 / AR)
+    rows = np.zeros((n, 7))
+    rows[:, 0] = Fnum
+    rows[:, 1:4] = rng.normal(0.0, sig, (n, 3))
+    rows[:, 1] *= 1.6
+    rows[:, 4] = (np.repeat(np.arange(n_cells), ppc) + rng.uniform(0.01, 0.99, n)) * 1e-5
+    pv, pia, ix, nt = _upload_cells(mb, ctx, np.split(rows, n_cells))
+    pia.upload(ix, nt, np.array([1], dtype=np.uint8))
+    d, omega, Tref = 4.11e-10, 0.81, 273.0
+    it = mb.make_interaction(AR, AR, d, omega, Tref)
+    # the reference's formulas, restated here (collision_utils.jl:218-223 with m = (m1 + m2) / 2, collision_fp.jl:143-151)
+    mu_ref = 30.0 * math.sqrt(AR * K_B * Tref) / (4.0 * math.sqrt(math.pi) * (5.0 - 2.0 * omega) * (7.0 - 2.0 * omega) * d * d)
+    assert abs(it.vhs_muref - mu_ref) <= 1e-15 * mu_ref
+
+    def cell_var(r):
+        v = r[:, 1:4].reshape(n_cells, ppc, 3)
+        return v.var(1)  # centred second moments per cell and component (equal weights)
+
+    var0 = cell_var(rows)
+    es = 0.5 * var0.sum(1)
+    T = es * AR / (1.5 * K_B)
+    tau = 2.0 * mu_ref * (T / Tref) ** omega / ((ppc * Fnum / V) * K_B * T)
+    dt = 0.05 * float(np.median(tau))
+    steps = 10
+    aniso = [float((var0[:, 0] - var0.mean(1)).sum())]
+    for t in range(1, steps + 1):
+        mb.fp_linear(mb.PhiloxRng(t), None, it, AR, pv, pia, (1, n_cells), 1, dt, V)
+        var = cell_var(pv.logical(1, n))
+        np.testing.assert_allclose(var.sum(1), var0.sum(1), rtol=1e-12)  # every cell keeps its energy, so tau stays put
+        aniso.append(float((var[:, 0] - var.mean(1)).sum()))
+    a0 = var0[:, 0] - var0.mean(1)
+    predicted = [float((a0 * np.exp(-2.0 * dt * k / tau)).sum()) for k in range(steps + 1)]
+    k = np.arange(steps + 1)
+    rate = -np.polyfit(k, np.log(aniso), 1)[0]
+    rate_pred = -np.polyfit(k, np.log(predicted), 1)[0]
+    assert abs(rate_pred - 2.0 * dt / np.median(tau)) < 0.01 * rate_pred
+    assert abs(rate - rate_pred) < 0.02 * rate_pred, (rate, rate_pred)
+    np.testing.assert_allclose(aniso, predicted, rtol=0.02)
+    pv.close()
+    pia.close()
+
+
+def test_fp_linear_normals_are_standard_normal(mb, ctx):
+    """The device's normals (fp32 Box-Muller from the cell's Philox stream, mb_normals.h, standardised in fp64) are checked against
+    N(0, 1) WITHOUT the shared header on the checking side: with dt >> tau the operator forgets the old velocities (A = 0), so the new
+    centred velocities of a cell are its standardised normals times one constant.  scipy's Kolmogorov-Smirnov test, the moments up to
+    order 6 and the correlations between components / neighbouring draws must be those of independent standard normals."""
+    from scipy import stats
+
+    n_cells, ppc, V = 8, 50000, 1e-5
+    rng = np.random.default_rng(22)
+    n = n_cells * ppc
+    rows = np.zeros((n, 7))
+    rows[:, 0] = V * 5e22 / ppc
+    rows[:, 1:4] = rng.uniform(-400.0, 400.0, (n, 3))  # decidedly non-normal input
+    pv, pia, ix, nt = _upload_cells(mb, ctx, np.split(rows, n_cells))
+    pia.upload(ix, nt, np.array([1], dtype=np.uint8))
+    it = mb.make_interaction(AR, AR, 4.11e-10, 0.81, 273.0)
+    mb.fp_linear(mb.PhiloxRng(1), None, it, AR, pv, pia, (1, n_cells), 1, 1.0, V)  # dt = 1 s ~ 1e8 tau
+    v = pv.logical(1, n)[:, 1:4].reshape(n_cells, ppc, 3)
+    z = (v - v.mean(1, keepdims=True)) / v.std(1, keepdims=True)
+    for c in range(n_cells):
+        for dcomp in range(3):
+            x = z[c, :, dcomp]
+            assert stats.kstest(x, "norm").pvalue > 1e-3, (c, dcomp)
+            assert abs(stats.skew(x)) < 5 * math.sqrt(6.0 / ppc)
+            assert abs(stats.kurtosis(x)) < 5 * math.sqrt(24.0 / ppc)
+            assert abs(np.mean(x ** 6) - 15.0) < 5 * math.sqrt((10395.0 - 225.0) / ppc)
+            assert abs(np.corrcoef(x[:-1], x[1:])[0, 1]) < 5 / math.sqrt(ppc)          # consecutive particles
+        assert abs(np.corrcoef(z[c, :, 0], z[c, :, 1])[0, 1]) < 5 / math.sqrt(ppc)     # components of one particle
+        assert abs(np.corrcoef(z[c, :, 1], z[c, :, 2])[0, 1]) < 5 / math.sqrt(ppc)
+    # different cells draw from different streams
+    assert abs(np.corrcoef(z[0, :, 0], z[1, :, 0])[0, 1]) < 5 / math.sqrt(ppc)
+    x = z.reshape(-1)
+    assert stats.kstest(x, "norm").pvalue > 1e-3
+    assert abs(np.mean(np.abs(x) > 3.0) - 0.0026998) < 5 * math.sqrt(0.0027 / x.size)  # the tails are there
+    pv.close()
+    pia.close()
