@@ -317,12 +317,13 @@ def run_c3(env, args, scaling, steps, warmup, e2e_steps, band=None):
     mb.sample_particles_equal_weight(mb.PhiloxRng(0, 0), slab, pv, pia, 1, AR, ppc, T_WALL, Fnum)
     ctx.sync()
     tstep = [0]
+    dt = DT * getattr(args, "dt_mult", 1.0)
 
     def step():
         tstep[0] += 1
         r = mb.PhiloxRng(tstep[0], 0)
-        mb.ntc_equal_weight(r, cf, None, it, pv, pia, (1, nx), 1, DT, slab.dx)
-        mb.convect_particles(r, slab, walls, pv, pia, 1, AR, DT)
+        mb.ntc_equal_weight(r, cf, None, it, pv, pia, (1, nx), 1, dt, slab.dx)
+        mb.convect_particles(r, slab, walls, pv, pia, 1, AR, dt)
         if world > 1:
             mb.exchange_slab(ctx, slab, pv, pia, 1)
         mb.sort_particles(None, slab, pv, pia, 1)
@@ -813,6 +814,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="do not append the short runs of the other configs / scalings to the default line")
+    ap.add_argument("--dt-mult", type=float, default=1.0, help="experiment knob: multiplies the time step (0: nothing moves, the sort is a pure segmented copy)")
     ap.add_argument("--band", type=int, default=None, help="band half-width of the sort fast path (0: general path only); default: the scaling's")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -329,10 +329,13 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_apply(const int32_t* __rest
 #ifndef MB_SC_MINB
 #define MB_SC_MINB 2
 #endif
+#ifndef MB_SC_BUF
+#define MB_SC_BUF 1  // 1: k_band_scatter_buf (movers coalesced through shared memory), 0: k_band_scatter (every particle stored directly)
+#endif
 constexpr int SC_U = MB_SC_U;  // particles per lane in flight
 #define MB_LD(p) (*(p))  // default cache policy: streaming hints (ld.cs / st.cs) measured 13 % slower here
 #define MB_ST(p, v) (*(p) = (v))
-template <int W>
+template <int W, bool MOM>
 __global__ void __launch_bounds__(256, MB_SC_MINB) k_band_scatter(SoA in_, SoA out_, const uint32_t* __restrict__ dr, const int32_t* __restrict__ M,
                                                       const int64_t* __restrict__ seg_lo, const int32_t* __restrict__ seg_n,
                                                       const int64_t* __restrict__ start, const int32_t* __restrict__ cntB, int64_t n_cells,
@@ -343,66 +346,70 @@ __global__ void __launch_bounds__(256, MB_SC_MINB) k_band_scatter(SoA in_, SoA o
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int64_t* off_s = s_off[wid];
-    for (int64_t c = warp0; c < n_cells; c += nwarps) {
-        const int64_t lo = seg_lo[c];
-        const int n = seg_n[c];
-        __syncwarp();
-        if (lane < W) {
-            const int64_t cd = c + lane - w;  // destination cell of group d = lane
-            int64_t off = 0;
-            if (cd >= 0 && cd < n_cells) {
-                off = start[cd] + cntB[cd];  // the extras that came from further left sit in front of the band groups
-                int acc = 0;
+    int64_t* off_s = s_off[wid];
+    // what a warp needs to know about a cell before it can stream it: the segment (lo, n) and, in lane d, the output position of
+    // destination group d.  All loads are independent of each other, and the NEXT cell's are issued before the current cell streams,
+    // so that no warp ever waits for metadata with nothing in flight.
+    auto load_meta = [&](int64_t c, int64_t& lo, int& n, int64_t& off) {
+        lo = seg_lo[c];
+        n = seg_n[c];
+        off = 0;
+        const int64_t cd = c + lane - w;  // destination cell of group d = lane
+        if (lane < W && cd >= 0 && cd < n_cells) {
+            int acc = 0;
 #pragma unroll
-                for (int k = 1; k < W; k++) {  // sources c - k < c that also feed cd (independent loads, all in flight together)
-                    const int64_t cs = c - k;
-                    if (lane + k < W && cs >= 0) acc += M[cs * W + lane + k];
-                }
-                off += acc;
+            for (int k = 1; k < W; k++) {  // sources c - k < c that also feed cd
+                const int64_t cs = c - k;
+                if (lane + k < W && cs >= 0) acc += M[cs * W + lane + k];
             }
-            s_off[wid][lane] = off;
+            off = start[cd] + cntB[cd] + acc;  // the extras that came from further left sit in front of the band groups
         }
+    };
+    int64_t lo = 0, off = 0, lo_n = 0, off_n = 0;
+    int n = 0, n_n = 0;
+    int64_t c = warp0;
+    if (c < n_cells) load_meta(c, lo, n, off);
+    for (; c < n_cells; c += nwarps) {
+        if (c + nwarps < n_cells) load_meta(c + nwarps, lo_n, n_n, off_n);
+        __syncwarp();
+        off_s[lane] = off;
         __syncwarp();
         const double* __restrict__ i0 = in_.a[0] + lo; const double* __restrict__ i1 = in_.a[1] + lo; const double* __restrict__ i2 = in_.a[2] + lo;
         const double* __restrict__ i3 = in_.a[3] + lo; const double* __restrict__ i4 = in_.a[4] + lo; const double* __restrict__ i5 = in_.a[5] + lo;
         const double* __restrict__ i6 = in_.a[6] + lo;
         const uint32_t* __restrict__ drc = dr + lo;
         double K1 = 0, K2 = 0, K3 = 0;
-        if (n > 0) { K1 = i1[0]; K2 = i2[0]; K3 = i3[0]; }
+        if (MOM && n > 0) { K1 = i1[0]; K2 = i2[0]; K3 = i3[0]; }
         double an = 0, ax = 0, ay = 0, az = 0, aq = 0;  // the staying group
-#define MB_MOVE(j, a0, a1, a2, a3, a4, a5, a6, v)                                                   \
-    if (v != DR_NONE) {                                                                             \
-        const int64_t pos = off_s[v >> 24] + (int64_t)(v & 0xFFFFFFu);                              \
-        MB_ST(&out_.a[0][pos], a0); MB_ST(&out_.a[1][pos], a1); MB_ST(&out_.a[2][pos], a2); MB_ST(&out_.a[3][pos], a3); \
-        MB_ST(&out_.a[4][pos], a4); MB_ST(&out_.a[5][pos], a5); MB_ST(&out_.a[6][pos], a6);         \
-        if ((v >> 24) == (uint32_t)w) {                                                             \
-            const double cx_ = a1 - K1, cy_ = a2 - K2, cz_ = a3 - K3;                               \
-            an += a0; ax += a0 * cx_; ay += a0 * cy_; az += a0 * cz_;                               \
-            aq += a0 * (cx_ * cx_ + cy_ * cy_ + cz_ * cz_);                                         \
-        }                                                                                           \
-    }
-        int j = lane;
-        for (; j + 32 * (SC_U - 1) < n; j += 32 * SC_U) {  // SC_U particles per lane in flight
+        for (int j0 = 0; j0 < n; j0 += 32 * SC_U) {  // SC_U particles per lane in flight; the last round is predicated, not serialised
             uint32_t v[SC_U];
             double a[SC_U][7];
 #pragma unroll
             for (int u = 0; u < SC_U; u++) {
-                const int ju = j + 32 * u;
-                v[u] = drc[ju];
-                a[u][0] = MB_LD(i0 + ju); a[u][1] = MB_LD(i1 + ju); a[u][2] = MB_LD(i2 + ju); a[u][3] = MB_LD(i3 + ju); a[u][4] = MB_LD(i4 + ju);
-                a[u][5] = MB_LD(i5 + ju); a[u][6] = MB_LD(i6 + ju);
+                const int ju = j0 + 32 * u + lane;
+                v[u] = DR_NONE;
+                if (ju < n) {
+                    v[u] = drc[ju];
+                    a[u][0] = MB_LD(i0 + ju); a[u][1] = MB_LD(i1 + ju); a[u][2] = MB_LD(i2 + ju); a[u][3] = MB_LD(i3 + ju);
+                    a[u][4] = MB_LD(i4 + ju); a[u][5] = MB_LD(i5 + ju); a[u][6] = MB_LD(i6 + ju);
+                }
             }
 #pragma unroll
-            for (int u = 0; u < SC_U; u++) MB_MOVE(j + 32 * u, a[u][0], a[u][1], a[u][2], a[u][3], a[u][4], a[u][5], a[u][6], v[u]);
+            for (int u = 0; u < SC_U; u++) {
+                if (v[u] != DR_NONE) {
+                    const int64_t pos = off_s[v[u] >> 24] + (int64_t)(v[u] & 0xFFFFFFu);
+                    MB_ST(&out_.a[0][pos], a[u][0]); MB_ST(&out_.a[1][pos], a[u][1]); MB_ST(&out_.a[2][pos], a[u][2]);
+                    MB_ST(&out_.a[3][pos], a[u][3]); MB_ST(&out_.a[4][pos], a[u][4]); MB_ST(&out_.a[5][pos], a[u][5]);
+                    MB_ST(&out_.a[6][pos], a[u][6]);
+                    if (MOM && (v[u] >> 24) == (uint32_t)w) {
+                        const double cx_ = a[u][1] - K1, cy_ = a[u][2] - K2, cz_ = a[u][3] - K3;
+                        an += a[u][0]; ax += a[u][0] * cx_; ay += a[u][0] * cy_; az += a[u][0] * cz_;
+                        aq += a[u][0] * (cx_ * cx_ + cy_ * cy_ + cz_ * cz_);
+                    }
+                }
+            }
         }
-        for (; j < n; j += 32) {
-            const uint32_t va = drc[j];
-            const double a0 = i0[j], a1 = i1[j], a2 = i2[j], a3 = i3[j], a4 = i4[j], a5 = i5[j], a6 = i6[j];
-            MB_MOVE(j, a0, a1, a2, a3, a4, a5, a6, va);
-        }
-#undef MB_MOVE
-        if (P != nullptr) {
+        if (MOM) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 an += __shfl_xor_sync(0xffffffffu, an, o); ax += __shfl_xor_sync(0xffffffffu, ax, o);
@@ -414,6 +421,133 @@ __global__ void __launch_bounds__(256, MB_SC_MINB) k_band_scatter(SoA in_, SoA o
                 q[0] = an; q[1] = ax; q[2] = ay; q[3] = az; q[4] = aq;
             }
         }
+        lo = lo_n; n = n_n; off = off_n;
+    }
+}
+
+// Pass B with the movers coalesced (the variant that runs).  Measured with the kernel above: with no movers at all the segmented copy
+// reaches 90 % of the copy peak, and every mover costs seven isolated 8-byte stores -- partial-sector writes that L2 has to merge
+// (same-dx: +20 % write transactions, -10 % bandwidth; at sigma_v dt = 2.6 cells, where 85 % of a cell moves: -35 %).  Here the
+// stayers still go straight from registers to their run, but a mover is parked in the warp's shared-memory buffer of its destination
+// group (slot = rank: the rank IS the position inside the group), and when the cell is through every group leaves as one run,
+// consecutive ranks in consecutive lanes: full sectors instead of single doubles.  Ranks beyond the buffer are stored directly.
+// No synchronisation inside the streaming loop.
+template <int W>
+struct ScBuf {
+    static constexpr int ND = W - 1;                          // mover groups
+    static constexpr int CAP = W >= 31 ? 8 : 192 / ND;        // ranks parked per group: 96 / 48 / 24 / 12 / 8 for w = 1 / 2 / 4 / 8 / 15
+    static constexpr int WARP_DOUBLES = ND * 7 * CAP;         // 10.5 KB per warp (13.1 KB for the 31-wide band)
+    static constexpr int SMEM = 8 * (WARP_DOUBLES * 8 + 32 * 8);  // + the per-warp output offsets
+};
+template <int W, bool MOM>
+__global__ void __launch_bounds__(256, MB_SC_MINB) k_band_scatter_buf(SoA in_, SoA out_, const uint32_t* __restrict__ dr, const int32_t* __restrict__ M,
+                                                          const int64_t* __restrict__ seg_lo, const int32_t* __restrict__ seg_n,
+                                                          const int64_t* __restrict__ start, const int32_t* __restrict__ cntB, int64_t n_cells,
+                                                          double* __restrict__ P, const int* flags) {
+    if (flags[2] != 0) return;  // general path takes over
+    using B = ScBuf<W>;
+    constexpr int w = W / 2, CAP = B::CAP;
+    extern __shared__ __align__(16) unsigned char sc_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double* buf = (double*)sc_smem + (size_t)wid * B::WARP_DOUBLES;                  // [group][field][rank]
+    int64_t* off_s = (int64_t*)((double*)sc_smem + 8 * B::WARP_DOUBLES) + wid * 32;  // output position of group d
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    double* const out0 = out_.a[0];
+    const int64_t ostride = out_.a[1] - out_.a[0];  // the seven arrays of a ParticleVector are equally spaced slices of one allocation
+    auto load_meta = [&](int64_t c, int64_t& lo, int& n, int64_t& off, int& gcnt) {
+        lo = seg_lo[c];
+        n = seg_n[c];
+        off = 0;
+        gcnt = lane < W ? M[c * W + lane] : 0;  // size of group d = lane
+        const int64_t cd = c + lane - w;        // its destination cell
+        if (lane < W && cd >= 0 && cd < n_cells) {
+            int acc = 0;
+#pragma unroll
+            for (int k = 1; k < W; k++) {  // sources c - k < c that also feed cd
+                const int64_t cs = c - k;
+                if (lane + k < W && cs >= 0) acc += M[cs * W + lane + k];
+            }
+            off = start[cd] + cntB[cd] + acc;  // the extras that came from further left sit in front of the band groups
+        }
+    };
+    int64_t lo = 0, off = 0, lo_n = 0, off_n = 0;
+    int n = 0, n_n = 0, gcnt = 0, gcnt_n = 0;
+    int64_t c = warp0;
+    if (c < n_cells) load_meta(c, lo, n, off, gcnt);
+    for (; c < n_cells; c += nwarps) {
+        if (c + nwarps < n_cells) load_meta(c + nwarps, lo_n, n_n, off_n, gcnt_n);
+        __syncwarp();
+        off_s[lane] = off;
+        __syncwarp();
+        const double* __restrict__ i0 = in_.a[0] + lo; const double* __restrict__ i1 = in_.a[1] + lo; const double* __restrict__ i2 = in_.a[2] + lo;
+        const double* __restrict__ i3 = in_.a[3] + lo; const double* __restrict__ i4 = in_.a[4] + lo; const double* __restrict__ i5 = in_.a[5] + lo;
+        const double* __restrict__ i6 = in_.a[6] + lo;
+        const uint32_t* __restrict__ drc = dr + lo;
+        double K1 = 0, K2 = 0, K3 = 0;
+        if (MOM && n > 0) { K1 = i1[0]; K2 = i2[0]; K3 = i3[0]; }
+        double an = 0, ax = 0, ay = 0, az = 0, aq = 0;  // the staying group
+        for (int j0 = 0; j0 < n; j0 += 32 * SC_U) {
+            uint32_t v[SC_U];
+            double a[SC_U][7];
+#pragma unroll
+            for (int u = 0; u < SC_U; u++) {
+                const int ju = j0 + 32 * u + lane;
+                v[u] = DR_NONE;
+                if (ju < n) {
+                    v[u] = drc[ju];
+                    a[u][0] = MB_LD(i0 + ju); a[u][1] = MB_LD(i1 + ju); a[u][2] = MB_LD(i2 + ju); a[u][3] = MB_LD(i3 + ju);
+                    a[u][4] = MB_LD(i4 + ju); a[u][5] = MB_LD(i5 + ju); a[u][6] = MB_LD(i6 + ju);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < SC_U; u++) {
+                if (v[u] == DR_NONE) continue;
+                const int d = (int)(v[u] >> 24), r = (int)(v[u] & 0xFFFFFFu);
+                if (d == w || r >= CAP) {  // stayer (or a rank beyond the buffer): straight to its place
+                    const int64_t pos = off_s[d] + r;
+                    MB_ST(&out_.a[0][pos], a[u][0]); MB_ST(&out_.a[1][pos], a[u][1]); MB_ST(&out_.a[2][pos], a[u][2]);
+                    MB_ST(&out_.a[3][pos], a[u][3]); MB_ST(&out_.a[4][pos], a[u][4]); MB_ST(&out_.a[5][pos], a[u][5]);
+                    MB_ST(&out_.a[6][pos], a[u][6]);
+                    if (MOM && d == w) {
+                        const double cx_ = a[u][1] - K1, cy_ = a[u][2] - K2, cz_ = a[u][3] - K3;
+                        an += a[u][0]; ax += a[u][0] * cx_; ay += a[u][0] * cy_; az += a[u][0] * cz_;
+                        aq += a[u][0] * (cx_ * cx_ + cy_ * cy_ + cz_ * cz_);
+                    }
+                } else {  // mover: parked at its rank
+                    double* dst = buf + (d > w ? d - 1 : d) * (7 * CAP) + r;
+                    dst[0] = a[u][0]; dst[CAP] = a[u][1]; dst[2 * CAP] = a[u][2]; dst[3 * CAP] = a[u][3];
+                    dst[4 * CAP] = a[u][4]; dst[5 * CAP] = a[u][5]; dst[6 * CAP] = a[u][6];
+                }
+            }
+        }
+        __syncwarp();
+        // every mover group leaves as one run: element t = (field, rank)
+        for (int g = 0; g < W - 1; g++) {
+            const int d = g < w ? g : g + 1;
+            int cnt = __shfl_sync(0xffffffffu, gcnt, d);
+            if (cnt == 0) continue;
+            cnt = cnt < CAP ? cnt : CAP;
+            const double* src = buf + g * (7 * CAP);
+            double* o = out0 + off_s[d];
+            for (int t = lane; t < 7 * CAP; t += 32) {
+                const int f = t / CAP, e = t - f * CAP;
+                if (e < cnt) MB_ST(o + f * ostride + e, src[t]);
+            }
+        }
+        if (MOM) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                an += __shfl_xor_sync(0xffffffffu, an, o); ax += __shfl_xor_sync(0xffffffffu, ax, o);
+                ay += __shfl_xor_sync(0xffffffffu, ay, o); az += __shfl_xor_sync(0xffffffffu, az, o);
+                aq += __shfl_xor_sync(0xffffffffu, aq, o);
+            }
+            if (lane == 0) {
+                double* q = P + c * 5;
+                q[0] = an; q[1] = ax; q[2] = ay; q[3] = az; q[4] = aq;
+            }
+        }
+        lo = lo_n; n = n_n; off = off_n; gcnt = gcnt_n;
     }
 }
 
@@ -1103,8 +1237,29 @@ static int launch_band(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pi
     }
     {
         ProfScope ps(ctx, PROF_SORT_SCATTER);
-        k_band_scatter<W><<<grid_for(nc * 32, 256, MB_SC_GRID), 256, 0, st>>>(pv->cur, pv->alt, B.dr, S.M, B.seg_lo, B.seg_n, S.start, B.E.cntB, nc,
-                                                                              B.P, S.flags);
+        const int sgrid = grid_for(nc * 32, 256, MB_SC_GRID);
+        // movers through shared memory pay off while the groups are long (narrow bands: ~25 movers per neighbour and cell at ppc = 1000);
+        // at w >= 4 a group holds a handful of particles and the direct stores are faster (measured, profiles/README.md)
+        bool buffered = MB_SC_BUF != 0 && W <= 5;
+        for (int f = 1; f < 7 && buffered; f++) buffered = pv->alt.a[f] - pv->alt.a[0] == f * (pv->alt.a[1] - pv->alt.a[0]);
+        if (buffered) {
+            static bool attr_done[64] = {false};  // function attributes are per device
+            if (!attr_done[ctx->device & 63]) {
+                MB_CUDA(cudaFuncSetAttribute(k_band_scatter_buf<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScBuf<W>::SMEM));
+                MB_CUDA(cudaFuncSetAttribute(k_band_scatter_buf<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScBuf<W>::SMEM));
+                attr_done[ctx->device & 63] = true;
+            }
+            if (B.P != nullptr)
+                k_band_scatter_buf<W, true><<<sgrid, 256, ScBuf<W>::SMEM, st>>>(pv->cur, pv->alt, B.dr, S.M, B.seg_lo, B.seg_n, S.start, B.E.cntB, nc,
+                                                                               B.P, S.flags);
+            else
+                k_band_scatter_buf<W, false><<<sgrid, 256, ScBuf<W>::SMEM, st>>>(pv->cur, pv->alt, B.dr, S.M, B.seg_lo, B.seg_n, S.start, B.E.cntB, nc,
+                                                                                nullptr, S.flags);
+        } else if (B.P != nullptr) {
+            k_band_scatter<W, true><<<sgrid, 256, 0, st>>>(pv->cur, pv->alt, B.dr, S.M, B.seg_lo, B.seg_n, S.start, B.E.cntB, nc, B.P, S.flags);
+        } else {
+            k_band_scatter<W, false><<<sgrid, 256, 0, st>>>(pv->cur, pv->alt, B.dr, S.M, B.seg_lo, B.seg_n, S.start, B.E.cntB, nc, nullptr, S.flags);
+        }
         MB_LAUNCH_CHECK(ctx);
     }
     {

@@ -22,7 +22,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmerzbild_b200.so")
+LIB_PATH = os.environ.get("MERZBILD_B200_LIB") or os.path.join(_HERE, "libmerzbild_b200.so")  # the override serves kernel-variant experiments
 
 MB_OK, MB_ERR_NO_DEVICE, MB_ERR_CUDA, MB_ERR_ARG, MB_ERR_CAPACITY, MB_ERR_PRECONDITION, MB_ERR_NCCL, MB_ERR_UNSUPPORTED = range(8)
 K_B = 1.380649e-23
