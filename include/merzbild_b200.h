@@ -48,6 +48,7 @@ typedef struct mb_pv mb_pv;         /* ParticleVector (particles.jl:194-212), de
 typedef struct mb_pia mb_pia;       /* ParticleIndexerArray (particles.jl:104-141) */
 typedef struct mb_cf mb_cf;         /* CollisionFactors per cell for one species pair (collision_ntc.jl:18-25, :46-155) */
 typedef struct mb_props mb_props;   /* PhysProps (physical_props.jl:24-37) */
+typedef struct mb_surf mb_surf;     /* SurfProps (surface_props.jl:22-50) of the two walls of a 1-D grid, one species */
 
 /* Grid1DUniform (grids/grid_uniform1D.jl:49-86); fill with mb_grid1d_init */
 typedef struct {
@@ -184,6 +185,23 @@ int mb_fp_linear(mb_ctx* ctx, const mb_interaction* it, double mass, mb_pv* pv, 
  *      passing it synchronises. ---- */
 int mb_convect_particles(mb_ctx* ctx, const mb_grid1d* grid, const mb_walls1d* walls, mb_pv* pv, mb_pia* pia, int64_t species, double mass,
                          double* surf22, double dt, int32_t compute_cell, uint32_t timestep, uint32_t substream);
+
+/* ---- SurfProps on the device (properties/surface_props.jl): 2 walls x 11 doubles = np, flux_incident, flux_reflected, force[3],
+ *      normal_pressure, shear_pressure[3], kinetic_energy_flux; wall 0 = left.  Everything but the download is stream-ordered.
+ *      mb_convect_particles_surf = convect_particles!(rng, grid, boundaries, pv, pia, species, species_data, surf_props, dt)
+ *      convection_1D.jl:176-206: clears surf (:179), accumulates incident / reflected contributions in the convection kernel
+ *      (surface_props.jl:77-131) and scales them (surface_props_scale! :144-160) without synchronising the stream. ---- */
+int mb_surf_create(mb_ctx* ctx, mb_surf** out);
+int mb_surf_destroy(mb_surf* s);
+int mb_surf_clear(mb_surf* s);                                           /* clear_props!(surf_props) :173-181 */
+int mb_surf_upload(mb_surf* s, const double* in22);
+int mb_surf_download(mb_surf* s, double* out22);                         /* synchronises */
+int mb_surf_avg(mb_surf* avg, mb_surf* cur, int64_t n_avg_timesteps);    /* avg_props!(surf_props_avg, surf_props, n) :202-222 */
+/* reduce_surf_props!(target, chunks) :232-252: target = sum over the n_chunks SurfProps of this process (list order); with
+ * across_ranks != 0 and a communicator of more than one rank (mb_comm_init) additionally summed over all ranks (ncclAllReduce). */
+int mb_surf_reduce(mb_surf* target, mb_surf* const* chunks, int32_t n_chunks, int32_t across_ranks);
+int mb_convect_particles_surf(mb_ctx* ctx, const mb_grid1d* grid, const mb_walls1d* walls, mb_pv* pv, mb_pia* pia, int64_t species, double mass,
+                              mb_surf* surf, double dt, int32_t compute_cell, uint32_t timestep, uint32_t substream);
 
 /* ---- PhysProps(n_cells, n_species, moment_powers; Tref) physical_props.jl:24-37,:55-71 ---- */
 int mb_props_create(mb_ctx* ctx, int64_t n_cells, int64_t n_species, int64_t n_moments, const int32_t* moment_powers, double Tref,

@@ -31,8 +31,14 @@ static __global__ void __launch_bounds__(256) k_convect_ranges(ConvectArgs a) {
 
 using namespace mb;
 
-extern "C" int mb_convect_particles(mb_ctx* ctx, const mb_grid1d* grid, const mb_walls1d* walls, mb_pv* pv, mb_pia* pia, int64_t species,
-                                    double mass, double* surf22, double dt, int32_t compute_cell, uint32_t timestep, uint32_t substream) {
+struct mb_surf;
+namespace mb {
+double* surf_device_ptr(mb_surf* s);            // mb_surf.cu
+int surf_scale(mb_ctx* ctx, mb_surf* s, double factor);
+}
+
+static int convect_impl(mb_ctx* ctx, const mb_grid1d* grid, const mb_walls1d* walls, mb_pv* pv, mb_pia* pia, int64_t species, double mass,
+                        double* surf22, mb_surf* surf, double dt, int32_t compute_cell, uint32_t timestep, uint32_t substream) {
     MB_ARG(ctx && grid && walls && pv && pia, "NULL handle");
     MB_ARG(species >= 1 && species <= pia->n_species, "species out of range");
     MB_ARG(mass > 0, "mass");
@@ -56,7 +62,10 @@ extern "C" int mb_convect_particles(mb_ctx* ctx, const mb_grid1d* grid, const mb
     a.compute_cell = compute_cell;
     a.surf = nullptr;
     ctx->state_gen++;
-    if (surf22) {
+    if (surf) {  // device-resident SurfProps: cleared, accumulated and scaled on the stream, nothing comes back to the host
+        a.surf = surf_device_ptr(surf);
+        MB_CUDA(cudaMemsetAsync(a.surf, 0, 22 * 8, ctx->stream));  // clear_props!(surf_props) convection_1D.jl:179
+    } else if (surf22) {
         a.surf = (double*)ctx_scratch(ctx, 6, 22 * 8);
         if (!a.surf) return MB_ERR_CUDA;
         MB_CUDA(cudaMemsetAsync(a.surf, 0, 22 * 8, ctx->stream));  // clear_props!(surf_props) convection_1D.jl:179
@@ -77,6 +86,7 @@ extern "C" int mb_convect_particles(mb_ctx* ctx, const mb_grid1d* grid, const mb
     }
     if (!fused) MB_LAUNCH_CHECK(ctx);
     }
+    if (surf) return surf_scale(ctx, surf, mass / dt);  // surface_props_scale! :144-160 (areas = 1)
     if (surf22) {
         MB_CUDA(cudaMemcpyAsync(surf22, a.surf, 22 * 8, cudaMemcpyDeviceToHost, ctx->stream));
         int r = mb_sync(ctx);
@@ -86,4 +96,14 @@ extern "C" int mb_convect_particles(mb_ctx* ctx, const mb_grid1d* grid, const mb
             for (int k = 1; k < 11; k++) surf22[11 * e + k] *= factor;
     }
     return MB_OK;
+}
+
+extern "C" int mb_convect_particles(mb_ctx* ctx, const mb_grid1d* grid, const mb_walls1d* walls, mb_pv* pv, mb_pia* pia, int64_t species,
+                                    double mass, double* surf22, double dt, int32_t compute_cell, uint32_t timestep, uint32_t substream) {
+    return convect_impl(ctx, grid, walls, pv, pia, species, mass, surf22, nullptr, dt, compute_cell, timestep, substream);
+}
+extern "C" int mb_convect_particles_surf(mb_ctx* ctx, const mb_grid1d* grid, const mb_walls1d* walls, mb_pv* pv, mb_pia* pia, int64_t species,
+                                         double mass, mb_surf* surf, double dt, int32_t compute_cell, uint32_t timestep, uint32_t substream) {
+    MB_ARG(surf != nullptr, "surf == NULL");
+    return convect_impl(ctx, grid, walls, pv, pia, species, mass, nullptr, surf, dt, compute_cell, timestep, substream);
 }

@@ -31,6 +31,7 @@ struct NcclApi {
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -59,6 +60,7 @@ static int nccl_load() {
     MB_SYM(CommDestroy, "ncclCommDestroy");
     MB_SYM(Send, "ncclSend");
     MB_SYM(Recv, "ncclRecv");
+    MB_SYM(AllReduce, "ncclAllReduce");
     MB_SYM(GroupStart, "ncclGroupStart");
     MB_SYM(GroupEnd, "ncclGroupEnd");
     MB_SYM(GetErrorString, "ncclGetErrorString");
@@ -74,6 +76,16 @@ static int nccl_load() {
             return MB_ERR_NCCL;                                                           \
         }                                                                                 \
     } while (0)
+
+// sum over the ranks of the context's communicator (SurfProps: 22 doubles; surface_props.jl:232-252 across GPUs)
+int nccl_allreduce_sum_f64(mb_ctx* ctx, double* buf, size_t n) {
+    if (!ctx->nccl_comm) {
+        set_error("reduction across ranks: call mb_comm_init first");
+        return MB_ERR_NCCL;
+    }
+    MB_NCCL(g_nccl.AllReduce(buf, buf, n, ncclFloat64, /* ncclSum */ 0, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    return MB_OK;
+}
 
 constexpr int XB = 256;      // threads per block
 constexpr int XI = 8;        // particles per thread (blocked)

@@ -734,9 +734,8 @@ __global__ void __launch_bounds__(256, MB_CB_MINB) k_convect_band(ConvectArgs a,
         __syncwarp();
         cnt_s[lane] = 0;
         __syncwarp();
-        bool bad = false, outside = false, far = false;
-        int xnc = 0;
-        // one particle: returns d (255: not counted, 254: an extra -- inside the slab but further than w cells away, cell in xnc)
+        bool bad = false, outside = false, far = false, any_ex = false;
+        // one particle: returns d (255: not counted; any_ex: an extra -- inside the slab but further than w cells away -- was seen)
         auto move = [&](int j, double x_old, double vx) -> int {
             double x_new = fma(vx, dt, x_old);  // @muladd x[1] + v[1] * dt
             if (x_new >= L || x_new <= 0.0) x_new = convect_wall(a, lo + j, x_old, vx, x_new);
@@ -748,8 +747,8 @@ __global__ void __launch_bounds__(256, MB_CB_MINB) k_convect_band(ConvectArgs a,
             const int d = nc - c + w;
             if (nc >= 0 && nc < n_cells) {
                 if (d >= 0 && d < W) return d;
-                xnc = nc;
-                return 254;
+                any_ex = true;
+                return 255;
             }
             outside = true;
             if ((nc < 0 && c >= w) || (nc >= n_cells && c < n_cells - w)) far = true;
@@ -778,11 +777,24 @@ __global__ void __launch_bounds__(256, MB_CB_MINB) k_convect_band(ConvectArgs a,
             issue(k + CB_PF);
             int d = 255;
             if (valid) d = move(j, x0, v0);
-            const bool ex = d == 254;
-            classify_batch(ex ? 255 : d, valid, lt, cnt_s, drc + (valid ? j : 0));
-            if (extras_append(E, ex, (int32_t)(lo + j), xnc, xnc < c ? 1 : 0, lane, lt)) bad = true;
+            classify_batch(d, valid, lt, cnt_s, drc + (valid ? j : 0));
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+        // extras are rare on the band path: the streaming loop only notes that the cell has some, and they are listed here from the
+        // positions just written (the cell is still in L1 / L2)
+        if (__any_sync(0xffffffffu, any_ex)) {
+            for (int k = 0; k < nb; k++) {
+                const int j = (k << 5) + lane;
+                bool ex = false;
+                int nc = 0;
+                if (j < n) {
+                    nc = __double2int_rd(Xc[j] * inv_dx) - cell_offset;
+                    const int d = nc - c + w;
+                    ex = nc >= 0 && nc < n_cells && (d < 0 || d >= W);
+                }
+                if (extras_append(E, ex, (int32_t)(lo + j), nc, nc < c ? 1 : 0, lane, lt)) bad = true;
+            }
+        }
         bad = __any_sync(0xffffffffu, bad);
         outside = __any_sync(0xffffffffu, outside);
         far = __any_sync(0xffffffffu, far);

@@ -21,7 +21,8 @@
 # is bound here with the right arity.
 module MerzbildB200
 
-export Context, PhiloxRng, DeviceParticleVector, DeviceParticleIndexerArray, DeviceCollisionFactors, DevicePhysProps,
+export Context, PhiloxRng, DeviceParticleVector, DeviceParticleIndexerArray, DeviceCollisionFactors, DevicePhysProps, DeviceSurfProps,
+       reduce_surf_props!,
        DeviceGrid1D, slab, sort_particles!, squash_pia!, restore_particle_ordering!, ntc!, ntc_equal_weight!, swpm!, fp_linear!,
        convect_particles!, convect_particles_and_compute_cell!, compute_props!, compute_props_sorted!,
        compute_props_with_total_moments!, avg_props!, clear_props!, merge_octree_N2_based!, exchange_particles!,
@@ -436,6 +437,54 @@ convect_particles_and_compute_cell!(rng::PhiloxRng, grid, boundaries, pv::Device
     (convect_impl(rng, grid, boundaries, pv, pia, species, species_data, Δt, false, true); nothing)
 convect_particles_and_compute_cell!(rng::PhiloxRng, grid, boundaries, pv::DeviceParticleVector, pia, species::Integer, species_data, surf_props,
                                     Δt::Real) = convect_impl(rng, grid, boundaries, pv, pia, species, species_data, Δt, true, true)
+
+# ------------------------------------------------------------------------------------------------------ surface properties
+"""
+    DeviceSurfProps(ctx)                                                                            surface_props.jl:22-50
+
+SurfProps of the two walls of a 1-D grid (one species) on the device.  Passing it as `surf_props` to `convect_particles!` keeps the
+whole step asynchronous: cleared, accumulated and scaled on the stream (convection_1D.jl:176-206, surface_props.jl:77-160).
+`download(s)` returns the 11 x 2 matrix (per wall: np, flux_incident, flux_reflected, force[1:3], normal_pressure,
+shear_pressure[1:3], kinetic_energy_flux).
+"""
+mutable struct DeviceSurfProps
+    ctx::Context
+    h::Ptr{Cvoid}
+    function DeviceSurfProps(ctx::Context)
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:mb_surf_create, libmb), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), ctx.h, out))
+        s = new(ctx, out[])
+        finalizer(q -> (q.h != C_NULL && ccall((:mb_surf_destroy, libmb), Cint, (Ptr{Cvoid},), q.h); q.h = C_NULL), s)
+        s
+    end
+end
+clear_props!(s::DeviceSurfProps) = check(ccall((:mb_surf_clear, libmb), Cint, (Ptr{Cvoid},), s.h))
+upload!(s::DeviceSurfProps, m::Matrix{Float64}) = check(ccall((:mb_surf_upload, libmb), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), s.h, m))
+function download(s::DeviceSurfProps)
+    m = zeros(Float64, 11, 2)
+    check(ccall((:mb_surf_download, libmb), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), s.h, m))
+    m
+end
+"avg_props!(surf_props_avg, surf_props, n_avg_timesteps)   surface_props.jl:202-222"
+avg_props!(avg::DeviceSurfProps, s::DeviceSurfProps, n_avg_timesteps::Integer) =
+    check(ccall((:mb_surf_avg, libmb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), avg.h, s.h, n_avg_timesteps))
+"reduce_surf_props!(surf_props_target, surf_props_chunks)   surface_props.jl:232-252; `across_ranks`: also over the NCCL communicator"
+function reduce_surf_props!(target::DeviceSurfProps, chunks::Vector{DeviceSurfProps}; across_ranks::Bool=false)
+    hs = Ptr{Cvoid}[c.h for c in chunks]
+    check(ccall((:mb_surf_reduce, libmb), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Int32, Int32), target.h, hs, length(hs), across_ranks))
+end
+function convect_surf_impl(rng::PhiloxRng, grid, boundaries, pv, pia, species, species_data, surf::DeviceSurfProps, Δt, compute_cell::Bool)
+    check(ccall((:mb_convect_particles_surf, libmb), Cint,
+                (Ptr{Cvoid}, Ptr{CGrid1D}, Ptr{CWalls1D}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cdouble, Ptr{Cvoid}, Cdouble, Int32, UInt32, UInt32),
+                pv.ctx.h, gridref(grid), Ref(boundaries isa CWalls1D ? boundaries : CWalls1D(boundaries)), pv.h, pia.h, species,
+                species_data[species].mass, surf.h, Δt, compute_cell, rng.timestep, rng.substream))
+    nothing
+end
+convect_particles!(rng::PhiloxRng, grid, boundaries, pv::DeviceParticleVector, pia, species::Integer, species_data, surf_props::DeviceSurfProps,
+                   Δt::Real) = convect_surf_impl(rng, grid, boundaries, pv, pia, species, species_data, surf_props, Δt, false)
+convect_particles_and_compute_cell!(rng::PhiloxRng, grid, boundaries, pv::DeviceParticleVector, pia, species::Integer, species_data,
+                                    surf_props::DeviceSurfProps, Δt::Real) =
+    convect_surf_impl(rng, grid, boundaries, pv, pia, species, species_data, surf_props, Δt, true)
 
 # ------------------------------------------------------------------------------------------------------ properties
 """

@@ -132,6 +132,14 @@ SIGNATURES = {
     "mb_comm_unique_id": (_int, [_vp]),
     "mb_comm_init": (_int, [_vp, _vp, _int, _int]),
     "mb_exchange_set_mode": (_int, [_vp, _i32]),
+    "mb_surf_create": (_int, [_vp, C.POINTER(_vp)]),
+    "mb_surf_destroy": (_int, [_vp]),
+    "mb_surf_clear": (_int, [_vp]),
+    "mb_surf_upload": (_int, [_vp, _vp]),
+    "mb_surf_download": (_int, [_vp, _vp]),
+    "mb_surf_avg": (_int, [_vp, _vp, _i64]),
+    "mb_surf_reduce": (_int, [_vp, _vp, _i32, _i32]),
+    "mb_convect_particles_surf": (_int, [_vp, C.POINTER(Grid1D), C.POINTER(Walls1D), _vp, _vp, _i64, _f64, _vp, _f64, _i32, _u32, _u32]),
     "mb_exchange_slab": (_int, [_vp, C.POINTER(Grid1D), _vp, _vp, _i64, _vp, _vp]),
     "mb_exchange_chunks": (_int, [_i32, _vp, _vp, _vp, _vp, _i64]),
 }
@@ -505,10 +513,53 @@ def fp_linear(rng, cd_fp, interaction, mass, pv, pia, cell, species, dt, V):
     _ck(lib().mb_fp_linear(pv.ctx.h, C.byref(interaction), mass, pv.h, pia.h, lo, hi, int(species), dt, V, rng.timestep, rng.substream))
 
 
+class SurfProps:
+    """SurfProps(pia, grid) (surface_props.jl:22-50) for the two walls of a 1-D grid and one species, device resident: rows = walls,
+    columns = np, flux_incident, flux_reflected, force[3], normal_pressure, shear_pressure[3], kinetic_energy_flux."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or default_context()
+        h = C.c_void_p()
+        _ck(lib().mb_surf_create(self.ctx.h, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().mb_surf_destroy(self.h)
+            self.h = None
+
+    def clear(self):
+        _ck(lib().mb_surf_clear(self.h))
+
+    def upload(self, rows):
+        _ck(lib().mb_surf_upload(self.h, _p(_f64arr(rows).reshape(2, 11))))
+
+    def download(self):
+        out = np.empty((2, 11))
+        _ck(lib().mb_surf_download(self.h, _p(out)))
+        return out
+
+
+def avg_surf_props(avg, surf, n_avg_timesteps):
+    """avg_props!(surf_props_avg, surf_props, n_avg_timesteps) (surface_props.jl:202-222)"""
+    _ck(lib().mb_surf_avg(avg.h, surf.h, int(n_avg_timesteps)))
+
+
+def reduce_surf_props(target, chunks, across_ranks=False):
+    """reduce_surf_props!(surf_props_target, surf_props_chunks) (surface_props.jl:232-252); across_ranks: also summed over the ranks of
+    the target context's communicator"""
+    hs = (C.c_void_p * max(len(chunks), 1))(*[c.h for c in chunks])
+    _ck(lib().mb_surf_reduce(target.h, hs, len(chunks), int(across_ranks)))
+
+
 def convect_particles(rng, grid, boundaries, pv, pia, species, mass, dt, surf_props=False, compute_cell=False):
     """convect_particles!(rng, grid, boundaries, particles, pia, species, species_data, [surf_props,] Δt) (convection_1D.jl:130,176);
     returns the 2x11 SurfProps rows (np, flux_incident, flux_reflected, force[3], normal_pressure, shear_pressure[3],
     kinetic_energy_flux) if surf_props."""
+    if isinstance(surf_props, SurfProps):  # device-resident SurfProps: no host synchronisation
+        _ck(lib().mb_convect_particles_surf(pv.ctx.h, grid.ref, boundaries.ref, pv.h, pia.h, int(species), float(mass), surf_props.h, dt,
+                                            int(compute_cell), rng.timestep, rng.substream))
+        return surf_props
     s = np.zeros((2, 11)) if surf_props else None
     _ck(lib().mb_convect_particles(pv.ctx.h, grid.ref, boundaries.ref, pv.h, pia.h, int(species), float(mass), _p(s), dt, int(compute_cell),
                                    rng.timestep, rng.substream))

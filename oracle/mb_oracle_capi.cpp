@@ -265,6 +265,22 @@ void mbo_compute_props_sorted(void** pvs, void* pia_, const double* masses, int6
     std::memcpy(np, pp.np.data(), N * 8); std::memcpy(n, pp.n.data(), N * 8); std::memcpy(T, pp.T.data(), N * 8);
     std::memcpy(v, pp.v.data(), 3 * N * 8);
 }
+// avg_props!(phys_props_avg, phys_props, n_avg_timesteps) physical_props.jl:281-299 on flat arrays (N = n_cells * n_species entries of
+// np, n, T; 3 N of v; n_species of lpa), in place on the avg arrays
+void mbo_avg_props(int64_t n_cells, int64_t n_species, double* a_lpa, double* a_np, double* a_n, double* a_v, double* a_T, const double* lpa,
+                   const double* np, const double* n, const double* v, const double* T, double n_avg_timesteps) {
+    PhysProps avg(n_cells, n_species, {}, false), pp(n_cells, n_species, {}, false);
+    const int64_t N = n_cells * n_species;
+    std::memcpy(avg.lpa.data(), a_lpa, n_species * 8); std::memcpy(pp.lpa.data(), lpa, n_species * 8);
+    std::memcpy(avg.np.data(), a_np, N * 8); std::memcpy(avg.n.data(), a_n, N * 8); std::memcpy(avg.T.data(), a_T, N * 8);
+    std::memcpy(avg.v.data(), a_v, 3 * N * 8);
+    std::memcpy(pp.np.data(), np, N * 8); std::memcpy(pp.n.data(), n, N * 8); std::memcpy(pp.T.data(), T, N * 8);
+    std::memcpy(pp.v.data(), v, 3 * N * 8);
+    avg_props(avg, pp, n_avg_timesteps);
+    std::memcpy(a_lpa, avg.lpa.data(), n_species * 8);
+    std::memcpy(a_np, avg.np.data(), N * 8); std::memcpy(a_n, avg.n.data(), N * 8); std::memcpy(a_T, avg.T.data(), N * 8);
+    std::memcpy(a_v, avg.v.data(), 3 * N * 8);
+}
 double mbo_compute_mixed_moment(void* pv, void* pia, int64_t cell, int64_t species, const int32_t* powers, double sum_scaler, double res_scaler) {
     const int p[3] = {powers[0], powers[1], powers[2]};
     return compute_mixed_moment(*(ParticleVector*)pv, *(ParticleIndexerArray*)pia, cell, species, p, sum_scaler, res_scaler);

@@ -107,6 +107,7 @@ def lib():
     sig("mbo_fp_linear", None, prs, vp, f64, vp, vp, i64, i64, i64, f64, f64)
     sig("mbo_compute_props", None, vp, vp, vp, i64, vp, f64, C.c_int, vp, vp, vp, vp, vp, vp)
     sig("mbo_compute_props_sorted", None, vp, vp, vp, i64, i64, C.c_int, f64, i64, vp, vp, vp, vp)
+    sig("mbo_avg_props", None, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f64)
     sig("mbo_compute_mixed_moment", f64, vp, vp, i64, i64, vp, f64, f64)
     sig("mbo_convect_particles", None, prs, f64, i64, vp, vp, vp, i64, vp, i64, vp, f64, C.c_int)
     sig("mbo_sample_equal_weight_grid", None, vp, f64, i64, vp, vp, i64, f64, f64, f64, f64, i64, i64)
@@ -422,6 +423,14 @@ def compute_props_sorted(pvs, pia, masses, cell_lo=1, cell_hi=None, grid=None, o
     lib().mbo_compute_props_sorted(_handles(pvs), pia.h, _p(masses), cell_lo, cell_hi, int(grid is not None), L, nx, _p(out.np), _p(out.n), _p(out.v),
                                    _p(out.T))
     return out
+
+
+def avg_props(avg, props, n_avg_timesteps):
+    """avg_props!(phys_props_avg, phys_props, n_avg_timesteps) (physical_props.jl:281-299), in place on ``avg`` (a Props)."""
+    ns, nc = props.np.shape
+    lib().mbo_avg_props(nc, ns, _p(avg.lpa), _p(avg.np), _p(avg.n), _p(avg.v), _p(avg.T), _p(props.lpa), _p(props.np), _p(props.n), _p(props.v),
+                        _p(props.T), float(n_avg_timesteps))
+    return avg
 
 
 def compute_mixed_moment(pv, pia, cell, species, powers, sum_scaler=1.0, res_scaler=1.0):

@@ -256,3 +256,80 @@ def test_octree_merging_buffer_sorting_reference_kat(mb, oracle, ctx):
         k = expect_after[0]
         assert tuple(ix[0, 0]) == (k, 1, k, k, 0, -1, 0) and tuple(ix[0, 1]) == (10, k + 1, k + 10, 10, 0, -1, 0) and ct[0] == 1 and nt[0] == k + 10
         assert_rows_close(pv.logical(1, k + 10), opv.logical(1, k + 10), 1e-13, "after merge + sort")
+
+
+# ------------------------------------------------------------------------------------------------------------ SurfProps / averaging
+def test_surf_props_device_handle_avg_and_reduce(mb, oracle, ctx):
+    """SurfProps kept on the device (surface_props.jl:22-252): convect_particles!(..., surf_props, dt) clears, accumulates and scales it
+    without a host round trip; avg_props!(surf_avg, surf, n) and reduce_surf_props!(target, chunks) run on the device too.  Against the
+    oracle's convect_particles! with SurfProps on the same Philox streams, step by step, and against the host-pointer variant."""
+    rng = np.random.default_rng(33)
+    n, nx, L, dt = 40000, 40, 4e-4, 2.59e-7
+    rows = maxwellian_rows(rng, n, L, w=1e10, vw=True)
+    opv, opia = oracle_state(oracle, rows, nx)
+    pv, pia = mirror_to_device(mb, ctx, opv, opia)
+    pv2, pia2 = mirror_to_device(mb, ctx, opv, opia)
+    g = mb.Grid1DUniform(L, nx)
+    walls, owalls = mb.MaxwellWalls1D(300.0, 450.0, -500.0, 500.0, 0.7, 1.0), (300.0, 450.0, -500.0, 500.0, 0.7, 1.0)
+    surf, avg = mb.SurfProps(ctx), mb.SurfProps(ctx)
+    n_avg = 3
+    avg_ref = np.zeros((2, 11))
+    for t in range(1, n_avg + 1):
+        l0 = ctx.kernel_launches
+        out = mb.convect_particles(mb.PhiloxRng(t, 1), g, walls, pv, pia, 1, AR, dt, surf_props=surf)
+        assert out is surf and ctx.kernel_launches - l0 >= 2  # convection + scaling kernels, nothing downloaded
+        mb.avg_surf_props(avg, surf, n_avg)
+        s_host = mb.convect_particles(mb.PhiloxRng(t, 1), g, walls, pv2, pia2, 1, AR, dt, surf_props=True)
+        so = oracle.convect_particles(oracle.Rng.philox(1234, t, 1), (L, nx), owalls, opv, opia, 1, [AR], dt, surf=True)
+        s = surf.download()
+        np.testing.assert_array_equal(s[:, 0], so[:, 0])  # np: exact counts
+        np.testing.assert_allclose(s, so, rtol=1e-10, atol=1e-10 * np.abs(so).max())
+        np.testing.assert_allclose(s, s_host, rtol=1e-12, atol=1e-12 * np.abs(so).max())  # same kernels, atomics in another order
+        avg_ref = avg_ref + so * (1.0 / n_avg)  # avg_props! surface_props.jl:202-222
+    np.testing.assert_allclose(avg.download(), avg_ref, rtol=1e-10, atol=1e-10 * np.abs(avg_ref).max())
+    assert avg_ref[0, 0] > 100 and avg_ref[1, 0] > 100
+    # reduce_surf_props! (surface_props.jl:232-252): the target is cleared, then the chunks are added in list order
+    a, b, target = mb.SurfProps(ctx), mb.SurfProps(ctx), mb.SurfProps(ctx)
+    ra, rb = rng.normal(size=(2, 11)), rng.normal(size=(2, 11))
+    a.upload(ra)
+    b.upload(rb)
+    target.upload(np.full((2, 11), 7.0))
+    mb.reduce_surf_props(target, [a, b, surf])
+    np.testing.assert_array_equal(target.download(), (ra + rb) + surf.download())
+    surf.clear()
+    assert not surf.download().any()
+    for o in (surf, avg, a, b, target, pv, pia, pv2, pia2):
+        o.close()
+
+
+def test_avg_props_parity(mb, oracle, ctx):
+    """avg_props!(phys_props_avg, phys_props, n_avg_timesteps) (physical_props.jl:281-299) on the device against the oracle's, over
+    several steps of changing cell properties: bit-identical accumulation (one multiply and one add per entry)."""
+    rng = np.random.default_rng(34)
+    n, n_cells, L = 30000, 25, 2.5
+    rows = maxwellian_rows(rng, n, L, vw=True)
+    opv, opia = oracle_state(oracle, rows, n_cells)
+    oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+    pv, pia = mirror_to_device(mb, ctx, opv, opia)
+    pp, pavg = mb.PhysProps(n_cells, 1, ctx=ctx), mb.PhysProps(n_cells, 1, ctx=ctx)
+    oavg = oracle.Props(n_cells, 1)
+    n_avg = 5
+    for t in range(n_avg):
+        cur = opv.logical(1, n)
+        cur[:, 1:4] *= 1.0 + 0.05 * t  # the properties change from step to step
+        opv.set_logical(1, cur)
+        pv.set_logical(1, cur)
+        mb.compute_props([pv], pia, [AR], pp)
+        mb.avg_props(pavg, pp, n_avg)
+        d = pp.download()
+        cur_props = oracle.Props(n_cells, 1)
+        cur_props.lpa[:] = d["lpa"]
+        cur_props.np[:], cur_props.n[:], cur_props.v[:], cur_props.T[:] = d["np"], d["n"], d["v"], d["T"]
+        oracle.avg_props(oavg, cur_props, n_avg)
+    a = pavg.download()
+    for k, ref in (("np", oavg.np), ("n", oavg.n), ("v", oavg.v), ("T", oavg.T), ("lpa", oavg.lpa)):
+        np.testing.assert_array_equal(a[k], ref)
+    o = oracle.compute_props([opv], opia, [AR])
+    np.testing.assert_allclose(d["T"], o.T, rtol=1e-12)
+    pv.close()
+    pia.close()
