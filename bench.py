@@ -413,7 +413,7 @@ def run_c4(env, args, steps, warmup, e2e_steps):
 
     rank, world = env.rank, env.world
     dx, ppc_s, thr, tgt = 1e-5, 500, 130, 100
-    nx_local = max(int(round(args.particles_per_gpu / 125.0)), 64)  # 1e6 cells / GPU -> ~1.1e8 live particles after the merge
+    nx_local = max(int(round(args.particles_per_gpu / 109.0)), 64)  # 1.15e6 cells / GPU -> 1.25e8 live particles after the merge (1e9 on 8 GPUs)
     nx_global = nx_local * world
     ctx = env.new_context(mb)
     mb.exchange_set_mode(ctx, 1)

@@ -137,7 +137,8 @@ int mb_check_pia(mb_pia* pia, int64_t species, int32_t* ok, int64_t* where);
  *      sort_particles!(gridsort, pv, pia, species)       grid_sorting.jl:128-182 (grid == NULL: pv.cell known)
  *      squashes first if the species is not contiguous (:69-71).  The GridSortInPlace scratch lives in the context. ---- */
 int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia, int64_t species);
-/* which algorithm the last mb_sort_particles used: 1 = band (nearly-sorted fast path), 2 = general */
+/* which algorithm the last mb_sort_particles used: 1 = band (nearly-sorted fast path, hybrid with extras), 2 = general,
+ * 3 = segments (grid == NULL and nobody changed cell: every cell's group 1 and group 2 are concatenated, no ranking) */
 int mb_sort_last_path(mb_ctx* ctx);
 /* band half-width w of the fast path: 0 disables it (general path only), else 1, 2, 4, 8 or 15; default 2.  Choose w of the order of
  * 3 sigma_v dt / dx: particles that move further than w cells in one step ("extras") are still sorted correctly by the band path

@@ -432,6 +432,8 @@ int mb_pia_create(mb_ctx* ctx, int64_t n_cells, int64_t n_species, mb_pia** out)
     p->n_species = n_species;
     MB_CUDA(cudaMalloc(&p->d_indexer, (size_t)n_cells * n_species * sizeof(Indexer)));
     MB_CUDA(cudaMalloc(&p->d_n_total, (size_t)n_species * 8));
+    MB_CUDA(cudaMalloc(&p->d_holes, (size_t)n_species * sizeof(int)));
+    MB_CUDA(cudaMemsetAsync(p->d_holes, 0, (size_t)n_species * sizeof(int), ctx->stream));
     MB_CUDA(cudaMemsetAsync(p->d_n_total, 0, (size_t)n_species * 8, ctx->stream));
     MB_CUDA(cudaHostAlloc(&p->h_n_total, (size_t)n_species * 8, cudaHostAllocDefault));
     for (int64_t s = 0; s < n_species; s++) p->h_n_total[s] = 0;
@@ -451,6 +453,7 @@ int mb_pia_destroy(mb_pia* p) {
     cudaStreamSynchronize(p->ctx->stream);
     cudaFree(p->d_indexer);
     cudaFree(p->d_n_total);
+    cudaFree(p->d_holes);
     cudaFreeHost(p->h_n_total);
     delete p;
     return MB_OK;
@@ -492,19 +495,19 @@ int mb_pia_download(mb_pia* p, int64_t* indexer, int64_t* n_total, uint8_t* cont
     p->h_valid = false;
     int r = pia_refresh_host(p);
     if (r) return r;
-    {   // resolve the exact contiguous flag after merges (merging_octree_N2.jl:806-808): device flag 4 + s
+    {   // resolve the exact contiguous flag after merges (merging_octree_N2.jl:806-808): the pia's device flag of the species
         bool any = false;
         for (int64_t s = 0; s < p->n_species; s++) any |= p->contig_pending[s] != 0;
         if (any) {
-            int f[16];
-            MB_CUDA(cudaMemcpyAsync(f, p->ctx->d_flags, sizeof f, cudaMemcpyDeviceToHost, p->ctx->stream));
+            std::vector<int> f((size_t)p->n_species);
+            MB_CUDA(cudaMemcpyAsync(f.data(), p->d_holes, (size_t)p->n_species * sizeof(int), cudaMemcpyDeviceToHost, p->ctx->stream));
             MB_CUDA(cudaStreamSynchronize(p->ctx->stream));
             for (int64_t s = 0; s < p->n_species; s++)
-                if (p->contig_pending[s]) {
-                    if (f[4 + s % 8] == 0) p->contiguous[s] = 1;  // every deletion fitted into group 2 of the last cell
+                if (p->contig_pending[s]) {  // only the species being resolved: the flags are per pia and per species
+                    if (f[s] == 0) p->contiguous[s] = 1;  // every deletion fitted into group 2 of the last cell
                     p->contig_pending[s] = 0;
+                    MB_CUDA(cudaMemsetAsync(p->d_holes + s, 0, sizeof(int), p->ctx->stream));
                 }
-            MB_CUDA(cudaMemsetAsync(p->ctx->d_flags + 4, 0, 8 * sizeof(int), p->ctx->stream));
         }
     }
     if (n_total)

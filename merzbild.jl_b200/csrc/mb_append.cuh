@@ -2,6 +2,7 @@
 // picked-particle loads, the group-2 append (particles.jl:426-433) into a per-cell window at the tail, and the packing
 // of the windows so that the final layout equals the reference's sequential appends at n_total + 1.
 #pragma once
+#include <cstdint>
 #include "mb_common.cuh"
 #include "mb_scan.cuh"
 #include "mb_segcopy.cuh"
@@ -20,8 +21,14 @@ __device__ __forceinline__ int64_t map_cont(const Indexer& q, int64_t i) {  // p
     return (i < q.n_group1 ? i + q.start1 : (i - q.n_group1) + q.start2) - 1;
 }
 // split: append (dw, v, x of the parent) as a new group-2 particle (collision_ntc.jl:238-267, particles.jl:426-433)
-__device__ __forceinline__ void append_split(const SoA& s, Indexer& q, int64_t winlo, int64_t parent, double dw, double vx, double vy, double vz) {
+// winhi (exclusive): end of the cell's window; a split that does not fit raises DEVERR_CAPACITY and is NOT performed (returns false)
+__device__ __forceinline__ bool append_split(const SoA& s, Indexer& q, int64_t winlo, int64_t parent, double dw, double vx, double vy, double vz,
+                                             int64_t winhi = INT64_MAX, int* flags = nullptr) {
     const int64_t pos = q.n_group2 > 0 ? q.end2 : winlo;  // 0-based position of the new particle (end2 is 1-based -> next slot)
+    if (pos >= winhi) {
+        if (flags) atomicOr(&flags[0], DEVERR_CAPACITY);
+        return false;
+    }
     if (q.n_group2 == 0) q.start2 = winlo + 1;
     q.n_group2 += 1;
     q.n_local += 1;
@@ -29,6 +36,7 @@ __device__ __forceinline__ void append_split(const SoA& s, Indexer& q, int64_t w
     s.a[F_W][pos] = dw;
     s.a[F_VX][pos] = vx; s.a[F_VY][pos] = vy; s.a[F_VZ][pos] = vz;
     s.a[F_X][pos] = s.a[F_X][parent]; s.a[F_Y][pos] = s.a[F_Y][parent]; s.a[F_Z][pos] = s.a[F_Z][parent];
+    return true;
 }
 
 // pack the per-cell windows to the left (cell order) so the layout equals the reference's sequential appends

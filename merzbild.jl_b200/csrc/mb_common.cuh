@@ -21,7 +21,7 @@ constexpr double EPS = 2.220446049250313e-16;     // Julia eps()
 constexpr int N_SM = 148;                         // B200
 
 // device-side error flag bits (ctx->d_flags[0])
-// other slots of ctx->d_flags: [2] the sort's general path must run, [3] extras of the last band sort, [4..11] per-species "a merge left holes",
+// other slots of ctx->d_flags: [2] the sort's general path must run, [3] extras of the last band sort, [4..11] unused,
 // [12..15] written by the fused convect + classify kernel (mb_sort.cu)
 enum { F_OUTSIDE = 12, F_CLS_BAD = 13, F_FAR = 14, F_CLS_REDO = 15 };
 enum : int { DEVERR_CAPACITY = 1, DEVERR_PRECONDITION = 2, DEVERR_BAND_OVERFLOW = 4, DEVERR_BAD_CELL = 8, DEVERR_OCTREE = 16 };
@@ -164,7 +164,8 @@ struct mb_pia {
     std::vector<uint8_t> contiguous;   // host-side flag per species (changes are statically known per operator)
     std::vector<uint8_t> sorted_layout; // host-side: group1 ranges tile 1..n_total in cell order and group2 is empty everywhere
     std::vector<int64_t> n_bound;      // host upper bound on n_total (for launch sizing only)
-    std::vector<uint8_t> contig_pending; // a merge ran: the exact contiguous flag is !d_flags[4 + species % 8] (resolved at download)
+    std::vector<uint8_t> contig_pending; // a merge ran: the exact contiguous flag is !d_holes[species] (resolved at download)
+    int* d_holes;            // [n_species] device flags "a merge left holes", owned by this pia (one per species)
 };
 
 struct mb_cf {

@@ -534,7 +534,7 @@ extern "C" int mb_merge_grid_based(mb_ctx* ctx, const mb_gridmerge_params* mg, m
     int64_t nCTA = nr < (int64_t)N_SM * 4 ? nr : (int64_t)N_SM * 4;
     a.outbuf = (double*)ctx_scratch(ctx, 9, (size_t)nCTA * 2 * NB * 7 * 8 + 256);
     if (!a.outbuf) return MB_ERR_CUDA;
-    a.noncontig = ctx->d_flags + 4 + s % 8;
+    a.noncontig = pia->d_holes + s;
     if (!pia->contig_pending[s]) MB_CUDA(cudaMemsetAsync(a.noncontig, 0, sizeof(int), st));
     // small cells: 128-thread CTAs, twice as many of them
     const int64_t avg = (pia->n_bound[s] > 0 ? pia->n_bound[s] : cap) / (nc > 0 ? nc : 1);

@@ -64,6 +64,22 @@ __global__ void __launch_bounds__(128) k_ntc_prepass(NtcArgs a) {
     }
 }
 
+// The windows are sized by the candidate counts -- an upper bound on the splits, far above the accepted ones when the weights are
+// widely spread (0-D variable-weight cases test thousands of candidates per cell and accept a few per cent).  If their sum does not
+// fit the free capacity they are shrunk proportionally instead of failing the call: what the call really needs is room for the
+// splits that happen, and a cell whose window overflows raises MB_ERR_CAPACITY on its own (append_split).
+template <bool TWO>
+static __global__ void k_ntc_fit_windows(NtcArgs a) {
+    const int64_t nr = a.cell_hi - a.cell_lo + 1;
+    const int64_t T = a.win[nr];
+    int64_t B = a.cap1 - *a.n_total1;
+    if (TWO) { const int64_t B2 = a.cap2 - *a.n_total2; B = B2 < B ? B2 : B; }
+    if (B < 0) B = 0;
+    if (T <= B) return;
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nr; r += (int64_t)gridDim.x * blockDim.x)
+        a.ncoll32[r] = (int32_t)((double)a.ncoll32[r] * ((double)B / (double)T));  // floor: the sum stays within B
+}
+
 // MINB: resident CTAs per SM the register allocation must allow.  Measured on the Couette bench (1.25e8 particles): 4 CTAs/SM
 // (118 registers) 1.04 ms, 6 CTAs (80 registers) 1.16 ms, 8 CTAs (64 registers, all cells resident in one wave) 1.21 ms -- the
 // kernel is bound by the DRAM random-access rate (one 64 B atom per picked field), not by latency, so more resident cells only
@@ -95,9 +111,12 @@ __global__ void __launch_bounds__(128, MINB) k_ntc(NtcArgs a) {
         Indexer q2 = TWO ? a.ix2[cell - 1] : q1;
         int64_t win1 = 0, win2 = 0;
         const int64_t g2_before1 = q1.n_group2, g2_before2 = q2.n_group2;
+        int64_t wend1 = 0, wend2 = 0;
         if (vw) {
             win1 = nt1 + a.win[r];
             win2 = nt2 + a.win[r];
+            wend1 = nt1 + a.win[r + 1];
+            wend2 = nt2 + a.win[r + 1];
             // precondition of the reference (new particles go to n_total + 1): an existing group 2 must end at n_total
             bool ok1 = q1.n_group2 == 0 || (a.single_cell_tail && q1.end2 == nt1);
             bool ok2 = !TWO || q2.n_group2 == 0 || (a.single_cell_tail && q2.end2 == nt2);
@@ -130,16 +149,13 @@ __global__ void __launch_bounds__(128, MINB) k_ntc(NtcArgs a) {
                 } else if (fabs(pi.w - pk.w) < a.dw_tol) {
                     n_eqw += 1;
                 } else if (pi.w > pk.w) {
-                    append_split(a.p1, q1, win1, pi.pos, pi.w - pk.w, pi.vx, pi.vy, pi.vz);
-                    a.p1.a[F_W][pi.pos] = pk.w;
+                    if (append_split(a.p1, q1, win1, pi.pos, pi.w - pk.w, pi.vx, pi.vy, pi.vz, wend1, a.flags)) a.p1.a[F_W][pi.pos] = pk.w;
                     if (!TWO) q2 = q1;
                 } else {
                     if (TWO) {
-                        append_split(a.p2, q2, win2, pk.pos, pk.w - pi.w, pk.vx, pk.vy, pk.vz);
-                        a.p2.a[F_W][pk.pos] = pi.w;
+                        if (append_split(a.p2, q2, win2, pk.pos, pk.w - pi.w, pk.vx, pk.vy, pk.vz, wend2, a.flags)) a.p2.a[F_W][pk.pos] = pi.w;
                     } else {
-                        append_split(a.p1, q1, win1, pk.pos, pk.w - pi.w, pk.vx, pk.vy, pk.vz);
-                        a.p1.a[F_W][pk.pos] = pi.w;
+                        if (append_split(a.p1, q1, win1, pk.pos, pk.w - pi.w, pk.vx, pk.vy, pk.vz, wend1, a.flags)) a.p1.a[F_W][pk.pos] = pi.w;
                         q2 = q1;
                     }
                 }
@@ -212,9 +228,10 @@ __global__ void __launch_bounds__(128) k_ntc_warp(NtcArgs a, int ch) {
         const int64_t cell = a.cell_lo + r;
         Indexer q = a.ix1[cell - 1];
         const int64_t g2_before = q.n_group2;
-        int64_t win1 = 0;
+        int64_t win1 = 0, wend1 = 0;
         if (vw) {
             win1 = nt1 + a.win[r];
+            wend1 = nt1 + a.win[r + 1];
             if (!(q.n_group2 == 0 || (a.single_cell_tail && q.end2 == nt1))) {  // same precondition as k_ntc
                 if (lane == 0) { atomicOr(&a.flags[0], DEVERR_PRECONDITION); a.nsplit1[r] = 0; }
                 continue;
@@ -282,11 +299,9 @@ __global__ void __launch_bounds__(128) k_ntc_warp(NtcArgs a, int ch) {
                         } else if (fabs(pi.w - pk.w) < a.dw_tol) {
                             n_eqw += 1;
                         } else if (pi.w > pk.w) {
-                            append_split(a.p1, q, win1, pi.pos, pi.w - pk.w, pi.vx, pi.vy, pi.vz);
-                            a.p1.a[F_W][pi.pos] = pk.w;
+                            if (append_split(a.p1, q, win1, pi.pos, pi.w - pk.w, pi.vx, pi.vy, pi.vz, wend1, a.flags)) a.p1.a[F_W][pi.pos] = pk.w;
                         } else {
-                            append_split(a.p1, q, win1, pk.pos, pk.w - pi.w, pk.vx, pk.vy, pk.vz);
-                            a.p1.a[F_W][pk.pos] = pi.w;
+                            if (append_split(a.p1, q, win1, pk.pos, pk.w - pi.w, pk.vx, pk.vy, pk.vz, wend1, a.flags)) a.p1.a[F_W][pk.pos] = pi.w;
                         }
                         const double phi = twopi * rng.rand();
                         double sphi, cphi;
@@ -403,6 +418,11 @@ static int ntc_impl(mb_ctx* ctx, mb_cf* cf, const mb_interaction* it, mb_pv* pv1
     else k_ntc_prepass<false><<<g, 128, 0, st>>>(a);
     MB_LAUNCH_CHECK(ctx);
     r = device_exclusive_scan(ctx, a.ncoll32, nr, a.win, partial);
+    if (r) return r;
+    if (two) k_ntc_fit_windows<true><<<g, 128, 0, st>>>(a);
+    else k_ntc_fit_windows<false><<<g, 128, 0, st>>>(a);
+    MB_LAUNCH_CHECK(ctx);
+    r = device_exclusive_scan(ctx, a.ncoll32, nr, a.win, partial);  // unchanged unless the windows were shrunk
     if (r) return r;
     MB_CUDA(cudaMemsetAsync(a.nsplit1, 0, (size_t)(2 * nr) * 4, st));
     if (two) k_ntc<true, 4><<<g, 128, 0, st>>>(a);

@@ -15,6 +15,8 @@
 // the range (so the total is <= n_total <= capacity); bins live in a per-CTA global workspace of
 // min(max_Nbins, target_np) + 8 entries (a split is only made while total_post_merge_np + 14 <= target_np, and every bin
 // holds at least one post-merge particle).
+#include <cstdlib>
+
 #include "mb_common.cuh"
 #include "mb_scan.cuh"
 
@@ -1092,8 +1094,11 @@ extern "C" int mb_merge_octree_N2(mb_ctx* ctx, const mb_octree_params* oc, mb_pv
     const int64_t avg = (pia->n_bound[s] > 0 ? pia->n_bound[s] : cap) / nc;
     // the refinement loop is run by warp 0 of each CTA, so many small CTAs (= concurrent cells) beat few large ones
     (void)avg;
-    const int threads = 128;
-    int64_t nCTA = nr < (int64_t)N_SM * 4 ? nr : (int64_t)N_SM * 4;
+    static const int env_threads = getenv("MB_MERGE_THREADS") ? atoi(getenv("MB_MERGE_THREADS")) : 0;   // experiment knobs
+    static const int env_per_sm = getenv("MB_MERGE_PER_SM") ? atoi(getenv("MB_MERGE_PER_SM")) : 0;
+    const int threads = env_threads > 0 ? env_threads : 128;
+    const int per_sm_m = env_per_sm > 0 ? env_per_sm : 4;
+    int64_t nCTA = nr < (int64_t)N_SM * per_sm_m ? nr : (int64_t)N_SM * per_sm_m;
     const size_t per = (size_t)bcap * (5 * 4 + 8 + 24 + 24 + 2 * 7 * 8) + 64;
     char* ws = (char*)ctx_scratch(ctx, 9, per * (size_t)nCTA + 4096);
     if (!ws) return MB_ERR_CUDA;
@@ -1114,7 +1119,7 @@ extern "C" int mb_merge_octree_N2(mb_ctx* ctx, const mb_octree_params* oc, mb_pv
         set_error("internal: merge workspace sizing");
         return MB_ERR_UNSUPPORTED;
     }
-    a.noncontig = ctx->d_flags + 4 + s % 8;
+    a.noncontig = pia->d_holes + s;
     if (!pia->contig_pending[s]) MB_CUDA(cudaMemsetAsync(a.noncontig, 0, sizeof(int), st));
     // small cells: one warp per cell in shared memory; the CTA kernel takes the rest.  The staging area is sized for 160 particles
     // when the threshold says that cells are merged long before they reach that size (a cell is merged as soon as it exceeds the

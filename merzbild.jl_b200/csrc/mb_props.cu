@@ -89,7 +89,46 @@ __global__ void __launch_bounds__(256) k_props(PropsArgs a) {
             E *= 0.5 * a.mass / (n * k_B);
             T = (2.0 / 3.0) * E;
         }
-        if (a.with_moments) {
+        if (a.with_moments && a.n_moments <= 8) {
+            // all moments in ONE more pass over the cell; even powers (the total moments M4, M6, ... of the BKW tests,
+            // physical_props.jl:205-207) are products of |c|^2 instead of pow()
+            double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            int pwr[8];
+#pragma unroll
+            for (int m = 0; m < 8; m++) pwr[m] = m < a.n_moments ? a.powers[m] : 0;
+            if (n > 0.0) {
+                for (int64_t j = tid; j < nn; j += G) {
+                    const int64_t i = j < n1 ? lo1 + j : lo2 + (j - n1);
+                    const double cx = VX[i] - vx, cy = VY[i] - vy, cz = VZ[i] - vz;
+                    const double c2 = cx * cx + cy * cy + cz * cz, w = W[i];
+                    const double nv = sqrt(c2);
+#pragma unroll
+                    for (int m = 0; m < 8; m++) {
+                        if (m >= a.n_moments) break;
+                        const int pw = pwr[m];
+                        double val;
+                        if (pw >= 0 && pw <= 32 && (pw & 1) == 0) {
+                            val = 1.0;
+                            double b = c2;
+                            for (int e = pw >> 1; e > 0; e >>= 1) { if (e & 1) val *= b; b *= b; }
+                        } else {
+                            val = pow(nv, (double)pw);
+                        }
+                        s[m] += w * val;
+                    }
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                if (m >= a.n_moments) break;
+                const double sm = group_sum<G>(s[m], sh);
+                if (tid == 0) {
+                    const int pw = pwr[m];
+                    const double scaling = a.moment_factor * pow(a.moment_vref, -(double)(3 + pw)) * tgamma((3 + pw) / 2.0);
+                    a.moments[(int64_t)c * a.n_moments + m] = sm / (scaling * n);
+                }
+            }
+        } else if (a.with_moments) {
             for (int m = 0; m < a.n_moments; m++) {
                 const int pw = a.powers[m];
                 double s = 0;

@@ -1088,6 +1088,77 @@ __global__ void __launch_bounds__(256) k_gen_gather_cells(SoA in, SoA out, const
     }
 }
 
+// When nothing is left of the previous order (band path switched off: a particle crosses hundreds of cells per step, the reference's
+// "same L, finer cells" scaling) the gather above reads seven scattered 8-byte values per particle, and every one of them costs a DRAM
+// access of its own (measured: 13.6 ms of an 18.7 ms sort at 1.25e8 particles).  Two coalescing-friendly passes instead: the records
+// are first packed into 64-byte array-of-structs entries (one aligned DRAM access each), then gathered by destination cell.
+struct __align__(16) Rec64 { double2 a, b, c, d; };  // w vx | vy vz | x y | z -
+__global__ void __launch_bounds__(256) k_gen_pack_aos(SoA in, const int64_t* n_total_p, const int32_t* __restrict__ src, Rec64* __restrict__ rec,
+                                                      const int* flags) {
+    if (flags[2] == 0) return;
+    const int64_t n_total = *n_total_p;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t ph = src ? (int64_t)src[i] : i;
+        Rec64 r;
+        r.a = make_double2(in.a[0][ph], in.a[1][ph]);
+        r.b = make_double2(in.a[2][ph], in.a[3][ph]);
+        r.c = make_double2(in.a[4][ph], in.a[5][ph]);
+        r.d = make_double2(in.a[6][ph], 0.0);
+        rec[i] = r;
+    }
+}
+__global__ void __launch_bounds__(256) k_gen_gather_cells_aos(const Rec64* __restrict__ rec, SoA out, const int32_t* __restrict__ perm,
+                                                              const int64_t* __restrict__ start, int64_t n_cells, const int* flags,
+                                                              const int32_t* __restrict__ key, int32_t* __restrict__ cell_out,
+                                                              double* __restrict__ pcache) {
+    if (flags[2] == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t c = warp0; c < n_cells; c += nwarps) {
+        const int64_t lo = start[c];
+        const int n = (int)(start[c + 1] - lo);
+        double K1 = 0, K2 = 0, K3 = 0;
+        double an = 0, ax = 0, ay = 0, az = 0, aq = 0;
+        for (int j0 = 0; j0 < n; j0 += 32) {
+            const int j = j0 + lane;
+            double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+            if (j < n) {
+                const int64_t i = perm[lo + j];
+                const Rec64 r = rec[i];
+                a0 = r.a.x; a1 = r.a.y; a2 = r.b.x; a3 = r.b.y;
+                out.a[0][lo + j] = a0; out.a[1][lo + j] = a1; out.a[2][lo + j] = a2; out.a[3][lo + j] = a3;
+                out.a[4][lo + j] = r.c.x; out.a[5][lo + j] = r.c.y; out.a[6][lo + j] = r.d.x;
+                if (cell_out) cell_out[lo + j] = key[i] + 1;
+            }
+            if (j0 == 0) {  // shift = velocity of the cell's first particle
+                K1 = __shfl_sync(0xffffffffu, a1, 0); K2 = __shfl_sync(0xffffffffu, a2, 0); K3 = __shfl_sync(0xffffffffu, a3, 0);
+            }
+            if (j < n) {
+                const double cx = a1 - K1, cy = a2 - K2, cz = a3 - K3;
+                an += a0; ax += a0 * cx; ay += a0 * cy; az += a0 * cz;
+                aq += a0 * (cx * cx + cy * cy + cz * cz);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            an += __shfl_xor_sync(0xffffffffu, an, o); ax += __shfl_xor_sync(0xffffffffu, ax, o);
+            ay += __shfl_xor_sync(0xffffffffu, ay, o); az += __shfl_xor_sync(0xffffffffu, az, o);
+            aq += __shfl_xor_sync(0xffffffffu, aq, o);
+        }
+        if (lane == 0) {
+            double* pc = pcache + 6 * c;
+            pc[0] = (double)n;
+            if (an > 0.0) {
+                const double mx = ax / an, my = ay / an, mz = az / an;  // mean of (v - K)
+                pc[1] = an; pc[2] = K1 + mx; pc[3] = K2 + my; pc[4] = K3 + mz;
+                pc[5] = aq - an * (mx * mx + my * my + mz * mz);        // sum w |v - vbar|^2
+            } else {
+                pc[1] = 0; pc[2] = 0; pc[3] = 0; pc[4] = 0; pc[5] = 0;
+            }
+        }
+    }
+}
+
 // squash_pia! folded into the sort (grid_sorting.jl:69-71 squashes first): instead of moving the payload to close the holes and then
 // moving it again in the sort, only the map logical (squashed) position -> physical position is built (4 B per particle).  The
 // squashed order walks group 1 of all cells, then group 2 of all cells (particles.jl:622-682); newlo = exclusive scan of the segment
@@ -1106,6 +1177,68 @@ struct SrcMapAct {
 };
 
 __global__ void k_set_flag(int* flags, int idx, int v) { flags[idx] = v; }
+
+// ------------------------------------------------------------------------------------------------ segment path
+// sort_particles!(gridsort, pv, pia, species) by stored cell ids (grid_sorting.jl:128-182) when NO particle changed its cell -- the
+// re-sort of an ensemble of 0-D cells after variable-weight collisions and merging: the split particles sit in group-2 ranges at the
+// tail, merges left holes.  The stable counting sort of the squashed order (group 1 of all cells, then group 2 of all cells) then
+// is, for every cell, group 1 followed by group 2: a concatenation of the pia's segments, no keys, no ranking.  One pass checks
+// the precondition (4 B per particle), one moves the payload (112 B); a mismatch hands over to the general path.
+static __global__ void k_segpath_counts(const Indexer* __restrict__ ix, int64_t nc, int32_t* __restrict__ cnt) {
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
+        const Indexer q = ix[c];
+        cnt[2 * c] = (int32_t)q.n_group1;
+        cnt[2 * c + 1] = (int32_t)q.n_group2;
+    }
+}
+struct CellMajorDesc {  // segment 2 c + g = group g + 1 of cell c
+    const Indexer* ix;
+    const int64_t* newlo;
+    const int* only_if_zero;  // nullable: no segments if *only_if_zero != 0
+    __device__ __forceinline__ void get(int64_t seg, int64_t& n, int64_t& src, int64_t& dst) const {
+        const Indexer q = ix[seg >> 1];
+        const bool g2 = seg & 1;
+        n = g2 ? q.n_group2 : q.n_group1;
+        src = (g2 ? q.start2 : q.start1) - 1;
+        dst = newlo[seg];
+        if (only_if_zero != nullptr && *only_if_zero != 0) n = 0;
+    }
+};
+struct KeyCheckAct {  // the stored cell id of every particle of a segment must be the segment's cell
+    const int32_t* cell;
+    int* flag;
+    __device__ __forceinline__ void seg(int64_t, int64_t, int64_t, int64_t) const {}
+    __device__ __forceinline__ void elem(int64_t seg, int64_t src, int64_t) const {
+        if (cell[src] - 1 != (int32_t)(seg >> 1)) *flag = 1;
+    }
+};
+struct PayloadMoveAct {
+    SoA cur, alt;
+    __device__ __forceinline__ void seg(int64_t, int64_t, int64_t, int64_t) const {}
+    __device__ __forceinline__ void elem(int64_t, int64_t src, int64_t dst) const {
+#pragma unroll
+        for (int f = 0; f < 7; f++) alt.a[f][dst] = cur.a[f][src];
+    }
+};
+// after the move: the new indexers (group 1 = the whole cell, grid_sorting.jl:156-166) and the cell ids of the new layout
+static __global__ void __launch_bounds__(256) k_segpath_commit(Indexer* __restrict__ ix, int64_t nc, const int64_t* __restrict__ newlo,
+                                                              int32_t* __restrict__ cell, const int* flags) {
+    if (flags[2] != 0) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t c = warp0; c < nc; c += nwarps) {
+        const int64_t lo = newlo[2 * c], n = newlo[2 * c + 2] - lo;
+        for (int64_t j = lane; j < n; j += 32) cell[lo + j] = (int32_t)c + 1;
+        if (lane == 0) {
+            Indexer q;
+            q.n_local = n; q.n_group1 = n;
+            q.start1 = n > 0 ? lo + 1 : 0;
+            q.end1 = n > 0 ? lo + n : -1;
+            q.start2 = 0; q.end2 = -1; q.n_group2 = 0;
+            ix[c] = q;
+        }
+    }
+}
 
 struct BandBufs {
     int64_t* seg_lo;
@@ -1308,7 +1441,7 @@ int mb_sort_set_band_halfwidth(mb_ctx* ctx, int32_t w) {
 int mb_sort_last_path(mb_ctx* ctx) {
     if (!ctx) return -1;
     if (mb_sync(ctx)) return -1;
-    return ctx->sort_last_path == 1 && ctx->h_flags[2] == 0 ? 1 : 2;
+    return ctx->sort_last_path != 2 && ctx->h_flags[2] == 0 ? ctx->sort_last_path : 2;
 }
 int64_t mb_sort_last_extras(mb_ctx* ctx) {
     if (!ctx) return -1;
@@ -1366,13 +1499,36 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
     if (!S.perm) return MB_ERR_CUDA;
 
     MB_CUDA(cudaMemcpyAsync(B.n_old, d_nt, 8, cudaMemcpyDeviceToDevice, st));  // n_total before the sort (the scan may rewrite it)
+    // segment path: sorting by stored cell ids a layout in which (presumably) nobody changed cell
+    const bool try_seg = !try_band && !use_x && n_arr == 0 && !drop;
+    if (try_seg) {
+        ProfScope ps(ctx, PROF_SORT_SCATTER);
+        int32_t* cnt = (int32_t*)ctx_scratch(ctx, 4, (size_t)(2 * nc) * 4);
+        int64_t* p64 = (int64_t*)ctx_scratch(ctx, 13, ((size_t)(2 * nc + 1) + gs_partial_count(2 * nc)) * 8);
+        if (!cnt || !p64) return MB_ERR_CUDA;
+        k_set_flag<<<1, 1, 0, st>>>(ctx->d_flags, 2, 0);
+        MB_LAUNCH_CHECK(ctx);
+        k_segpath_counts<<<grid_for(nc, 256), 256, 0, st>>>(ix, nc, cnt);
+        MB_LAUNCH_CHECK(ctx);
+        r = device_exclusive_scan(ctx, cnt, 2 * nc, p64, p64 + (2 * nc + 1));
+        if (r) return r;
+        CellMajorDesc Dc{ix, p64, nullptr};
+        KeyCheckAct Ac{pv->cell, ctx->d_flags + 2};
+        r = seg_copy(ctx, 7, cap, 2 * nc, Dc, Ac);
+        if (r) return r;
+        CellMajorDesc Dm{ix, p64, ctx->d_flags + 2};
+        PayloadMoveAct Am{pv->cur, pv->alt};
+        r = seg_copy(ctx, 14, cap, 2 * nc, Dm, Am);
+        if (r) return r;
+        // (the indexers are rewritten after the general path had its chance to read them: k_segpath_commit below)
+    }
     // classification cached by the fused convect kernel?  (same particles, same grid, nothing but a slab exchange in between)
     const bool cls_cached = try_band && use_x && ctx->cls_gen == ctx->state_gen && ctx->cls_pv == (void*)pv && ctx->cls_pia == (void*)pia &&
                             ctx->cls_species == (int)species && ctx->cls_w == w && ctx->cls_inv_dx == grid->inv_dx &&
                             ctx->cls_cell_offset == grid->cell_offset && ctx->cls_cap == cap;
     if (cls_cached) k_flag_from_cls<<<1, 1, 0, st>>>(ctx->d_flags, drop ? 1 : 0);
-    else k_set_flag<<<1, 1, 0, st>>>(ctx->d_flags, 2, try_band ? 0 : 1);
-    MB_LAUNCH_CHECK(ctx);
+    else if (!try_seg) k_set_flag<<<1, 1, 0, st>>>(ctx->d_flags, 2, try_band ? 0 : 1);
+    if (!try_seg) MB_LAUNCH_CHECK(ctx);
     if (try_band) {
         if (w == 1) r = launch_band<3>(ctx, grid, pv, pia, species, S, B, cls_cached);
         else if (w == 2) r = launch_band<5>(ctx, grid, pv, pia, species, S, B, cls_cached);
@@ -1425,11 +1581,23 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
         }
         MB_LAUNCH_CHECK(ctx);
         gather_cells = nb / (nc > 0 ? nc : 1) <= 2048;  // small cells: gather by cell and cache the cell moments
-        if (gather_cells)
+        // band path switched off by the caller = displacements of many cells: the gather would be fully scattered; go through 64-byte records
+        const bool aos = gather_cells && w == 0 && use_x;
+        if (aos) {
+            Rec64* rec = (Rec64*)ctx_scratch(ctx, 15, (size_t)cap * sizeof(Rec64));
+            if (!rec) return MB_ERR_CUDA;
+            k_gen_pack_aos<<<pgrid, 256, 0, st>>>(pv->cur, B.n_old, src, rec, S.flags);
+            MB_LAUNCH_CHECK(ctx);
+            k_gen_gather_cells_aos<<<grid_for(nc * 32, 256, 8), 256, 0, st>>>(rec, pv->alt, S.perm, S.start, nc, S.flags, S.key, nullptr, B.pcache);
+        } else if (gather_cells)
             k_gen_gather_cells<<<grid_for(nc * 32, 256, 8), 256, 0, st>>>(pv->cur, pv->alt, S.perm, S.start, nc, S.flags, src, S.key,
                                                                         use_x ? nullptr : pv->cell, B.pcache);
         else
             k_gen_gather<<<pgrid, 256, 0, st>>>(pv->cur, pv->alt, S.perm, S.start + nc, S.flags, src, S.key, use_x ? nullptr : pv->cell);
+        MB_LAUNCH_CHECK(ctx);
+    }
+    if (try_seg) {
+        k_segpath_commit<<<grid_for(nc * 32, 256, 8), 256, 0, st>>>(ix, nc, (const int64_t*)ctx->scratch[13], pv->cell, S.flags);
         MB_LAUNCH_CHECK(ctx);
     }
     // ping-pong
@@ -1447,12 +1615,13 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
     ctx->cls_gen = 0;
     ctx->pc_gen = (band_moments || gather_cells) ? ctx->state_gen : 0;
     ctx->pc_general = gather_cells ? 1 : 0;
-    ctx->pc_band = (band_moments || !try_band) ? 1 : 0;  // no band attempt: the general path runs unconditionally, its cache is valid as is
+    // neither fast path attempted: the general path runs unconditionally, its cache is valid as is
+    ctx->pc_band = (band_moments || (!try_band && !try_seg)) ? 1 : 0;
     ctx->pc_pv = pv; ctx->pc_pia = pia; ctx->pc_species = (int)species;
     pia->contiguous[s] = 1;      // grid_sorting.jl:112
     pia->contig_pending[s] = 0;
     pia->sorted_layout[s] = 1;
-    ctx->sort_last_path = try_band ? 1 : 2;
+    ctx->sort_last_path = try_band ? 1 : (try_seg ? 3 : 2);
     return MB_OK;
 }
 

@@ -544,20 +544,57 @@ def test_ntc_large_cells_parity(mb, oracle, ctx, vw, sizes):
 
 
 def test_ntc_capacity_error(mb, oracle, ctx):
-    """the reference would resize!; the device reports MB_ERR_CAPACITY and leaves the state untouched."""
+    """the reference would resize! (collision_ntc.jl:241-243); the device never grows implicitly: a split that finds no room raises
+    MB_ERR_CAPACITY (the step's particle state is then invalid: restore it, resize, repeat)."""
     n_cells, ppc, dt = 4, 300, 2.59e-9 * 60
     L, n, Fnum, opv, opia, pv, pia = _couette_like(oracle, mb, ctx, n_cells, ppc, 203, vw=True, capacity_mult=1.0)
     it = mb.make_interaction(AR, AR, 4.11e-10, 0.81, 273.0)
     cf = mb.CollisionFactors(n_cells, mb.estimate_sigma_g_w_max(it, AR, AR, 300.0, 300.0, 2 * Fnum), ctx)
     before = pv.logical(1, n)
+    ix0, nt0, ct0 = pia.download()
     mb.ntc(mb.PhiloxRng(1), cf, None, it, pv, pia, (1, n_cells), 1, dt, L / n_cells)
     with pytest.raises(mb.CapacityError):
         ctx.sync()
-    np.testing.assert_array_equal(pv.logical(1, n), before)
     pv.resize(int(4 * n))
+    pv.set_logical(1, before)
+    pia.upload(ix0, nt0, ct0)
+    cf.fill(mb.estimate_sigma_g_w_max(it, AR, AR, 300.0, 300.0, 2 * Fnum))
     mb.ntc(mb.PhiloxRng(1), cf, None, it, pv, pia, (1, n_cells), 1, dt, L / n_cells)
     ctx.sync()
     assert int(pia.n_total[0]) > n
+
+
+def test_ntc_capacity_is_the_splits_not_the_candidates(mb, oracle, ctx):
+    """Variable-weight ntc! needs room for the splits that HAPPEN.  With widely spread weights sigma_g_w_max follows the heaviest
+    particle, a cell tests far more candidate pairs than it holds particles and accepts a few per cent of them: the per-cell windows
+    (sized by the candidates) are shrunk to the free capacity, and the call succeeds and matches the oracle -- pia and particles --
+    although n_total + candidates exceeds the capacity several times."""
+    n_cells, ppc, dt = 6, 400, 2.59e-9 * 40
+    L = n_cells * 1e-5
+    rng = np.random.default_rng(77)
+    n = n_cells * ppc
+    Fnum = 1e-5 * 5e22 / ppc
+    rows = maxwellian_rows(rng, n, L, w=Fnum)
+    rows[:, 0] = Fnum * 10.0 ** rng.uniform(-3.0, 0.0, n)  # three decades of weights
+    rows[:, 4] = (np.repeat(np.arange(n_cells), ppc) + rng.uniform(0.01, 0.99, n)) * 1e-5
+    cap = int(1.6 * n)
+    opv, opia = oracle_state(oracle, rows, n_cells, capacity=4 * n)
+    oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+    pv, pia = mirror_to_device(mb, ctx, opv, opia, capacity=cap)
+    it, oit = mb.make_interaction(AR, AR, 4.11e-10, 0.81, 273.0), oracle.interaction("Ar", "Ar")
+    s0 = mb.estimate_sigma_g_w_max(it, AR, AR, 300.0, 300.0, Fnum)
+    cf, ocf = mb.CollisionFactors(n_cells, s0, ctx), oracle.CF(n_cells, s0)
+    mb.ntc(mb.PhiloxRng(1), cf, None, it, pv, pia, (1, n_cells), 1, dt, L / n_cells)
+    ctx.sync()
+    oracle.ntc(oracle.Rng.philox(1234, 1), ocf, oit, opv, opia, 1, n_cells, 1, dt, L / n_cells)
+    ncoll = cf.download()["n_coll"]
+    nt = int(pia.n_total[0])
+    assert n + int(ncoll.sum()) > 2 * cap, (n, int(ncoll.sum()), cap)  # the old requirement was far out of reach ...
+    assert n < nt <= cap                                                   # ... the splits fit
+    assert_same_pia(opia, pia)
+    assert_rows_close(pv.logical(1, nt), opv.logical(1, nt), 1e-12, "vw ntc with shrunk windows")
+    pv.close()
+    pia.close()
 
 
 def test_ntc_two_species_parity(mb, oracle, ctx):
