@@ -580,9 +580,12 @@ def test_ntc_capacity_is_the_splits_not_the_candidates(mb, oracle, ctx):
     cap = int(1.6 * n)
     opv, opia = oracle_state(oracle, rows, n_cells, capacity=4 * n)
     oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
-    pv, pia = mirror_to_device(mb, ctx, opv, opia, capacity=cap)
+    pv, pia = mb.ParticleVector(cap, ctx), mb.ParticleIndexerArray(n_cells, 1, ctx)
+    pv.set_logical(1, opv.logical(1, n))
+    pia.upload(opia.indexer.copy(), opia.n_total.copy(), opia.contiguous.copy())
     it, oit = mb.make_interaction(AR, AR, 4.11e-10, 0.81, 273.0), oracle.interaction("Ar", "Ar")
-    s0 = mb.estimate_sigma_g_w_max(it, AR, AR, 300.0, 300.0, Fnum)
+    # sigma_g_w_max as a rare heavy, fast pair leaves it: 20 x the estimate -> 20 x the candidates, 1 / 20 of the acceptance probability
+    s0 = 20.0 * mb.estimate_sigma_g_w_max(it, AR, AR, 300.0, 300.0, Fnum)
     cf, ocf = mb.CollisionFactors(n_cells, s0, ctx), oracle.CF(n_cells, s0)
     mb.ntc(mb.PhiloxRng(1), cf, None, it, pv, pia, (1, n_cells), 1, dt, L / n_cells)
     ctx.sync()
