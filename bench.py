@@ -405,8 +405,8 @@ def run_c3(env, args, scaling, steps, warmup, e2e_steps, band=None):
 def run_c4(env, args, steps, warmup, e2e_steps):
     """BASELINE.json configs[3]: 1-D Couette, variable weight, octree merging (couette_multithreaded_varweight_octree.jl:205-206,
     couette_varweight_octree.jl:86-135): 500 particles sampled per cell, merged to 100 at t = 0; per step ntc! (splits) ->
-    merge_octree_N2_based! where n_local > 130 -> [squash_pia!, N > 1: the exchange needs a contiguous layout] -> convect_particles! ->
-    [slab exchange] -> sort_particles! (squashes first) -> compute_props_sorted!.  Slab-partitioned like C3; ~1.1e8 live particles/GPU."""
+    merge_octree_N2_based! where n_local > 130 -> convect_particles! -> [slab exchange: reads the non-contiguous layout through the
+    squash map] -> sort_particles! (squashes first) -> compute_props_sorted!.  Slab-partitioned like C3; ~1.1e8 live particles/GPU."""
     import numpy as np
 
     import merzbild_b200 as mb
@@ -416,7 +416,7 @@ def run_c4(env, args, steps, warmup, e2e_steps):
     nx_local = max(int(round(args.particles_per_gpu / 109.0)), 64)  # 1.15e6 cells / GPU -> 1.25e8 live particles after the merge (1e9 on 8 GPUs)
     nx_global = nx_local * world
     ctx = env.new_context(mb)
-    mb.exchange_set_mode(ctx, 1)
+    mb.exchange_set_mode(ctx, 0)  # edge exchange: sigma_v dt = 0.065 cells, the leavers sit in the w = 2 cells next to a slab face
     G = mb.Grid1DUniform(nx_global * dx, nx_global, wall_offset=1e-6)  # L ~ 10 m: the default offset dx * 1e-12 is below ulp(L)
     slab = G.slab(rank, world)
     nx = slab.n_cells
@@ -441,8 +441,6 @@ def run_c4(env, args, steps, warmup, e2e_steps):
         r = mb.PhiloxRng(tstep[0], 0)
         mb.ntc(r, cf, None, it, pv, pia, (1, nx), 1, DT, slab.dx)
         mb.merge_octree_N2_based(r, oc, pv, pia, (1, nx), 1, tgt, slab, threshold=thr)
-        if world > 1:
-            mb.squash_pia(pv, pia, 1)
         mb.convect_particles(r, slab, walls, pv, pia, 1, AR, DT)
         if world > 1:
             mb.exchange_slab(ctx, slab, pv, pia, 1)

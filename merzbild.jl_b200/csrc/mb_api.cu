@@ -127,8 +127,8 @@ int mb_ctx_create(int device, uint64_t seed, mb_ctx** out) {
     MB_CUDA(cudaHostAlloc(&c->h_flags, 16 * sizeof(int), cudaHostAllocDefault));
     MB_CUDA(cudaEventCreate(&c->ev0));
     MB_CUDA(cudaEventCreate(&c->ev1));
-    MB_CUDA(cudaMalloc(&c->d_xch_counts, 8 * sizeof(int64_t)));
-    MB_CUDA(cudaMemset(c->d_xch_counts, 0, 8 * sizeof(int64_t)));
+    MB_CUDA(cudaMalloc(&c->d_xch_counts, 12 * sizeof(int64_t)));  // [8..9]: leavers packed by the edge exchange, [10]: particles the sort dropped
+    MB_CUDA(cudaMemset(c->d_xch_counts, 0, 12 * sizeof(int64_t)));
     MB_CUDA(cudaHostAlloc(&c->h_xch_counts, 8 * sizeof(int64_t), cudaHostAllocDefault));
     c->nranks = 1;
     c->prof_ev = new std::vector<cudaEvent_t>();
@@ -278,6 +278,7 @@ int mb_pv_create(mb_ctx* ctx, int64_t np, mb_pv** out) {
     p->has_alt = false;
     p->drop_oob = 0;
     p->n_arrivals = 0;
+    p->arrivals_at_end = 0;
     p->cell = nullptr;
     p->d_n_arr = nullptr;
     for (int f = 0; f < 7; f++) p->alt.a[f] = nullptr;

@@ -152,6 +152,7 @@ struct mb_pv {
                         // (1: every leaver was sent; 2: edge exchange -- only leavers from the w cells next to a slab face were sent)
     int64_t n_arrivals; // host upper bound on the slab-exchange arrivals appended after the sorted layout (merged by the next sort)
     int64_t* d_n_arr;   // device: exact number of those arrivals (the edge exchange never tells the host)
+    int arrivals_at_end; // the species was not contiguous at the exchange: the arrivals are parked at [cap - n_arr, cap), not behind n_total
 };
 
 struct mb_pia {

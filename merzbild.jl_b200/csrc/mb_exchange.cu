@@ -16,6 +16,7 @@
 
 #include "mb_common.cuh"
 #include "mb_scan.cuh"
+#include "mb_segcopy.cuh"
 
 namespace mb {
 
@@ -97,8 +98,10 @@ __device__ __forceinline__ int xch_dir(double x, double inv_dx, int64_t cell_off
     return c < 0 ? 1 : (c >= n_cells ? 2 : 0);
 }
 
+// src (nullable): logical -> physical position of a non-contiguous species (build_src_map)
 static __global__ void __launch_bounds__(XB) k_xch_count(const double* __restrict__ X, const int64_t* n_total_p, double inv_dx, int64_t cell_offset,
-                                                        int64_t n_cells, int32_t* __restrict__ cntL, int32_t* __restrict__ cntR) {
+                                                        int64_t n_cells, int32_t* __restrict__ cntL, int32_t* __restrict__ cntR,
+                                                        const int32_t* __restrict__ src) {
     __shared__ int sl[XB / 32], sr[XB / 32];
     const int64_t n = *n_total_p;
     const int64_t base = (int64_t)blockIdx.x * XT + (int64_t)threadIdx.x * XI;
@@ -106,7 +109,7 @@ static __global__ void __launch_bounds__(XB) k_xch_count(const double* __restric
     for (int k = 0; k < XI; k++) {
         const int64_t i = base + k;
         if (i < n) {
-            const int d = xch_dir(X[i], inv_dx, cell_offset, n_cells);
+            const int d = xch_dir(X[src ? (int64_t)src[i] : i], inv_dx, cell_offset, n_cells);
             l += d == 1;
             r += d == 2;
         }
@@ -125,7 +128,8 @@ static __global__ void __launch_bounds__(XB) k_xch_count(const double* __restric
 // stable pack (logical order) of the leavers into particle-major send buffers (7 doubles per particle)
 static __global__ void __launch_bounds__(XB) k_xch_pack(SoA pv, const int64_t* n_total_p, double inv_dx, int64_t cell_offset, int64_t n_cells,
                                                        const int64_t* __restrict__ offL, const int64_t* __restrict__ offR, double* __restrict__ sendL,
-                                                       double* __restrict__ sendR, int64_t cap, int64_t nblocks, int64_t* counts, int* flags) {
+                                                       double* __restrict__ sendR, int64_t cap, int64_t nblocks, int64_t* counts, int* flags,
+                                                       const int32_t* __restrict__ src) {
     __shared__ int sl[XB], sr[XB];
     const int64_t n = *n_total_p;
     const int64_t base = (int64_t)blockIdx.x * XT + (int64_t)threadIdx.x * XI;
@@ -134,7 +138,7 @@ static __global__ void __launch_bounds__(XB) k_xch_pack(SoA pv, const int64_t* n
 #pragma unroll
     for (int k = 0; k < XI; k++) {
         const int64_t i = base + k;
-        dir[k] = i < n ? xch_dir(pv.a[F_X][i], inv_dx, cell_offset, n_cells) : 0;
+        dir[k] = i < n ? xch_dir(pv.a[F_X][src ? (int64_t)src[i] : i], inv_dx, cell_offset, n_cells) : 0;
         l += dir[k] == 1;
         r += dir[k] == 2;
     }
@@ -163,7 +167,7 @@ static __global__ void __launch_bounds__(XB) k_xch_pack(SoA pv, const int64_t* n
 #pragma unroll
     for (int k = 0; k < XI; k++) {
         if (dir[k] == 0) continue;
-        const int64_t i = base + k;
+        const int64_t i = src ? (int64_t)src[base + k] : base + k;
         double* dst;
         if (dir[k] == 1) { if (pl >= cap) { pl++; continue; } dst = sendL + 7 * pl; pl++; }
         else { if (pr >= cap) { pr++; continue; } dst = sendR + 7 * pr; pr++; }
@@ -173,13 +177,14 @@ static __global__ void __launch_bounds__(XB) k_xch_pack(SoA pv, const int64_t* n
 }
 
 // arrivals (left neighbour's first, then the right neighbour's) are appended after n_total
+// at_end: the species is not contiguous -- the arrivals are parked at [cap - nL - nR, cap) (SrcMapDesc checks that no live particle is there)
 static __global__ void __launch_bounds__(256) k_xch_unpack(SoA pv, int64_t* n_total_p, int64_t cap, const double* __restrict__ recvL, int64_t nL,
-                                                          const double* __restrict__ recvR, int64_t nR, int* flags) {
-    const int64_t n0 = *n_total_p;
-    if (n0 + nL + nR > cap) {
+                                                          const double* __restrict__ recvR, int64_t nR, int* flags, int at_end) {
+    const int64_t n0 = at_end ? cap - nL - nR : *n_total_p;
+    if ((at_end ? *n_total_p : n0) + nL + nR > cap) {
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             atomicOr(&flags[0], DEVERR_CAPACITY);
-            flags[1] = (int)(n0 + nL + nR);
+            flags[1] = (int)(*n_total_p + nL + nR);
         }
         return;
     }
@@ -198,44 +203,46 @@ static __global__ void __launch_bounds__(256) k_xch_unpack(SoA pv, int64_t* n_to
 constexpr int XE_CAP = 8192;             // leavers per direction and step
 constexpr int XE_MSG = 8 + 7 * XE_CAP;   // doubles per message: [0] = count (int64 bits), payload from [8] (64-byte aligned)
 
+// Works on any layout the indexers describe (sorted, or group 2 at the tail / holes after a merge): the ranges of the w cells next
+// to the face are scanned cell by cell, group 1 then group 2, so the leavers are packed in (cell, group, position) order.
 static __global__ void __launch_bounds__(256) k_xch_edge_pack(SoA pv, const Indexer* __restrict__ ix, int64_t n_cells, int w, double inv_dx,
                                                             int64_t cell_offset, double* __restrict__ sendL, double* __restrict__ sendR, int hasL,
-                                                            int hasR, int* flags) {
+                                                            int hasR, int* flags, int64_t* __restrict__ sent2) {
     __shared__ int s_w[8];
     const int side = blockIdx.x;  // 0: left face, 1: right face
     const int want = side + 1;
     double* __restrict__ send = side == 0 ? sendL : sendR;
     const int64_t c_lo = side == 0 ? 0 : (n_cells - w > 0 ? n_cells - w : 0);
     const int64_t c_hi = side == 0 ? (w < n_cells ? w : n_cells) : n_cells;
-    int64_t lo = INT64_MAX, hi = -1;
-    for (int64_t c = c_lo; c < c_hi; c++) {
-        const Indexer q = ix[c];
-        if (q.n_group1 > 0) {
-            if (q.start1 - 1 < lo) lo = q.start1 - 1;
-            if (q.end1 > hi) hi = q.end1;
-        }
-    }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     int base = 0;
-    for (int64_t i0 = lo; i0 < hi; i0 += 256) {
-        const int64_t i = i0 + threadIdx.x;
-        const bool is = i < hi && xch_dir(pv.a[F_X][i], inv_dx, cell_offset, n_cells) == want;
-        const unsigned bal = __ballot_sync(0xffffffffu, is);
-        if (lane == 0) s_w[wid] = __popc(bal);
-        __syncthreads();
-        int off = 0, tot = 0;
-        for (int k = 0; k < 8; k++) { if (k < wid) off += s_w[k]; tot += s_w[k]; }
-        const int pos = base + off + __popc(bal & lt);
-        if (is && pos < XE_CAP) {
+    for (int64_t c = c_lo; c < c_hi; c++) {
+        const Indexer q = ix[c];
+        for (int g = 0; g < 2; g++) {
+            const int64_t lo = (g == 0 ? q.start1 : q.start2) - 1;
+            const int64_t hi = lo + (g == 0 ? q.n_group1 : q.n_group2);
+            for (int64_t i0 = lo; i0 < hi; i0 += 256) {  // block-uniform bounds
+                const int64_t i = i0 + threadIdx.x;
+                const bool is = i < hi && xch_dir(pv.a[F_X][i], inv_dx, cell_offset, n_cells) == want;
+                const unsigned bal = __ballot_sync(0xffffffffu, is);
+                if (lane == 0) s_w[wid] = __popc(bal);
+                __syncthreads();
+                int off = 0, tot = 0;
+                for (int k = 0; k < 8; k++) { if (k < wid) off += s_w[k]; tot += s_w[k]; }
+                const int pos = base + off + __popc(bal & lt);
+                if (is && pos < XE_CAP) {
 #pragma unroll
-            for (int f = 0; f < 7; f++) send[8 + 7 * (int64_t)pos + f] = pv.a[f][i];
+                    for (int f = 0; f < 7; f++) send[8 + 7 * (int64_t)pos + f] = pv.a[f][i];
+                }
+                base += tot;
+                __syncthreads();
+            }
         }
-        base += tot;
-        __syncthreads();
     }
     if (threadIdx.x == 0) {
         send[0] = __longlong_as_double((long long)(base < XE_CAP ? base : XE_CAP));
+        sent2[side] = base;  // the sort that drops the leavers checks that it dropped exactly the particles sent
         if (base > XE_CAP) { atomicOr(&flags[0], DEVERR_CAPACITY); flags[1] = base; }
         if (base > 0 && !(side == 0 ? hasL : hasR)) atomicOr(&flags[0], DEVERR_PRECONDITION);  // left the global domain
         if (side == 0 && flags[F_FAR] != 0) atomicOr(&flags[0], DEVERR_BAND_OVERFLOW);
@@ -243,15 +250,15 @@ static __global__ void __launch_bounds__(256) k_xch_edge_pack(SoA pv, const Inde
 }
 
 static __global__ void __launch_bounds__(256) k_xch_edge_unpack(SoA pv, const int64_t* n_total_p, int64_t cap, const double* __restrict__ recvL,
-                                                              const double* __restrict__ recvR, int hasL, int hasR, int* flags) {
+                                                              const double* __restrict__ recvR, int hasL, int hasR, int* flags, int at_end) {
     int64_t nL = hasL ? (int64_t)__double_as_longlong(recvL[0]) : 0, nR = hasR ? (int64_t)__double_as_longlong(recvR[0]) : 0;
     nL = nL < 0 ? 0 : (nL > XE_CAP ? XE_CAP : nL);
     nR = nR < 0 ? 0 : (nR > XE_CAP ? XE_CAP : nR);
-    const int64_t n0 = *n_total_p;
-    if (n0 + nL + nR > cap) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) { atomicOr(&flags[0], DEVERR_CAPACITY); flags[1] = (int)(n0 + nL + nR); }
+    if (*n_total_p + nL + nR > cap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) { atomicOr(&flags[0], DEVERR_CAPACITY); flags[1] = (int)(*n_total_p + nL + nR); }
         return;
     }
+    const int64_t n0 = at_end ? cap - nL - nR : *n_total_p;  // non-contiguous species: parked at the end of the capacity
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nL + nR; t += (int64_t)gridDim.x * blockDim.x) {
         const double* src = t < nL ? recvL + 8 + 7 * t : recvR + 8 + 7 * (t - nL);
 #pragma unroll
@@ -277,7 +284,7 @@ static __global__ void k_xch_add_total(int64_t* n_total_p, int64_t cap, int64_t 
 // mb_exchange_slab (one rank per process, NCCL transport) and mb_exchange_chunks (all chunks in one process, copy transport) share
 // these: xch_begin packs the leavers, the transport moves the staging buffers, xch_finish_* appends the arrivals.
 struct XchPlan {
-    bool edge, hasL, hasR;
+    bool edge, hasL, hasR, at_end;
     int left, right, s;
 };
 struct XchCounts {
@@ -291,8 +298,8 @@ static int xch_begin(mb_ctx* ctx, const mb_grid1d* slab, mb_pv* pv, mb_pia* pia,
     MB_ARG(pia->n_cells == slab->n_cells, "slab.n_cells != pia.n_cells");
     MB_CUDA(cudaSetDevice(ctx->device));
     const int s = (int)species - 1;
-    if (!pia->contiguous[s]) {
-        set_error("mb_exchange_slab needs a contiguous species (sort or squash first)");
+    if (!pia->contiguous[s] && pv->n_arrivals != 0) {
+        set_error("mb_exchange_slab on a non-contiguous species with arrivals pending: sort first");
         return MB_ERR_PRECONDITION;
     }
     {   // the own particles are not touched: a classification cached by the fused convect kernel stays valid
@@ -319,12 +326,13 @@ static int xch_begin(mb_ctx* ctx, const mb_grid1d* slab, mb_pv* pv, mb_pia* pia,
     P.hasL = nranks > 1 && P.left >= 0;
     P.hasR = nranks > 1 && P.right < nranks;
     // edge exchange: every rank takes the same decision (it only depends on the operator sequence)
-    P.edge = ctx->xch_mode == 0 && pia->sorted_layout[s] && ctx->band_w > 0 && pv->n_arrivals == 0 && !want_counts;
+    P.edge = ctx->xch_mode == 0 && ctx->band_w > 0 && pv->n_arrivals == 0 && !want_counts;
+    P.at_end = !pia->contiguous[s];
     int64_t* d_nt = pia->d_n_total + s;
     if (P.edge) {
         k_xch_edge_pack<<<2, 256, 0, st>>>(pv->cur, pia->d_indexer + (int64_t)s * pia->n_cells, pia->n_cells, ctx->band_w, slab->inv_dx,
                                          slab->cell_offset, (double*)ctx->xch_send[0], (double*)ctx->xch_send[1], P.hasL ? 1 : 0, P.hasR ? 1 : 0,
-                                         ctx->d_flags);
+                                         ctx->d_flags, ctx->d_xch_counts + 8);
         MB_LAUNCH_CHECK(ctx);
         return MB_OK;
     }
@@ -336,14 +344,24 @@ static int xch_begin(mb_ctx* ctx, const mb_grid1d* slab, mb_pv* pv, mb_pia* pia,
     int64_t* offL = p64;
     int64_t* offR = p64 + (nblocks + 1);
     int64_t* partial = p64 + 2 * (nblocks + 1);
-    k_xch_count<<<(int)nblocks, XB, 0, st>>>(pv->cur.a[F_X], d_nt, slab->inv_dx, slab->cell_offset, slab->n_cells, cnt, cnt + nblocks);
+    // a non-contiguous species (after a merge) is read through the logical -> physical map instead of being squashed first
+    int32_t* src = nullptr;
+    if (P.at_end) {
+        int rr = build_src_map(ctx, pv->cap, pia->d_indexer + (int64_t)s * pia->n_cells, pia->n_cells, nullptr, &src);
+        if (rr) return rr;
+        cnt = (int32_t*)ctx_scratch(ctx, 13, (size_t)(2 * nblocks) * 4);  // (slots 4 / 5 were used by the map)
+        p64 = (int64_t*)ctx_scratch(ctx, 14, ((size_t)2 * (nblocks + 1) + gs_partial_count(nblocks)) * 8);
+        if (!cnt || !p64) return MB_ERR_CUDA;
+        offL = p64; offR = p64 + (nblocks + 1); partial = p64 + 2 * (nblocks + 1);
+    }
+    k_xch_count<<<(int)nblocks, XB, 0, st>>>(pv->cur.a[F_X], d_nt, slab->inv_dx, slab->cell_offset, slab->n_cells, cnt, cnt + nblocks, src);
     MB_LAUNCH_CHECK(ctx);
     int r = device_exclusive_scan(ctx, cnt, nblocks, offL, partial);
     if (r) return r;
     r = device_exclusive_scan(ctx, cnt + nblocks, nblocks, offR, partial);
     if (r) return r;
     k_xch_pack<<<(int)nblocks, XB, 0, st>>>(pv->cur, d_nt, slab->inv_dx, slab->cell_offset, slab->n_cells, offL, offR, (double*)ctx->xch_send[0],
-                                            (double*)ctx->xch_send[1], (int64_t)ctx->xch_cap, nblocks, ctx->d_xch_counts, ctx->d_flags);
+                                            (double*)ctx->xch_send[1], (int64_t)ctx->xch_cap, nblocks, ctx->d_xch_counts, ctx->d_flags, src);
     MB_LAUNCH_CHECK(ctx);
     return MB_OK;
 }
@@ -365,11 +383,12 @@ static int xch_finish_edge(mb_ctx* ctx, mb_pv* pv, mb_pia* pia, const XchPlan& P
     if (P.hasL || P.hasR) {
         const double* rL = (const double*)ctx->xch_recv[0];
         const double* rR = (const double*)ctx->xch_recv[1];
-        k_xch_edge_unpack<<<16, 256, 0, st>>>(pv->cur, d_nt, pv->cap, rL, rR, P.hasL ? 1 : 0, P.hasR ? 1 : 0, ctx->d_flags);
+        k_xch_edge_unpack<<<16, 256, 0, st>>>(pv->cur, d_nt, pv->cap, rL, rR, P.hasL ? 1 : 0, P.hasR ? 1 : 0, ctx->d_flags, P.at_end ? 1 : 0);
         MB_LAUNCH_CHECK(ctx);
         k_xch_edge_commit<<<1, 1, 0, st>>>(d_nt, pv->cap, rL, rR, P.hasL ? 1 : 0, P.hasR ? 1 : 0, pv->d_n_arr);
         MB_LAUNCH_CHECK(ctx);
         pv->n_arrivals += 2 * XE_CAP;  // upper bound; the exact number stays on the device
+        pv->arrivals_at_end = P.at_end ? 1 : 0;
     }
     pv->drop_oob = 2;
     pia->h_valid = false;
@@ -383,7 +402,7 @@ static int xch_finish_full(mb_ctx* ctx, mb_pv* pv, mb_pia* pia, const XchPlan& P
     const int64_t* h = ctx->h_xch_counts;
     if (K.rL + K.rR > 0) {
         k_xch_unpack<<<grid_for(K.rL + K.rR, 256), 256, 0, st>>>(pv->cur, d_nt, pv->cap, (const double*)ctx->xch_recv[0], K.rL,
-                                                               (const double*)ctx->xch_recv[1], K.rR, ctx->d_flags);
+                                                               (const double*)ctx->xch_recv[1], K.rR, ctx->d_flags, P.at_end ? 1 : 0);
         MB_LAUNCH_CHECK(ctx);
         k_xch_add_total<<<1, 1, 0, st>>>(d_nt, pv->cap, K.rL + K.rR);
         MB_LAUNCH_CHECK(ctx);
@@ -393,6 +412,7 @@ static int xch_finish_full(mb_ctx* ctx, mb_pv* pv, mb_pia* pia, const XchPlan& P
     // the layout of the own particles is untouched: the next sort drops the leavers and merges the arrivals (band path if sorted)
     if (h[0] + h[2] > 0 && pv->drop_oob == 0) pv->drop_oob = 1;
     pv->n_arrivals += K.rL + K.rR;
+    if (K.rL + K.rR > 0) pv->arrivals_at_end = P.at_end ? 1 : 0;
     pia->h_valid = false;
     pia->n_bound[P.s] = pv->cap;
     if (n_sent2) { n_sent2[0] = K.sL; n_sent2[1] = K.sR; }

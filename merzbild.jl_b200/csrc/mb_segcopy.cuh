@@ -8,6 +8,7 @@
 // once per non-empty segment (lane 0).
 #pragma once
 #include "mb_common.cuh"
+#include "mb_scan.cuh"
 
 namespace mb {
 
@@ -101,5 +102,59 @@ struct SquashDesc {
         }
     }
 };
+
+// The map logical (squashed) position -> physical position of a non-contiguous species: group 1 of all cells, group 2 of all cells
+// (the order squash_pia! produces, particles.jl:622-682), then -- after a slab exchange on a non-contiguous layout -- the arrivals,
+// which mb_exchange_slab parks at the END of the capacity (they are in no indexer yet).  The sort's general path and the exchange's
+// pack read the particles through this map instead of moving the payload twice.
+struct SrcMapDesc {
+    const Indexer* ix;
+    int64_t nc;
+    const int64_t* newlo;
+    const int64_t* n_arr;  // nullable
+    int64_t cap;
+    int* flags;
+    __device__ __forceinline__ void get(int64_t seg, int64_t& n, int64_t& src, int64_t& dst) const {
+        const int64_t na = n_arr ? *n_arr : 0;
+        dst = newlo[seg];
+        if (seg == 2 * nc) { n = na; src = cap - na; return; }
+        const bool g2 = seg >= nc;
+        const Indexer q = ix[g2 ? seg - nc : seg];
+        n = g2 ? q.n_group2 : q.n_group1;
+        src = (g2 ? q.start2 : q.start1) - 1;
+        if (n > 0 && src + n > cap - na) atomicOr(&flags[0], DEVERR_CAPACITY);  // the live particles reach into the parked arrivals
+    }
+};
+struct SrcMapAct {
+    int32_t* srcmap;
+    __device__ __forceinline__ void seg(int64_t, int64_t, int64_t, int64_t) const {}
+    __device__ __forceinline__ void elem(int64_t, int64_t src, int64_t dst) const { srcmap[dst] = (int32_t)src; }
+};
+static __global__ void k_srcmap_counts(const Indexer* __restrict__ ix, int64_t nc, const int64_t* n_arr, int32_t* __restrict__ cnt) {
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
+        const Indexer q = ix[c];
+        cnt[c] = (int32_t)q.n_group1;
+        cnt[nc + c] = (int32_t)q.n_group2;
+        if (c == 0) cnt[2 * nc] = n_arr ? (int32_t)*n_arr : 0;
+    }
+}
+// scratch slots: 8 (map), 4 (counts), 5 (offsets), 7 (queue of the big segments)
+static inline int build_src_map(mb_ctx* ctx, int64_t cap, const Indexer* ix, int64_t nc, const int64_t* d_n_arr, int32_t** src_out) {
+    int32_t* src = (int32_t*)ctx_scratch(ctx, 8, (size_t)cap * 4);
+    int32_t* cnt = (int32_t*)ctx_scratch(ctx, 4, (size_t)(2 * nc + 1) * 4);
+    int64_t* p64 = (int64_t*)ctx_scratch(ctx, 5, ((size_t)(2 * nc + 2) + gs_partial_count(2 * nc + 1)) * 8);
+    if (!src || !cnt || !p64) return MB_ERR_CUDA;
+    ProfScope ps(ctx, PROF_SQUASH);
+    k_srcmap_counts<<<grid_for(nc, 256), 256, 0, ctx->stream>>>(ix, nc, d_n_arr, cnt);
+    MB_LAUNCH_CHECK(ctx);
+    int r = device_exclusive_scan(ctx, cnt, 2 * nc + 1, p64, p64 + (2 * nc + 2));
+    if (r) return r;
+    SrcMapDesc D{ix, nc, p64, d_n_arr, cap, ctx->d_flags};
+    SrcMapAct A{src};
+    r = seg_copy(ctx, 7, cap, 2 * nc + 1, D, A);
+    if (r) return r;
+    *src_out = src;
+    return MB_OK;
+}
 
 }  // namespace mb

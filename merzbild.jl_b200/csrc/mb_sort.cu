@@ -820,7 +820,7 @@ __global__ void k_flag_from_cls(int* flags, int drop) { flags[2] = (flags[F_CLS_
 __global__ void __launch_bounds__(256) k_gen_classify(const double* __restrict__ X, const int32_t* cell_in, int32_t* cell_out,
                                                       int32_t* __restrict__ key, const int64_t* n_total_p, int64_t n_cells, double inv_dx,
                                                       int64_t cell_offset, int use_x, int drop, int32_t* __restrict__ hist, int* flags,
-                                                      const int32_t* __restrict__ src) {
+                                                      const int32_t* __restrict__ src, unsigned long long* __restrict__ n_dropped) {
     // drop != 0 (after a slab exchange): a particle whose cell is outside [0, n_cells) left the slab and is dropped
     if (flags[2] == 0) return;
     const int64_t n_total = *n_total_p;
@@ -843,6 +843,10 @@ __global__ void __launch_bounds__(256) k_gen_classify(const double* __restrict__
             }
             key[i] = nc;
             counted = nc >= 0;
+        }
+        if (n_dropped != nullptr) {  // after an edge exchange: the sort must drop exactly the particles that were sent
+            const unsigned dm = __ballot_sync(0xffffffffu, valid && nc < 0);
+            if (dm != 0 && lane == __ffs(dm) - 1) atomicAdd(n_dropped, (unsigned long long)__popc(dm));
         }
         // run-length aggregation: keys of neighbouring lanes are mostly equal
         const unsigned act = __ballot_sync(0xffffffffu, counted);
@@ -1163,20 +1167,12 @@ __global__ void __launch_bounds__(256) k_gen_gather_cells_aos(const Rec64* __res
 // moving it again in the sort, only the map logical (squashed) position -> physical position is built (4 B per particle).  The
 // squashed order walks group 1 of all cells, then group 2 of all cells (particles.jl:622-682); newlo = exclusive scan of the segment
 // sizes.  Load balance over segment sizes: mb_segcopy.cuh.
-static __global__ void k_sq_counts(const Indexer* __restrict__ ix, int64_t nc, int32_t* __restrict__ cnt) {
-    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
-        const Indexer q = ix[c];
-        cnt[c] = (int32_t)q.n_group1;
-        cnt[nc + c] = (int32_t)q.n_group2;
-    }
-}
-struct SrcMapAct {
-    int32_t* srcmap;
-    __device__ __forceinline__ void seg(int64_t, int64_t, int64_t, int64_t) const {}
-    __device__ __forceinline__ void elem(int64_t, int64_t src, int64_t dst) const { srcmap[dst] = (int32_t)src; }
-};
-
 __global__ void k_set_flag(int* flags, int idx, int v) { flags[idx] = v; }
+// edge exchange + general-path sort: a leaver from a cell further than w from its slab face was not sent, the sort would drop it
+// silently -- the counts of sent and dropped particles must agree
+__global__ void k_check_dropped(const int64_t* xc, int* flags) {
+    if (flags[2] != 0 && xc[10] != xc[8] + xc[9]) atomicOr(&flags[0], DEVERR_BAND_OVERFLOW);
+}
 
 // ------------------------------------------------------------------------------------------------ segment path
 // sort_particles!(gridsort, pv, pia, species) by stored cell ids (grid_sorting.jl:128-182) when NO particle changed its cell -- the
@@ -1458,7 +1454,12 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
     const int s = (int)species - 1;
     // grid_sorting.jl:69-71: squash first.  A non-contiguous species never has the sorted layout (a merge cleared it), so the sort
     // takes the general path and the squash is folded into it (k_build_src); the separate payload pass is only the fallback.
-    const bool fuse_squash = !pia->contiguous[s] && !(ctx->band_w > 0 && pia->sorted_layout[s]) && pv->n_arrivals == 0 && !pv->drop_oob;
+    // (arrivals of a slab exchange on a non-contiguous layout are parked at the end of the capacity and enter through the same map)
+    const bool fuse_squash = !pia->contiguous[s] && !(ctx->band_w > 0 && pia->sorted_layout[s]) && (pv->n_arrivals == 0 || pv->arrivals_at_end);
+    if (pv->n_arrivals > 0 && pv->arrivals_at_end && !fuse_squash) {
+        set_error("sort_particles!: arrivals of a slab exchange on a non-contiguous layout are pending, but the layout is contiguous now");
+        return MB_ERR_PRECONDITION;
+    }
     if (!pia->contiguous[s] && !fuse_squash) {
         int r = mb_squash_pia(ctx, pv, pia, species);
         if (r) return r;
@@ -1544,25 +1545,20 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
         const int64_t nb = pia->n_bound[s] > 0 ? pia->n_bound[s] : cap;
         int32_t* src = nullptr;
         if (fuse_squash) {
-            src = (int32_t*)ctx_scratch(ctx, 8, (size_t)cap * 4);
-            int32_t* cnt = (int32_t*)ctx_scratch(ctx, 4, (size_t)(2 * nc) * 4);
-            int64_t* p64 = (int64_t*)ctx_scratch(ctx, 5, ((size_t)(2 * nc + 1) + gs_partial_count(2 * nc)) * 8);
-            if (!src || !cnt || !p64) return MB_ERR_CUDA;
-            ProfScope ps2(ctx, PROF_SQUASH);
-            k_sq_counts<<<grid_for(nc, 256), 256, 0, st>>>(ix, nc, cnt);
-            MB_LAUNCH_CHECK(ctx);
-            r = device_exclusive_scan(ctx, cnt, 2 * nc, p64, p64 + (2 * nc + 1));
-            if (r) return r;
-            SquashDesc D{ix, nc, p64, ctx->d_flags};
-            SrcMapAct A{src};
-            r = seg_copy(ctx, 7, cap, 2 * nc, D, A);
+            r = build_src_map(ctx, cap, ix, nc, n_arr > 0 ? pv->d_n_arr : nullptr, &src);
             if (r) return r;
         }
         MB_CUDA(cudaMemsetAsync(S.hist, 0, (size_t)nc * 4, st));  // harmless for the band result: hist is not read again
         const int pgrid = grid_for(nb, 256, 16);
+        if (drop == 2) MB_CUDA(cudaMemsetAsync(ctx->d_xch_counts + 10, 0, 8, st));
         k_gen_classify<<<pgrid, 256, 0, st>>>(pv->cur.a[F_X], pv->cell, pv->cell, S.key, B.n_old, nc, use_x ? grid->inv_dx : 0.0,
-                                             use_x ? grid->cell_offset : 0, use_x ? 1 : 0, drop ? 1 : 0, S.hist, S.flags, src);
+                                             use_x ? grid->cell_offset : 0, use_x ? 1 : 0, drop ? 1 : 0, S.hist, S.flags, src,
+                                             drop == 2 ? (unsigned long long*)(ctx->d_xch_counts + 10) : nullptr);
         MB_LAUNCH_CHECK(ctx);
+        if (drop == 2) {
+            k_check_dropped<<<1, 1, 0, st>>>(ctx->d_xch_counts, S.flags);
+            MB_LAUNCH_CHECK(ctx);
+        }
         k_scan_reduce<3><<<nscan, SCAN_BLOCK, 0, st>>>(nullptr, nullptr, nullptr, S.hist, nc, S.partial, S.flags, 1);
         MB_LAUNCH_CHECK(ctx);
         k_scan_partials<<<1, 1024, 0, st>>>(S.partial, nscan, S.flags, 1);
@@ -1607,6 +1603,7 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
     if (rewrite_total) {
         pv->drop_oob = 0;
         pv->n_arrivals = 0;
+        pv->arrivals_at_end = 0;
         pia->h_valid = false;
         MB_CUDA(cudaMemsetAsync(pv->d_n_arr, 0, sizeof(int64_t), st));
     }

@@ -52,6 +52,10 @@ extern "C" int mb_squash_pia(mb_ctx* ctx, mb_pv* pv, mb_pia* pia, int64_t specie
     MB_ARG(ctx && pv && pia && species >= 1 && species <= pia->n_species, "squash_pia");
     const int s = (int)species - 1;
     if (pia->contiguous[s]) return MB_OK;  // particles.jl:623-625
+    if (pv->n_arrivals > 0) {
+        mb::set_error("squash_pia!: arrivals of a slab exchange are pending (they are in no indexer yet): sort_particles! first");
+        return MB_ERR_PRECONDITION;
+    }
     MB_CUDA(cudaSetDevice(ctx->device));
     int r = pv_ensure_alt(pv);
     if (r) return r;
