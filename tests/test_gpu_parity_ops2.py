@@ -333,3 +333,29 @@ def test_avg_props_parity(mb, oracle, ctx):
     np.testing.assert_allclose(d["T"], o.T, rtol=1e-12)
     pv.close()
     pia.close()
+
+
+def test_fp_linear_rejects_cells_with_a_second_group(mb, oracle, ctx):
+    """fp_linear! is only defined for sorted cells (the reference's group-2 branch throws, collision_fp.jl:57): a cell whose particles
+    sit in two index groups is skipped and reported as MB_ERR_PRECONDITION instead of being relaxed with its neighbours' particles."""
+    rng = np.random.default_rng(35)
+    n = 600
+    rows = maxwellian_rows(rng, n, 3.0)
+    pv, pia = mb.ParticleVector(n, ctx), mb.ParticleIndexerArray(3, 1, ctx)
+    pv.set_logical(1, rows)
+    ix = np.zeros((1, 3, 7), dtype=np.int64)
+    ix[0, 0] = (150, 1, 100, 100, 551, 600, 50)   # group 2 at the tail (as variable-weight ntc! leaves it)
+    ix[0, 1] = (200, 101, 300, 200, 0, -1, 0)
+    ix[0, 2] = (250, 301, 550, 250, 0, -1, 0)
+    pia.upload(ix, np.array([n]), np.array([1], dtype=np.uint8))
+    it = mb.make_interaction(AR, AR, 4.11e-10, 0.81, 273.0)
+    mb.fp_linear(mb.PhiloxRng(1), None, it, AR, pv, pia, (1, 3), 1, 2.59e-9 * 50, 1e-5)
+    with pytest.raises(mb.MerzbildError) as e:
+        ctx.sync()
+    assert e.value.status == mb.MB_ERR_PRECONDITION
+    after = pv.logical(1, n)
+    np.testing.assert_array_equal(after[:100], rows[:100])      # the offending cell was left alone, both groups
+    np.testing.assert_array_equal(after[550:], rows[550:])
+    assert np.any(after[100:550, 1:4] != rows[100:550, 1:4])    # the sorted cells were relaxed
+    pv.close()
+    pia.close()
