@@ -809,7 +809,7 @@ def main():
     ap.add_argument("--config", default="c3", choices=["c3", "c4", "c2", "c5"])
     ap.add_argument("--scaling", default="same-dx", choices=sorted(SCALINGS))
     ap.add_argument("--particles-per-gpu", type=float, default=1.25e8)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=3, help="0 (experiments only): skip the end-to-end leg, the line then carries e2e = null")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="do not append the short runs of the other configs / scalings to the default line")
     ap.add_argument("--dt-mult", type=float, default=1.0, help="experiment knob: multiplies the time step (0: nothing moves, the sort is a pure segmented copy)")
@@ -827,7 +827,7 @@ def main():
     sampler.start()
     time.sleep(0.3)
     if args.config == "c3":
-        res = run_c3(env, args, args.scaling, args.steps, args.warmup, max(args.e2e_steps, 1), args.band)
+        res = run_c3(env, args, args.scaling, args.steps, args.warmup, args.e2e_steps, args.band)
     else:
         res = {"c4": run_c4, "c2": run_c2, "c5": run_c5}[args.config](env, args, args.steps, args.warmup, max(args.e2e_steps, 1))
     clocks = sampler.stop(*res["wall"])

@@ -142,7 +142,7 @@ int mb_ctx_destroy(mb_ctx* c) {
     if (!c) return MB_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (int i = 0; i < 16; i++)
+    for (int i = 0; i < 24; i++)
         if (c->scratch[i]) cudaFree(c->scratch[i]);
     if (c->l2_scratch) cudaFree(c->l2_scratch);
     for (int i = 0; i < 2; i++) {

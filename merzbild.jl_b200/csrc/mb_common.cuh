@@ -106,8 +106,8 @@ struct mb_ctx {
     void* l2_scratch;
     size_t l2_scratch_bytes;
     // generic scratch arena (grown on demand, stream-ordered reuse)
-    void* scratch[16];
-    size_t scratch_bytes[16];
+    void* scratch[24];
+    size_t scratch_bytes[24];
     int sort_last_path;
     int band_w;
     // moments cached by the band sort's gather pass (valid while state_gen == pc_gen)

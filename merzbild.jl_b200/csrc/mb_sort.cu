@@ -28,6 +28,7 @@
 #include "mb_convect.cuh"
 #include "mb_scan.cuh"
 #include "mb_segcopy.cuh"
+#include "mb_sort_tile.cuh"
 
 namespace mb {
 
@@ -1257,7 +1258,7 @@ constexpr int W_MAX = 31;  // widest band (w = 15): the group id lives in a lane
 static int sort_scratch_layout(mb_ctx* ctx, int64_t cap, int64_t nc, int W, SortScratch& S, BandBufs& B) {
     const int nscan = (int)((nc + SCAN_TILE - 1) / SCAN_TILE);
     S.flags = ctx->d_flags;
-    S.key = (int32_t*)ctx_scratch(ctx, 0, (size_t)cap * 4);  // general: keys; band: dr
+    S.key = (int32_t*)ctx_scratch(ctx, 0, (size_t)cap * 4 + 64);  // general: keys; band: dr (+ slack: the tile kernel's bulk loads are 16-byte granular)
     // slot 1 (int32): hist | cursor | seg_n | cntB | cntA | curB | curA | ex_n (64) | M; sized for the widest band so that W may change
     const size_t n32 = (size_t)nc * (7 + W_MAX) + 128;
     int32_t* p32 = (int32_t*)ctx_scratch(ctx, 1, n32 * 4);
@@ -1343,9 +1344,102 @@ int convect_band_launch(mb_ctx* ctx, const ConvectArgs& a, const mb_grid1d* grid
     return MB_OK;
 }
 
+
+// ---- tile pass B (mb_sort_tile.cuh)
+// MB_SORT_TILE: 0 never, 1 (default) when the mean cell population suits the tile size, 2 always (tests of the direct mode)
+static int tile_mode() {
+    const char* e = getenv("MB_SORT_TILE");
+    return e ? atoi(e) : 1;
+}
+// MB_TILE_CFG selects the compiled shape (tile particles / consumer threads / particles per stage x stages):
+// 0 = 2048 / 256 / 1024 x 4, 1 = 4096 / 512 / 1024 x 8, 2 = 4096 / 512 / 2048 x 4, 3 = 4096 / 512 / 4096 x 2, 4 = 4096 / 256 / 1024 x 8
+static int tile_cfg() {
+    const char* e = getenv("MB_TILE_CFG");
+    return e ? atoi(e) : 1;
+}
+static int tile_ncap(int cfg) { return cfg == 0 ? 2048 : 4096; }
+template <int NCAP, int NT, int SUB, int S, int MINB>
+static int launch_tile_kernel(mb_ctx* ctx, const TileArgs& a, bool mom) {
+    static bool attr_done[64] = {false};  // function attributes are per device
+    if (!attr_done[ctx->device & 63]) {
+        MB_CUDA(cudaFuncSetAttribute(k_band_tile<NCAP, NT, SUB, S, true, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileSmem<NCAP, SUB, S, true>::BYTES));
+        MB_CUDA(cudaFuncSetAttribute(k_band_tile<NCAP, NT, SUB, S, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileSmem<NCAP, SUB, S, false>::BYTES));
+        attr_done[ctx->device & 63] = true;
+    }
+    const int g = N_SM * MINB;
+    if (mom) k_band_tile<NCAP, NT, SUB, S, true, MINB><<<g, NT + 64, TileSmem<NCAP, SUB, S, true>::BYTES, ctx->stream>>>(a);
+    else k_band_tile<NCAP, NT, SUB, S, false, MINB><<<g, NT + 64, TileSmem<NCAP, SUB, S, false>::BYTES, ctx->stream>>>(a);
+    MB_LAUNCH_CHECK(ctx);
+    return MB_OK;
+}
+struct TileBufs {
+    int64_t* old_start;    // [nc + 1]
+    int64_t* partial;
+    int64_t* tp;           // NI, NK, largest cell, n_old
+    int32_t* chunk_first;  // [NK + 2]
+    double* Pp;            // partial moments
+};
+static int tile_scratch(mb_ctx* ctx, int64_t cap, int64_t nc, int w, bool mom, TileBufs& T) {
+    const size_t n64 = (size_t)(nc + 1) + gs_partial_count(nc) + 8;
+    int64_t* p64 = (int64_t*)ctx_scratch(ctx, 16, n64 * 8);
+    const int64_t nk_max = cap / 512 + 4;  // NI >= NCAP / 4 >= 512
+    T.chunk_first = (int32_t*)ctx_scratch(ctx, 17, (size_t)(nk_max + 4) * 4);
+    if (!p64 || !T.chunk_first) return MB_ERR_CUDA;
+    T.old_start = p64;
+    T.partial = p64 + (nc + 1);
+    T.tp = T.partial + gs_partial_count(nc);
+    T.Pp = nullptr;
+    if (mom) {
+        T.Pp = (double*)ctx_scratch(ctx, 18, (size_t)(2 * w * (nk_max + 1) + nc + 2 * w + 4) * 5 * 8);
+        if (!T.Pp) return MB_ERR_CUDA;
+    }
+    return MB_OK;
+}
+// old_start / tiles from the old cell sizes, then the tile kernel; moments: combine (+ the fallback if a tile went the direct way)
+static int launch_tile_pass_b(mb_ctx* ctx, mb_pv* pv, int64_t nc, int W, const SortScratch& S, const BandBufs& B, bool mom) {
+    cudaStream_t st = ctx->stream;
+    const int cfg = tile_cfg();
+    const int ncap = tile_ncap(cfg);
+    TileBufs T;
+    if (tile_scratch(ctx, pv->cap, nc, W / 2, mom, T)) return MB_ERR_CUDA;
+    MB_CUDA(cudaMemsetAsync(T.tp, 0, 8 * 8, st));
+    if (mom) MB_CUDA(cudaMemsetAsync(ctx->d_flags + F_MOM_BAD, 0, sizeof(int), st));
+    const int nb = (int)((nc + GS_TILE - 1) / GS_TILE);
+    k_tile_reduce<<<nb, GS_BLOCK, 0, st>>>(B.seg_n, nc, T.partial, T.tp, S.flags);
+    MB_LAUNCH_CHECK(ctx);
+    k_tile_partials<<<1, 1024, 0, st>>>(T.partial, nb, T.tp, ncap, S.flags);
+    MB_LAUNCH_CHECK(ctx);
+    k_tile_apply<<<nb, GS_BLOCK, 0, st>>>(B.seg_n, nc, T.partial, T.old_start, T.chunk_first, T.tp, S.flags);
+    MB_LAUNCH_CHECK(ctx);
+    TileArgs a;
+    a.in = pv->cur; a.out = pv->alt;
+    a.dr = B.dr; a.M = S.M; a.old_start = T.old_start; a.chunk_first = T.chunk_first; a.tp = T.tp;
+    a.start = S.start; a.cntB = B.E.cntB; a.n_cells = nc; a.W = W; a.Pp = T.Pp; a.flags = S.flags;
+    a.debug = getenv("MB_TILE_DEBUG") != nullptr;
+    int r;
+    if (cfg == 0) r = launch_tile_kernel<2048, 256, 1024, 4, 1>(ctx, a, mom);
+    else if (cfg == 2) r = launch_tile_kernel<4096, 512, 2048, 4, 1>(ctx, a, mom);
+    else if (cfg == 3) r = launch_tile_kernel<4096, 512, 4096, 2, 1>(ctx, a, mom);
+    else if (cfg == 4) r = launch_tile_kernel<4096, 256, 1024, 8, 1>(ctx, a, mom);
+    else r = launch_tile_kernel<4096, 512, 1024, 8, 1>(ctx, a, mom);
+    if (r) return r;
+    return MB_OK;
+}
+static int launch_tile_moments(mb_ctx* ctx, mb_pv* pv, int64_t nc, int W, const SortScratch& S, const BandBufs& B) {
+    cudaStream_t st = ctx->stream;
+    const int64_t* p64 = (const int64_t*)ctx->scratch[16];
+    const int64_t* tp = p64 + (nc + 1) + gs_partial_count(nc);
+    k_tile_combine<<<grid_for(nc, 128, 16), 128, 0, st>>>((const double*)ctx->scratch[18], S.M, B.E.cntB, B.E.cntA, p64, tp, S.start, pv->cur, pv->alt,
+                                                         nc, W, B.pcache, S.flags);
+    MB_LAUNCH_CHECK(ctx);
+    k_tile_moments_fallback<<<grid_for(nc * 32, 256, 8), 256, 0, st>>>(pv->alt, S.start, nc, B.pcache, S.flags);
+    MB_LAUNCH_CHECK(ctx);
+    return MB_OK;
+}
+
 template <int W>
 static int launch_band(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia, int64_t species, SortScratch& S, const BandBufs& B,
-                       bool cls_cached) {
+                       bool cls_cached, bool use_tile, bool tile_mom) {
     const int64_t nc = pia->n_cells;
     Indexer* ix = pia->d_indexer + (species - 1) * nc;
     cudaStream_t st = ctx->stream;
@@ -1383,7 +1477,10 @@ static int launch_band(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pi
         // at w >= 4 a group holds a handful of particles and the direct stores are faster (measured, profiles/README.md)
         bool buffered = MB_SC_BUF != 0 && W <= 5;
         for (int f = 1; f < 7 && buffered; f++) buffered = pv->alt.a[f] - pv->alt.a[0] == f * (pv->alt.a[1] - pv->alt.a[0]);
-        if (buffered) {
+        if (use_tile) {
+            int r = launch_tile_pass_b(ctx, pv, nc, W, S, B, tile_mom);
+            if (r) return r;
+        } else if (buffered) {
             static bool attr_done[64] = {false};  // function attributes are per device
             if (!attr_done[ctx->device & 63]) {
                 MB_CUDA(cudaFuncSetAttribute(k_band_scatter_buf<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScBuf<W>::SMEM));
@@ -1401,7 +1498,7 @@ static int launch_band(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pi
         } else {
             k_band_scatter<W, false><<<sgrid, 256, 0, st>>>(pv->cur, pv->alt, B.dr, S.M, B.seg_lo, B.seg_n, S.start, B.E.cntB, nc, nullptr, S.flags);
         }
-        MB_LAUNCH_CHECK(ctx);
+        if (!use_tile) MB_LAUNCH_CHECK(ctx);
     }
     {
         ProfScope ps(ctx, PROF_SORT_EXTRAS);
@@ -1412,7 +1509,11 @@ static int launch_band(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pi
         k_save_extras<<<1, 1, 0, st>>>(B.E.n, S.flags);
         MB_LAUNCH_CHECK(ctx);
     }
-    if (B.P != nullptr) {
+    if (use_tile && tile_mom) {
+        ProfScope ps(ctx, PROF_SORT_SCAN);
+        int r = launch_tile_moments(ctx, pv, nc, W, S, B);
+        if (r) return r;
+    } else if (B.P != nullptr) {
         ProfScope ps(ctx, PROF_SORT_SCAN);
         k_band_combine<W><<<grid_for(nc, 128, 16), 128, 0, st>>>(B.P, S.M, B.E.cntB, B.E.cntA, B.seg_lo, B.seg_n, S.start, pv->cur, pv->alt, nc,
                                                                B.pcache, S.flags);
@@ -1491,8 +1592,15 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
     B.pcache = (double*)ctx_scratch(ctx, 10, (size_t)nc * 6 * 8);
     if (!B.pcache) return MB_ERR_CUDA;
     // the band path caches the cell moments only for narrow bands (most of a cell stays: the few movers are re-read by k_band_combine)
-    const bool band_moments = try_band && w <= 2;
-    if (band_moments) {
+    // pass B as a tile kernel (mb_sort_tile.cuh) when the mean cell population suits the tile size; it caches the moments for every band width
+    bool use_tile = false;
+    if (try_band) {
+        const int tm = tile_mode();
+        const int64_t avg = (pia->n_bound[s] > 0 ? pia->n_bound[s] : cap) / (nc > 0 ? nc : 1);
+        use_tile = tm >= 2 || (tm == 1 && avg >= 24 && avg <= tile_ncap(tile_cfg()) / 2);
+    }
+    const bool band_moments = try_band && (w <= 2 || use_tile);
+    if (band_moments && !use_tile) {
         B.P = (double*)ctx_scratch(ctx, 11, (size_t)nc * 5 * 8);
         if (!B.P) return MB_ERR_CUDA;
     }
@@ -1531,11 +1639,11 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
     else if (!try_seg) k_set_flag<<<1, 1, 0, st>>>(ctx->d_flags, 2, try_band ? 0 : 1);
     if (!try_seg) MB_LAUNCH_CHECK(ctx);
     if (try_band) {
-        if (w == 1) r = launch_band<3>(ctx, grid, pv, pia, species, S, B, cls_cached);
-        else if (w == 2) r = launch_band<5>(ctx, grid, pv, pia, species, S, B, cls_cached);
-        else if (w == 4) r = launch_band<9>(ctx, grid, pv, pia, species, S, B, cls_cached);
-        else if (w == 8) r = launch_band<17>(ctx, grid, pv, pia, species, S, B, cls_cached);
-        else r = launch_band<31>(ctx, grid, pv, pia, species, S, B, cls_cached);
+        if (w == 1) r = launch_band<3>(ctx, grid, pv, pia, species, S, B, cls_cached, use_tile, band_moments);
+        else if (w == 2) r = launch_band<5>(ctx, grid, pv, pia, species, S, B, cls_cached, use_tile, band_moments);
+        else if (w == 4) r = launch_band<9>(ctx, grid, pv, pia, species, S, B, cls_cached, use_tile, band_moments);
+        else if (w == 8) r = launch_band<17>(ctx, grid, pv, pia, species, S, B, cls_cached, use_tile, band_moments);
+        else r = launch_band<31>(ctx, grid, pv, pia, species, S, B, cls_cached, use_tile, band_moments);
         if (r) return r;
     }
     // general path (every kernel returns immediately unless flags[2] != 0)

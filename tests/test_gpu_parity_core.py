@@ -806,6 +806,67 @@ def test_cached_moments_meet_1e12(mb, oracle, ctx, w):
         ctx.set_band_halfwidth(2)
 
 
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("n_cells,ppc,w", [(64, 1000, 2), (300, 250, 15), (500, 100, 4), (40, 3000, 1), (900, 9, 2), (7, 5000, 8), (257, 333, 1)])
+def test_sort_tile_pass_b(mb, oracle, ctx, cfg, n_cells, ppc, w):
+    """Pass B of the band sort as the tile kernel (TMA slices of consecutive old cells, permutation in shared memory, coalesced runs;
+    mb_sort_tile.cuh) in every compiled shape: the bit-exact stable counting sort of grid_sorting.jl:58-113 and the cached moments at
+    1e-12 for every band width -- tiles of a few big cells, of dozens of small ones (more than a tile's table holds: scattered
+    directly), cells that do not fit a tile at all, a few outliers (hybrid extras) and empty cells."""
+    import os
+    rng = np.random.default_rng(7000 + 13 * cfg + n_cells)
+    L = n_cells * 1e-5
+    n = n_cells * ppc
+    dx = L / n_cells
+    rows = maxwellian_rows(rng, n, L, vw=True)
+    rows[:, 1:4] += np.array([500.0, -500.0, 500.0])
+    if n_cells > 20:
+        lo, hi = 5 * dx, 8 * dx   # three empty cells
+        inside = (rows[:, 4] >= lo) & (rows[:, 4] < hi)
+        rows[inside, 4] = rng.uniform(10 * dx, 12 * dx, int(inside.sum()))
+    opv, opia = oracle_state(oracle, rows, n_cells)
+    pv, pia = mirror_to_device(mb, ctx, opv, opia)
+    g = mb.Grid1DUniform(L, n_cells)
+    pp = mb.PhysProps(n_cells, 1, ctx=ctx)
+    ctx.set_band_halfwidth(w)
+    old = {k: os.environ.get(k) for k in ("MB_SORT_TILE", "MB_TILE_CFG")}
+    os.environ["MB_SORT_TILE"] = "2"
+    os.environ["MB_TILE_CFG"] = str(cfg)
+    try:
+        mb.sort_particles(None, g, pv, pia, 1)
+        oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+        for step in range(4):
+            cur = opv.logical(1, n)
+            sig = (0.35 if step % 2 else 0.1) * w * dx
+            cur[:, 4] = np.clip(cur[:, 4] + rng.normal(0, sig, n).clip(-0.95 * w * dx, 0.95 * w * dx), 1e-12, L - 1e-12)
+            if step == 2:
+                cur[::701, 4] = rng.uniform(1e-12, L - 1e-12, len(cur[::701]))  # a few extras
+            opv.set_logical(1, cur)
+            pv.set_logical(1, cur)
+            mb.sort_particles(None, g, pv, pia, 1)
+            oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
+            assert ctx.sort_last_path == 1
+            assert_same_pia(opia, pia)
+            np.testing.assert_array_equal(pv.logical(1, n), opv.logical(1, n))
+            assert pia.check(1) == (True, 0)
+            l0 = ctx.kernel_launches
+            mb.compute_props_sorted([pv], pia, [AR], pp)
+            if ppc <= 2048:  # (above that the general path does not fill the cache, and its stand-by kernels are launched as stubs)
+                assert ctx.kernel_launches - l0 == 1  # the cached kernel only
+            d, o = pp.download(), oracle.compute_props_sorted([opv], opia, [AR])
+            np.testing.assert_array_equal(d["np"], o.np)
+            np.testing.assert_allclose(d["n"], o.n, rtol=1e-13)
+            np.testing.assert_allclose(d["v"], o.v, rtol=1e-12, atol=1e-12 * 500)
+            np.testing.assert_allclose(d["T"], o.T, rtol=1e-12, atol=1e-10)  # (atol: a cell of one particle has T = 0 up to round-off)
+    finally:
+        ctx.set_band_halfwidth(2)
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 # --------------------------------------------------------------------------------------- fused convect + band classification
 @pytest.mark.parametrize("n_cells,ppc,w,dt_mult,acc", [(40, 300, 2, 4, 1.0), (6, 3000, 1, 2, 0.5), (64, 50, 4, 12, 1.0), (3, 700, 8, 30, 0.0),
                                                         (200, 7, 2, 4, 1.0), (64, 50, 1, 24, 1.0), (300, 40, 15, 100, 0.7)])
@@ -832,8 +893,9 @@ def test_convect_then_sort_uses_cached_classification(mb, oracle, ctx, n_cells, 
             assert_same_pia(opia, pia)
             assert_rows_close(pv.logical(1, n), opv.logical(1, n), 1e-12, f"fused convect+sort step {t}")
         assert paths.count(1) == len(paths), paths  # outliers (dt_mult 24 with w = 1: every fifth particle) no longer leave the band path
-        # clear + convect_band | flag, classify stub, 3 scan, scatter, 3 extras, combine (narrow bands), 8 general-path stubs
-        assert launches == (20 if w <= 2 else 19), launches
+        # clear + convect_band | flag, classify stub, 3 scan, scatter, 3 extras, combine (narrow bands), 8 general-path stubs;
+        # with the tile pass B (cells of 24 .. 2048 particles): 3 tile-setup kernels + the tile kernel, combine + its fallback stub
+        assert launches == (24 if 24 <= ppc <= 2048 else (20 if w <= 2 else 19)), launches
         if (w, dt_mult) == (1, 24):
             assert ctx.sort_last_extras > n // 20
     finally:
