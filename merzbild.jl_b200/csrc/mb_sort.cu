@@ -1346,7 +1346,8 @@ int convect_band_launch(mb_ctx* ctx, const ConvectArgs& a, const mb_grid1d* grid
 
 
 // ---- tile pass B (mb_sort_tile.cuh)
-// MB_SORT_TILE: 0 never, 1 (default) when the mean cell population suits the tile size, 2 always (tests of the direct mode)
+// MB_SORT_TILE: 0 never, 1 (default) for bands of w >= 4 when the mean cell population suits the tile size, 3 the same for every w,
+// 2 always (tests of the direct mode)
 static int tile_mode() {
     const char* e = getenv("MB_SORT_TILE");
     return e ? atoi(e) : 1;
@@ -1355,7 +1356,7 @@ static int tile_mode() {
 // 0 = 2048 / 256 / 1024 x 4, 1 = 4096 / 512 / 1024 x 8, 2 = 4096 / 512 / 2048 x 4, 3 = 4096 / 512 / 4096 x 2, 4 = 4096 / 256 / 1024 x 8
 static int tile_cfg() {
     const char* e = getenv("MB_TILE_CFG");
-    return e ? atoi(e) : 1;
+    return e ? atoi(e) : 2;
 }
 static int tile_ncap(int cfg) { return cfg == 0 ? 2048 : 4096; }
 template <int NCAP, int NT, int SUB, int S, int MINB>
@@ -1597,7 +1598,8 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
     if (try_band) {
         const int tm = tile_mode();
         const int64_t avg = (pia->n_bound[s] > 0 ? pia->n_bound[s] : cap) / (nc > 0 ? nc : 1);
-        use_tile = tm >= 2 || (tm == 1 && avg >= 24 && avg <= tile_ncap(tile_cfg()) / 2);
+        // measured (profiles/README.md): at w <= 2 (95 % of a cell stays) the warp-per-cell scatter is faster, from w = 4 on the tile kernel
+        use_tile = tm == 2 || ((tm == 3 || (tm == 1 && w >= 4)) && avg >= 24 && avg <= tile_ncap(tile_cfg()) / 2);
     }
     const bool band_moments = try_band && (w <= 2 || use_tile);
     if (band_moments && !use_tile) {

@@ -35,6 +35,7 @@ constexpr int TL_WMAX = 31;     // widest band
 constexpr int TL_NRMAX = TL_CMAX + TL_WMAX - 1;  // runs (destination cells) per tile
 constexpr int TL_LOS = 32;      // row stride of LO
 constexpr int TL_PIECE = 128;   // elements of a run one warp reduces at a time
+constexpr int TL_BULK_MIN = 192;  // shortest segment that leaves as a bulk store
 enum { F_MOM_BAD = 5 };         // ctx->d_flags slot: a tile was scattered directly, its moments are missing
 
 // ---- PTX helpers (sm_100a): mbarrier + 1-D bulk copy
@@ -67,6 +68,12 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                  "r"(tl_smem(bar))
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_1d(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(tl_smem(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 template <int NTHREADS>
 __device__ __forceinline__ void tl_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 
@@ -181,23 +188,29 @@ template <int NCAP, int SUB, int S, bool MOM>
 struct TileSmem {
     static constexpr int NB = MOM ? 3 : 2;                                    // output-order buffers (MOM: B0 keeps w until vz is through)
     static constexpr int A_BYTES = (SUB + 4) * 8;                             // one stage: SUB particles of a field slice (16-byte granular)
+    static constexpr int B_ELEMS = NCAP + 2 * TL_NRMAX + 4;                   // + parity padding (at most two elements per run)
+    static constexpr int B_BYTES = (B_ELEMS * 8 + 15) / 16 * 16;
     static constexpr int UMAX = NCAP / TL_PIECE + TL_NRMAX;                   // moment units (run, piece)
+    static constexpr int RQ = ((TL_NRMAX + 1) * 4 + 15) / 16 * 16;            // an int32 [NRMAX + 1] array
     // one table buffer
-    static constexpr int T_HDR = 0;                                           // ints: mode ncell n ntot NR ca nunits pad | int64 p0 kappa
-    static constexpr int T_SEGB = 64;                                         // int32 [CMAX + 1]
-    static constexpr int T_LP = T_SEGB + ((TL_CMAX + 1) * 4 + 15) / 16 * 16;   // int32 [NRMAX + 1] local prefix of the run sizes
-    static constexpr int T_UST = T_LP + ((TL_NRMAX + 1) * 4 + 15) / 16 * 16;   // int32 [NRMAX + 1] first unit of a run
-    static constexpr int T_DELTA = T_UST + ((TL_NRMAX + 1) * 4 + 15) / 16 * 16;  // int64 [NRMAX] global position of the run - local prefix
-    static constexpr int T_K = T_DELTA + TL_NRMAX * 8;                        // double [NRMAX][3] shifts
+    static constexpr int T_HDR = 0;                                           // ints: mode ncell n nseg NR ca nunits pad | int64 p0 kappa
+    static constexpr int T_SEGB = 64;                                         // int32 [CMAX + 1] cell boundaries relative to p0
+    static constexpr int T_LP = T_SEGB + ((TL_CMAX + 1) * 4 + 15) / 16 * 16;   // int32 [NRMAX + 1] local start of a run (parity padded)
+    static constexpr int T_R = T_LP + RQ;                                     // int32 [NRMAX] run sizes
+    static constexpr int T_UST = T_R + RQ;                                    // int32 [NRMAX + 1] first moment unit of a run
+    static constexpr int T_SL = T_UST + RQ;                                   // int32 [NRMAX] segment: local start
+    static constexpr int T_SN = T_SL + RQ;                                    // int32 [NRMAX] segment: elements
+    static constexpr int T_SG = T_SN + RQ;                                    // int64 [NRMAX] segment: global start
+    static constexpr int T_G = T_SG + TL_NRMAX * 8;                           // int64 [NRMAX] global start of a run
+    static constexpr int T_K = T_G + TL_NRMAX * 8;                            // double [NRMAX][3] shifts
     static constexpr int T_LO = T_K + (MOM ? TL_NRMAX * 24 : 0);              // uint16 [CMAX][32]
-    static constexpr int T_RID = T_LO + TL_CMAX * TL_LOS * 2;                 // uint8 [NCAP] run of local output index l
-    static constexpr int T_URUN = T_RID + NCAP;                               // uint8 [UMAX] run of a unit
+    static constexpr int T_URUN = T_LO + TL_CMAX * TL_LOS * 2;                // uint8 [UMAX] run of a unit
     static constexpr int T_COF = T_URUN + (MOM ? UMAX : 0);                   // uint8 [NCAP / 32] cell of position 32 i
     static constexpr int T_BYTES = (T_COF + NCAP / 32 + 15) / 16 * 16;
     // whole CTA
     static constexpr int O_A = 0;
     static constexpr int O_B = O_A + S * A_BYTES;
-    static constexpr int O_T = O_B + NB * NCAP * 8;
+    static constexpr int O_T = O_B + NB * B_BYTES;
     static constexpr int O_PP = O_T + 2 * T_BYTES;                            // double [UMAX][7]
     static constexpr int O_BAR = O_PP + (MOM ? UMAX * 56 : 0);                // full[S] empty[S] tfull[2] tempty[2]
     static constexpr int O_OFF = O_BAR + (2 * S + 4) * 8;                     // int64 [32] direct mode: group offsets
@@ -319,25 +332,35 @@ __global__ void __launch_bounds__(NT + 64, MINB) k_band_tile(TileArgs a) {
     if (warp == NCW) {
         // ------------------------------------------------------------------ table warp
         uint32_t it = 0;
+        const bool tdbg = a.debug && blockIdx.x == 0 && lane == 0;
+        long long tw_wait = 0, tw_load = 0, tw_rg = 0, tw_serial = 0, tw_lo = 0, tq = 0;
         for (int64_t kap = blockIdx.x; kap < NK; kap += gridDim.x) {
+            // (the consumers learn everything about a tile from its table buffer, also that there is nothing to do: no global loads,
+            // no load latency on their side)
             const int64_t ca = a.chunk_first[kap], cb = a.chunk_first[kap + 1];
-            if (cb <= ca) continue;
-            const int64_t p0 = a.old_start[ca];
-            const int64_t n = a.old_start[cb] - p0;
-            if (n == 0) continue;
+            const int64_t p0 = cb > ca ? a.old_start[ca] : 0;
+            const int64_t n = cb > ca ? a.old_start[cb] - p0 : 0;
             const int tb = it & 1;
+            if (tdbg) tq = clock64();
             mbar_wait(tempty + tb, ((it >> 1) & 1) ^ 1);
+            if (tdbg) { const long long t1 = clock64(); tw_wait += t1 - tq; tq = t1; }
             unsigned char* T = sm + L::O_T + tb * L::T_BYTES;
             int* hdr = (int*)(T + L::T_HDR);
             const int ncell = (int)(cb - ca);
             const bool direct = n > NCAP || ncell > TL_CMAX;
-            if (direct) {
+            if (n == 0) {
+                if (lane == 0) hdr[0] = 2;  // empty tile
+            } else if (direct) {
                 if (lane == 0) { hdr[0] = 1; hdr[1] = ncell; hdr[5] = (int)ca; }
             } else {
                 int* segb = (int*)(T + L::T_SEGB);
                 int* Lp = (int*)(T + L::T_LP);
+                int* Rs = (int*)(T + L::T_R);
                 int* ust = (int*)(T + L::T_UST);
-                int64_t* delta = (int64_t*)(T + L::T_DELTA);
+                int* seg_l = (int*)(T + L::T_SL);
+                int* seg_n = (int*)(T + L::T_SN);
+                int64_t* seg_g = (int64_t*)(T + L::T_SG);
+                int64_t* Gs = (int64_t*)(T + L::T_G);
                 double* Ksh = (double*)(T + L::T_K);
                 uint16_t* LO = (uint16_t*)(T + L::T_LO);
                 uint8_t* urun = (uint8_t*)(T + L::T_URUN);
@@ -348,21 +371,22 @@ __global__ void __launch_bounds__(NT + 64, MINB) k_band_tile(TileArgs a) {
                 // the extras in front, and the first particle of the old cell (the moments' shift)
                 const int64_t c_lo = ca - 2 * w;
                 const int mtot = NR * W;
-                for (int t = lane; t < mtot; t += 32) Msm[t] = c_lo + t / W >= 0 ? a.M[c_lo * W + t] : 0;
-                for (int i = lane; i <= ncell; i += 32) segb[i] = (int)(a.old_start[ca + i] - p0);
-                __syncwarp();
-                {   // cell of every 32nd position: the last cell that starts at or before it
-                    uint8_t* cof = (uint8_t*)(T + L::T_COF);
-                    for (int i = lane; i < (int)((n + 31) >> 5); i += 32) {
-                        const int pos = i << 5;
-                        int lo_ = 0, hi_ = ncell;
-                        while (hi_ - lo_ > 1) {
-                            const int mid = (lo_ + hi_) >> 1;
-                            if (segb[mid] <= pos) lo_ = mid; else hi_ = mid;
+                {
+                    const int tneg = c_lo < 0 ? (int)(-c_lo) * W : 0;  // rows of cells < 0 (the first tiles): zeros
+                    const int32_t* __restrict__ Mg = a.M + c_lo * W;
+                    for (int t0 = lane; t0 < mtot; t0 += 32 * 8) {
+                        int mv[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const int t = t0 + 32 * u;
+                            mv[u] = (t < mtot && t >= tneg) ? Mg[t] : 0;
                         }
-                        cof[i] = (uint8_t)lo_;
+#pragma unroll
+                        for (int u = 0; u < 8; u++)
+                            if (t0 + 32 * u < mtot) Msm[t0 + 32 * u] = mv[u];
                     }
                 }
+                for (int i = lane; i <= ncell; i += 32) segb[i] = (int)(a.old_start[ca + i] - p0);
                 constexpr int RR = (TL_NRMAX + 31) / 32;  // rounds of 32 runs
                 int64_t gst[RR], f0[RR];
                 bool rv[RR], hasp[RR];
@@ -387,59 +411,144 @@ __global__ void __launch_bounds__(NT + 64, MINB) k_band_tile(TileArgs a) {
                     }
                 }
                 __syncwarp();
-                // run sizes, local prefix, first unit; row i of Msm = cell c_lo + i, the tile's cells are rows 2w .. 2w + ncell - 1
-                int carry = 0, ucarry = 0;
+                if (tdbg) { const long long t1 = clock64(); tw_load += t1 - tq; tq = t1; }
+                {   // cell of every 32nd position: the last cell that starts at or before it
+                    uint8_t* cof = (uint8_t*)(T + L::T_COF);
+                    for (int i = lane; i < (int)((n + 31) >> 5); i += 32) {
+                        const int pos = i << 5;
+                        int lo_ = 0, hi_ = ncell;
+                        while (hi_ - lo_ > 1) {
+                            const int mid = (lo_ + hi_) >> 1;
+                            if (segb[mid] <= pos) lo_ = mid; else hi_ = mid;
+                        }
+                        cof[i] = (uint8_t)lo_;
+                    }
+                }
+                // run sizes and global starts; row i of Msm = cell c_lo + i, the tile's cells are rows 2w .. 2w + ncell - 1
+                int Rv[RR];
+                int64_t Gv[RR];
 #pragma unroll
                 for (int i = 0; i < RR; i++) {
-                    if (32 * i >= NR) break;  // warp-uniform
                     const int r = lane + 32 * i;
-                    // sources of run r inside the tile: cells max(ca, cd - w) .. min(cb - 1, cd + w)  ->  rows
-                    const int row_cd = r + w;  // row index of the destination cell itself (cd - c_lo)
-                    const int t0 = row_cd - w > 2 * w ? row_cd - w : 2 * w, t1 = row_cd + w < 2 * w + ncell - 1 ? row_cd + w : 2 * w + ncell - 1;
                     int R = 0;
-                    if (rv[i])
+                    int64_t G = gst[i];
+                    if (r < NR && rv[i]) {
+                        const int row_cd = r + w;  // row of the destination cell itself
+                        const int t0 = row_cd - w > 2 * w ? row_cd - w : 2 * w, t1 = row_cd + w < 2 * w + ncell - 1 ? row_cd + w : 2 * w + ncell - 1;
                         for (int row = t0; row <= t1; row++) R += Msm[row * W + (row_cd - row + w)];
-                    const int U = (R + TL_PIECE - 1) / TL_PIECE;
-                    int incl = R, uincl = U;
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int t = __shfl_up_sync(0xffffffffu, incl, o), tu = __shfl_up_sync(0xffffffffu, uincl, o);
-                        if (lane >= o) { incl += t; uincl += tu; }
+                        const int e0 = row_cd - w > 0 ? row_cd - w : 0;  // sources in earlier tiles: rows e0 .. 2w - 1
+                        for (int row = e0; row < 2 * w; row++) G += Msm[row * W + (row_cd - row + w)];
                     }
-                    if (r < NR) {
-                        const int lp = carry + incl - R;
-                        Lp[r] = lp;
-                        int64_t G = gst[i];
-                        if (rv[i]) {
-                            const int e0 = row_cd - w > 0 ? row_cd - w : 0;  // sources in earlier tiles: rows e0 .. 2w - 1
-                            for (int row = e0; row < 2 * w; row++) G += Msm[row * W + (row_cd - row + w)];
-                            int acc = lp;
-                            for (int row = t0; row <= t1; row++) {
-                                LO[(row - 2 * w) * TL_LOS + (row_cd - row + w)] = (uint16_t)acc;
-                                acc += Msm[row * W + (row_cd - row + w)];
-                            }
+                    Rv[i] = R;
+                    Gv[i] = G;
+                    if (r < NR) Rs[r] = R;
+                }
+                if (tdbg) { const long long t1 = clock64(); tw_rg += t1 - tq; tq = t1; }
+                // The local layout (output order).  Runs that are neighbours in global memory stay neighbours (one SEGMENT = one bulk
+                // store per field); a run starts at a local index of the same parity as its global start, so that the 16-byte aligned
+                // middle of a segment is 16-byte aligned in shared memory too:  Lp(r) = E(r) + pad(r),  E = exclusive prefix of the run
+                // sizes,  pad(r) = 2 (number of parity changes among the non-empty runs up to r) + b(r),  b(r) = (G(r) - E(r)) & 1.
+                // pad never decreases, and neighbours in global memory have the same b, hence the same pad.  All with warp scans.
+                int Lv[RR];
+                {
+                    const unsigned le = 0xffffffffu >> (31 - lane);  // lanes <= this one
+                    int cE = 0, cK = 0, cS = 0, cU = 0, cB = -1;     // carries: prefix of R, parity changes, segments, units, last parity
+                    int64_t cGend = -1;
+#pragma unroll
+                    for (int i = 0; i < RR; i++) {
+                        if (32 * i >= NR) break;  // warp-uniform
+                        const int r = lane + 32 * i;
+                        const int R = Rv[i];
+                        int incl = R;
+                        const int U = MOM ? (R + TL_PIECE - 1) / TL_PIECE : 0;
+                        int uincl = U;
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int t = __shfl_up_sync(0xffffffffu, incl, o), tu = __shfl_up_sync(0xffffffffu, uincl, o);
+                            if (lane >= o) { incl += t; uincl += tu; }
                         }
-                        delta[r] = G - lp;
-                        if (MOM) {
-                            const int u0 = ucarry + uincl - U;
+                        const int E = cE + incl - R;
+                        const int b = (int)((Gv[i] - E) & 1);
+                        const int64_t gend = Gv[i] + R;
+                        const unsigned ne = __ballot_sync(0xffffffffu, R > 0);
+                        const unsigned lower = ne & (le >> 1);           // non-empty runs in lower lanes
+                        const int src = lower ? 31 - __clz(lower) : 0;
+                        const int64_t gend_s = __shfl_sync(0xffffffffu, gend, src);
+                        const int b_s = __shfl_sync(0xffffffffu, b, src);
+                        const int64_t gprev = lower ? gend_s : cGend;
+                        const int bprev = lower ? b_s : cB;
+                        const bool segstart = R > 0 && Gv[i] != gprev;
+                        const bool change = R > 0 && bprev >= 0 && b != bprev;
+                        const unsigned mch = __ballot_sync(0xffffffffu, change), mss = __ballot_sync(0xffffffffu, segstart);
+                        const int kc = cK + __popc(mch & le);
+                        // an empty run takes the parity of the last non-empty run before it (it only needs a valid slot)
+                        const int lp = E + 2 * kc + (R > 0 ? b : (bprev >= 0 ? bprev : 0));
+                        Lv[i] = lp;
+                        if (r < NR) Lp[r] = lp;
+                        if (segstart) {
+                            const int si = cS + __popc(mss & le) - 1;
+                            seg_l[si] = lp; seg_g[si] = Gv[i]; seg_n[si] = E;  // (E for now: the sizes follow from the next segment's E)
+                        }
+                        if (MOM && r < NR) {
+                            const int u0 = cU + uincl - U;
                             ust[r] = u0;
                             for (int k = 0; k < U; k++) urun[u0 + k] = (uint8_t)r;
                         }
+                        cE += __shfl_sync(0xffffffffu, incl, 31);
+                        cU += __shfl_sync(0xffffffffu, uincl, 31);
+                        cK += __popc(mch);
+                        cS += __popc(mss);
+                        if (ne) {
+                            const int last = 31 - __clz(ne);
+                            cGend = __shfl_sync(0xffffffffu, gend, last);
+                            cB = __shfl_sync(0xffffffffu, b, last);
+                        }
                     }
-                    carry += __shfl_sync(0xffffffffu, incl, 31);
-                    ucarry += __shfl_sync(0xffffffffu, uincl, 31);
+                    __syncwarp();
+                    int e0v[RR], e1v[RR];
+#pragma unroll
+                    for (int i = 0; i < RR; i++) {
+                        const int si = lane + 32 * i;
+                        e0v[i] = si < cS ? seg_n[si] : 0;
+                        e1v[i] = si + 1 < cS ? seg_n[si + 1] : cE;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < RR; i++) {
+                        const int si = lane + 32 * i;
+                        if (si < cS) seg_n[si] = e1v[i] - e0v[i];
+                    }
+                    if (lane == 0) {
+                        if (MOM) ust[NR] = cU;
+                        hdr[0] = 0; hdr[1] = ncell; hdr[2] = (int)n; hdr[3] = cS; hdr[4] = NR; hdr[5] = (int)ca; hdr[6] = cU;
+                        *(int64_t*)(hdr + 8) = p0;
+                        *(int64_t*)(hdr + 10) = kap;
+                    }
                 }
-                if (lane == 0) {
-                    Lp[NR] = carry;
-                    if (MOM) ust[NR] = ucarry;
-                    hdr[0] = 0; hdr[1] = ncell; hdr[2] = (int)n; hdr[3] = carry; hdr[4] = NR; hdr[5] = (int)ca; hdr[6] = ucarry;
-                    *(int64_t*)(hdr + 8) = p0;
-                    *(int64_t*)(hdr + 10) = kap;
+                __syncwarp();
+                if (tdbg) { const long long t1 = clock64(); tw_serial += t1 - tq; tq = t1; }
+                // local offset of every (source cell, destination) group
+#pragma unroll
+                for (int i = 0; i < RR; i++) {
+                    const int r = lane + 32 * i;
+                    if (r < NR && rv[i]) {
+                        const int row_cd = r + w;
+                        const int t0 = row_cd - w > 2 * w ? row_cd - w : 2 * w, t1 = row_cd + w < 2 * w + ncell - 1 ? row_cd + w : 2 * w + ncell - 1;
+                        int acc = Lv[i];
+                        for (int row = t0; row <= t1; row++) {
+                            LO[(row - 2 * w) * TL_LOS + (row_cd - row + w)] = (uint16_t)acc;
+                            acc += Msm[row * W + (row_cd - row + w)];
+                        }
+                    }
                 }
             }
             __syncwarp();
+            if (tdbg) { const long long t1 = clock64(); tw_lo += t1 - tq; tq = t1; }
             if (lane == 0) mbar_arrive(tfull + tb);
             it++;
         }
+        if (tdbg)
+            printf("k_band_tile CTA 0 table warp: %u tiles; waiting for a free buffer %lld, loads %lld, cof + run sizes %lld, layout (lane 0) %lld, LO %lld cycles\n", it,
+                   tw_wait, tw_load, tw_rg, tw_serial, tw_lo);
         return;
     }
 
@@ -447,36 +556,37 @@ __global__ void __launch_bounds__(NT + 64, MINB) k_band_tile(TileArgs a) {
     uint32_t q = 0, it = 0, bsel = 0;
     long long t_tab = 0, t_full = 0, t_bar = 0, t_all = clock64(), tt = 0;
     const bool dbg = a.debug && blockIdx.x == 0 && tid == 0;
-    double* Bbase = (double*)(sm + L::O_B);
+    const double* Bbase = (const double*)(sm + L::O_B);
     double* pp = (double*)(sm + L::O_PP);
     for (int64_t kap = blockIdx.x; kap < NK; kap += gridDim.x) {
-        const int64_t ca64 = a.chunk_first[kap], cb64 = a.chunk_first[kap + 1];
-        if (cb64 <= ca64) continue;
-        if (a.old_start[cb64] == a.old_start[ca64]) continue;
         const int tb = it & 1;
         if (dbg) tt = clock64();
         mbar_wait(tfull + tb, (it >> 1) & 1);
         if (dbg) t_tab += clock64() - tt;
         unsigned char* T = sm + L::O_T + tb * L::T_BYTES;
         const int* hdr = (const int*)(T + L::T_HDR);
-        if (hdr[0] != 0) {  // direct
-            tile_direct<NT>(a, ca64, cb64, (int64_t*)(sm + L::O_OFF), tid);
-            if (MOM && tid == 0) a.flags[F_MOM_BAD] = 1;
+        if (hdr[0] != 0) {  // empty (2) or direct (1)
+            if (hdr[0] == 1) {
+                tile_direct<NT>(a, hdr[5], (int64_t)hdr[5] + hdr[1], (int64_t*)(sm + L::O_OFF), tid);
+                if (MOM && tid == 0) a.flags[F_MOM_BAD] = 1;
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty + tb);
             it++;
             continue;
         }
-        const int n = hdr[2], ntot = hdr[3], NR = hdr[4], nunits = hdr[6];
+        const int n = hdr[2], nseg = hdr[3], NR = hdr[4], nunits = hdr[6];
         const int64_t p0 = *(const int64_t*)(hdr + 8);
         const int* segb = (const int*)(T + L::T_SEGB);
         const int* Lp = (const int*)(T + L::T_LP);
+        const int* Rs = (const int*)(T + L::T_R);
         const int* ust = (const int*)(T + L::T_UST);
-        const int64_t* delta = (const int64_t*)(T + L::T_DELTA);
         const double* Ksh = (const double*)(T + L::T_K);
         const uint16_t* LO = (const uint16_t*)(T + L::T_LO);
-        uint8_t* rid = (uint8_t*)(T + L::T_RID);
         const uint8_t* urun = (const uint8_t*)(T + L::T_URUN);
+        const int64_t* seg_g = (const int64_t*)(T + L::T_SG);
+        const int* seg_l = (const int*)(T + L::T_SL);
+        const int* seg_n = (const int*)(T + L::T_SN);
         const uint8_t* cof = (const uint8_t*)(T + L::T_COF);
         // ---- dr: local output index of every particle
         int li[PPT];
@@ -511,11 +621,7 @@ __global__ void __launch_bounds__(NT + 64, MINB) k_band_tile(TileArgs a) {
                 for (int kk = 0; kk < KPS; kk++) {
                     const int k = m * KPS + kk;
                     li[k] = -1;
-                    if (v[kk] != 0xFFFFFFFFu) {
-                        const int l = lo16[kk] + (int)(v[kk] & 0xFFFFFFu);
-                        li[k] = l;
-                        rid[l] = (uint8_t)(cc[kk] + (int)(v[kk] >> 24));
-                    }
+                    if (v[kk] != 0xFFFFFFFFu) li[k] = lo16[kk] + (int)(v[kk] & 0xFFFFFFu);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty + s);
@@ -525,7 +631,6 @@ __global__ void __launch_bounds__(NT + 64, MINB) k_band_tile(TileArgs a) {
                 for (int kk = 0; kk < KPS; kk++) li[m * KPS + kk] = -1;
             }
         }
-        int64_t gpos[PPT];  // global position of output element tid + k NT (known after the first barrier)
         const int sh = (int)(p0 & 1);
 #pragma unroll 1
         for (int f = 0; f < 7; f++) {
@@ -533,7 +638,7 @@ __global__ void __launch_bounds__(NT + 64, MINB) k_band_tile(TileArgs a) {
             int b;
             if (MOM) b = f == 0 ? 0 : (f <= 3 ? 1 + ((f - 1) & 1) : (f - 4) % 3);
             else { b = bsel & 1; bsel++; }
-            double* B = Bbase + (size_t)b * NCAP;
+            double* B = (double*)(sm + L::O_B + b * L::B_BYTES);
 #pragma unroll
             for (int m = 0; m < NSUB; m++) {
                 if (m * SUB < n) {
@@ -553,26 +658,20 @@ __global__ void __launch_bounds__(NT + 64, MINB) k_band_tile(TileArgs a) {
                     q++;
                 }
             }
+            // B is complete after the barrier; the copy engine reads it through the async proxy, and the buffer the NEXT field is
+            // permuted into must have been read by its previous bulk stores (issued a field or two ago)
+            fence_async_smem();
+            tma_store_wait_read();  // (every thread: the issuers of the previous tile may not be issuers of this one)
             if (dbg) tt = clock64();
             tl_consumer_sync<NT>();
             if (dbg) t_bar += clock64() - tt;
-            if (f == 0) {
-                int rr[PPT];
-#pragma unroll
-                for (int k = 0; k < PPT; k++) rr[k] = rid[min(tid + k * NT, ntot - 1)];
-#pragma unroll
-                for (int k = 0; k < PPT; k++) {
-                    const int l = tid + k * NT;
-                    gpos[k] = l < ntot ? delta[rr[k]] + l : -1;
-                }
-            }
             if (MOM && f >= 1 && f <= 3) {
                 // partial moments of component f over the units (run, piece): sum w, sum w c, sum w c^2
                 const double* Bw = Bbase;
                 for (int u = warp; u < nunits; u += NCW) {
                     const int r = urun[u];
                     const int l0 = Lp[r] + (u - ust[r]) * TL_PIECE;
-                    const int l1 = min(l0 + TL_PIECE, Lp[r + 1]);
+                    const int l1 = min(l0 + TL_PIECE, Lp[r] + Rs[r]);
                     const double K = Ksh[3 * r + (f - 1)];
                     double s0 = 0, s1 = 0, s2 = 0;
                     for (int l = l0 + lane; l < l1; l += 32) {
@@ -593,13 +692,25 @@ __global__ void __launch_bounds__(NT + 64, MINB) k_band_tile(TileArgs a) {
                 }
             }
             {
-                double v[PPT];
+                // write-out, a warp per segment: a long segment leaves as ONE bulk store (its 16-byte aligned middle; at most one element
+                // at either end is stored by hand), a short one lane by lane (consecutive lanes, consecutive addresses)
                 double* __restrict__ of = a.out.a[f];
-#pragma unroll
-                for (int k = 0; k < PPT; k++) v[k] = B[tid + k * NT];
-#pragma unroll
-                for (int k = 0; k < PPT; k++)
-                    if (gpos[k] >= 0) of[gpos[k]] = v[k];
+                for (int sgi = warp; sgi < nseg; sgi += NCW) {
+                    const int64_t g = seg_g[sgi];
+                    const int l = seg_l[sgi], ns = seg_n[sgi];
+                    if (ns >= TL_BULK_MIN) {
+                        if (lane == 0) {
+                            const int head = (int)(g & 1);
+                            const int nb = (ns - head) & ~1;
+                            if (head) of[g] = B[l];
+                            tma_store_1d(of + g + head, B + l + head, (uint32_t)nb * 8);
+                            if (ns - head - nb) of[g + ns - 1] = B[l + ns - 1];
+                            tma_store_commit();
+                        }
+                    } else {
+                        for (int e = lane; e < ns; e += 32) of[g + e] = B[l + e];
+                    }
+                }
             }
             if (MOM && f == 3) {
                 tl_consumer_sync<NT>();  // pp complete; B0 (w) may be overwritten by x afterwards
@@ -622,6 +733,7 @@ __global__ void __launch_bounds__(NT + 64, MINB) k_band_tile(TileArgs a) {
         if (lane == 0) mbar_arrive(tempty + tb);
         it++;
     }
+    tma_store_wait_read();  // the bulk stores read shared memory: it must outlive them
     if (dbg)
         printf("k_band_tile CTA 0: %u tiles, %lld cycles; waiting for tables %lld, for TMA stages %lld, at the field barrier %lld\n", it,
                clock64() - t_all, t_tab, t_full, t_bar);

@@ -895,7 +895,7 @@ def test_convect_then_sort_uses_cached_classification(mb, oracle, ctx, n_cells, 
         assert paths.count(1) == len(paths), paths  # outliers (dt_mult 24 with w = 1: every fifth particle) no longer leave the band path
         # clear + convect_band | flag, classify stub, 3 scan, scatter, 3 extras, combine (narrow bands), 8 general-path stubs;
         # with the tile pass B (cells of 24 .. 2048 particles): 3 tile-setup kernels + the tile kernel, combine + its fallback stub
-        assert launches == (24 if 24 <= ppc <= 2048 else (20 if w <= 2 else 19)), launches
+        assert launches == (24 if (24 <= ppc <= 2048 and w >= 4) else (20 if w <= 2 else 19)), launches
         if (w, dt_mult) == (1, 24):
             assert ctx.sort_last_extras > n // 20
     finally:
