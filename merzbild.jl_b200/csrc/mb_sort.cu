@@ -1353,7 +1353,7 @@ static int tile_mode() {
     return e ? atoi(e) : 1;
 }
 // MB_TILE_CFG selects the compiled shape (tile particles / consumer threads / particles per stage x stages):
-// 0 = 2048 / 256 / 1024 x 4, 1 = 4096 / 512 / 1024 x 8, 2 = 4096 / 512 / 2048 x 4, 3 = 4096 / 512 / 4096 x 2, 4 = 4096 / 256 / 1024 x 8
+// 0 = 2048 / 256 / 1024 x 4, 1 = 4096 / 512 / 1024 x 8, 2 = 4096 / 512 / 2048 x 4 (default), 3 = 4096 / 512 / 4096 x 2, 4 = 4096 / 512 / 1024 x 9
 static int tile_cfg() {
     const char* e = getenv("MB_TILE_CFG");
     return e ? atoi(e) : 2;
@@ -1421,7 +1421,7 @@ static int launch_tile_pass_b(mb_ctx* ctx, mb_pv* pv, int64_t nc, int W, const S
     if (cfg == 0) r = launch_tile_kernel<2048, 256, 1024, 4, 1>(ctx, a, mom);
     else if (cfg == 2) r = launch_tile_kernel<4096, 512, 2048, 4, 1>(ctx, a, mom);
     else if (cfg == 3) r = launch_tile_kernel<4096, 512, 4096, 2, 1>(ctx, a, mom);
-    else if (cfg == 4) r = launch_tile_kernel<4096, 256, 1024, 8, 1>(ctx, a, mom);
+    else if (cfg == 4) r = launch_tile_kernel<4096, 512, 1024, 9, 1>(ctx, a, mom);
     else r = launch_tile_kernel<4096, 512, 1024, 8, 1>(ctx, a, mom);
     if (r) return r;
     return MB_OK;
@@ -1601,7 +1601,7 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
         // measured (profiles/README.md): at w <= 2 (95 % of a cell stays) the warp-per-cell scatter is faster, from w = 4 on the tile kernel
         use_tile = tm == 2 || ((tm == 3 || (tm == 1 && w >= 4)) && avg >= 24 && avg <= tile_ncap(tile_cfg()) / 2);
     }
-    const bool band_moments = try_band && (w <= 2 || use_tile);
+    const bool band_moments = try_band && (w <= 2 || (use_tile && getenv("MB_TILE_NOMOM") == nullptr));  // (MB_TILE_NOMOM: experiment knob)
     if (band_moments && !use_tile) {
         B.P = (double*)ctx_scratch(ctx, 11, (size_t)nc * 5 * 8);
         if (!B.P) return MB_ERR_CUDA;

@@ -34,7 +34,7 @@ constexpr int TL_CMAX = 64;     // cells per tile
 constexpr int TL_WMAX = 31;     // widest band
 constexpr int TL_NRMAX = TL_CMAX + TL_WMAX - 1;  // runs (destination cells) per tile
 constexpr int TL_LOS = 32;      // row stride of LO
-constexpr int TL_PIECE = 128;   // elements of a run one warp reduces at a time
+constexpr int TL_PIECE = 16;    // elements of a run one thread sums (a "strip": strips never cross runs)
 constexpr int TL_BULK_MIN = 192;  // shortest segment that leaves as a bulk store
 enum { F_MOM_BAD = 5 };         // ctx->d_flags slot: a tile was scattered directly, its moments are missing
 
@@ -635,6 +635,8 @@ __global__ void __launch_bounds__(NT + 64, MINB) k_band_tile(TileArgs a) {
 #pragma unroll 1
         for (int f = 0; f < 7; f++) {
             // MOM: w stays in B0 while vx, vy, vz alternate between B1 and B2; x, y, z then rotate over all three
+            // (a fourth buffer -- all of w, v resident, one moments pass instead of three -- was measured: the shared memory it takes from
+            // the load stages costs more than the two passes it saves)
             int b;
             if (MOM) b = f == 0 ? 0 : (f <= 3 ? 1 + ((f - 1) & 1) : (f - 4) % 3);
             else { b = bsel & 1; bsel++; }
@@ -666,29 +668,28 @@ __global__ void __launch_bounds__(NT + 64, MINB) k_band_tile(TileArgs a) {
             tl_consumer_sync<NT>();
             if (dbg) t_bar += clock64() - tt;
             if (MOM && f >= 1 && f <= 3) {
-                // partial moments of component f over the units (run, piece): sum w, sum w c, sum w c^2
+                // partial moments of component f, a thread per strip of <= TL_PIECE consecutive elements of one run: sum w, sum w c,
+                // sum w c^2 (c = v - K(run)); no shuffles, every thread busy.  The lanes walk their strips rotated against each other
+                // (strips start TL_PIECE doubles apart: without the rotation all lanes of a wavefront would hit one bank).
                 const double* Bw = Bbase;
-                for (int u = warp; u < nunits; u += NCW) {
+                for (int u = tid; u < nunits; u += NT) {
                     const int r = urun[u];
                     const int l0 = Lp[r] + (u - ust[r]) * TL_PIECE;
                     const int l1 = min(l0 + TL_PIECE, Lp[r] + Rs[r]);
                     const double K = Ksh[3 * r + (f - 1)];
                     double s0 = 0, s1 = 0, s2 = 0;
-                    for (int l = l0 + lane; l < l1; l += 32) {
-                        const double pw = Bw[l], c = B[l] - K;
-                        s0 += pw; s1 += pw * c; s2 += pw * (c * c);
-                    }
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                    for (int k = 0; k < TL_PIECE; k++) {
+                        const int l = l0 + ((k + lane) & (TL_PIECE - 1));
+                        if (l < l1) {
+                            const double pw = Bw[l], c = B[l] - K;
+                            s0 += pw; s1 += pw * c; s2 += pw * (c * c);
+                        }
                     }
-                    if (lane == 0) {
-                        double* o_ = pp + u * 7;
-                        if (f == 1) o_[0] = s0;
-                        o_[f] = s1;
-                        o_[3 + f] = s2;
-                    }
+                    double* o_ = pp + u * 7;
+                    if (f == 1) o_[0] = s0;
+                    o_[f] = s1;
+                    o_[3 + f] = s2;
                 }
             }
             {
@@ -714,17 +715,42 @@ __global__ void __launch_bounds__(NT + 64, MINB) k_band_tile(TileArgs a) {
             }
             if (MOM && f == 3) {
                 tl_consumer_sync<NT>();  // pp complete; B0 (w) may be overwritten by x afterwards
+                // the strips of a run -> the run's sums, a warp per run: lanes stride over the strips, then ONE reduction of the seven values
+                // together (the lanes halve the set of values they carry in each of the first three steps: 9 shuffles instead of 35)
                 const int ca = hdr[5];
-                for (int r = tid; r < NR; r += NT) {
+                for (int r = warp; r < NR; r += NCW) {
                     const int u0 = ust[r], u1 = ust[r + 1];
-                    if (u1 > u0) {
-                        double an = 0, ax = 0, ay = 0, az = 0, qx = 0, qy = 0, qz = 0;
-                        for (int u = u0; u < u1; u++) {
-                            const double* o_ = pp + u * 7;
-                            an += o_[0]; ax += o_[1]; ay += o_[2]; az += o_[3]; qx += o_[4]; qy += o_[5]; qz += o_[6];
-                        }
+                    if (u1 <= u0) continue;  // warp-uniform
+                    double v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) v[i] = 0.0;
+                    for (int u = u0 + lane; u < u1; u += 32) {
+                        const double* o_ = pp + u * 7;
+#pragma unroll
+                        for (int i = 0; i < 7; i++) v[i] += o_[i];
+                    }
+                    double a4[4], a2[2];
+                    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const double recv = __shfl_xor_sync(0xffffffffu, h16 ? v[i] : v[i + 4], 16);
+                        a4[i] = (h16 ? v[i + 4] : v[i]) + recv;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        const double recv = __shfl_xor_sync(0xffffffffu, h8 ? a4[i] : a4[i + 2], 8);
+                        a2[i] = (h8 ? a4[i + 2] : a4[i]) + recv;
+                    }
+                    double c1 = (h4 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? a2[0] : a2[1], 4);
+                    c1 += __shfl_xor_sync(0xffffffffu, c1, 2);
+                    c1 += __shfl_xor_sync(0xffffffffu, c1, 1);
+                    // value i = 4 b16 + 2 b8 + b4 sits in the lanes with those bits
+                    double t[7];
+#pragma unroll
+                    for (int i = 0; i < 7; i++) t[i] = __shfl_sync(0xffffffffu, c1, ((i >> 2) & 1) * 16 + ((i >> 1) & 1) * 8 + (i & 1) * 4);
+                    if (lane == 0) {
                         double* P = a.Pp + ((int64_t)2 * w * kap + ca + r) * 5;
-                        P[0] = an; P[1] = ax; P[2] = ay; P[3] = az; P[4] = qx + qy + qz;
+                        P[0] = t[0]; P[1] = t[1]; P[2] = t[2]; P[3] = t[3]; P[4] = t[4] + t[5] + t[6];
                     }
                 }
             }
