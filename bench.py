@@ -365,7 +365,11 @@ def run_c3(env, args, scaling, steps, warmup, e2e_steps, band=None):
            "workload": "%s, %.3g particles/GPU, slab partition" % (S["name"], n), "scaling_rule": scaling}
     sc_ms, sc_n = sections.get("sort.scatter", (0.0, 0))
     if sort_path == 1 and sc_n:
-        res["dominant"] = ("k_band_scatter (sort_particles! pass B: stable scatter by source cell)", BYTES_SORT, sc_ms / sc_n)
+        if ctx.sort_last_pass_b == 1:
+            res["dominant"] = ("k_band_tile (sort_particles! pass B: a CTA per tile of cells, TMA bulk loads / stores, permutation in shared memory)", BYTES_SORT,
+                               sc_ms / sc_n)
+        else:
+            res["dominant"] = ("k_band_scatter (sort_particles! pass B: stable scatter by source cell)", BYTES_SORT, sc_ms / sc_n)
     else:
         g_ms, g_n = sections.get("sort.general", (0.0, 0))
         res["dominant"] = ("general sort path (classify, scan, index scatter, per-cell index sort, gather by cell)", BYTES_SORT, g_ms / max(g_n, 1))
@@ -788,7 +792,8 @@ def summary(res, peak, peak_src):
     k, bpp, ms = res["dominant"]
     out = {"workload": res["workload"], "value": res["value"], "unit": "particle-timesteps/s", "ms_per_step": res["ms_per_step"], "particles": res["particles"],
            "cells": res["cells"], "gpu_launches": res["launches"], "sections_ms_per_step": res["sections"], "mean_T_K": res.get("mean_T_K"),
-           "roofline": roofline_block(k, bpp, res["n_rank"], ms, peak, peak_src)}
+           "roofline": roofline_block(k, bpp, res["n_rank"], ms, peak, peak_src,
+                                      committed_traffic(k.split(" ")[0], res["n_rank"]) if k.startswith("k_band_") else None)}
     for key in ("sort_path", "band_halfwidth", "sort_extras_last_step", "sigma_v_dt_over_dx", "initial_merge", "weight_conservation", "merges_in_timed_steps",
                 "mean_M4", "scaling_rule"):
         if key in res:
@@ -846,7 +851,7 @@ def main():
         return
 
     kname, bpp, kms = res["dominant"]
-    traffic = committed_traffic("k_band_scatter", res["n_rank"]) if kname.startswith("k_band_scatter") else None
+    traffic = committed_traffic(kname.split(" ")[0], res["n_rank"]) if kname.startswith("k_band_") else None
     roofline = roofline_block(kname, bpp, res["n_rank"], kms, peak, peak_src, traffic)
     roofline["sections_ms_per_step"] = res["sections"]
     if args.config == "c3":

@@ -146,6 +146,9 @@ int mb_sort_last_path(mb_ctx* ctx);
 int mb_sort_set_band_halfwidth(mb_ctx* ctx, int32_t w);
 /* number of extras (band outliers + slab-exchange arrivals) the last band-path sort placed; -1 if the general path ran.  Synchronises. */
 int64_t mb_sort_last_extras(mb_ctx* ctx);
+/* pass B of the last band-path sort: 0 = a warp per old cell (k_band_scatter), 1 = a CTA per tile of cells with TMA bulk copies
+ * (k_band_tile; chosen for bands of w >= 4 and cells of 24 .. 2048 particles).  Same result, bit for bit. */
+int mb_sort_last_pass_b(mb_ctx* ctx);
 
 /* ---- squash_pia!(pv, pia, species) particles.jl:622-682; restore_particle_ordering! :1086-1137 (no-op on device) ---- */
 int mb_squash_pia(mb_ctx* ctx, mb_pv* pv, mb_pia* pia, int64_t species);

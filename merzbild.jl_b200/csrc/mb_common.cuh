@@ -109,6 +109,7 @@ struct mb_ctx {
     void* scratch[24];
     size_t scratch_bytes[24];
     int sort_last_path;
+    int sort_last_tile;     // pass B of the last band sort: 1 = tile kernel
     int band_w;
     // moments cached by the band sort's gather pass (valid while state_gen == pc_gen)
     uint64_t state_gen, pc_gen;

@@ -1541,6 +1541,7 @@ int mb_sort_last_path(mb_ctx* ctx) {
     if (mb_sync(ctx)) return -1;
     return ctx->sort_last_path != 2 && ctx->h_flags[2] == 0 ? ctx->sort_last_path : 2;
 }
+int mb_sort_last_pass_b(mb_ctx* ctx) { return ctx ? ctx->sort_last_tile : -1; }
 int64_t mb_sort_last_extras(mb_ctx* ctx) {
     if (!ctx) return -1;
     if (mb_sync(ctx)) return -1;
@@ -1729,6 +1730,7 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
     pia->contig_pending[s] = 0;
     pia->sorted_layout[s] = 1;
     ctx->sort_last_path = try_band ? 1 : (try_seg ? 3 : 2);
+    ctx->sort_last_tile = use_tile ? 1 : 0;
     return MB_OK;
 }
 

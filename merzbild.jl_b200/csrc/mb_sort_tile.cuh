@@ -5,26 +5,36 @@
 // 85 % of a cell moves, spread over ~17 neighbours).  Here a CTA takes a TILE of consecutive old cells -- one contiguous slice of the
 // input of at most NCAP particles -- and uses the fact that the particles a tile sends to one destination cell are CONTIGUOUS in the
 // output (consecutive source cells are consecutive in the stable order): the tile's output is a handful of runs, one per destination
-// cell, and the runs of the tile's interior cells are complete cells lying back to back.
+// cell, and runs that are neighbours in global memory (complete interior cells) form one SEGMENT.
 //
-//   producer warp : 1-D TMA (cp.async.bulk global -> shared, mbarrier complete_tx) of the tile's slice of dr and of the seven fields,
-//                   one field per stage of a ring, running ahead of the consumers across tile boundaries
-//   table warp    : for the NEXT tile (double-buffered): run sizes R(r), local prefix, global position of every run, the local
-//                   offset LO(c', d) of every (source cell, destination) group -- from the band matrix M and the scanned cell starts
-//   consumer warps: local output index l = LO(c', d) + rank of every particle (registers), then per field: A[j] -> B[l] (shared
-//                   memory permutation), barrier, B[l] -> out[G(run of l) + l] : consecutive threads store consecutive addresses.
+//   producer warp : 1-D TMA loads (cp.async.bulk global -> shared, mbarrier complete_tx; SASS UBLKCP.S.G) of the tile's slice of dr and
+//                   of the seven fields, SUB particles per stage of an S-deep ring, running ahead of the consumers across tile boundaries
+//   table warp    : for the NEXT tile (double-buffered): the band-matrix rows of the tile and of the 2 w cells before it staged in
+//                   shared memory, run sizes R(r) and global starts G(r), the local layout Lp(r) (warp scans; parity padded, below),
+//                   the segment list, the local offset LO(c', d) of every (source cell, destination) group, the moments' shifts
+//   consumer warps: local output index l = LO(c', d) + rank of every particle (registers), then per field: A[j] -> B[l] (permutation
+//                   in shared memory), fence.proxy.async + barrier, write-out a warp per segment: a long segment leaves as ONE bulk
+//                   store (cp.async.bulk shared -> global; SASS UBLKCP.G.S) of its 16-byte aligned middle, a short one lane by lane.
 //
-// HBM traffic is what the warp-per-cell kernel moves (4 + 56 + 56 B per particle), but every store instruction now writes full sectors
-// and the loads are issued by the copy engine: no registers are tied up by bytes in flight.
-// Moments (compute_props_sorted! for free): when w, vx, vy, vz of a tile are in shared memory in OUTPUT order, every run is a
-// contiguous slice; warps reduce the runs in pieces of TL_PIECE elements (shifted by K(c) = velocity of the first particle of old
-// cell c, like the warp-per-cell kernel), and the partial sums of (tile kappa, run r) go to Pp[2 w kappa + c + w] -- a collision-free
+// Parity padding: a bulk store needs 16-byte aligned addresses on both sides, so every run starts at a local index of the same parity
+// as its global start:  Lp(r) = E(r) + pad(r),  E = exclusive prefix of the run sizes,  pad(r) = 2 (parity changes so far) + b(r),
+// b(r) = (G(r) - E(r)) & 1 -- monotone, and equal for runs that are neighbours in global memory.
+//
+// HBM traffic is what the warp-per-cell kernel moves (4 + 56 + 56 B per particle; ncu: 14.6 GB at 1.25e8 particles = 1.006 x the
+// algorithmic bytes), but the loads are issued by the copy engine (no registers tied up by bytes in flight) and the stores are full
+// sectors.  Measured (profiles/README.md): published grid 3.87 -> 3.16 ms (70 % of the measured HBM peak; 2.61 ms = 85 % without the
+// moments); at dx = 1e-5 m the warp-per-cell kernel stays faster (2.62 against 2.93 ms), so the sort picks the tile kernel from w = 4 on.
+//
+// Moments (compute_props_sorted! for free, every band width): when w and a velocity component of a tile are in shared memory in OUTPUT
+// order, every run is a contiguous slice.  A thread sums a strip of <= TL_PIECE consecutive elements of one run (shifted by K(c) =
+// velocity of the first particle of old cell c, like the warp-per-cell kernel; no shuffles), after vz a warp per run adds the strips
+// (one halving reduction of the seven sums), and the partial sums of (tile kappa, run r) go to Pp[2 w kappa + c + w] -- a collision-free
 // slot, because tile kappa starts at cell ca(kappa) >= kappa.  k_tile_combine adds the (1-3) partials of a cell in tile order.
 //
 // Tiles: old cell c belongs to tile floor(old_start(c) / NI), NI = NCAP - (largest cell), so a tile never exceeds NCAP particles;
 // chunk_first[kappa] = first cell of tile kappa.  A tile with more than TL_CMAX cells, or a cell that does not fit, is scattered
 // directly (every particle stored on its own, correct for any population); the cached moments are then recomputed by
-// k_tile_moments_fallback.
+// k_tile_moments_fallback.  MB_TILE_DEBUG=1 makes CTA 0 print where its consumers and its table warp spent their cycles.
 #pragma once
 #include "mb_common.cuh"
 
@@ -201,8 +211,7 @@ struct TileSmem {
     static constexpr int T_SL = T_UST + RQ;                                   // int32 [NRMAX] segment: local start
     static constexpr int T_SN = T_SL + RQ;                                    // int32 [NRMAX] segment: elements
     static constexpr int T_SG = T_SN + RQ;                                    // int64 [NRMAX] segment: global start
-    static constexpr int T_G = T_SG + TL_NRMAX * 8;                           // int64 [NRMAX] global start of a run
-    static constexpr int T_K = T_G + TL_NRMAX * 8;                            // double [NRMAX][3] shifts
+    static constexpr int T_K = T_SG + TL_NRMAX * 8;                            // double [NRMAX][3] shifts
     static constexpr int T_LO = T_K + (MOM ? TL_NRMAX * 24 : 0);              // uint16 [CMAX][32]
     static constexpr int T_URUN = T_LO + TL_CMAX * TL_LOS * 2;                // uint8 [UMAX] run of a unit
     static constexpr int T_COF = T_URUN + (MOM ? UMAX : 0);                   // uint8 [NCAP / 32] cell of position 32 i
@@ -360,7 +369,6 @@ __global__ void __launch_bounds__(NT + 64, MINB) k_band_tile(TileArgs a) {
                 int* seg_l = (int*)(T + L::T_SL);
                 int* seg_n = (int*)(T + L::T_SN);
                 int64_t* seg_g = (int64_t*)(T + L::T_SG);
-                int64_t* Gs = (int64_t*)(T + L::T_G);
                 double* Ksh = (double*)(T + L::T_K);
                 uint16_t* LO = (uint16_t*)(T + L::T_LO);
                 uint8_t* urun = (uint8_t*)(T + L::T_URUN);

@@ -133,6 +133,7 @@ function prof_read(ctx::Context, section::Integer)
 end
 sort_last_path(ctx::Context) = ccall((:mb_sort_last_path, libmb), Cint, (Ptr{Cvoid},), ctx.h)
 sort_last_extras(ctx::Context) = ccall((:mb_sort_last_extras, libmb), Int64, (Ptr{Cvoid},), ctx.h)
+sort_last_pass_b(ctx::Context) = ccall((:mb_sort_last_pass_b, libmb), Cint, (Ptr{Cvoid},), ctx.h)
 set_band_halfwidth!(ctx::Context, w::Integer) = check(ccall((:mb_sort_set_band_halfwidth, libmb), Cint, (Ptr{Cvoid}, Int32), ctx.h, w))
 
 """

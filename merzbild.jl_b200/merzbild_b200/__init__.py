@@ -104,6 +104,7 @@ SIGNATURES = {
     "mb_sort_last_path": (_int, [_vp]),
     "mb_sort_set_band_halfwidth": (_int, [_vp, _i32]),
     "mb_sort_last_extras": (_i64, [_vp]),
+    "mb_sort_last_pass_b": (_int, [_vp]),
     "mb_squash_pia": (_int, [_vp, _vp, _vp, _i64]),
     "mb_restore_particle_ordering": (_int, [_vp, _vp]),
     "mb_make_interaction": (_int, [_f64, _f64, _f64, _f64, _f64, C.POINTER(Interaction)]),
@@ -252,6 +253,11 @@ class Context:
     def sort_last_extras(self):
         """band outliers + slab-exchange arrivals placed by the last band-path sort (-1: the general path ran)"""
         return int(lib().mb_sort_last_extras(self.h))
+
+    @property
+    def sort_last_pass_b(self):
+        """pass B of the last band-path sort: 0 = warp per old cell, 1 = tile kernel (TMA bulk copies)"""
+        return int(lib().mb_sort_last_pass_b(self.h))
 
 
 _default_ctx = None
