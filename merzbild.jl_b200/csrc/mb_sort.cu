@@ -1022,6 +1022,43 @@ __global__ void __launch_bounds__(256) k_gen_sort_segments(int32_t* __restrict__
     }
 }
 
+// The slice perm[0 .. n) of one cell (n <= WSEG) staged in the warp's shared-memory buffer in ASCENDING order: a check when the atomics
+// happened to land in order (nearly sorted input), else the normalised bitonic network of k_gen_sort_segments_warp.  Used by the gathers
+// by destination cell, which makes a separate sorting pass over the permutation (and its write-back) unnecessary for small cells.
+__device__ __forceinline__ void warp_stage_sorted(const int32_t* __restrict__ seg, int n, int32_t* sh, int lane) {
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) sh[i] = seg[i];
+    __syncwarp();
+    bool uns = false;
+    for (int i = lane; i + 1 < n; i += 32) uns |= sh[i] > sh[i + 1];
+    if (!__any_sync(0xffffffffu, uns)) return;
+    int m = 1;
+    while (m < n) m <<= 1;
+    for (int k = 2; k <= m; k <<= 1) {
+        const int hk = k >> 1;
+        for (int t = lane; t < (m >> 1); t += 32) {
+            const int blk = t / hk, off = t - blk * hk;
+            const int i = blk * k + off, p = blk * k + k - 1 - off;
+            if (p < n) {
+                const int32_t x = sh[i], y = sh[p];
+                if (x > y) { sh[i] = y; sh[p] = x; }
+            }
+        }
+        __syncwarp();
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            for (int t = lane; t < (m >> 1); t += 32) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int p = i + j;
+                if (p < n) {
+                    const int32_t x = sh[i], y = sh[p];
+                    if (x > y) { sh[i] = y; sh[p] = x; }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // cell_out (nullable; the variant that sorts by stored cell ids, grid_sorting.jl:128): the ids are permuted along with the particles,
 // so that an ensemble of 0-D cells can be re-sorted step after step (device-side extension: the reference leaves particles.cell stale)
 __global__ void __launch_bounds__(256) k_gen_gather(SoA in, SoA out, const int32_t* __restrict__ perm, const int64_t* n_total_p, const int* flags,
@@ -1045,18 +1082,22 @@ __global__ void __launch_bounds__(256) k_gen_gather_cells(SoA in, SoA out, const
                                                           int64_t n_cells, const int* flags, const int32_t* __restrict__ src,
                                                           const int32_t* __restrict__ key, int32_t* __restrict__ cell_out, double* __restrict__ pcache) {
     if (flags[2] == 0) return;
+    __shared__ int32_t shw[8][WSEG];
     const int lane = threadIdx.x & 31;
+    int32_t* sh = shw[threadIdx.x >> 5];
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t c = warp0; c < n_cells; c += nwarps) {
         const int64_t lo = start[c];
         const int n = (int)(start[c + 1] - lo);
+        const bool staged = n <= WSEG;  // larger cells were put in order by k_gen_sort_segments
+        if (staged) warp_stage_sorted(perm + lo, n, sh, lane);
         double K1 = 0, K2 = 0, K3 = 0;
         double an = 0, ax = 0, ay = 0, az = 0, aq = 0;
         for (int j0 = 0; j0 < n; j0 += 32) {
             const int j = j0 + lane;
             double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
             if (j < n) {
-                const int64_t i = perm[lo + j];
+                const int64_t i = staged ? sh[j] : perm[lo + j];
                 const int64_t ph = src ? (int64_t)src[i] : i;
                 a0 = in.a[0][ph]; a1 = in.a[1][ph]; a2 = in.a[2][ph]; a3 = in.a[3][ph];
                 const double a4 = in.a[4][ph], a5 = in.a[5][ph], a6 = in.a[6][ph];
@@ -1117,18 +1158,22 @@ __global__ void __launch_bounds__(256) k_gen_gather_cells_aos(const Rec64* __res
                                                               const int32_t* __restrict__ key, int32_t* __restrict__ cell_out,
                                                               double* __restrict__ pcache) {
     if (flags[2] == 0) return;
+    __shared__ int32_t shw[8][WSEG];
     const int lane = threadIdx.x & 31;
+    int32_t* sh = shw[threadIdx.x >> 5];
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t c = warp0; c < n_cells; c += nwarps) {
         const int64_t lo = start[c];
         const int n = (int)(start[c + 1] - lo);
+        const bool staged = n <= WSEG;  // larger cells were put in order by k_gen_sort_segments
+        if (staged) warp_stage_sorted(perm + lo, n, sh, lane);
         double K1 = 0, K2 = 0, K3 = 0;
         double an = 0, ax = 0, ay = 0, az = 0, aq = 0;
         for (int j0 = 0; j0 < n; j0 += 32) {
             const int j = j0 + lane;
             double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
             if (j < n) {
-                const int64_t i = perm[lo + j];
+                const int64_t i = staged ? sh[j] : perm[lo + j];
                 const Rec64 r = rec[i];
                 a0 = r.a.x; a1 = r.a.y; a2 = r.b.x; a3 = r.b.y;
                 out.a[0][lo + j] = a0; out.a[1][lo + j] = a1; out.a[2][lo + j] = a2; out.a[3][lo + j] = a3;
@@ -1678,8 +1723,11 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
         MB_LAUNCH_CHECK(ctx);
         k_gen_scatter_idx<<<pgrid, 256, 0, st>>>(S.key, B.n_old, S.start, S.cursor, S.perm, S.flags);
         MB_LAUNCH_CHECK(ctx);
-        k_gen_sort_segments_warp<<<grid_for(nc * 8, 256, 6), 256, 0, st>>>(S.perm, S.start, nc, S.flags);
-        MB_LAUNCH_CHECK(ctx);
+        gather_cells = nb / (nc > 0 ? nc : 1) <= 2048;  // small cells: gather by cell and cache the cell moments
+        if (!gather_cells) {  // (the gathers by cell put the indices of a cell of up to WSEG particles in order themselves)
+            k_gen_sort_segments_warp<<<grid_for(nc * 8, 256, 6), 256, 0, st>>>(S.perm, S.start, nc, S.flags);
+            MB_LAUNCH_CHECK(ctx);
+        }
         {
             const int gseg = grid_for(nc * 256, 256, 8);
             int cpb = 256;  // cells a CTA looks at per round: 256 on long grids, fewer when there are few (large) cells
@@ -1687,7 +1735,6 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
             k_gen_sort_segments<<<gseg, 256, 0, st>>>(S.perm, S.start, nc, S.flags, cpb);
         }
         MB_LAUNCH_CHECK(ctx);
-        gather_cells = nb / (nc > 0 ? nc : 1) <= 2048;  // small cells: gather by cell and cache the cell moments
         // band path switched off by the caller = displacements of many cells: the gather would be fully scattered; go through 64-byte records
         const bool aos = gather_cells && w == 0 && use_x;
         if (aos) {
