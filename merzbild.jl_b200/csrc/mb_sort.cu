@@ -1142,15 +1142,17 @@ struct __align__(16) Rec64 { double2 a, b, c, d; };  // w vx | vy vz | x y | z -
 __global__ void __launch_bounds__(256) k_gen_pack_aos(SoA in, const int64_t* n_total_p, const int32_t* __restrict__ src, Rec64* __restrict__ rec,
                                                       const int* flags) {
     if (flags[2] == 0) return;
-    const int64_t n_total = *n_total_p;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_total; i += (int64_t)gridDim.x * blockDim.x) {
+    // four threads per record, one 16-byte quarter each: a warp reads 8 consecutive values of every field (full sectors) and writes
+    // 512 contiguous bytes
+    const int64_t n4 = *n_total_p * 4;
+    double2* __restrict__ out = (double2*)rec;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n4; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t >> 2;
+        const int p = (int)(t & 3);
         const int64_t ph = src ? (int64_t)src[i] : i;
-        Rec64 r;
-        r.a = make_double2(in.a[0][ph], in.a[1][ph]);
-        r.b = make_double2(in.a[2][ph], in.a[3][ph]);
-        r.c = make_double2(in.a[4][ph], in.a[5][ph]);
-        r.d = make_double2(in.a[6][ph], 0.0);
-        rec[i] = r;
+        const double v0 = in.a[2 * p][ph];
+        const double v1 = p < 3 ? in.a[2 * p + 1][ph] : 0.0;
+        out[t] = make_double2(v0, v1);
     }
 }
 __global__ void __launch_bounds__(256) k_gen_gather_cells_aos(const Rec64* __restrict__ rec, SoA out, const int32_t* __restrict__ perm,
@@ -1740,7 +1742,7 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
         if (aos) {
             Rec64* rec = (Rec64*)ctx_scratch(ctx, 15, (size_t)cap * sizeof(Rec64));
             if (!rec) return MB_ERR_CUDA;
-            k_gen_pack_aos<<<pgrid, 256, 0, st>>>(pv->cur, B.n_old, src, rec, S.flags);
+            k_gen_pack_aos<<<grid_for(nb * 4, 256, 16), 256, 0, st>>>(pv->cur, B.n_old, src, rec, S.flags);
             MB_LAUNCH_CHECK(ctx);
             k_gen_gather_cells_aos<<<grid_for(nc * 32, 256, 8), 256, 0, st>>>(rec, pv->alt, S.perm, S.start, nc, S.flags, S.key, nullptr, B.pcache);
         } else if (gather_cells)

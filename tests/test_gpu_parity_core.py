@@ -202,10 +202,20 @@ def test_sort_large_cell_segments(mb, oracle, ctx):
 
 
 # ------------------------------------------------------------------------------------------------------------ props
-@pytest.mark.parametrize("n,n_cells", [(20000, 37), (3000, 64), (50000, 5)])
-def test_props_after_general_sort_use_the_cached_moments(mb, oracle, ctx, n, n_cells):
+@pytest.mark.parametrize("band", [2, 0])
+@pytest.mark.parametrize("n,n_cells", [(20000, 37), (3000, 64), (50000, 5), (40000, 700)])
+def test_props_after_general_sort_use_the_cached_moments(mb, oracle, ctx, n, n_cells, band):
     """compute_props_sorted! right after a general-path sort of small cells reads the moments the gather-by-cell pass cached (no particle
-    traffic); they must match the oracle's two-pass values like the band path's do (1e-12 on T and v, 1e-13 on n)."""
+    traffic); they must match the oracle's two-pass values like the band path's do (1e-12 on T and v, 1e-13 on n).  band = 0 (the caller
+    switched the band path off: a fully scattered sort) takes the gather through 64-byte records."""
+    ctx.set_band_halfwidth(band)
+    try:
+        _props_after_general_sort(mb, oracle, ctx, n, n_cells)
+    finally:
+        ctx.set_band_halfwidth(2)
+
+
+def _props_after_general_sort(mb, oracle, ctx, n, n_cells):
     rng = np.random.default_rng(n + n_cells)
     L = 2.0
     rows = maxwellian_rows(rng, n, L, vw=True)
@@ -216,6 +226,8 @@ def test_props_after_general_sort_use_the_cached_moments(mb, oracle, ctx, n, n_c
     mb.sort_particles(None, g, pv, pia, 1)
     oracle.sort_particles(opv, opia, 1, grid=(L, n_cells))
     assert ctx.sort_last_path == 2
+    assert_same_pia(opia, pia)
+    np.testing.assert_array_equal(pv.logical(1, n), opv.logical(1, n))
     pp = mb.PhysProps(n_cells, 1, ctx=ctx)
     l0 = ctx.kernel_launches
     mb.compute_props_sorted([pv], pia, [AR], pp)
