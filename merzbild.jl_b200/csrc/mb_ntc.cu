@@ -42,6 +42,8 @@ struct NtcArgs {
     int* flags;
     int single_cell_tail;  // VW: one cell whose existing group 2 ends at n_total (0-D usage)
     int64_t warp_min;      // one species: cells with n_local >= warp_min are collided by k_ntc_warp (0: never)
+    int64_t n_cells_all;   // cells of the pia (for the mean population)
+    int thin;              // one species: with a mean population >= NTC_THIN_PPC only the first N_SM CTAs work (see ntc_impl)
 };
 
 __device__ __forceinline__ int64_t ncoll_of(double dt, double V, double sgwm, int64_t n1, int64_t n2, bool two, double R) {
@@ -49,6 +51,8 @@ __device__ __forceinline__ int64_t ncoll_of(double dt, double V, double sgwm, in
     const double f = two ? dt * (double)n1 * (double)n2 * sgwm / V + R : 0.5 * dt * (double)n1 * (double)(n1 - 1) * sgwm / V + R;
     return (int64_t)floor(f);
 }
+
+constexpr int64_t NTC_THIN_PPC = 200;
 
 template <bool TWO>
 __global__ void __launch_bounds__(128) k_ntc_prepass(NtcArgs a) {
@@ -104,7 +108,11 @@ __global__ void __launch_bounds__(128, MINB) k_ntc(NtcArgs a) {
     }
     const mb_interaction it = a.it;
     const double pw = 1.0 - 2 * it.vhs_o;
-    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nr; r += (int64_t)gridDim.x * blockDim.x) {
+    // resident threads per SM (see ntc_impl): large cells -> one CTA per SM, decided here from the exact particle count
+    int64_t nblocks = gridDim.x;
+    if (!TWO && a.thin && nblocks > N_SM && *a.n_total1 / a.n_cells_all >= NTC_THIN_PPC) nblocks = N_SM;
+    if ((int64_t)blockIdx.x >= nblocks) return;
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nr; r += nblocks * blockDim.x) {
         const int64_t cell = a.cell_lo + r;
         Indexer q1 = a.ix1[cell - 1];
         if (!TWO && a.warp_min > 0 && q1.n_local >= a.warp_min) continue;  // large cells: k_ntc_warp
@@ -374,7 +382,17 @@ static int ntc_impl(mb_ctx* ctx, mb_cf* cf, const mb_interaction* it, mb_pv* pv1
     a.single_cell_tail = (nr == 1);
     a.ncoll32 = nullptr; a.win = nullptr; a.nsplit1 = nullptr; a.nsplit2 = nullptr;
     cudaStream_t st = ctx->stream;
-    const int g = grid_for(nr, 128, 16);
+    static const int env_grid = getenv("MB_NTC_GRID_PER_SM") ? atoi(getenv("MB_NTC_GRID_PER_SM")) : 0;  // experiment knob: CTAs per SM in the grid
+    static const int env_block = getenv("MB_NTC_BLOCK") ? atoi(getenv("MB_NTC_BLOCK")) : 0;  // experiment knob: threads per CTA of k_ntc
+    const int nblk = env_block > 0 ? env_block : 128;
+    // Resident threads per SM.  The kernel is bound by the DRAM random-access rate, and past the point where the memory system is saturated
+    // more concurrent gathers only thrash it: measured on the Couette step at 1.25e8 particles (ppc = 1000 / 250), 128 threads per SM
+    // take 0.90 / 0.81 ms, 256: 0.97 / -, 512 (what the registers allow): 1.05 / 0.85, 64: 1.20 / 1.29.  Small cells (C4: ~110 particles,
+    // where a thread spends more of its time on the per-cell bookkeeping than on gathers) want all the threads they can get:
+    // 4.06 ms at 512 per SM, 4.20 / 4.30 / 6.08 at 384 / 256 / 128.  The kernel decides from the exact mean population (device n_total).
+    const int g = grid_for(nr, nblk, env_grid > 0 ? env_grid : 16);
+    a.n_cells_all = nc;
+    a.thin = env_grid > 0 ? 0 : 1;
     ProfScope ps(ctx, PROF_NTC);
     ctx->state_gen++;
     a.warp_min = two ? 0 : 2048;
@@ -388,9 +406,9 @@ static int ntc_impl(mb_ctx* ctx, mb_cf* cf, const mb_interaction* it, mb_pv* pv1
         minb = e ? atoi(e) : 4;
     }
     auto launch_one = [&]() {
-        if (minb >= 8) k_ntc<false, 8><<<g, 128, 0, st>>>(a);
-        else if (minb >= 6) k_ntc<false, 6><<<g, 128, 0, st>>>(a);
-        else k_ntc<false, 4><<<g, 128, 0, st>>>(a);
+        if (minb >= 8) k_ntc<false, 8><<<g, nblk, 0, st>>>(a);
+        else if (minb >= 6) k_ntc<false, 6><<<g, nblk, 0, st>>>(a);
+        else k_ntc<false, 4><<<g, nblk, 0, st>>>(a);
     };
     if (equal_weight) {
         if (two) k_ntc<true, 4><<<g, 128, 0, st>>>(a);
