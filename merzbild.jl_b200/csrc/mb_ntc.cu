@@ -211,7 +211,10 @@ __device__ __forceinline__ double stream_draw(uint32_t k0, uint32_t k1, uint32_t
     return (d & 1) ? u64_to_unit_double(o[2], o[3]) : u64_to_unit_double(o[0], o[1]);
 }
 
-__global__ void __launch_bounds__(128) k_ntc_warp(NtcArgs a, int ch) {
+#ifndef MB_NTCW_MINB
+#define MB_NTCW_MINB 1  // resident CTAs per SM k_ntc_warp is compiled for (register budget)
+#endif
+__global__ void __launch_bounds__(128, MB_NTCW_MINB) k_ntc_warp(NtcArgs a, int ch) {
     const int64_t nr = a.cell_hi - a.cell_lo + 1;
     const bool vw = !a.equal_weight;
     const unsigned FULL = 0xffffffffu;
@@ -399,7 +402,8 @@ static int ntc_impl(mb_ctx* ctx, mb_cf* cf, const mb_interaction* it, mb_pv* pv1
     // k_ntc_warp: a warp takes ch cells at a time -- 32 when the range is long enough to keep every warp busy, fewer otherwise
     int ch = 32;
     while (ch > 1 && nr < (int64_t)N_SM * 8 * 4 * ch) ch >>= 1;
-    const int gwarp = grid_for((nr + ch - 1) / ch * 32, 128, 8);
+    static const int env_wgrid = getenv("MB_NTCW_PER_SM") ? atoi(getenv("MB_NTCW_PER_SM")) : 0;  // experiment knob: CTAs per SM of k_ntc_warp
+    const int gwarp = grid_for((nr + ch - 1) / ch * 32, 128, env_wgrid > 0 ? env_wgrid : 8);
     static int minb = -1;
     if (minb < 0) {
         const char* e = getenv("MB_NTC_MINB");
