@@ -1739,14 +1739,16 @@ int mb_sort_particles(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pia
         MB_LAUNCH_CHECK(ctx);
         // band path switched off by the caller = displacements of many cells: the gather would be fully scattered; go through 64-byte records
         const bool aos = gather_cells && w == 0 && use_x;
+        static const int env_gat = getenv("MB_GATHER_PER_SM") ? atoi(getenv("MB_GATHER_PER_SM")) : 0;  // experiment knob
+        const int gat_per_sm = env_gat > 0 ? env_gat : 8;
         if (aos) {
             Rec64* rec = (Rec64*)ctx_scratch(ctx, 15, (size_t)cap * sizeof(Rec64));
             if (!rec) return MB_ERR_CUDA;
             k_gen_pack_aos<<<grid_for(nb * 4, 256, 16), 256, 0, st>>>(pv->cur, B.n_old, src, rec, S.flags);
             MB_LAUNCH_CHECK(ctx);
-            k_gen_gather_cells_aos<<<grid_for(nc * 32, 256, 8), 256, 0, st>>>(rec, pv->alt, S.perm, S.start, nc, S.flags, S.key, nullptr, B.pcache);
+            k_gen_gather_cells_aos<<<grid_for(nc * 32, 256, gat_per_sm), 256, 0, st>>>(rec, pv->alt, S.perm, S.start, nc, S.flags, S.key, nullptr, B.pcache);
         } else if (gather_cells)
-            k_gen_gather_cells<<<grid_for(nc * 32, 256, 8), 256, 0, st>>>(pv->cur, pv->alt, S.perm, S.start, nc, S.flags, src, S.key,
+            k_gen_gather_cells<<<grid_for(nc * 32, 256, gat_per_sm), 256, 0, st>>>(pv->cur, pv->alt, S.perm, S.start, nc, S.flags, src, S.key,
                                                                         use_x ? nullptr : pv->cell, B.pcache);
         else
             k_gen_gather<<<pgrid, 256, 0, st>>>(pv->cur, pv->alt, S.perm, S.start + nc, S.flags, src, S.key, use_x ? nullptr : pv->cell);
