@@ -212,7 +212,7 @@ __device__ __forceinline__ double stream_draw(uint32_t k0, uint32_t k1, uint32_t
 }
 
 #ifndef MB_NTCW_MINB
-#define MB_NTCW_MINB 1  // resident CTAs per SM k_ntc_warp is compiled for (register budget)
+#define MB_NTCW_MINB 4  // resident CTAs per SM k_ntc_warp is compiled for (register budget: 128; measured on C2: 12.0 ms, 13.8 ms at 160 registers, 17 ms at 80)
 #endif
 __global__ void __launch_bounds__(128, MB_NTCW_MINB) k_ntc_warp(NtcArgs a, int ch) {
     const int64_t nr = a.cell_hi - a.cell_lo + 1;
