@@ -45,7 +45,14 @@ constexpr int TL_WMAX = 31;     // widest band
 constexpr int TL_NRMAX = TL_CMAX + TL_WMAX - 1;  // runs (destination cells) per tile
 constexpr int TL_LOS = 32;      // row stride of LO
 constexpr int TL_PIECE = 16;    // elements of a run one thread sums (a "strip": strips never cross runs)
-constexpr int TL_BULK_MIN = 192;  // shortest segment that leaves as a bulk store
+#ifndef MB_TL_SPLIT
+#define MB_TL_SPLIT 2
+#endif
+constexpr int TL_SPLIT = MB_TL_SPLIT;  // threads per strip in the moments pass; measured (published / same-dx pass B): 1: 3.16 / 2.93 ms, 2: 3.13 / 2.79, 4: 3.18 / 2.92
+#ifndef MB_TL_BULK_MIN
+#define MB_TL_BULK_MIN 192
+#endif
+constexpr int TL_BULK_MIN = MB_TL_BULK_MIN;  // shortest segment that leaves as a bulk store
 enum { F_MOM_BAD = 5 };         // ctx->d_flags slot: a tile was scattered directly, its moments are missing
 
 // ---- PTX helpers (sm_100a): mbarrier + 1-D bulk copy
@@ -680,24 +687,36 @@ __global__ void __launch_bounds__(NT + 64, MINB) k_band_tile(TileArgs a) {
                 // sum w c^2 (c = v - K(run)); no shuffles, every thread busy.  The lanes walk their strips rotated against each other
                 // (strips start TL_PIECE doubles apart: without the rotation all lanes of a wavefront would hit one bank).
                 const double* Bw = Bbase;
-                for (int u = tid; u < nunits; u += NT) {
+                // TL_SPLIT threads per strip (a part of the strip each, combined with shuffles): more threads busy, shorter dependent chains
+                constexpr int SP = TL_SPLIT, PART = TL_PIECE / SP;
+                for (int uu0 = 0; uu0 < SP * nunits; uu0 += NT) {  // CTA-uniform trip count: every lane takes part in the shuffles
+                    const int uu = uu0 + tid;
+                    const bool valid = uu < SP * nunits;
+                    const int u = valid ? uu / SP : 0, part = uu % SP;
                     const int r = urun[u];
-                    const int l0 = Lp[r] + (u - ust[r]) * TL_PIECE;
-                    const int l1 = min(l0 + TL_PIECE, Lp[r] + Rs[r]);
+                    const int lb = Lp[r] + (u - ust[r]) * TL_PIECE;
+                    const int l0 = lb + part * PART;
+                    const int l1 = valid ? min(lb + TL_PIECE, Lp[r] + Rs[r]) : 0;
                     const double K = Ksh[3 * r + (f - 1)];
                     double s0 = 0, s1 = 0, s2 = 0;
 #pragma unroll
-                    for (int k = 0; k < TL_PIECE; k++) {
-                        const int l = l0 + ((k + lane) & (TL_PIECE - 1));
+                    for (int k = 0; k < PART; k++) {
+                        const int l = l0 + ((k + lane / SP) & (PART - 1));
                         if (l < l1) {
                             const double pw = Bw[l], c = B[l] - K;
                             s0 += pw; s1 += pw * c; s2 += pw * (c * c);
                         }
                     }
-                    double* o_ = pp + u * 7;
-                    if (f == 1) o_[0] = s0;
-                    o_[f] = s1;
-                    o_[3 + f] = s2;
+#pragma unroll
+                    for (int o = 1; o < SP; o <<= 1) {
+                        s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                    }
+                    if (valid && part == 0) {
+                        double* o_ = pp + u * 7;
+                        if (f == 1) o_[0] = s0;
+                        o_[f] = s1;
+                        o_[3 + f] = s2;
+                    }
                 }
             }
             {

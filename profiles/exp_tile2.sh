@@ -1,11 +1,9 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-TAG=${TAG:-r2s}
-timeout 900 python -m pytest tests/test_gpu_parity_core.py -x -q -m gpu -k "tile" > gpurun_out/${TAG}_pytest_tile.log 2>&1
-echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest_tile.log
-tail -3 gpurun_out/${TAG}_pytest_tile.log
-for v in "published-dx 1 2" "published-dx 1 4" "same-dx 3 2" "same-dx 3 4"; do set -- $v
-  MB_SORT_TILE=$2 MB_TILE_CFG=$3 timeout 300 python bench.py --scaling $1 --no-others --no-cpu-baseline --e2e-steps 0 --steps 10 --warmup 5 > gpurun_out/${TAG}_$1_$2_$3.json 2> gpurun_out/${TAG}_$1_$2_$3.err
-  echo "$1 tile=$2 cfg=$3"; python profiles/show_bench.py gpurun_out/${TAG}_$1_$2_$3.json 2>/dev/null | sed -n 1,2p
+TAG=${TAG:-r3j}
+timeout 900 python -m pytest tests/test_gpu_parity_core.py -x -q -m gpu -k "tile" 2>&1 | tail -1
+for v in "published-dx 1 2" "same-dx 3 2"; do set -- $v
+  MB_SORT_TILE=$2 MB_TILE_CFG=$3 timeout 300 python bench.py --scaling $1 --no-others --no-cpu-baseline --e2e-steps 0 --steps 10 --warmup 5 > gpurun_out/${TAG}_$1_$2_$3.json 2> /dev/null
+  echo "$1 tile=$2 cfg=$3"; python profiles/show_bench.py gpurun_out/${TAG}_$1_$2_$3.json 2>/dev/null | sed -n 2,2p | grep -oE "'sort.scatter': [0-9.]+"
 done
