@@ -22,8 +22,8 @@
 //
 // HBM traffic is what the warp-per-cell kernel moves (4 + 56 + 56 B per particle; ncu: 14.6 GB at 1.25e8 particles = 1.006 x the
 // algorithmic bytes), but the loads are issued by the copy engine (no registers tied up by bytes in flight) and the stores are full
-// sectors.  Measured (profiles/README.md): published grid 3.87 -> 3.16 ms (70 % of the measured HBM peak; 2.61 ms = 85 % without the
-// moments); at dx = 1e-5 m the warp-per-cell kernel stays faster (2.62 against 2.93 ms), so the sort picks the tile kernel from w = 4 on.
+// sectors.  Measured (profiles/README.md): published grid 3.87 -> 3.08 ms (72 % of the measured HBM peak; 2.61 ms = 85 % without the
+// moments); at dx = 1e-5 m the warp-per-cell kernel stays faster (2.62 against 2.77 ms), so the sort picks the tile kernel from w = 4 on.
 //
 // Moments (compute_props_sorted! for free, every band width): when w and a velocity component of a tile are in shared memory in OUTPUT
 // order, every run is a contiguous slice.  A thread sums a strip of <= TL_PIECE consecutive elements of one run (shifted by K(c) =
@@ -50,9 +50,9 @@ constexpr int TL_PIECE = 16;    // elements of a run one thread sums (a "strip":
 #endif
 constexpr int TL_SPLIT = MB_TL_SPLIT;  // threads per strip in the moments pass; measured (published / same-dx pass B): 1: 3.16 / 2.93 ms, 2: 3.13 / 2.79, 4: 3.18 / 2.92
 #ifndef MB_TL_BULK_MIN
-#define MB_TL_BULK_MIN 192
+#define MB_TL_BULK_MIN 64
 #endif
-constexpr int TL_BULK_MIN = MB_TL_BULK_MIN;  // shortest segment that leaves as a bulk store
+constexpr int TL_BULK_MIN = MB_TL_BULK_MIN;  // shortest segment that leaves as a bulk store; measured (published-grid pass B): 16: 3.08 ms, 32 / 64: 3.07, 192: 3.11, 512: 3.31
 enum { F_MOM_BAD = 5 };         // ctx->d_flags slot: a tile was scattered directly, its moments are missing
 
 // ---- PTX helpers (sm_100a): mbarrier + 1-D bulk copy
