@@ -40,6 +40,44 @@ __device__ __forceinline__ double wsum(double x) {
     return x;
 }
 
+// All-reduce of 8 (4) values over the warp in ONE pass: in each of the first steps a lane hands half of the values it carries to its
+// partner and keeps the other half, so the set halves while the sums grow; after the last step every value sits (complete) in a
+// group of lanes and is broadcast from there.  16 (10) 64-bit shuffles instead of the 40 (20) of eight (four) separate butterflies.
+__device__ __forceinline__ void wallreduce8(double v[8], int lane) {
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+    double a4[4], a2[2];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const double recv = __shfl_xor_sync(0xffffffffu, h16 ? v[i] : v[i + 4], 16);
+        a4[i] = (h16 ? v[i + 4] : v[i]) + recv;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const double recv = __shfl_xor_sync(0xffffffffu, h8 ? a4[i] : a4[i + 2], 8);
+        a2[i] = (h8 ? a4[i + 2] : a4[i]) + recv;
+    }
+    double c = (h4 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? a2[0] : a2[1], 4);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __shfl_sync(0xffffffffu, c, ((i >> 2) & 1) * 16 + ((i >> 1) & 1) * 8 + (i & 1) * 4);
+}
+__device__ __forceinline__ void wallreduce4(double v[4], int lane) {
+    const bool h16 = lane & 16, h8 = lane & 8;
+    double a2[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const double recv = __shfl_xor_sync(0xffffffffu, h16 ? v[i] : v[i + 2], 16);
+        a2[i] = (h16 ? v[i + 2] : v[i]) + recv;
+    }
+    double c = (h8 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h8 ? a2[0] : a2[1], 8);
+    c += __shfl_xor_sync(0xffffffffu, c, 4);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+#pragma unroll
+    for (int i = 0; i < 4; i++) v[i] = __shfl_sync(0xffffffffu, c, ((i >> 1) & 1) * 16 + (i & 1) * 8);
+}
+
 static __global__ void __launch_bounds__(256) k_fp_linear(FpArgs a, int n_lo) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -124,8 +162,8 @@ static __global__ void __launch_bounds__(256) k_fp_linear(FpArgs a, int n_lo) {
 }
 
 // Small cells (n <= 32 K): the whole cell lives in registers -- K particles per lane, the normals are generated ONCE, the cell is
-// read once and written once.  The arithmetic (per-lane accumulation in ascending j, then the xor butterfly) is the same as in
-// k_fp_linear, so both kernels give bit-identical results.  Handles the cells with n_lo < n_local <= 32 K; the others are skipped.
+// read once and written once.  The per-lane accumulation (ascending j) is the same as in k_fp_linear; the cross-lane sums are taken
+// with the multi-value reductions above (a different association: the two kernels agree to round-off, not bit for bit).  Handles the cells with n_lo < n_local <= 32 K; the others are skipped.
 template <int K>
 static __global__ void __launch_bounds__(128, K == 4 ? 4 : 2) k_fp_linear_reg(FpArgs a, int n_lo) {
     const int lane = threadIdx.x & 31;
@@ -162,6 +200,7 @@ static __global__ void __launch_bounds__(128, K == 4 ? 4 : 2) k_fp_linear_reg(Fp
             vz[k] = valid ? VZ[lo + j] : 0.0;
         }
         double m[3] = {0, 0, 0}, s2[3] = {0, 0, 0};
+        double lw = 0, ux = 0, uy = 0, uz = 0;
 #pragma unroll
         for (int k = 0; k < K; k++) {
             const int j = lane + 32 * k;
@@ -171,33 +210,32 @@ static __global__ void __launch_bounds__(128, K == 4 ? 4 : 2) k_fp_linear_reg(Fp
                 fp_normals(a, (uint32_t)cell, j, o);
                 o0[k] = o[0]; o1[k] = o[1]; o2[k] = o[2];
                 m[0] += o[0]; m[1] += o[1]; m[2] += o[2];
+                lw += w[k];
+                ux += vx[k] * w[k]; uy += vy[k] * w[k]; uz += vz[k] * w[k];
             }
         }
-        for (int d = 0; d < 3; d++) m[d] = wsum(m[d]) / (double)n;
+        {   // the sums of the normals and the weighted velocity sums in one reduction
+            double r8[8] = {m[0], m[1], m[2], lw, ux, uy, uz, 0.0};
+            wallreduce8(r8, lane);
+            for (int d = 0; d < 3; d++) m[d] = r8[d] / (double)n;
+            lw = r8[3];
+            ux = r8[4] / lw; uy = r8[5] / lw; uz = r8[6] / lw;
+        }
+        double es_old = 0;
 #pragma unroll
         for (int k = 0; k < K; k++)
             if (lane + 32 * k < n) {
                 const double x0 = o0[k] - m[0], x1 = o1[k] - m[1], x2 = o2[k] - m[2];
                 s2[0] += x0 * x0; s2[1] += x1 * x1; s2[2] += x2 * x2;
-            }
-        for (int d = 0; d < 3; d++) s2[d] = sqrt((double)n / wsum(s2[d]));
-        double lw = 0, ux = 0, uy = 0, uz = 0;
-#pragma unroll
-        for (int k = 0; k < K; k++)
-            if (lane + 32 * k < n) {
-                lw += w[k];
-                ux += vx[k] * w[k]; uy += vy[k] * w[k]; uz += vz[k] * w[k];
-            }
-        lw = wsum(lw);
-        ux = wsum(ux) / lw; uy = wsum(uy) / lw; uz = wsum(uz) / lw;
-        double es_old = 0;
-#pragma unroll
-        for (int k = 0; k < K; k++)
-            if (lane + 32 * k < n) {
                 const double cx = vx[k] - ux, cy = vy[k] - uy, cz = vz[k] - uz;
                 es_old += (cx * cx + cy * cy + cz * cz) * w[k];
             }
-        es_old = 0.5 * wsum(es_old) / lw;
+        {   // the variances of the normals and the thermal energy in one reduction
+            double r4[4] = {s2[0], s2[1], s2[2], es_old};
+            wallreduce4(r4, lane);
+            for (int d = 0; d < 3; d++) s2[d] = sqrt((double)n / r4[d]);
+            es_old = 0.5 * r4[3] / lw;
+        }
         const double T = es_old * a.mass / ((3.0 / 2.0) * k_B);
         const double p = (lw / a.V) * k_B * T;
         const double mu = a.it.vhs_muref * pow(T / a.it.vhs_Tref, a.it.vhs_o);
