@@ -685,6 +685,70 @@ __global__ void __launch_bounds__(128) k_band_combine(const double* __restrict__
     }
 }
 
+// The same, a WARP per cell: the movers / arrivals / extras of a cell (everything but the stayers' run) are summed lane-strided instead
+// of by one thread in a dependent chain of loads (0.13 -> 0.05 ms at 125 000 cells of 1000).  Lane k + 1 looks up the size of group k.
+template <int W>
+__global__ void __launch_bounds__(256) k_band_combine_warp(const double* __restrict__ P, const int32_t* __restrict__ M, const int32_t* __restrict__ cntB,
+                                                           const int32_t* __restrict__ cntA, const int64_t* __restrict__ seg_lo,
+                                                           const int32_t* __restrict__ seg_n, const int64_t* __restrict__ start, SoA in_, SoA out_,
+                                                           int64_t n_cells, double* __restrict__ pcache, const int* flags) {
+    if (flags[2] != 0) return;
+    constexpr int w = W / 2;
+    static_assert(W + 2 <= 32, "one lane per group");
+    const int lane = threadIdx.x & 31;
+    const double* __restrict__ o0 = out_.a[0]; const double* __restrict__ o1 = out_.a[1]; const double* __restrict__ o2 = out_.a[2];
+    const double* __restrict__ o3 = out_.a[3];
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t c = warp0; c < n_cells; c += nwarps) {
+        double K1 = 0, K2 = 0, K3 = 0;
+        if (seg_n[c] > 0) { const int64_t f = seg_lo[c]; K1 = in_.a[1][f]; K2 = in_.a[2][f]; K3 = in_.a[3][f]; }
+        // group k = lane - 1: k == -1 the extras before the band, 0 .. W - 1 the band groups by source cell, k == W the extras after
+        int cnt = 0;
+        const int k = lane - 1;
+        if (k == -1) cnt = cntB[c];
+        else if (k < W) {
+            const int64_t cs = c - w + k;
+            if (cs >= 0 && cs < n_cells) cnt = M[cs * W + (W - 1 - k)];
+        } else if (k == W) cnt = cntA[c];
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int stay_lo = __shfl_sync(0xffffffffu, incl - cnt, w + 1), stay_n = __shfl_sync(0xffffffffu, cnt, w + 1);
+        const int64_t pos0 = start[c];
+        const int n_mov = total - stay_n;
+        double an = 0, ax = 0, ay = 0, az = 0, aq = 0;
+        for (int i = lane; i < n_mov; i += 32) {
+            const int64_t p = pos0 + (i < stay_lo ? i : i + stay_n);
+            const double pw = o0[p], cx = o1[p] - K1, cy = o2[p] - K2, cz = o3[p] - K3;
+            an += pw; ax += pw * cx; ay += pw * cy; az += pw * cz;
+            aq += pw * (cx * cx + cy * cy + cz * cz);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            an += __shfl_xor_sync(0xffffffffu, an, o); ax += __shfl_xor_sync(0xffffffffu, ax, o);
+            ay += __shfl_xor_sync(0xffffffffu, ay, o); az += __shfl_xor_sync(0xffffffffu, az, o);
+            aq += __shfl_xor_sync(0xffffffffu, aq, o);
+        }
+        if (lane == 0) {
+            const double* q = P + c * 5;
+            an += q[0]; ax += q[1]; ay += q[2]; az += q[3]; aq += q[4];
+            double* pc = pcache + 6 * c;
+            pc[0] = (double)total;
+            if (an > 0.0) {
+                const double mx = ax / an, my = ay / an, mz = az / an;  // mean of (v - K)
+                pc[1] = an; pc[2] = K1 + mx; pc[3] = K2 + my; pc[4] = K3 + mz;
+                pc[5] = aq - an * (mx * mx + my * my + mz * mz);        // sum w |v - vbar|^2
+            } else {
+                pc[1] = 0; pc[2] = 0; pc[3] = 0; pc[4] = 0; pc[5] = 0;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ fused convect + classify
 // convect_particles! on a sorted layout knows everything pass A of the band sort needs: it holds x_new of every particle of
 // old cell c' in registers.  This kernel is k_convect_contiguous and k_band_classify in one pass over HBM (x, vx read through a
@@ -1563,8 +1627,12 @@ static int launch_band(mb_ctx* ctx, const mb_grid1d* grid, mb_pv* pv, mb_pia* pi
         if (r) return r;
     } else if (B.P != nullptr) {
         ProfScope ps(ctx, PROF_SORT_SCAN);
-        k_band_combine<W><<<grid_for(nc, 128, 16), 128, 0, st>>>(B.P, S.M, B.E.cntB, B.E.cntA, B.seg_lo, B.seg_n, S.start, pv->cur, pv->alt, nc,
-                                                               B.pcache, S.flags);
+        if constexpr (W + 2 <= 32)
+            k_band_combine_warp<W><<<grid_for(nc * 32, 256, 8), 256, 0, st>>>(B.P, S.M, B.E.cntB, B.E.cntA, B.seg_lo, B.seg_n, S.start, pv->cur, pv->alt,
+                                                                            nc, B.pcache, S.flags);
+        else
+            k_band_combine<W><<<grid_for(nc, 128, 16), 128, 0, st>>>(B.P, S.M, B.E.cntB, B.E.cntA, B.seg_lo, B.seg_n, S.start, pv->cur, pv->alt, nc,
+                                                                   B.pcache, S.flags);
         MB_LAUNCH_CHECK(ctx);
     }
     return MB_OK;
